@@ -1,0 +1,162 @@
+"""Pins oracle/hotpath.py to outputs of the REAL reference code (tests/golden/*.npz made by
+oracle/make_goldens.py).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import hotpath as hp
+from mfb_testutil import t32
+
+
+def _screens1d(edges, k, bandwidth=0.5, direction=None):
+    return [[hp.Screen1D(edges=edges, bandwidth=bandwidth, axis=0, direction=direction)] for _ in range(k)]
+
+
+def test_kde1d_6d_matches_reference(golden):
+    g = golden("kde1d_6d")
+    x, mats, edges = t32(g["x"]), t32(g["matrices"]), t32(g["edges"])
+    out = hp.simulate(x, list(mats), _screens1d(edges, len(mats)))
+    got = torch.stack([o[0] for o in out])
+    assert torch.allclose(got, t32(g["kde"]), rtol=0, atol=2e-7)
+    # chunked evaluation = same arithmetic per row
+    out = hp.simulate(x, list(mats), _screens1d(edges, len(mats)), chunk=512)
+    got = torch.stack([o[0] for o in out])
+    assert torch.allclose(got, t32(g["kde"]), rtol=1e-5, atol=1e-7)
+
+
+def test_hard_hist_1d_matches_reference_bitwise(golden):
+    g = golden("kde1d_6d")
+    x, mats, edges = t32(g["x"]), t32(g["matrices"]), t32(g["edges"])
+    out = hp.simulate(x, list(mats), _screens1d(edges, len(mats)), kde=False)
+    got = torch.stack([o[0] for o in out])
+    assert torch.equal(got, t32(g["hard"]))
+    # integer counts -> density reproduces torch.histogram(density=True) bit for bit
+    for k in range(len(mats)):
+        u = t32(g["uproj"][k])
+        counts = hp.hist_counts_1d(u, edges)
+        assert torch.equal(hp.density_from_counts_1d(counts, edges), t32(g["hard"][k]))
+
+
+def test_kde1d_2d_rotations_and_direction(golden):
+    g = golden("kde1d_2d")
+    x, mats, edges = t32(g["x"]), t32(g["matrices"]), t32(g["edges"])
+    got = torch.stack([o[0] for o in hp.simulate(x, list(mats), _screens1d(edges, len(mats)))])
+    assert torch.allclose(got, t32(g["kde"]), rtol=0, atol=2e-7)
+    scr = _screens1d(edges, len(mats), bandwidth=float(g["bandwidth_dir"]), direction=t32(g["direction"]))
+    got = torch.stack([o[0] for o in hp.simulate(x, list(mats), scr)])
+    assert torch.allclose(got, t32(g["kde_dir"]), rtol=0, atol=2e-7)
+
+
+def test_kde2d_and_hard2d(golden):
+    g = golden("kde2d_4d")
+    x, mats = t32(g["x"]), t32(g["matrices"])
+    ex, ey = t32(g["edges_x"]), t32(g["edges_y"])
+    bw = tuple(float(b) for b in g["bandwidth"])
+    scr = [[hp.Screen2D(axis=(0, 2), edges_x=ex, edges_y=ey, bandwidth=bw)] for _ in mats]
+    got = torch.stack([o[0] for o in hp.simulate(x, list(mats), scr)])
+    assert torch.allclose(got, t32(g["kde"]), rtol=1e-6, atol=1e-8)
+    hard = torch.stack([o[0] for o in hp.simulate(x, list(mats), scr, kde=False)])
+    assert torch.equal(hard, t32(g["hard"]))
+    # counts rule == np.histogramdd
+    u = hp.linear_map(x, mats[0])[:, [0, 2]]
+    counts = hp.hist_counts_2d(u, ex, ey)
+    dens = counts.double() / counts.sum() / (torch.diff(ex).double()[:, None] * torch.diff(ey).double()[None, :])
+    assert torch.allclose(dens.float(), t32(g["hard"][0]), rtol=1e-6, atol=0)
+    kl = torch.stack([hp.kl_div(p, m) for p, m in zip(got, t32(g["meas"]))])
+    assert torch.allclose(kl, t32(g["kl"]), rtol=1e-5, atol=1e-8)
+
+
+def test_discrepancies_and_gradient(golden):
+    g = golden("kde1d_6d")
+    kde, meas = t32(g["kde"]), t32(g["meas"])
+    assert torch.allclose(torch.stack([hp.kl_div(p, m) for p, m in zip(kde, meas)]), t32(g["kl"]), rtol=1e-6)
+    assert torch.allclose(torch.stack([hp.mae(p, m) for p, m in zip(kde, meas)]), t32(g["mae"]), rtol=1e-6)
+    assert torch.allclose(torch.stack([hp.mse(p, m) for p, m in zip(kde, meas)]), t32(g["mse"]), rtol=1e-6)
+    x = t32(g["x"]).requires_grad_(True)
+    mats, edges = t32(g["matrices"]), t32(g["edges"])
+    out = hp.simulate(x, list(mats), _screens1d(edges, len(mats)))
+    loss = sum(hp.kl_div(o[0], m) for o, m in zip(out, meas)) / len(mats)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["mean_kl"])) <= 1e-6 * abs(float(g["mean_kl"]))
+    ref = t32(g["grad_x"])
+    assert (x.grad - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_prior_entropy_loss(golden):
+    g = golden("entropy_loss")
+    x, logq = t32(g["x"]), t32(g["logq"])
+    s = float(g["prior_scale"])
+    assert torch.allclose(hp.gaussian_log_prob(x, s), t32(g["prior_log_prob"]), rtol=1e-6, atol=1e-6)
+    assert abs(float(hp.mc_entropy(x, logq, s)) - float(g["h_mc"])) < 1e-5
+    assert abs(float(hp.mc_entropy(x, logq, None)) - float(g["h_mc_noprior"])) < 1e-5
+    assert abs(float(hp.cov_entropy(x)) - float(g["h_cov"])) < 1e-5
+    k = golden("kde1d_6d")
+    xs, mats, edges, meas = t32(k["x"]), t32(k["matrices"]), t32(k["edges"]), t32(k["meas"])
+    n = int(g["loss_n"])
+    L, H, D = hp.mentflow_loss(xs[:n], t32(g["loss_logq"])[:n], list(mats), _screens1d(edges, len(mats)),
+                               [[m] for m in meas], s, float(g["loss_penalty"]))
+    assert abs(float(L) - float(g["loss_L"])) <= 1e-5 * abs(float(g["loss_L"]))
+    assert abs(float(H) - float(g["loss_H"])) <= 1e-5 * abs(float(g["loss_H"]))
+    assert torch.allclose(torch.stack(D), t32(g["loss_D"]), rtol=1e-5)
+
+
+def test_ment_prob_sampling_and_update(golden):
+    g = golden("ment_4d")
+    mats, edges, meas = t32(g["matrices"]), t32(g["edges"]), t32(g["meas"])
+    k = len(mats)
+    scr = _screens1d(edges, k)
+    tables = [[t] for t in t32(g["tables0"])]
+    s = float(g["prior_scale"])
+    prob = hp.ment_prob(t32(g["xq"]), list(mats), scr, tables, s)
+    assert torch.allclose(prob, t32(g["prob_q"]), rtol=1e-5, atol=1e-30)
+    res, xmax = int(g["grid_res"]), float(g["grid_xmax"])
+    gedges = [torch.linspace(-xmax, xmax, res + 1) for _ in range(4)]
+    pts = hp.grid_points([hp.centres(e) for e in gedges])
+    pg = hp.ment_prob(pts, list(mats), scr, tables, s)
+    assert torch.allclose(pg, t32(g["prob_grid"]), rtol=1e-5, atol=1e-30)
+    # same global RNG stream as the reference's sampler (sample.py:27-57)
+    torch.manual_seed(int(g["sample_seed"]))
+    xs = hp.sample_grid(pg.reshape(4 * [res]), gedges, int(g["n_samples"]))
+    assert torch.equal(xs[:512], t32(g["xs_head"]))
+    # one simulate(0, 0) in sample mode: sample -> transform -> KDE -> normalise
+    torch.manual_seed(int(g["sample_seed"]))
+    xs = hp.sample_grid(pg.reshape(4 * [res]), gedges, int(g["n_samples"]))
+    pred = hp.kde_profile_1d(hp.linear_map(xs, mats[0])[:, 0], edges, scr[0][0].sigma)
+    pred = hp.normalize_projection(pred, edges[1] - edges[0])
+    assert torch.allclose(pred, t32(g["pred0"]), rtol=1e-5, atol=1e-8)
+    # a whole Gauss-Seidel sweep (ment.py:336-371): sequential over k, tables feed forward
+    torch.manual_seed(int(g["gs_seed"]))
+    cur = [t.clone() for t in t32(g["tables0"])]
+    for i in range(k):
+        pgi = hp.ment_prob(pts, list(mats), scr, [[t] for t in cur], s)
+        xs = hp.sample_grid(pgi.reshape(4 * [res]), gedges, int(g["n_samples"]))
+        pred = hp.kde_profile_1d(hp.linear_map(xs, mats[i])[:, 0], edges, scr[i][0].sigma)
+        pred = hp.normalize_projection(pred, edges[1] - edges[0])
+        cur[i] = hp.gauss_seidel_table(cur[i], meas[i], pred, float(g["lr"]), float(g["thresh"]))
+    assert torch.allclose(torch.stack(cur), t32(g["tables1"]), rtol=1e-5, atol=1e-8)
+
+
+def test_ment_integrate_mode(golden):
+    g = golden("ment_2d_integrate")
+    mats, edges, meas = t32(g["matrices"]), t32(g["edges"]), t32(g["meas"])
+    k, s = len(mats), float(g["prior_scale"])
+    scr = _screens1d(edges, k)
+    lo, hi = [float(v) for v in g["int_limits"]]
+    ipts = torch.linspace(lo, hi, int(g["int_shape"]))
+    c = hp.centres(edges)
+
+    def integrate(i, tables):
+        """ment.py:267-317 for a 1-D screen in 2-D: u = (pixel, t); x = M^-1 u; sum rho."""
+        minv = torch.linalg.inv(mats[i])
+        pred = torch.zeros(len(c))
+        for b in range(len(c)):
+            u = torch.stack([torch.full_like(ipts, float(c[b])), ipts], dim=1)
+            pred[b] = hp.ment_prob(torch.matmul(u, minv.T), list(mats), scr, tables, s).sum()
+        return hp.normalize_projection(pred, edges[1] - edges[0])
+
+    tables = [[hp.initial_table(m)] for m in meas]
+    assert torch.allclose(integrate(1, tables), t32(g["pred_1_0"]), rtol=1e-5, atol=1e-8)
+    for _ in range(2):
+        for i in range(k):
+            tables[i][0] = hp.gauss_seidel_table(tables[i][0], meas[i], integrate(i, tables), 1.0, 1e-10)
+    got = torch.stack([t[0] for t in tables])
+    assert torch.allclose(got, t32(g["tables_after_2"]), rtol=1e-4, atol=1e-7)
