@@ -1,0 +1,129 @@
+/*
+ * mentflow_b200 -- C ABI of the B200-native MENT-Flow hot path.
+ *
+ * The reference (austin-hoover/ment-flow) is pure Python/PyTorch and has no FFI layer of
+ * its own; the functions below are what a reference-side binding (ctypes, see
+ * INTEGRATION.md) calls in place of the reference Python functions cited on each entry
+ * (paths relative to the reference's `mentflow/` package, per-file line numbers).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 / int32 / int64 data owned by the caller
+ *     (PyTorch tensors in the shipped host layer); row-major, contiguous, 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates, synchronises or
+ *     keeps global mutable state, so calls are safe from autograd worker threads;
+ *   - return value: 0 on success, a cudaError_t code (>0) for CUDA failures,
+ *     negative MFB_E_* for argument errors; mfb_error_string() decodes both;
+ *   - workspaces are caller-allocated; query the size with the matching *_workspace_bytes.
+ *   - there is no CPU implementation behind any entry point.
+ */
+#ifndef MENTFLOW_B200_H
+#define MENTFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB_ABI_VERSION 1
+
+#define MFB_E_BADARG (-1)      /* null pointer / non-positive size / unsupported shape   */
+#define MFB_E_UNSUPPORTED (-2) /* combination not compiled (e.g. D > 8, hidden != 64)    */
+#define MFB_E_WORKSPACE (-3)   /* workspace too small                                    */
+
+int mfb_abi_version(void);
+const char* mfb_error_string(int code);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int mfb_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Screen geometry of one 1-D projection, 8 floats per projection (device array [K][8]):
+ *   [0] c0        first bin centre            (diagnostics/diagnostics.py:111 `coords`)
+ *   [1] delta     centre spacing c[1]-c[0]    (diagnostics/histogram.py:40)
+ *   [2] sigma     absolute kernel width       (diagnostics/diagnostics.py:113-114)
+ *   [3..7]        reserved (0)
+ * 2-D screens use two consecutive records (x axis, then y axis).
+ * ------------------------------------------------------------------------------------ */
+#define MFB_GEOM_STRIDE 8
+
+/* ---- fused linear projection + Gaussian KDE, 1-D screens ------------------------------
+ * Replaces, for all K (transform, Histogram1D) pairs at once:
+ *   simulate/simulate.py:29-33        for transform ...: u = transform(x.clone())
+ *   simulate/transform.py:67-68       u = x @ M.T            (only the measured row)
+ *   diagnostics/diagnostics.py:116-127  project -> kde_histogram_1d
+ *   diagnostics/histogram.py:37-39    K_nb = exp(-0.5((u-c_b)/sigma)^2), sum over n
+ * x[n][d]; proj[K][d] (row `axis` of M_k, or M_k^T d_hat); out partial sums are reduced
+ * deterministically into sums[K][B] = S_kb = sum_n K_nb (unnormalised; this is what ranks
+ * all-reduce).  max_sigma_over_delta = largest sigma/delta of the K screens (host value; sets
+ * the deposit window: bins further than ~6.4 sigma from a particle are skipped).         */
+int64_t mfb_kde1d_workspace_bytes(int64_t n, int d, int k, int b);
+int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
+                          int k, int b, float max_sigma_over_delta, float* sums, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+/* diagnostics/histogram.py:39-43: p = (S/N) / (sum_b (S_b/N) * delta + 1e-10)            */
+int mfb_kde1d_normalize(const float* sums, double n_total, const float* geom, int k, int b,
+                        float* profiles, void* stream);
+/* backward of the normalisation: gsums = dL/dS given gprof = dL/dp    */
+int mfb_kde1d_normalize_bwd(const float* sums, double n_total, const float* geom, int k, int b,
+                            const float* gprof, float* gsums, void* stream);
+/* dL/dx[n][d] (+)= sum_k proj_k * sum_b gsums[k][b] K_nb (-(u-c_b)/sigma^2); accumulate!=0
+ * adds into gx instead of overwriting it.                                               */
+int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
+                          int k, int b, float max_sigma_over_delta, const float* gsums, float* gx,
+                          int accumulate, void* stream);
+
+/* ---- fused projection + exact histogram, 1-D screens -----------------------------------
+ * Replaces diagnostics/diagnostics.py:128-131 (torch.histogram(x_proj, edges)): bin i holds
+ * edges[i] <= u < edges[i+1], last bin closed, everything else dropped.  edges[K][B+1];
+ * counts[K][B] int64, ADDED to (zero them first; integer adds => bit-reproducible).     */
+int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, const float* edges,
+                       int k, int b, int64_t* counts, void* stream);
+
+/* ---- 2-D screens ------------------------------------------------------------------------
+ * diagnostics/diagnostics.py:179-191 -> histogram.py:89-101, 47-74: P = Kx^T Ky.
+ * proj[K][2][d], geom[K][2][8]; sums[K][bx][by] unnormalised.  Deposits are accumulated in
+ * fixed point (2^-20 per deposit in shared memory, 64-bit integers globally) so the result
+ * is independent of the atomics' order, the CTA decomposition and the rank count.
+ * workspace = int64 accumulators [K][bx][by] (this is what ranks all-reduce exactly).    */
+#define MFB_KDE2D_FRAC_BITS 20
+int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by);
+int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
+                          int k, int bx, int by, float max_sigma_over_delta, float* sums,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+/* P <- P / (sum(P) dx dy + 1e-10)  (histogram.py:70-73) and its backward                */
+int mfb_kde2d_normalize(const float* sums, const float* geom, int k, int bx, int by,
+                        float* profiles, void* stream);
+int mfb_kde2d_normalize_bwd(const float* sums, const float* geom, int k, int bx, int by,
+                            const float* gprof, float* gsums, void* stream);
+int mfb_project_kde2d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
+                          int k, int bx, int by, float max_sigma_over_delta, const float* gsums,
+                          float* gx, int accumulate, void* stream);
+/* diagnostics/diagnostics.py:192-201 (np.histogramdd): edges_x[K][bx+1], edges_y[K][by+1];
+ * counts[K][bx][by] int64, added to                                                      */
+int mfb_project_hist2d(const float* x, int64_t n, int d, const float* proj, const float* edges_x,
+                       const float* edges_y, int k, int bx, int by, int64_t* counts, void* stream);
+
+/* ---- neural spline flow (zuko 1.3.1 NSF as built by generate/build.py:36-46) ------------
+ * One autoregressive layer per call: y = RQS(MaskedMLP(v))(v), logq_out = logq_in - ladj.
+ * Replaces generate/flows/zuko.py:24-29 (rsample_and_log_prob / transform.inv) layer by layer.
+ * params: packed fp32 block of one layer (layout: mfb_nsf_layer_param_floats / nsf.cu).
+ * first_layer != 0: logq_in is ignored and replaced by log N(v; 0, I).
+ * logq_in/logq_out may be NULL (sample only).  order_host: HOST array of d ints, the
+ * layer's autoregressive order (feature with order 0 has a bias-only spline); may be NULL.*/
+int64_t mfb_nsf_layer_param_floats(int d, int hidden_units, int hidden_layers, int bins);
+int mfb_nsf_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hidden_layers,
+                      int bins, const float* params, const int32_t* order_host, const float* logq_in,
+                      int first_layer, float* y, float* logq_out, void* stream);
+
+/* ---- Monte-Carlo entropy pieces (entropy.py:58-62, prior.py:25-26) ----------------------
+ * out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j
+ * (double precision, deterministic two-stage reduction; the x_i / x_i x_j block only when
+ * with_cov != 0; logq may be NULL).  entropy.py:35-38 (torch.cov) uses the second block. */
+int64_t mfb_moments_workspace_bytes(int64_t n, int d);
+int mfb_moments(const float* x, const float* logq, int64_t n, int d, int with_cov, double* out,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MENTFLOW_B200_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of the C ABI declared in ``include/mentflow_b200.h``.
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is
+missing (or a symbol is), importing the ops fails loudly.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libmentflow_b200.so")
+
+P = c_void_p  # every device pointer crosses the ABI as a plain address
+
+# name -> (restype, argtypes); mirrors include/mentflow_b200.h line by line
+SIGNATURES = {
+    "mfb_abi_version": (c_int, []),
+    "mfb_error_string": (c_char_p, [c_int]),
+    "mfb_sm_count": (c_int, []),
+    "mfb_kde1d_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "mfb_project_kde1d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int64, P]),
+    "mfb_kde1d_normalize": (c_int, [P, c_double, P, c_int, c_int, P, P]),
+    "mfb_kde1d_normalize_bwd": (c_int, [P, c_double, P, c_int, c_int, P, P, P]),
+    "mfb_project_kde1d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int, P]),
+    "mfb_project_hist1d": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P]),
+    "mfb_kde2d_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
+    "mfb_project_kde2d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int64, P]),
+    "mfb_kde2d_normalize": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "mfb_kde2d_normalize_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "mfb_project_kde2d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
+    "mfb_project_hist2d": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_int, P, P]),
+    "mfb_nsf_layer_param_floats": (c_int64, [c_int, c_int, c_int, c_int]),
+    "mfb_nsf_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
+    "mfb_moments_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "mfb_moments": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
+}
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load ``libmentflow_b200.so`` (built by ``python -m mentflow_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found. mentflow_b200 has no CPU/PyTorch fallback: build the CUDA "
+            "library first with `python -m mentflow_b200.build` (needs nvcc, targets sm_100a).")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise LibraryMissing(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mfb_error_string(rc).decode()
+        raise RuntimeError(f"mentflow_b200 {what} failed: {msg} (code {rc})")

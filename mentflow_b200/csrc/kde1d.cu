@@ -1,0 +1,559 @@
+// Fused linear projection + 1-D binning (Gaussian KDE deposit or exact histogram).
+//
+// Replaces, for all K measurements in ONE pass over the particles (reference file:line,
+// relative to mentflow/):
+//   simulate/simulate.py:29-33, simulate/transform.py:67-68   u = x.clone() @ M_k^T  (K SGEMMs + K clones)
+//   diagnostics/diagnostics.py:116-131                       project, then KDE or torch.histogram
+//   diagnostics/histogram.py:37-39                           dense (N,B) kernel matrix + mean
+//
+// Design (B200): the particle block streams HBM -> smem through the TMA engine
+// (cp.async.bulk + mbarrier, double buffered).  Thread t of a CTA owns projection
+// k = t % Kc and particle slice t / Kc, and a PRIVATE column of bins in shared memory
+// (bins[b][t]: bank = t % 32, conflict free), so deposits are plain LDS/FADD/STS -- no
+// atomics, and the accumulation order is fixed => run-to-run deterministic.  Each particle
+// touches only the 2R+1 bins within ~6.4 sigma of its projection (everything else is below
+// fp32 resolution of the sum), instead of all B.  Per-CTA partials are merged in a fixed
+// order by a second tiny kernel.
+#include "common.cuh"
+
+namespace mfb {
+
+constexpr int kTile = 1024;        // particles per TMA stage
+constexpr int kBinThreads = 256;   // upper bound on threads per CTA of the deposit kernels
+
+struct ProjLaunch {
+  int kc;        // projections handled per CTA (<= kBinThreads)
+  int slices;    // particle slices per CTA
+  int threads;   // kc * slices
+  int kchunks;   // gridDim.y
+  int grid_x;    // particle-tile CTAs
+  int tile;      // particles per stage (multiple of 4, <= kTile)
+  size_t smem;   // dynamic shared memory bytes
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// window radius in bins: taps further than (R+0.5) bins from the particle contribute
+// < exp(-0.5*6.44^2) ~ 1e-9 of a central tap.
+static inline int window_radius(double sigma_over_delta) {
+  double r = 6.44 * sigma_over_delta - 0.5;
+  int ri = (int)r;
+  if ((double)ri < r) ++ri;
+  return ri < 1 ? 1 : ri;
+}
+
+static ProjLaunch plan_launch(int64_t n, int d, int k, int b, int bytes_per_bin, size_t extra_smem) {
+  ProjLaunch L;
+  L.kchunks = (k + kBinThreads - 1) / kBinThreads;
+  L.kc = (k + L.kchunks - 1) / L.kchunks;
+  // private bins must fit: b * threads * bytes_per_bin + 2 stages of x
+  size_t budget = 200 * 1024 - extra_smem;
+  int max_threads = kBinThreads;
+  while (max_threads > L.kc && (size_t)b * max_threads * bytes_per_bin + 2ull * kTile * d * 4 > budget)
+    max_threads -= 32;
+  L.slices = max_threads / L.kc;
+  if (L.slices < 1) L.slices = 1;
+  L.threads = L.kc * L.slices;
+  int sms = sm_count();
+  // small batches: shrink the tile so that every SM gets work
+  int tile = kTile;
+  while (tile > 128 && ceil_div64(n, tile) < 2 * sms) tile >>= 1;
+  L.tile = tile;
+  int64_t tiles = ceil_div64(n, tile);
+  size_t smem = 2ull * tile * d * 4 + 64 + (size_t)b * L.threads * bytes_per_bin + extra_smem;
+  int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  int64_t gx = (int64_t)sms * ctas_per_sm;
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  L.grid_x = (int)gx;
+  L.smem = smem;
+  return L;
+}
+
+// ---- TMA tile pipeline ---------------------------------------------------------------------
+struct TilePipe {
+  float* buf[2];
+  uint64_t* bar;  // 2 barriers
+};
+
+__device__ __forceinline__ void issue_tile(const TilePipe& tp, int stage, const float* __restrict__ x,
+                                           int64_t n, int d, int tile, int64_t tile_idx) {
+  // called by thread 0 only
+  int64_t first = tile_idx * tile;
+  int64_t rows = n - first;
+  if (rows > tile) rows = tile;
+  uint32_t bytes = (uint32_t)(rows * d * 4);
+  uint32_t bulk = bytes & ~15u;
+  const float* src = x + first * d;
+  // ragged tail (< 16 B): plain stores, ordered before the arrive below
+  for (uint32_t i = bulk / 4; i < bytes / 4; ++i) tp.buf[stage][i] = src[i];
+  mbar_expect_tx(&tp.bar[stage], bulk);
+  if (bulk) tma_load_1d(tp.buf[stage], src, bulk, &tp.bar[stage]);
+}
+
+template <int D>
+__device__ __forceinline__ float project_row(const float* __restrict__ xr, const float (&w)[kMaxDim], int d) {
+  float u = 0.f;
+  if (D > 0) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) u = fmaf(w[i], xr[i], u);
+  } else {
+    for (int i = 0; i < d; ++i) u = fmaf(w[i], xr[i], u);
+  }
+  return u;
+}
+
+// ---- forward: KDE deposit --------------------------------------------------------------------
+template <int D, int R>
+__global__ void __launch_bounds__(kBinThreads)
+kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
+                     const float* __restrict__ geom, int K, int B, int kc, int tile,
+                     float* __restrict__ partial /* [gridDim.x][K][B] */) {
+  const int d = D > 0 ? D : d_rt;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TilePipe tp;
+  tp.buf[0] = reinterpret_cast<float*>(smem_raw);
+  tp.buf[1] = tp.buf[0] + (size_t)tile * d;
+  tp.bar = reinterpret_cast<uint64_t*>(tp.buf[1] + (size_t)tile * d);
+  float* bins = reinterpret_cast<float*>(tp.bar + 8);
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int kbase = blockIdx.y * kc;
+  const int kloc = tid % kc;
+  const int slice = tid / kc;
+  const int slices = nthreads / kc;
+  const int k = kbase + kloc;
+  const bool active = k < K;
+
+  for (int i = tid; i < B * nthreads; i += nthreads) bins[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&tp.bar[0], 1);
+    mbar_init(&tp.bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  float w[kMaxDim];
+  float c0 = 0.f, inv_delta = 0.f, alpha = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) w[i] = i < d ? proj[(size_t)k * d + i] : 0.f;
+    const float* g = geom + (size_t)k * MFB_GEOM_STRIDE;
+    c0 = g[0];
+    inv_delta = 1.0f / g[1];
+    float r = g[1] / g[2];
+    alpha = -0.5f * r * r * kLog2e;
+  }
+
+  const int64_t ntiles = (n + tile - 1) / tile;
+  if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
+  float* mybins = bins + tid;
+  const float lo = -(float)(R + 2), hi = (float)(B + R + 1);
+
+  int it = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int64_t nxt = t + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue_tile(tp, stage ^ 1, x, n, d, tile, nxt);
+    mbar_wait(&tp.bar[stage], (it >> 1) & 1);
+    int64_t rows64 = n - t * tile;
+    const int rows = rows64 > tile ? tile : (int)rows64;
+    const float* xs = tp.buf[stage];
+    if (active) {
+      for (int p = slice; p < rows; p += slices) {
+        const float u = project_row<D>(xs + (size_t)p * d, w, d);
+        float a = (u - c0) * inv_delta;
+        a = fminf(fmaxf(a, lo), hi);
+        const float fb = rintf(a);
+        const int b0 = (int)fb;
+        const float f = a - fb;
+#pragma unroll
+        for (int j = -R; j <= R; ++j) {
+          const int b = b0 + j;
+          const float tt = f - (float)j;
+          const float val = fast_exp2(alpha * tt * tt);
+          if ((unsigned)b < (unsigned)B) mybins[(size_t)b * nthreads] += val;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with buf[stage] before it is refilled
+  }
+
+  // fixed-order merge of the private columns -> per-CTA partial
+  float* out = partial + (size_t)blockIdx.x * K * B;
+  for (int idx = tid; idx < kc * B; idx += nthreads) {
+    const int kk = idx % kc, b = idx / kc;
+    if (kbase + kk < K) {
+      float s = 0.f;
+      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)b * nthreads + sl * kc + kk];
+      out[(size_t)(kbase + kk) * B + b] = s;
+    }
+  }
+}
+
+// sums[k][b] = sum over CTAs (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, int64_t len,
+                                       float* __restrict__ sums) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * len + i];
+    sums[i] = s;
+  }
+}
+
+// ---- normalisation and its backward: one CTA per projection ---------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  // deterministic: warp shuffle tree, then thread 0 adds the 8 warp sums in order
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    red[32] = t;
+  }
+  __syncthreads();
+  t = red[32];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+kde1d_normalize_kernel(const float* __restrict__ sums, float inv_n, const float* __restrict__ geom, int B,
+                       float* __restrict__ prof) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 1];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) acc += sums[(size_t)k * B + b] * inv_n * delta;
+  const float z = block_sum_256(acc, red) + 1.0e-10f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) prof[(size_t)k * B + b] = sums[(size_t)k * B + b] * inv_n / z;
+}
+
+__global__ void __launch_bounds__(256)
+kde1d_normalize_bwd_kernel(const float* __restrict__ sums, float inv_n, const float* __restrict__ geom, int B,
+                           const float* __restrict__ gprof, float* __restrict__ gsums) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 1];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) acc += sums[(size_t)k * B + b] * inv_n * delta;
+  const float z = block_sum_256(acc, red) + 1.0e-10f;
+  float dot = 0.f;  // sum_j gp_j p_j
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+    dot += gprof[(size_t)k * B + b] * (sums[(size_t)k * B + b] * inv_n / z);
+  const float g = block_sum_256(dot, red);
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+    gsums[(size_t)k * B + b] = (gprof[(size_t)k * B + b] / z - delta * g / z) * inv_n;
+}
+
+// ---- backward w.r.t. the particles: thread per particle ---------------------------------------
+template <int D, int R>
+__global__ void __launch_bounds__(256)
+kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
+                 const float* __restrict__ geom, int K, int B, const float* __restrict__ gsums,
+                 float* __restrict__ gx, int accumulate) {
+  const int d = D > 0 ? D : d_rt;
+  extern __shared__ __align__(16) float sm[];
+  float* s_g = sm;                          // [K][B]
+  float* s_w = s_g + (size_t)K * B;         // [K][d]
+  float4* s_q = reinterpret_cast<float4*>(s_w + (((size_t)K * d + 3) & ~(size_t)3));  // [K] c0, inv_delta, alpha, beta
+  for (int i = threadIdx.x; i < K * B; i += blockDim.x) s_g[i] = gsums[i];
+  for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_w[i] = proj[i];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float* g = geom + (size_t)k * MFB_GEOM_STRIDE;
+    const float r = g[1] / g[2];
+    s_q[k] = make_float4(g[0], 1.0f / g[1], -0.5f * r * r * kLog2e, -g[1] / (g[2] * g[2]));
+  }
+  __syncthreads();
+  const float lo = -(float)(R + 2), hi = (float)(B + R + 1);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    float xr[kMaxDim], g[kMaxDim];
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) {
+      xr[i] = (i < d) ? x[p * d + i] : 0.f;
+      g[i] = 0.f;
+    }
+    for (int k = 0; k < K; ++k) {
+      const float* wk = s_w + (size_t)k * d;
+      float u = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i)
+        if (i < d) u = fmaf(wk[i], xr[i], u);
+      const float4 q = s_q[k];
+      float a = (u - q.x) * q.y;
+      a = fminf(fmaxf(a, lo), hi);
+      const float fb = rintf(a);
+      const int b0 = (int)fb;
+      const float f = a - fb;
+      const float* grow = s_g + (size_t)k * B;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = -R; j <= R; ++j) {
+        const int b = b0 + j;
+        const float tt = f - (float)j;
+        const float val = fast_exp2(q.z * tt * tt);
+        if ((unsigned)b < (unsigned)B) acc = fmaf(grow[b], val * tt, acc);
+      }
+      const float gu = q.w * acc;
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i)
+        if (i < d) g[i] = fmaf(wk[i], gu, g[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i)
+      if (i < d) {
+        if (accumulate) gx[p * d + i] += g[i];
+        else gx[p * d + i] = g[i];
+      }
+  }
+}
+
+// ---- exact histogram deposit ----------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kBinThreads)
+hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
+                      const float* __restrict__ edges, int K, int B, int kc, int tile,
+                      unsigned long long* __restrict__ counts /* [K][B] */) {
+  const int d = D > 0 ? D : d_rt;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TilePipe tp;
+  tp.buf[0] = reinterpret_cast<float*>(smem_raw);
+  tp.buf[1] = tp.buf[0] + (size_t)tile * d;
+  tp.bar = reinterpret_cast<uint64_t*>(tp.buf[1] + (size_t)tile * d);
+  unsigned int* bins = reinterpret_cast<unsigned int*>(tp.bar + 8);
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  float* s_edges = reinterpret_cast<float*>(bins + (size_t)B * nthreads);  // [kc][B+1]
+  const int kbase = blockIdx.y * kc;
+  const int kloc = tid % kc;
+  const int slice = tid / kc;
+  const int slices = nthreads / kc;
+  const int k = kbase + kloc;
+  const bool active = k < K;
+
+  for (int i = tid; i < B * nthreads; i += nthreads) bins[i] = 0u;
+  for (int i = tid; i < kc * (B + 1); i += nthreads) {
+    const int kk = kbase + i / (B + 1);
+    s_edges[i] = kk < K ? edges[(size_t)kk * (B + 1) + i % (B + 1)] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&tp.bar[0], 1);
+    mbar_init(&tp.bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  float w[kMaxDim];
+  const float* E = s_edges + (size_t)kloc * (B + 1);
+  float e0 = 0.f, eB = 0.f, inv_w = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) w[i] = i < d ? proj[(size_t)k * d + i] : 0.f;
+    e0 = E[0];
+    eB = E[B];
+    inv_w = (float)B / (eB - e0);
+  }
+
+  const int64_t ntiles = (n + tile - 1) / tile;
+  if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
+  unsigned int* mybins = bins + tid;
+
+  int it = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int64_t nxt = t + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue_tile(tp, stage ^ 1, x, n, d, tile, nxt);
+    mbar_wait(&tp.bar[stage], (it >> 1) & 1);
+    int64_t rows64 = n - t * tile;
+    const int rows = rows64 > tile ? tile : (int)rows64;
+    const float* xs = tp.buf[stage];
+    if (active) {
+      for (int p = slice; p < rows; p += slices) {
+        const float u = project_row<D>(xs + (size_t)p * d, w, d);
+        if (u >= e0 && u <= eB) {  // NaN fails both
+          int b = (int)((u - e0) * inv_w);
+          b = min(max(b, 0), B - 1);
+          while (b > 0 && u < E[b]) --b;
+          while (b < B - 1 && u >= E[b + 1]) ++b;
+          mybins[(size_t)b * nthreads] += 1u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int idx = tid; idx < kc * B; idx += nthreads) {
+    const int kk = idx % kc, b = idx / kc;
+    if (kbase + kk < K) {
+      unsigned long long s = 0ull;
+      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)b * nthreads + sl * kc + kk];
+      if (s) atomicAdd(&counts[(size_t)(kbase + kk) * B + b], s);
+    }
+  }
+}
+
+// ---- host-side dispatch -----------------------------------------------------------------------------
+template <int D>
+static int launch_kde1d_deposit(int r, const ProjLaunch& L, const float* x, int64_t n, int d, const float* proj,
+                                const float* geom, int k, int b, float* partial, cudaStream_t st) {
+  dim3 grid(L.grid_x, L.kchunks), block(L.threads);
+#define MFB_LAUNCH_R(RR)                                                                                   \
+  {                                                                                                        \
+    MFB_CUDA(cudaFuncSetAttribute(kde1d_deposit_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)L.smem));                                                           \
+    kde1d_deposit_kernel<D, RR><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, partial); \
+  }
+  if (r <= 3) MFB_LAUNCH_R(3)
+  else if (r <= 6) MFB_LAUNCH_R(6)
+  else if (r <= 12) MFB_LAUNCH_R(12)
+  else return MFB_E_UNSUPPORTED;
+#undef MFB_LAUNCH_R
+  return launch_status();
+}
+
+template <int D>
+static int launch_kde1d_bwd(int r, int grid, size_t smem, const float* x, int64_t n, int d, const float* proj,
+                            const float* geom, int k, int b, const float* gsums, float* gx, int acc,
+                            cudaStream_t st) {
+#define MFB_LAUNCH_R(RR)                                                                                \
+  {                                                                                                     \
+    MFB_CUDA(cudaFuncSetAttribute(kde1d_bwd_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)smem));                                                          \
+    kde1d_bwd_kernel<D, RR><<<grid, 256, smem, st>>>(x, n, d, proj, geom, k, b, gsums, gx, acc);         \
+  }
+  if (r <= 3) MFB_LAUNCH_R(3)
+  else if (r <= 6) MFB_LAUNCH_R(6)
+  else if (r <= 12) MFB_LAUNCH_R(12)
+  else return MFB_E_UNSUPPORTED;
+#undef MFB_LAUNCH_R
+  return launch_status();
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+// The window radius must be known on the host while geom lives on the device, so the caller
+// passes the largest sigma/delta ratio of the launch (<= 0 means the default bandwidth 0.5).
+static int radius_from_hint(float hint) { return window_radius(hint > 0.f ? hint : 0.5); }
+
+extern "C" {
+
+int64_t mfb_kde1d_workspace_bytes(int64_t n, int d, int k, int b) {
+  if (n < 0 || d < 1 || d > kMaxDim || k < 1 || b < 1) return 0;
+  ProjLaunch L = plan_launch(n > 0 ? n : 1, d, k, b, 4, 0);
+  return (int64_t)L.grid_x * k * b * 4;
+}
+
+int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                            float max_sigma_over_delta, float* sums, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && sums && workspace);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return (int)cudaMemsetAsync(sums, 0, (size_t)k * b * 4, st);
+  ProjLaunch L = plan_launch(n, d, k, b, 4, 0);
+  if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
+  if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
+  const int r = radius_from_hint(max_sigma_over_delta);
+  float* partial = (float*)workspace;
+  int rc;
+  switch (d) {
+    case 2: rc = launch_kde1d_deposit<2>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    case 4: rc = launch_kde1d_deposit<4>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    case 6: rc = launch_kde1d_deposit<6>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    default: rc = launch_kde1d_deposit<0>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+  }
+  if (rc) return rc;
+  const int64_t len = (int64_t)k * b;
+  int rgrid = (int)((len + 255) / 256);
+  reduce_partials_kernel<<<rgrid, 256, 0, st>>>(partial, L.grid_x, len, sums);
+  return launch_status();
+}
+
+int mfb_kde1d_normalize(const float* sums, double n_total, const float* geom, int k, int b, float* profiles,
+                        void* stream) {
+  MFB_CHECK_ARG(sums && geom && profiles && k >= 1 && b >= 2 && n_total > 0);
+  kde1d_normalize_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(sums, (float)(1.0 / n_total), geom, b, profiles);
+  return launch_status();
+}
+
+int mfb_kde1d_normalize_bwd(const float* sums, double n_total, const float* geom, int k, int b,
+                            const float* gprof, float* gsums, void* stream) {
+  MFB_CHECK_ARG(sums && geom && gprof && gsums && k >= 1 && b >= 2 && n_total > 0);
+  kde1d_normalize_bwd_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(sums, (float)(1.0 / n_total), geom, b, gprof,
+                                                                  gsums);
+  return launch_status();
+}
+
+int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                            float max_sigma_over_delta, const float* gsums, float* gx, int accumulate,
+                            void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && gsums && gx);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = radius_from_hint(max_sigma_over_delta);
+  // projections are processed in chunks whose gradient table fits in shared memory
+  const size_t per_k = (size_t)b * 4 + (size_t)d * 4 + 16;
+  int kchunk = (int)((160 * 1024) / per_k);
+  if (kchunk < 1) return MFB_E_UNSUPPORTED;
+  if (kchunk > k) kchunk = k;
+  const int sms = sm_count();
+  int64_t blocks = (n + 255) / 256;
+  for (int k0 = 0; k0 < k; k0 += kchunk) {
+    const int kk = (k - k0 < kchunk) ? (k - k0) : kchunk;
+    const size_t smem = (size_t)kk * b * 4 + (((size_t)kk * d + 3) & ~(size_t)3) * 4 + (size_t)kk * 16 + 16;
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > blocks) grid = blocks;
+    const int acc = (accumulate || k0 > 0) ? 1 : 0;
+    int rc;
+    const float* pj = proj + (size_t)k0 * d;
+    const float* gm = geom + (size_t)k0 * MFB_GEOM_STRIDE;
+    const float* gs = gsums + (size_t)k0 * b;
+    switch (d) {
+      case 2: rc = launch_kde1d_bwd<2>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
+      case 4: rc = launch_kde1d_bwd<4>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
+      case 6: rc = launch_kde1d_bwd<6>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
+      default: rc = launch_kde1d_bwd<0>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, const float* edges, int k, int b,
+                       int64_t* counts, void* stream) {
+  MFB_CHECK_ARG(x && proj && edges && counts);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 1);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // edges of the CTA's projections live in smem next to the private bins
+  int kc_guess = k < kBinThreads ? k : kBinThreads;
+  ProjLaunch L = plan_launch(n, d, k, b, 4, (size_t)kc_guess * (b + 1) * 4 + 16);
+  if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
+  dim3 grid(L.grid_x, L.kchunks), block(L.threads);
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+#define MFB_LAUNCH_D(DD)                                                                                  \
+  {                                                                                                       \
+    MFB_CUDA(cudaFuncSetAttribute(hist1d_deposit_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)L.smem));                                                          \
+    hist1d_deposit_kernel<DD><<<grid, block, L.smem, st>>>(x, n, d, proj, edges, k, b, L.kc, L.tile, c);   \
+  }
+  switch (d) {
+    case 2: MFB_LAUNCH_D(2) break;
+    case 4: MFB_LAUNCH_D(4) break;
+    case 6: MFB_LAUNCH_D(6) break;
+    default: MFB_LAUNCH_D(0) break;
+  }
+#undef MFB_LAUNCH_D
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// Fused linear projection + 2-D binning (separable Gaussian KDE deposit or exact histogram).
+//
+// Replaces (reference file:line, relative to mentflow/):
+//   simulate/simulate.py:29-33, simulate/transform.py:67-68    u = x.clone() @ M_k^T
+//   diagnostics/diagnostics.py:179-191                         u[:, axis] -> kde_histogram_2d
+//   diagnostics/histogram.py:89-101, 47-74                     two (N,B) kernel matrices, Kx^T Ky SGEMM
+//   diagnostics/diagnostics.py:192-201                         np.histogramdd on the host
+//
+// Design: one CTA = one screen x one contiguous block of particles; the screen's (Bx, By) bins
+// live in shared memory.  Each particle deposits the (2R+1)^2 window of Kx_a * Ky_b around its
+// image.  Deposits are accumulated as *fixed point* integers (scale 2^kFracBits) with native
+// shared-memory integer atomics: integer addition is associative, so the result does not depend
+// on the order of the atomics, the CTA decomposition, or the number of ranks (bit-reproducible).
+// The per-CTA bins are flushed to 64-bit global accumulators before they could overflow.
+#include "common.cuh"
+
+namespace mfb {
+
+constexpr int kFracBits = 20;                 // smem accumulators: u32, value * 2^20
+constexpr float kFixScale = 1048576.0f;       // 2^20
+constexpr int k2dThreads = 256;
+constexpr int kFlushParticles = 3840;         // 3840 * 2^20 < 2^32: no overflow between flushes
+
+struct Axis {
+  float c0, inv_delta, alpha, beta;  // beta = -delta / sigma^2
+};
+
+__device__ __forceinline__ Axis load_axis(const float* g) {
+  Axis a;
+  a.c0 = g[0];
+  a.inv_delta = 1.0f / g[1];
+  const float r = g[1] / g[2];
+  a.alpha = -0.5f * r * r * kLog2e;
+  a.beta = -g[1] / (g[2] * g[2]);
+  return a;
+}
+
+template <int R>
+__device__ __forceinline__ void window(const Axis& ax, float u, int nb, int& b0, float (&val)[2 * R + 1],
+                                       float (&tt)[2 * R + 1]) {
+  float a = (u - ax.c0) * ax.inv_delta;
+  a = fminf(fmaxf(a, -(float)(R + 2)), (float)(nb + R + 1));
+  const float fb = rintf(a);
+  b0 = (int)fb;
+  const float f = a - fb;
+#pragma unroll
+  for (int j = -R; j <= R; ++j) {
+    const float t = f - (float)j;
+    tt[j + R] = t;
+    val[j + R] = fast_exp2(ax.alpha * t * t);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(k2dThreads)
+kde2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
+                     const float* __restrict__ geom, int BX, int BY, int64_t chunk,
+                     unsigned long long* __restrict__ acc /* [K][BX][BY] */) {
+  extern __shared__ __align__(16) unsigned int s_bins[];
+  __shared__ float s_w[2 * kMaxDim];
+  const int k = blockIdx.y;
+  const int nbins = BX * BY;
+  for (int i = threadIdx.x; i < nbins; i += k2dThreads) s_bins[i] = 0u;
+  if (threadIdx.x < 2 * d) s_w[threadIdx.x] = proj[(size_t)k * 2 * d + threadIdx.x];
+  const Axis ax = load_axis(geom + (size_t)(2 * k) * MFB_GEOM_STRIDE);
+  const Axis ay = load_axis(geom + (size_t)(2 * k + 1) * MFB_GEOM_STRIDE);
+  __syncthreads();
+
+  const int64_t first = (int64_t)blockIdx.x * chunk;
+  int64_t last = first + chunk;
+  if (last > n) last = n;
+  unsigned long long* out = acc + (size_t)k * nbins;
+
+  for (int64_t base = first; base < last; base += kFlushParticles) {
+    int64_t stop = base + kFlushParticles;
+    if (stop > last) stop = last;
+    for (int64_t p = base + threadIdx.x; p < stop; p += k2dThreads) {
+      float ux = 0.f, uy = 0.f;
+      for (int i = 0; i < d; ++i) {
+        const float xi = x[p * d + i];
+        ux = fmaf(s_w[i], xi, ux);
+        uy = fmaf(s_w[d + i], xi, uy);
+      }
+      int bx0, by0;
+      float vx[2 * R + 1], vy[2 * R + 1], tx[2 * R + 1], ty[2 * R + 1];
+      window<R>(ax, ux, BX, bx0, vx, tx);
+      window<R>(ay, uy, BY, by0, vy, ty);
+#pragma unroll
+      for (int ja = 0; ja <= 2 * R; ++ja) {
+        const int a = bx0 + ja - R;
+        if ((unsigned)a < (unsigned)BX) {
+          const float sx = vx[ja] * kFixScale;
+          unsigned int* row = s_bins + a * BY;
+#pragma unroll
+          for (int jb = 0; jb <= 2 * R; ++jb) {
+            const int b = by0 + jb - R;
+            const unsigned int q = __float2uint_rn(sx * vy[jb]);
+            if ((unsigned)b < (unsigned)BY && q) atomicAdd(row + b, q);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += k2dThreads) {
+      const unsigned int v = s_bins[i];
+      if (v) {
+        atomicAdd(out + i, (unsigned long long)v);
+        s_bins[i] = 0u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void fixed_to_float_kernel(const unsigned long long* __restrict__ acc, int64_t len,
+                                      float* __restrict__ sums) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    sums[i] = (float)((double)acc[i] * (1.0 / (double)kFixScale));
+}
+
+// ---- normalisation P / (sum(P) dx dy + 1e-10) and its backward: one CTA per screen -------------
+__device__ __forceinline__ float block_sum_2d(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    red[32] = t;
+  }
+  __syncthreads();
+  t = red[32];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+kde2d_normalize_kernel(const float* __restrict__ sums, const float* __restrict__ geom, int nbins,
+                       float* __restrict__ prof) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 1], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 1];
+  const float* s = sums + (size_t)k * nbins;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) acc += s[i] * dx * dy;
+  const float z = block_sum_2d(acc, red) + 1.0e-10f;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) prof[(size_t)k * nbins + i] = s[i] / z;
+}
+
+__global__ void __launch_bounds__(256)
+kde2d_normalize_bwd_kernel(const float* __restrict__ sums, const float* __restrict__ geom, int nbins,
+                           const float* __restrict__ gprof, float* __restrict__ gsums) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 1], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 1];
+  const float* s = sums + (size_t)k * nbins;
+  const float* gp = gprof + (size_t)k * nbins;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) acc += s[i] * dx * dy;
+  const float z = block_sum_2d(acc, red) + 1.0e-10f;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) dot += gp[i] * (s[i] / z);
+  const float g = block_sum_2d(dot, red);
+  // p = S / Z, Z = dx dy sum S + eps  =>  dL/dS_i = gp_i / Z - dx dy (sum_j gp_j p_j) / Z
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) gsums[(size_t)k * nbins + i] = gp[i] / z - dx * dy * g / z;
+}
+
+// ---- backward w.r.t. particles: CTA keeps its particles in registers, loops over screens --------
+template <int R>
+__global__ void __launch_bounds__(k2dThreads)
+kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
+                 const float* __restrict__ geom, int K, int BX, int BY, const float* __restrict__ gsums,
+                 float* __restrict__ gx, int accumulate) {
+  extern __shared__ __align__(16) float s_g[];  // [BX][BY] of the current screen
+  __shared__ float s_w[2 * kMaxDim];
+  __shared__ float s_geo[2 * MFB_GEOM_STRIDE];
+  const int nbins = BX * BY;
+  for (int64_t p0 = (int64_t)blockIdx.x * k2dThreads; p0 < n; p0 += (int64_t)gridDim.x * k2dThreads) {
+    const int64_t p = p0 + threadIdx.x;
+    const bool valid = p < n;
+    float xr[kMaxDim], g[kMaxDim];
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) {
+      xr[i] = (valid && i < d) ? x[p * d + i] : 0.f;
+      g[i] = 0.f;
+    }
+    for (int k = 0; k < K; ++k) {
+      __syncthreads();
+      const float4* src = reinterpret_cast<const float4*>(gsums + (size_t)k * nbins);
+      if ((((size_t)k * nbins) & 3) == 0) {
+        for (int i = threadIdx.x; i < (nbins >> 2); i += k2dThreads) reinterpret_cast<float4*>(s_g)[i] = src[i];
+        for (int i = (nbins & ~3) + threadIdx.x; i < nbins; i += k2dThreads) s_g[i] = gsums[(size_t)k * nbins + i];
+      } else {
+        for (int i = threadIdx.x; i < nbins; i += k2dThreads) s_g[i] = gsums[(size_t)k * nbins + i];
+      }
+      if (threadIdx.x < 2 * d) s_w[threadIdx.x] = proj[(size_t)k * 2 * d + threadIdx.x];
+      if (threadIdx.x < 2 * MFB_GEOM_STRIDE) s_geo[threadIdx.x] = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + threadIdx.x];
+      __syncthreads();
+      const Axis ax = load_axis(s_geo), ay = load_axis(s_geo + MFB_GEOM_STRIDE);
+      float ux = 0.f, uy = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i)
+        if (i < d) {
+          ux = fmaf(s_w[i], xr[i], ux);
+          uy = fmaf(s_w[d + i], xr[i], uy);
+        }
+      int bx0, by0;
+      float vx[2 * R + 1], vy[2 * R + 1], tx[2 * R + 1], ty[2 * R + 1];
+      window<R>(ax, ux, BX, bx0, vx, tx);
+      window<R>(ay, uy, BY, by0, vy, ty);
+      float gux = 0.f, guy = 0.f;
+#pragma unroll
+      for (int ja = 0; ja <= 2 * R; ++ja) {
+        const int a = bx0 + ja - R;
+        if ((unsigned)a < (unsigned)BX) {
+          const float* row = s_g + a * BY;
+          float r0 = 0.f, r1 = 0.f;  // sum_b g_ab Ky_b  and  sum_b g_ab Ky_b ty_b
+#pragma unroll
+          for (int jb = 0; jb <= 2 * R; ++jb) {
+            const int b = by0 + jb - R;
+            if ((unsigned)b < (unsigned)BY) {
+              const float gv = row[b] * vy[jb];
+              r0 += gv;
+              r1 = fmaf(gv, ty[jb], r1);
+            }
+          }
+          gux = fmaf(vx[ja] * tx[ja], r0, gux);
+          guy = fmaf(vx[ja], r1, guy);
+        }
+      }
+      gux *= ax.beta;
+      guy *= ay.beta;
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i)
+        if (i < d) g[i] = fmaf(s_w[i], gux, fmaf(s_w[d + i], guy, g[i]));
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i)
+        if (i < d) {
+          if (accumulate) gx[p * d + i] += g[i];
+          else gx[p * d + i] = g[i];
+        }
+    }
+  }
+}
+
+// ---- exact 2-D histogram ----------------------------------------------------------------------------
+__device__ __forceinline__ int exact_bin(const float* E, int nb, float u) {
+  // e[i] <= u < e[i+1], last bin closed; -1 if outside / NaN
+  if (!(u >= E[0] && u <= E[nb])) return -1;
+  int b = (int)((u - E[0]) * ((float)nb / (E[nb] - E[0])));
+  b = min(max(b, 0), nb - 1);
+  while (b > 0 && u < E[b]) --b;
+  while (b < nb - 1 && u >= E[b + 1]) ++b;
+  return b;
+}
+
+__global__ void __launch_bounds__(k2dThreads)
+hist2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
+                      const float* __restrict__ edges_x, const float* __restrict__ edges_y, int BX, int BY,
+                      int64_t chunk, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned int s_bins[];
+  __shared__ float s_w[2 * kMaxDim];
+  const int k = blockIdx.y;
+  const int nbins = BX * BY;
+  float* s_ex = reinterpret_cast<float*>(s_bins + nbins);
+  float* s_ey = s_ex + BX + 1;
+  for (int i = threadIdx.x; i < nbins; i += k2dThreads) s_bins[i] = 0u;
+  for (int i = threadIdx.x; i <= BX; i += k2dThreads) s_ex[i] = edges_x[(size_t)k * (BX + 1) + i];
+  for (int i = threadIdx.x; i <= BY; i += k2dThreads) s_ey[i] = edges_y[(size_t)k * (BY + 1) + i];
+  if (threadIdx.x < 2 * d) s_w[threadIdx.x] = proj[(size_t)k * 2 * d + threadIdx.x];
+  __syncthreads();
+  const int64_t first = (int64_t)blockIdx.x * chunk;
+  int64_t last = first + chunk;
+  if (last > n) last = n;
+  for (int64_t p = first + threadIdx.x; p < last; p += k2dThreads) {
+    float ux = 0.f, uy = 0.f;
+    for (int i = 0; i < d; ++i) {
+      const float xi = x[p * d + i];
+      ux = fmaf(s_w[i], xi, ux);
+      uy = fmaf(s_w[d + i], xi, uy);
+    }
+    const int a = exact_bin(s_ex, BX, ux);
+    const int b = exact_bin(s_ey, BY, uy);
+    if (a >= 0 && b >= 0) atomicAdd(s_bins + a * BY + b, 1u);
+  }
+  __syncthreads();
+  unsigned long long* out = counts + (size_t)k * nbins;
+  for (int i = threadIdx.x; i < nbins; i += k2dThreads) {
+    const unsigned int v = s_bins[i];
+    if (v) atomicAdd(out + i, (unsigned long long)v);
+  }
+}
+
+// particle block per CTA so that grid.x * K fills the machine a few times over
+static int64_t plan_chunk(int64_t n, int k, int* grid_x) {
+  const int sms = sm_count();
+  int64_t want = ((int64_t)sms * 8 + k - 1) / k;  // CTAs along the particle axis
+  if (want < 1) want = 1;
+  int64_t chunk = (n + want - 1) / want;
+  // keep chunks a multiple of the block size and below 2^31 particles
+  chunk = ((chunk + k2dThreads - 1) / k2dThreads) * k2dThreads;
+  if (chunk < k2dThreads) chunk = k2dThreads;
+  if (chunk > (1ll << 30)) chunk = 1ll << 30;
+  *grid_x = (int)((n + chunk - 1) / chunk);
+  return chunk;
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+static int radius2d(float hint) {
+  double r = 6.44 * (hint > 0.f ? hint : 0.5) - 0.5;
+  int ri = (int)r;
+  if ((double)ri < r) ++ri;
+  return ri < 1 ? 1 : ri;
+}
+
+extern "C" {
+
+int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by) {
+  (void)n;
+  (void)d;
+  if (k < 1 || bx < 1 || by < 1) return 0;
+  return (int64_t)k * bx * by * 8;
+}
+
+int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx,
+                          int by, float max_sigma_over_delta, float* sums, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && sums && workspace);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 2 && by >= 2);
+  const int64_t len = (int64_t)k * bx * by;
+  if (workspace_bytes < len * 8) return MFB_E_WORKSPACE;
+  const size_t smem = (size_t)bx * by * 4;
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* acc = (unsigned long long*)workspace;
+  MFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)len * 8, st));
+  if (n > 0) {
+    int gx;
+    const int64_t chunk = plan_chunk(n, k, &gx);
+    dim3 grid(gx, k);
+    const int r = radius2d(max_sigma_over_delta);
+    if (r <= 3) {
+      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kde2d_deposit_kernel<3><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc);
+    } else if (r <= 6) {
+      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kde2d_deposit_kernel<6><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc);
+    } else {
+      return MFB_E_UNSUPPORTED;
+    }
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  int fgrid = (int)((len + 255) / 256);
+  if (fgrid > 4096) fgrid = 4096;
+  fixed_to_float_kernel<<<fgrid, 256, 0, st>>>(acc, len, sums);
+  return launch_status();
+}
+
+int mfb_kde2d_normalize(const float* sums, const float* geom, int k, int bx, int by, float* profiles, void* stream) {
+  MFB_CHECK_ARG(sums && geom && profiles && k >= 1 && bx >= 2 && by >= 2);
+  kde2d_normalize_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(sums, geom, bx * by, profiles);
+  return launch_status();
+}
+
+int mfb_kde2d_normalize_bwd(const float* sums, const float* geom, int k, int bx, int by, const float* gprof,
+                            float* gsums, void* stream) {
+  MFB_CHECK_ARG(sums && geom && gprof && gsums && k >= 1 && bx >= 2 && by >= 2);
+  kde2d_normalize_bwd_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(sums, geom, bx * by, gprof, gsums);
+  return launch_status();
+}
+
+int mfb_project_kde2d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx,
+                          int by, float max_sigma_over_delta, const float* gsums, float* gx, int accumulate,
+                          void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && gsums && gx);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 2 && by >= 2);
+  if (n == 0) return 0;
+  const size_t smem = (size_t)bx * by * 4;
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int per_sm = (int)((200 * 1024) / (smem + 2048));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  const int64_t blocks = (n + k2dThreads - 1) / k2dThreads;
+  if (grid > blocks) grid = blocks;
+  const int r = radius2d(max_sigma_over_delta);
+  if (r <= 3) {
+    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kde2d_bwd_kernel<3><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
+  } else if (r <= 6) {
+    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kde2d_bwd_kernel<6><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
+  } else {
+    return MFB_E_UNSUPPORTED;
+  }
+  return launch_status();
+}
+
+int mfb_project_hist2d(const float* x, int64_t n, int d, const float* proj, const float* edges_x,
+                       const float* edges_y, int k, int bx, int by, int64_t* counts, void* stream) {
+  MFB_CHECK_ARG(x && proj && edges_x && edges_y && counts);
+  MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 1 && by >= 1);
+  if (n == 0) return 0;
+  const size_t smem = (size_t)bx * by * 4 + (size_t)(bx + by + 2) * 4;
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int gx;
+  const int64_t chunk = plan_chunk(n, k, &gx);
+  dim3 grid(gx, k);
+  MFB_CUDA(cudaFuncSetAttribute(hist2d_deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hist2d_deposit_kernel<<<grid, k2dThreads, smem, st>>>(x, n, d, proj, edges_x, edges_y, bx, by, chunk,
+                                                       reinterpret_cast<unsigned long long*>(counts));
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Particle moments for the entropy estimators.
+//
+// Replaces entropy.py:58-62 (torch.mean(log_prob), torch.mean(prior.log_prob(x))) with
+// prior.py:25-26 (MultivariateNormal(0, s^2 I).log_prob = -|x|^2/(2 s^2) - D log s - D/2 log 2pi)
+// and entropy.py:35-38 (torch.cov): one pass producing, in double precision,
+//   out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j.
+// Two-stage reduction with a fixed order => deterministic.
+#include "common.cuh"
+
+namespace mfb {
+
+constexpr int kMomThreads = 256;
+
+template <int D, bool COV>
+__global__ void __launch_bounds__(kMomThreads)
+moments_kernel(const float* __restrict__ x, const float* __restrict__ logq, int64_t n, double* __restrict__ partial) {
+  constexpr int M = COV ? 2 + D + D * D : 2;
+  double acc[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) acc[i] = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * kMomThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kMomThreads) {
+    float xr[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xr[i] = x[p * D + i];
+    if (logq) acc[0] += (double)logq[p];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) ss = fmaf(xr[i], xr[i], ss);
+    acc[1] += (double)ss;
+    if (COV) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        acc[2 + i] += (double)xr[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[2 + D + i * D + j] += (double)xr[i] * (double)xr[j];
+      }
+    }
+  }
+  __shared__ double red[kMomThreads / 32][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const double s = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < M) {
+    double s = 0.0;
+    for (int w = 0; w < kMomThreads / 32; ++w) s += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * M + threadIdx.x] = s;
+  }
+}
+
+__global__ void moments_finish_kernel(const double* __restrict__ partial, int nparts, int m, double* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < m) {
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * m + i];
+    out[i] = s;
+  }
+}
+
+static int moments_grid(int64_t n) {
+  int64_t g = (n + kMomThreads - 1) / kMomThreads;
+  int64_t cap = (int64_t)sm_count() * 4;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+template <int D>
+static int launch_moments(const float* x, const float* logq, int64_t n, int cov, double* out, double* partial,
+                          cudaStream_t st) {
+  const int grid = moments_grid(n);
+  const int m = cov ? 2 + D + D * D : 2;
+  if (cov) moments_kernel<D, true><<<grid, kMomThreads, 0, st>>>(x, logq, n, partial);
+  else moments_kernel<D, false><<<grid, kMomThreads, 0, st>>>(x, logq, n, partial);
+  int rc = launch_status();
+  if (rc) return rc;
+  moments_finish_kernel<<<1, 128, 0, st>>>(partial, grid, m, out);
+  return launch_status();
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" {
+
+int64_t mfb_moments_workspace_bytes(int64_t n, int d) {
+  if (d < 1 || d > kMaxDim) return 0;
+  return (int64_t)moments_grid(n > 0 ? n : 1) * (2 + d + d * d) * 8;
+}
+
+int mfb_moments(const float* x, const float* logq, int64_t n, int d, int with_cov, double* out, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+  MFB_CHECK_ARG(x && out && workspace && n >= 1 && d >= 1 && d <= kMaxDim);
+  if (workspace_bytes < mfb_moments_workspace_bytes(n, d)) return MFB_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partial = (double*)workspace;
+  switch (d) {
+    case 1: return launch_moments<1>(x, logq, n, with_cov, out, partial, st);
+    case 2: return launch_moments<2>(x, logq, n, with_cov, out, partial, st);
+    case 3: return launch_moments<3>(x, logq, n, with_cov, out, partial, st);
+    case 4: return launch_moments<4>(x, logq, n, with_cov, out, partial, st);
+    case 5: return launch_moments<5>(x, logq, n, with_cov, out, partial, st);
+    case 6: return launch_moments<6>(x, logq, n, with_cov, out, partial, st);
+    case 7: return launch_moments<7>(x, logq, n, with_cov, out, partial, st);
+    default: return launch_moments<8>(x, logq, n, with_cov, out, partial, st);
+  }
+}
+
+}  // extern "C"

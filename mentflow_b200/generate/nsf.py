@@ -1,0 +1,194 @@
+"""Neural spline flow generator on the CUDA kernels.
+
+Stands in for ``mentflow.generate.WrappedZukoFlow`` around ``zuko.flows.NSF`` inverted by
+``build_flow`` (generate/build.py:36-46, generate/flows/zuko.py:10-53): same methods
+(``sample``, ``sample_base``, ``log_prob``, ``sample_and_log_prob``, ``forward``, ``inverse``,
+``forward_steps``, ``inverse_steps``), sampling direction = one conditioner pass per layer.
+
+Parameters are stored stacked over the flow's layers (one tensor per role, so the optimiser
+touches 2*(2+L) tensors instead of 40) and exposed under zuko-style names in ``state_dict``:
+``_flow.transform.transforms.{t}.hyper.{2l}.{weight,bias,mask}``.  (The exact key layout of
+zuko 1.3.1 cannot be verified here -- zuko is not installable)
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .base import GenerativeModel
+
+
+def layer_order(features: int, layer: int) -> List[int]:
+    """Autoregressive order of layer ``layer``: natural for even layers, reversed for odd ones
+    (zuko MAF without randperm)."""
+    order = list(range(features))
+    return order if layer % 2 == 0 else order[::-1]
+
+
+def conditioner_masks(order: Sequence[int], total: int, hidden_units: int, hidden_layers: int):
+    """Closed form of zuko's MaskedMLP masks for a strict autoregressive ordering.
+
+    A unit/output of dependency class c may read the c features whose order is smallest.
+    Hidden unit h has class 1 + h mod (D-1); output rows of feature i have class order[i];
+    a connection a -> b exists iff class(a) <= class(b) (for inputs: order[j] < class(b)).
+    Returns [mask_in (H, D), mask_hid (H, H) x (L-1), mask_out (D*total, H)] as bool tensors.
+    """
+    d = len(order)
+    order_t = torch.as_tensor(list(order))
+    if d > 1:
+        hid_class = 1 + torch.arange(hidden_units) % (d - 1)
+    else:
+        raise ValueError("an autoregressive flow needs at least 2 features")
+    out_class = torch.repeat_interleave(order_t, total)
+    masks = [order_t[None, :] < hid_class[:, None]]
+    for _ in range(hidden_layers - 1):
+        masks.append(hid_class[None, :] <= hid_class[:, None])
+    masks.append(hid_class[None, :] <= out_class[:, None])
+    return masks
+
+
+class NSFGenerator(GenerativeModel):
+    def __init__(self, features: int, hidden_units: int = 64, hidden_layers: int = 3, transforms: int = 5,
+                 bins: int = 20, device=None) -> None:
+        super().__init__()
+        if hidden_units != 64:
+            raise NotImplementedError("the CUDA conditioner is compiled for hidden_units=64")
+        if not (2 <= features <= 6):
+            raise NotImplementedError("the CUDA flow is compiled for 2..6 features")
+        if 3 * bins - 1 > 64 or bins < 2:
+            raise NotImplementedError("bins must satisfy 3*bins-1 <= 64")
+        self.features, self.hidden_units, self.hidden_layers = features, hidden_units, hidden_layers
+        self.transforms, self.bins = transforms, bins
+        self.total = 3 * bins - 1
+        T, H, L, D, P = transforms, hidden_units, hidden_layers, features, self.total
+        # default nn.Linear initialisation, drawn layer by layer in construction order
+        w_in, b_in, w_hid, b_hid, w_out, b_out = [], [], [], [], [], []
+        for _ in range(T):
+            lin = nn.Linear(D, H)
+            w_in.append(lin.weight.detach()), b_in.append(lin.bias.detach())
+            wh, bh = [], []
+            for _ in range(L - 1):
+                lin = nn.Linear(H, H)
+                wh.append(lin.weight.detach()), bh.append(lin.bias.detach())
+            w_hid.append(torch.stack(wh) if wh else torch.zeros(0, H, H))
+            b_hid.append(torch.stack(bh) if bh else torch.zeros(0, H))
+            lin = nn.Linear(H, D * P)
+            w_out.append(lin.weight.detach()), b_out.append(lin.bias.detach())
+        self.w_in = nn.Parameter(torch.stack(w_in))      # (T, H, D)
+        self.b_in = nn.Parameter(torch.stack(b_in))      # (T, H)
+        self.w_hid = nn.Parameter(torch.stack(w_hid))    # (T, L-1, H, H)
+        self.b_hid = nn.Parameter(torch.stack(b_hid))    # (T, L-1, H)
+        self.w_out = nn.Parameter(torch.stack(w_out))    # (T, D*P, H)
+        self.b_out = nn.Parameter(torch.stack(b_out))    # (T, D*P)
+        m_in, m_hid, m_out = [], [], []
+        for t in range(T):
+            masks = conditioner_masks(layer_order(D, t), P, H, L)
+            m_in.append(masks[0])
+            m_hid.append(torch.stack(masks[1:-1]) if L > 1 else torch.zeros(0, H, H, dtype=torch.bool))
+            m_out.append(masks[-1])
+        self.register_buffer("m_in", torch.stack(m_in).float(), persistent=False)
+        self.register_buffer("m_hid", torch.stack(m_hid).float(), persistent=False)
+        self.register_buffer("m_out", torch.stack(m_out).float(), persistent=False)
+        self._orders = [layer_order(D, t) for t in range(T)]
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------ parameters
+    def dim(self) -> int:
+        return self.features
+
+    def packed_parameters(self) -> torch.Tensor:
+        """(T, floats_per_layer) block in the kernels' layout: masked, transposed to [in][out],
+        per-feature output blocks padded from 3*bins-1 to 64 (differentiable torch ops)."""
+        T, H, D, P = self.transforms, self.hidden_units, self.features, self.total
+        parts = [(self.w_in * self.m_in).transpose(1, 2).reshape(T, -1), self.b_in]
+        if self.hidden_layers > 1:
+            wh = (self.w_hid * self.m_hid).transpose(2, 3)             # (T, L-1, in, out)
+            hid = torch.cat([wh.reshape(T, self.hidden_layers - 1, -1), self.b_hid], dim=2)
+            parts.append(hid.reshape(T, -1))
+        wo = (self.w_out * self.m_out).reshape(T, D, P, H).permute(0, 1, 3, 2)   # (T, D, in, P)
+        wo = torch.nn.functional.pad(wo, (0, 64 - P))
+        bo = torch.nn.functional.pad(self.b_out.reshape(T, D, P), (0, 64 - P))
+        parts += [wo.reshape(T, -1), bo.reshape(T, -1)]
+        return torch.cat(parts, dim=1).contiguous()
+
+    # zuko-style names in checkpoints ------------------------------------------------
+    def _zuko_items(self):
+        for t in range(self.transforms):
+            base = f"_flow.transform.transforms.{t}.hyper."
+            yield base + "0.weight", self.w_in, (t,), self.m_in
+            yield base + "0.bias", self.b_in, (t,), None
+            for l in range(self.hidden_layers - 1):
+                yield base + f"{2 * (l + 1)}.weight", self.w_hid, (t, l), self.m_hid
+                yield base + f"{2 * (l + 1)}.bias", self.b_hid, (t, l), None
+            yield base + f"{2 * self.hidden_layers}.weight", self.w_out, (t,), self.m_out
+            yield base + f"{2 * self.hidden_layers}.bias", self.b_out, (t,), None
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kwargs):
+        out = {} if destination is None else destination
+        for name, tensor, idx, mask in self._zuko_items():
+            value = tensor[idx]
+            out[prefix + name] = value if keep_vars else value.detach().clone()
+            if mask is not None:
+                out[prefix + name[:-len("weight")] + "mask"] = mask[idx].bool().clone()
+        for t in range(self.transforms):
+            out[prefix + f"_flow.transform.transforms.{t}.order"] = torch.tensor(self._orders[t])
+        out[prefix + "_flow.base.loc"] = torch.zeros(self.features)
+        out[prefix + "_flow.base.scale"] = torch.ones(self.features)
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing = []
+        with torch.no_grad():
+            for name, tensor, idx, _ in self._zuko_items():
+                if name in state_dict:
+                    tensor[idx].copy_(state_dict[name])
+                else:
+                    missing.append(name)
+        if strict and missing:
+            raise RuntimeError(f"missing keys in state_dict: {missing[:4]} ...")
+        return torch.nn.modules.module._IncompatibleKeys(missing, [])
+
+    # ------------------------------------------------------------------ sampling direction
+    def sample_base(self, n: int) -> torch.Tensor:
+        return torch.randn((int(n), self.features), dtype=torch.float32, device=self.w_in.device)
+
+    def _run(self, z: torch.Tensor, want_logq: bool, want_steps: bool = False):
+        return ops.nsf_forward(z, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
+                               self.bins, want_logq, want_steps)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        return self._run(z, False)[0]
+
+    def forward_and_log_prob(self, z: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        x, logq, _ = self._run(z, True)
+        return x, logq
+
+    def sample(self, n: int) -> torch.Tensor:
+        return self.forward(self.sample_base(n))
+
+    def sample_and_log_prob(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.forward_and_log_prob(self.sample_base(n))
+
+    def forward_steps(self, z: torch.Tensor) -> List[torch.Tensor]:
+        with torch.no_grad():
+            _, _, steps = self._run(z, False, want_steps=True)
+        return steps
+
+    # ------------------------------------------------------------------ density direction
+    def inverse(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
+                               self.bins, False, False)[0]
+
+    def inverse_steps(self, x: torch.Tensor) -> List[torch.Tensor]:
+        with torch.no_grad():
+            return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units,
+                                   self.hidden_layers, self.bins, False, True)[2]
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
+                               self.bins, True, False)[1]

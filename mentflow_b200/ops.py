@@ -1,0 +1,323 @@
+"""Thin torch layer over the C ABI: device pointers in, device pointers out.
+
+Each function validates its tensors (CUDA, fp32, contiguous), allocates outputs/workspaces
+with torch, and launches on torch's *current* stream (autograd runs backward on a worker
+thread, so nothing here caches streams or keeps global state).  Differentiable ops are
+``torch.autograd.Function`` s whose backward is again a hand-written kernel.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+GEOM_STRIDE = 8
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: mentflow_b200 kernels need CUDA tensors (got {t.device}); "
+                           "there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous() or t.data_ptr() % 16:
+        t = t.contiguous()
+        if t.data_ptr() % 16:
+            t = t.clone()
+    return t
+
+
+# --------------------------------------------------------------------------------------
+# projection + KDE, 1-D screens
+# --------------------------------------------------------------------------------------
+def kde1d_sums(x: torch.Tensor, proj: torch.Tensor, geom: torch.Tensor, ratio: float, nbins: int) -> torch.Tensor:
+    """S[k, b] = sum_n exp(-0.5 ((proj_k . x_n - c_b) / sigma_k)^2)  (unnormalised)."""
+    lib = _lib.load()
+    x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
+    n, d = x.shape
+    k = proj.shape[0]
+    sums = torch.empty((k, nbins), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        wbytes = lib.mfb_kde1d_workspace_bytes(n, d, k, nbins)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.mfb_project_kde1d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, nbins, float(ratio),
+                                             _ptr(sums), _ptr(work), wbytes, _stream()), "project_kde1d_fwd")
+    return sums
+
+
+def kde1d_normalize(sums: torch.Tensor, n_total: float, geom: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    k, b = sums.shape
+    prof = torch.empty_like(sums)
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_kde1d_normalize(_ptr(sums), float(n_total), _ptr(geom), k, b, _ptr(prof), _stream()),
+                   "kde1d_normalize")
+    return prof
+
+
+def kde1d_normalize_bwd(sums, n_total, geom, gprof):
+    lib = _lib.load()
+    k, b = sums.shape
+    gprof = _check_f32("gprof", gprof)
+    gsums = torch.empty_like(sums)
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_kde1d_normalize_bwd(_ptr(sums), float(n_total), _ptr(geom), k, b, _ptr(gprof),
+                                               _ptr(gsums), _stream()), "kde1d_normalize_bwd")
+    return gsums
+
+
+def kde1d_grad_x(x, proj, geom, ratio, gsums, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    n, d = x.shape
+    k, b = gsums.shape
+    acc = 1 if out is not None else 0
+    gx = out if out is not None else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_project_kde1d_bwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, b, float(ratio),
+                                             _ptr(gsums), _ptr(gx), acc, _stream()), "project_kde1d_bwd")
+    return gx
+
+
+class ProjectKDE1D(torch.autograd.Function):
+    """profiles[k, b] of K one-dimensional screens, differentiable w.r.t. the particles.
+
+    ``reducer`` (optional) all-reduces the unnormalised sums across ranks *before* the
+    non-linear normalisation and returns the global particle count.
+    """
+
+    @staticmethod
+    def forward(ctx, x, proj, geom, ratio, nbins, reducer):
+        x = _check_f32("x", x)
+        sums = kde1d_sums(x, proj, geom, ratio, nbins)
+        n_total = float(x.shape[0])
+        if reducer is not None:
+            n_total = reducer(sums, n_total)
+        prof = kde1d_normalize(sums, n_total, geom)
+        ctx.save_for_backward(x, proj, geom, sums)
+        ctx.ratio, ctx.n_total = ratio, n_total
+        return prof
+
+    @staticmethod
+    def backward(ctx, gprof):
+        x, proj, geom, sums = ctx.saved_tensors
+        gsums = kde1d_normalize_bwd(sums, ctx.n_total, geom, gprof)
+        gx = kde1d_grad_x(x, proj, geom, ctx.ratio, gsums)
+        return gx, None, None, None, None, None
+
+
+def project_kde1d(x, proj, geom, ratio, nbins, reducer=None):
+    return ProjectKDE1D.apply(x, proj, geom, ratio, nbins, reducer)
+
+
+# --------------------------------------------------------------------------------------
+# projection + exact histogram, 1-D screens
+# --------------------------------------------------------------------------------------
+def project_hist1d(x: torch.Tensor, proj: torch.Tensor, edges: torch.Tensor,
+                   counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64 counts[k, b]; edges is (K, B+1).  Adds into ``counts`` when given."""
+    lib = _lib.load()
+    x, proj, edges = _check_f32("x", x), _check_f32("proj", proj), _check_f32("edges", edges)
+    n, d = x.shape
+    k, b = proj.shape[0], edges.shape[1] - 1
+    if counts is None:
+        counts = torch.zeros((k, b), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_project_hist1d(_ptr(x), n, d, _ptr(proj), _ptr(edges), k, b, _ptr(counts), _stream()),
+                   "project_hist1d")
+    return counts
+
+
+# --------------------------------------------------------------------------------------
+# 2-D screens
+# --------------------------------------------------------------------------------------
+def kde2d_sums(x, proj, geom, ratio, bx, by):
+    """(sums float32 [K,bx,by], acc int64 [K,bx,by]): acc holds the exact fixed-point
+    accumulators (value * 2^20) that ranks all-reduce."""
+    lib = _lib.load()
+    x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
+    n, d = x.shape
+    k = proj.shape[0]
+    sums = torch.empty((k, bx, by), dtype=torch.float32, device=x.device)
+    acc = torch.empty((k, bx, by), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_project_kde2d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, bx, by, float(ratio),
+                                             _ptr(sums), _ptr(acc), acc.numel() * 8, _stream()),
+                   "project_kde2d_fwd")
+    return sums, acc
+
+
+def kde2d_normalize(sums, geom):
+    lib = _lib.load()
+    k, bx, by = sums.shape
+    prof = torch.empty_like(sums)
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_kde2d_normalize(_ptr(sums), _ptr(geom), k, bx, by, _ptr(prof), _stream()),
+                   "kde2d_normalize")
+    return prof
+
+
+class ProjectKDE2D(torch.autograd.Function):
+    """profiles[k, a, b] of K two-dimensional screens, differentiable w.r.t. the particles."""
+
+    @staticmethod
+    def forward(ctx, x, proj, geom, ratio, bx, by, reducer):
+        x = _check_f32("x", x)
+        sums, acc = kde2d_sums(x, proj, geom, ratio, bx, by)
+        if reducer is not None:
+            reducer(acc, float(x.shape[0]))          # exact integer all-reduce
+            sums = acc.to(torch.float64).mul_(2.0 ** -20).to(torch.float32)
+        prof = kde2d_normalize(sums, geom)
+        ctx.save_for_backward(x, proj, geom, sums)
+        ctx.ratio = ratio
+        return prof
+
+    @staticmethod
+    def backward(ctx, gprof):
+        lib = _lib.load()
+        x, proj, geom, sums = ctx.saved_tensors
+        k, bx, by = sums.shape
+        gprof = _check_f32("gprof", gprof)
+        gsums = torch.empty_like(sums)
+        gx = torch.empty_like(x)
+        n, d = x.shape
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mfb_kde2d_normalize_bwd(_ptr(sums), _ptr(geom), k, bx, by, _ptr(gprof), _ptr(gsums),
+                                                   _stream()), "kde2d_normalize_bwd")
+            _lib.check(lib.mfb_project_kde2d_bwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, bx, by,
+                                                 float(ctx.ratio), _ptr(gsums), _ptr(gx), 0, _stream()),
+                       "project_kde2d_bwd")
+        return gx, None, None, None, None, None, None
+
+
+def project_kde2d(x, proj, geom, ratio, bx, by, reducer=None):
+    return ProjectKDE2D.apply(x, proj, geom, ratio, bx, by, reducer)
+
+
+def project_hist2d(x, proj, edges_x, edges_y, counts=None):
+    """int64 counts[k, a, b]; edges_x (K, bx+1), edges_y (K, by+1)."""
+    lib = _lib.load()
+    x, proj = _check_f32("x", x), _check_f32("proj", proj)
+    edges_x, edges_y = _check_f32("edges_x", edges_x), _check_f32("edges_y", edges_y)
+    n, d = x.shape
+    k, bx, by = proj.shape[0], edges_x.shape[1] - 1, edges_y.shape[1] - 1
+    if counts is None:
+        counts = torch.zeros((k, bx, by), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_project_hist2d(_ptr(x), n, d, _ptr(proj), _ptr(edges_x), _ptr(edges_y), k, bx, by,
+                                          _ptr(counts), _stream()), "project_hist2d")
+    return counts
+
+
+# --------------------------------------------------------------------------------------
+# neural spline flow
+# --------------------------------------------------------------------------------------
+def nsf_layer_param_floats(d: int, hidden_units: int, hidden_layers: int, bins: int) -> int:
+    return int(_lib.load().mfb_nsf_layer_param_floats(d, hidden_units, hidden_layers, bins))
+
+
+def nsf_layer_forward(v, params, order, hidden_units, hidden_layers, bins, logq_in, first_layer,
+                      want_logq=True):
+    """One autoregressive spline layer: returns (y, logq_out)."""
+    lib = _lib.load()
+    v, params = _check_f32("v", v), _check_f32("params", params)
+    n, d = v.shape
+    y = torch.empty_like(v)
+    logq_out = torch.empty(n, dtype=torch.float32, device=v.device) if want_logq else None
+    order_arr = (ctypes.c_int32 * d)(*[int(o) for o in order])
+    with torch.cuda.device(v.device):
+        _lib.check(lib.mfb_nsf_layer_fwd(_ptr(v), n, d, hidden_units, hidden_layers, bins, _ptr(params),
+                                         ctypes.cast(order_arr, ctypes.c_void_p), _ptr(logq_in),
+                                         1 if first_layer else 0, _ptr(y), _ptr(logq_out), _stream()),
+                   "nsf_layer_fwd")
+    return y, logq_out
+
+
+# --------------------------------------------------------------------------------------
+# moments
+# --------------------------------------------------------------------------------------
+def moments(x: torch.Tensor, logq: Optional[torch.Tensor], with_cov: bool = False) -> torch.Tensor:
+    """float64 vector: [sum logq, sum |x|^2, (sum x_i), (sum x_i x_j)]."""
+    lib = _lib.load()
+    x = _check_f32("x", x)
+    if logq is not None:
+        logq = _check_f32("logq", logq)
+    n, d = x.shape
+    m = 2 + d + d * d
+    out = torch.zeros(m, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        wbytes = lib.mfb_moments_workspace_bytes(n, d)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.mfb_moments(_ptr(x), _ptr(logq), n, d, 1 if with_cov else 0, _ptr(out), _ptr(work), wbytes,
+                                   _stream()), "moments")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# whole flow (all layers), differentiable
+# --------------------------------------------------------------------------------------
+class NSFForward(torch.autograd.Function):
+    """x, log q = flow(z): one kernel launch per autoregressive layer.  The layer inputs are
+    kept (24 B / particle / layer) so that backward recomputes conditioner activations tile
+    by tile instead of storing them (10.9 KB / particle in the reference's autograd graph)."""
+
+    @staticmethod
+    def forward(ctx, z, packed, meta):
+        orders, hidden_units, hidden_layers, bins, want_logq = meta
+        z = _check_f32("z", z)
+        packed = _check_f32("packed", packed)
+        steps = [z]
+        logq = None
+        for t, order in enumerate(orders):
+            y, logq = nsf_layer_forward(steps[-1], packed[t], order, hidden_units, hidden_layers, bins, logq,
+                                        first_layer=(t == 0), want_logq=want_logq)
+            steps.append(y)
+        ctx.meta = meta
+        ctx.save_for_backward(packed, *steps[:-1])
+        ctx.mark_non_differentiable(*[])
+        if logq is None:
+            logq = z.new_empty(0)
+        return steps[-1], logq
+
+    @staticmethod
+    def backward(ctx, gx, glogq):
+        orders, hidden_units, hidden_layers, bins, want_logq = ctx.meta
+        packed, *inputs = ctx.saved_tensors
+        gx = _check_f32("gx", gx) if gx is not None else None
+        return nsf_backward(inputs, packed, orders, hidden_units, hidden_layers, bins, gx,
+                            glogq if want_logq else None) + (None,)
+
+
+def nsf_backward(inputs, packed, orders, hidden_units, hidden_layers, bins, gx, glogq):
+    raise NotImplementedError("mentflow_b200: the NSF backward kernel is not built yet")
+
+
+def nsf_forward(z, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
+    """Returns (x, logq or None, steps or None)."""
+    if want_steps:
+        z = _check_f32("z", z)
+        steps, logq = [z], None
+        for t, order in enumerate(orders):
+            y, logq = nsf_layer_forward(steps[-1], packed[t].contiguous(), order, hidden_units, hidden_layers, bins,
+                                        logq, first_layer=(t == 0), want_logq=want_logq)
+            steps.append(y)
+        return steps[-1], logq, steps
+    meta = (tuple(tuple(o) for o in orders), hidden_units, hidden_layers, bins, bool(want_logq))
+    x, logq = NSFForward.apply(z, packed, meta)
+    return x, (logq if want_logq else None), None
+
+
+def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
+    raise NotImplementedError("mentflow_b200: the NSF inverse (density of given x) kernel is not built yet")

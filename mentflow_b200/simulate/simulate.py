@@ -1,0 +1,200 @@
+"""Forward simulation: particles -> predicted profiles on every screen.
+
+``forward(x, transforms, diagnostics)`` has the signature and return structure of
+``mentflow/simulate/simulate.py:8-33`` (``predictions[i][j]`` = diagnostic j after transform i).
+Where the reference loops in Python (K clones, K full D x D matmuls, K dense (N, B) kernel
+matrices), this builds a *plan* -- one projection row per linear (transform, screen) pair --
+and launches the fused projection+binning kernel once per group of equally shaped screens.
+Pairs that cannot be fused (a non-linear transform, a custom diagnostic) fall back to calling
+the objects one by one, exactly like the reference; the screen itself still bins with the
+CUDA kernel.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..diagnostics.diagnostics import Histogram1D, Histogram2D
+from .transform import CompositeTransform, LinearTransform
+
+# set by mentflow_b200.distributed when particles are sharded across ranks: a callable
+# reducer(sums_tensor, n_local) -> n_global that all-reduces in place
+_default_reducer: Optional[Callable] = None
+
+
+def set_default_reducer(reducer: Optional[Callable]) -> None:
+    global _default_reducer
+    _default_reducer = reducer
+
+
+def _geom_tensor(rows, device):
+    return torch.tensor([[c0, delta, sigma, 0.0, 0.0, 0.0, 0.0, 0.0] for c0, delta, sigma in rows],
+                        dtype=torch.float32, device=device)
+
+
+def _density_from_counts(counts: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
+    """torch.histogram(density=True) from integer counts: counts / total / bin widths, all in
+    fp32 like the reference's CPU op."""
+    c = counts.to(torch.float32)
+    total = c.sum(dim=tuple(range(1, c.ndim)), keepdim=True)
+    return c / total / widths
+
+
+def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D], kde: bool = True,
+                reducer: Optional[Callable] = None, cache: Optional[dict] = None) -> torch.Tensor:
+    """(K, B) profiles of K one-dimensional screens sharing the same number of bins.
+    proj is (K, D): x_proj_k = x . proj_k.  ``cache`` keeps the device-side geometry between
+    calls (filled on first use)."""
+    reducer = reducer if reducer is not None else _default_reducer
+    cache = {} if cache is None else cache
+    nb = diags[0].nbins
+    if kde:
+        if "geom" not in cache:
+            rows = [d.geometry() for d in diags]
+            cache["geom"] = _geom_tensor(rows, x.device)
+            cache["ratio"] = max(s / dl for _, dl, s in rows)
+        return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer)
+    if "edges" not in cache:
+        cache["edges"] = torch.stack([d.edges.to(x.device) for d in diags]).contiguous()
+        cache["widths"] = torch.diff(cache["edges"], dim=1)
+    counts = ops.project_hist1d(x.detach(), proj, cache["edges"])
+    if reducer is not None:
+        reducer(counts, 0.0)
+    return _density_from_counts(counts, cache["widths"])
+
+
+def profiles_2d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram2D], kde: bool = True,
+                reducer: Optional[Callable] = None, cache: Optional[dict] = None) -> torch.Tensor:
+    """(K, Bx, By) profiles of K two-dimensional screens of equal shape; proj is (K, 2, D)."""
+    reducer = reducer if reducer is not None else _default_reducer
+    cache = {} if cache is None else cache
+    bx, by = diags[0].shape
+    if kde:
+        if "geom" not in cache:
+            rows = []
+            for d in diags:
+                gx, gy = d.geometry()
+                rows += [gx, gy]
+            cache["geom"] = _geom_tensor(rows, x.device).reshape(len(diags), 2, -1)
+            cache["ratio"] = max(s / dl for _, dl, s in rows)
+        return ops.project_kde2d(x, proj, cache["geom"], cache["ratio"], bx, by, reducer)
+    if "ex" not in cache:
+        cache["ex"] = torch.stack([d.edges_x.to(x.device) for d in diags]).contiguous()
+        cache["ey"] = torch.stack([d.edges_y.to(x.device) for d in diags]).contiguous()
+        cache["area"] = torch.diff(cache["ex"], dim=1)[:, :, None] * torch.diff(cache["ey"], dim=1)[:, None, :]
+    counts = ops.project_hist2d(x.detach(), proj, cache["ex"], cache["ey"])
+    if reducer is not None:
+        reducer(counts, 0.0)
+    return _density_from_counts(counts, cache["area"])
+
+
+# --------------------------------------------------------------------------------------
+# plan: which (transform, screen) pairs fuse, grouped by screen shape
+# --------------------------------------------------------------------------------------
+class _Group:
+    __slots__ = ("kind", "kde", "slots", "diags", "proj", "cache")
+
+    def __init__(self, kind, kde):
+        self.kind, self.kde = kind, kde
+        self.slots, self.diags, self.proj = [], [], []
+        self.cache = {}
+
+
+class _Plan:
+    def __init__(self):
+        self.groups: "OrderedDict[tuple, _Group]" = OrderedDict()
+        self.fallback: List[tuple] = []
+        self.shape: List[int] = []
+
+
+def _linear_matrix(transform) -> Optional[torch.Tensor]:
+    if isinstance(transform, LinearTransform):
+        return transform.matrix
+    if isinstance(transform, CompositeTransform):
+        return transform.as_matrix()
+    if transform is None or isinstance(transform, nn.Identity):
+        return None
+    return NotImplemented
+
+
+def _plan_key(transforms, diagnostics):
+    key = []
+    for t, row in zip(transforms, diagnostics):
+        m = getattr(t, "matrix", None)
+        key.append((id(t), id(m), getattr(m, "_version", 0)))
+        for d in row:
+            key.append((id(d), getattr(d, "kde", None), getattr(d, "axis", None), id(getattr(d, "direction", None))))
+    return tuple(key)
+
+
+_plan_cache: "OrderedDict[tuple, _Plan]" = OrderedDict()
+_PLAN_CACHE_SIZE = 16
+
+
+def _build_plan(x, transforms, diagnostics) -> _Plan:
+    plan = _Plan()
+    ndim, device = x.shape[1], x.device
+    for i, (t, row) in enumerate(zip(transforms, diagnostics)):
+        plan.shape.append(len(row))
+        matrix = _linear_matrix(t)
+        for j, d in enumerate(row):
+            if matrix is NotImplemented or type(d) not in (Histogram1D, Histogram2D):
+                plan.fallback.append((i, j))
+                continue
+            if type(d) is Histogram1D:
+                gkey = ("1d", bool(d.kde), d.nbins)
+                vec = d.projection_vector(matrix, ndim, device)
+            else:
+                gkey = ("2d", bool(d.kde), d.shape)
+                vec = d.projection_vectors(matrix, ndim, device)
+            grp = plan.groups.get(gkey)
+            if grp is None:
+                grp = plan.groups[gkey] = _Group(gkey[0], gkey[1])
+            grp.slots.append((i, j))
+            grp.diags.append(d)
+            grp.proj.append(vec)
+    for grp in plan.groups.values():
+        grp.proj = torch.stack(grp.proj).contiguous()
+    return plan
+
+
+def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List[nn.Module]],
+            reducer: Optional[Callable] = None) -> List[List[torch.Tensor]]:
+    """Predicted profiles for every transform / diagnostic pair (simulate/simulate.py:8-33)."""
+    key = (_plan_key(transforms, diagnostics), x.shape[1], str(x.device))
+    plan = _plan_cache.get(key)
+    if plan is None:
+        plan = _build_plan(x, transforms, diagnostics)
+        _plan_cache[key] = plan
+        while len(_plan_cache) > _PLAN_CACHE_SIZE:
+            _plan_cache.popitem(last=False)
+    else:
+        _plan_cache.move_to_end(key)
+    out: List[List[Optional[torch.Tensor]]] = [[None] * n for n in plan.shape]
+    for grp in plan.groups.values():
+        fn = profiles_1d if grp.kind == "1d" else profiles_2d
+        prof = fn(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache)
+        for row, (i, j), d in zip(prof.unbind(0), grp.slots, grp.diags):
+            out[i][j] = d.apply_noise(row)
+    if plan.fallback:
+        cache = {}
+        for i, j in plan.fallback:
+            if i not in cache:
+                cache[i] = transforms[i](x.clone())
+            out[i][j] = diagnostics[i][j](cache[i])
+    return out
+
+
+class Simulator:
+    """simulate/simulate.py:36-47."""
+
+    def __init__(self, transforms, diagnostics) -> None:
+        self.transforms = transforms
+        self.diagnostics = diagnostics
+
+    def forward(self, x: torch.Tensor) -> List[List[torch.Tensor]]:
+        return forward(x, self.transforms, self.diagnostics)

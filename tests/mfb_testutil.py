@@ -9,3 +9,44 @@ def t32(a):
 
 def cuda(a):
     return t32(a).cuda()
+
+
+def oracle_from_generator(gen, dtype=torch.float64):
+    """NSFOracle carrying the weights of a mentflow_b200 NSFGenerator (via zuko-style names)."""
+    from oracle.zuko_nsf import NSFOracle
+    flow = NSFOracle(gen.features, gen.hidden_units, gen.hidden_layers, gen.transforms, gen.bins)
+    sd = gen.state_dict()
+    new = {}
+    for k, v in flow.state_dict().items():
+        # layers.{t}.hyper.{i}.{weight,bias,mask} / layers.{t}.order
+        parts = k.split(".")
+        src = "_flow.transform.transforms." + ".".join(parts[1:])
+        new[k] = sd[src].detach().cpu().to(v.dtype)
+    flow.load_state_dict(new)
+    return flow.to(dtype)
+
+
+def generator_from_golden(g, device="cpu"):
+    """NSFGenerator loaded with the weights stored in tests/golden/nsf_*.npz."""
+    import mentflow_b200 as mf
+    d = g["z"].shape[1]
+    gen = mf.generate.NSFGenerator(d)
+    sd = {}
+    for k, v in g.items():
+        if k.startswith("sd:") and (k.endswith("weight") or k.endswith("bias")):
+            sd["_flow.transform.transforms." + k[len("sd:layers."):]] = torch.from_numpy(v).float()
+    gen.load_state_dict(sd)
+    return gen.to(device)
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1, |b|) elementwise (SURVEY 8c metric for x and log q)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
+
+
+def profile_err(a, b):
+    """max over profiles of max|a-b| / max|b| (SURVEY 8c metric for KDE profiles)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    return float(((a - b).abs().max(dim=1).values / b.abs().max(dim=1).values).max())

@@ -1,0 +1,143 @@
+"""CPU tests of the host layer: C-ABI library loads and exports what include/*.h declares,
+mask construction / parameter packing agree with the oracle, API objects behave like the
+reference's, and compute entry points refuse CPU tensors (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mentflow_b200 as mf
+from mentflow_b200 import _lib, ops
+from mfb_testutil import generator_from_golden, oracle_from_generator, t32
+from oracle.zuko_nsf import layer_order, masked_mlp_masks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mentflow_b200.h")).read()
+    declared = set(re.findall(r"\b(mfb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert lib.mfb_abi_version() == 1
+    assert b"workspace" in lib.mfb_error_string(-3)
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 6])
+def test_closed_form_masks_equal_zuko_construction(d):
+    for layer in (0, 1):
+        mine = mf.generate.conditioner_masks(mf.generate.layer_order(d, layer), 59, 64, 3)
+        ref = masked_mlp_masks(layer_order(d, layer), 59, [64] * 3)
+        assert len(mine) == len(ref)
+        for a, b in zip(mine, ref):
+            assert torch.equal(a.bool(), b.bool())
+
+
+def test_generator_matches_oracle_initialisation_and_names():
+    torch.manual_seed(7)
+    gen = mf.generate.build_generator("nsf", input_features=6, output_features=6, hidden_layers=3,
+                                      hidden_units=64, transforms=5, bins=20)
+    from oracle.zuko_nsf import NSFOracle
+    torch.manual_seed(7)
+    ref = NSFOracle(6)
+    cp = oracle_from_generator(gen, torch.float32)
+    for (ka, a), (kb, b) in zip(ref.state_dict().items(), cp.state_dict().items()):
+        assert ka == kb and torch.equal(a, b), ka
+    assert sum(p.numel() for p in gen.parameters()) == 158890
+    sd = gen.state_dict()
+    gen2 = mf.generate.NSFGenerator(6)
+    gen2.load_state_dict(sd)
+    assert torch.equal(gen2.w_out, gen.w_out) and torch.equal(gen2.b_hid, gen.b_hid)
+
+
+def _emulate_packed_layer(packed, v, d, hidden_layers, bins):
+    """What the CUDA kernel computes from one layer's packed block, in torch (float64)."""
+    H, PP = 64, 64
+    o = 0
+    w1 = packed[o:o + d * H].reshape(d, H); o += d * H
+    b1 = packed[o:o + H]; o += H
+    h = torch.relu(v @ w1 + b1)
+    for _ in range(hidden_layers - 1):
+        w = packed[o:o + H * H].reshape(H, H); o += H * H
+        b = packed[o:o + H]; o += H
+        h = torch.relu(h @ w + b)
+    wo = packed[o:o + d * H * PP].reshape(d, H, PP); o += d * H * PP
+    bo = packed[o:o + d * PP].reshape(d, PP); o += d * PP
+    assert o == packed.numel()
+    phi = torch.einsum("nh,dhp->ndp", h, wo) + bo
+    return phi[:, :, :3 * bins - 1]
+
+
+def test_packed_layout_reproduces_conditioner(golden):
+    g = golden("nsf_6d")
+    gen = generator_from_golden(g)
+    ref = oracle_from_generator(gen)
+    packed = gen.packed_parameters().double()
+    assert packed.shape[1] == ops.nsf_layer_param_floats(6, 64, 3, 20)
+    v = torch.from_numpy(g["z"])
+    for t, layer in enumerate(ref.layers):
+        phi = _emulate_packed_layer(packed[t], v, 6, 3, 20)
+        want = layer.hyper(v).unflatten(-1, (6, 59))
+        assert torch.allclose(phi, want, atol=1e-12)
+
+
+def test_packing_is_differentiable_and_masked():
+    gen = mf.generate.NSFGenerator(4, transforms=2)
+    packed = gen.packed_parameters()
+    packed.sum().backward()
+    assert gen.w_in.grad is not None
+    # masked-out weights get zero gradient
+    assert torch.equal(gen.w_in.grad != 0, gen.m_in.bool())
+    assert torch.equal(gen.w_out.grad != 0, gen.m_out.bool())
+
+
+def test_diagnostic_interface_and_no_cpu_fallback():
+    e = torch.linspace(-3.5, 3.5, 65)
+    d = mf.diagnostics.Histogram1D(axis=0, edges=e, bandwidth=0.5, noise=True, noise_scale=0.0, seed=1)
+    assert d.ndim == 1 and d.kde and d.edges.shape == (65,) and d.coords.shape == (64,)
+    assert abs(float(d.bandwidth) - 0.5 * float(e[1] - e[0])) < 1e-9
+    c0, delta, sigma = d.geometry()
+    assert abs(c0 - float(d.coords[0])) < 1e-7 and abs(delta - float(d.coords[1] - d.coords[0])) < 1e-7
+    x = torch.randn(10, 6)
+    assert torch.equal(d.project(x), x[:, 0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d(x)
+    d2 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=[e, e], bandwidth=(0.5, 0.5))
+    assert d2.ndim == 2 and d2.shape == (64, 64) and len(d2.edges) == 2
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d2(x)
+    with pytest.raises(NotImplementedError):
+        mf.diagnostics.Histogram1D(edges=torch.tensor([0.0, 1.0, 3.0, 7.0])).geometry()
+    gen = mf.generate.NSFGenerator(2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gen.forward(torch.randn(4, 2))
+
+
+def test_projection_vectors_follow_transform_and_direction():
+    m = torch.randn(4, 4)
+    e = torch.linspace(-1, 1, 9)
+    d_axis = mf.diagnostics.Histogram1D(axis=2, edges=e)
+    d_dir = mf.diagnostics.Histogram1D(edges=e, direction=torch.tensor([1.0, 2.0, 0.0, -1.0]))
+    x = torch.randn(50, 4)
+    u = x @ m.T
+    assert torch.allclose(x @ d_axis.projection_vector(m, 4, "cpu"), d_axis.project(u), atol=1e-5)
+    assert torch.allclose(x @ d_dir.projection_vector(m, 4, "cpu"), d_dir.project(u), atol=1e-5)
+    d2 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=[e, e])
+    assert torch.allclose(x @ d2.projection_vectors(m, 4, "cpu").T, d2.project(u), atol=1e-5)
+
+
+def test_kl_matches_torch_kl_div():
+    torch.manual_seed(0)
+    p, t = torch.rand(64) + 0.01, torch.rand(64)
+    t[:5] = 0.0
+    want = torch.nn.functional.kl_div(torch.log(p + 1e-12), t, reduction="batchmean")
+    assert torch.allclose(mf.loss.kl_divergence(p, t), want, rtol=1e-6)
+    P, T = torch.rand(3, 8, 9) + 0.01, torch.rand(3, 8, 9)
+    want = torch.stack([torch.nn.functional.kl_div(torch.log(a + 1e-12), b, reduction="batchmean")
+                        for a, b in zip(P, T)])
+    assert torch.allclose(mf.loss.kl_divergence_batched(P, T), want, rtol=1e-6)
