@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the MENT-Flow hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one pass of the hot path over one batch of particles on every rank:
+flow sample + log-density (5 fused NSF layers) -> Monte-Carlo entropy -> fused projection + KDE
+for all K screens -> KL discrepancies -> loss  (MENTFlow.loss, forward).  Workload = BASELINE
+config C3: 6D, K=100 random 1-D projections, 64 bins, `--particles` (default 1e6) per GPU.
+
+Prints ONE JSON line (rank 0).  `value` = particles/s over all ranks with the base-noise z
+already resident in HBM, timed with CUDA events (max over ranks); `e2e` = the same through the
+public API with z arriving from pinned host memory and the loss read back every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic work per particle, D=6, K=100, B=64 (SURVEY.md 8d / DESIGN.md)
+FLOP_MASK_AWARE = {6: 165_520, 4: 132_000, 2: 120_320}
+FLOP_DENSE = {6: 312_320, 4: 235_520, 2: 158_720}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU per step")
+    ap.add_argument("--ndim", type=int, default=6)
+    ap.add_argument("--num-proj", type=int, default=100)
+    ap.add_argument("--bins", type=int, default=64)
+    ap.add_argument("--cpu-particles", type=int, default=25_000, help="sample size of the CPU baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------
+def trained_like_(module, factor=3.0):
+    """Default initialisation leaves the flow close to the identity; scaling the weights makes
+    particles spread over the screens and over the spline bins."""
+    with torch.no_grad():
+        for p in module.parameters():
+            p.mul_(factor)
+
+
+def build_model(args, device):
+    import mentflow_b200 as mf
+    from mentflow_b200 import workloads
+    wl = workloads.isotropic_1d(ndim=args.ndim, num=args.num_proj, bins=args.bins, xmax=3.5, seed=0)
+    torch.manual_seed(0)
+    gen = mf.generate.build_generator("nsf", input_features=args.ndim, output_features=args.ndim, hidden_layers=3,
+                                      hidden_units=64, transforms=5, bins=20)
+    trained_like_(gen)
+    gen = gen.to(device)
+    tfs = [mf.simulate.LinearTransform(m.to(device)) for m in wl["matrices"]]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(device)
+    diags = [[diag] for _ in tfs]
+    # measurements: exact histograms of a synthetic 6-D Gaussian mixture (experiments/setup.py:52-73)
+    truth = workloads.gaussian_mixture(200_000, ndim=args.ndim, seed=1, device=device)
+    diag.kde = False
+    meas = mf.simulate.forward(truth, tfs, diags)
+    diag.kde = True
+    width = float(wl["edges"][1] - wl["edges"][0])
+    meas = [[m[0] / m[0].sum() / width] for m in meas]
+    prior = mf.prior.Gaussian(ndim=args.ndim, scale=3.0)
+    model = mf.MENTFlow(transforms=tfs, diagnostics=diags, measurements=meas, generator=gen, prior=prior,
+                        entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                        discrepancy_function=mf.loss.kl_divergence, penalty_parameter=25.0)
+    return model, wl
+
+
+def cpu_step_factory(args):
+    """The same step through the CPU oracle (torch-CPU port of the reference's dense arithmetic
+    + restatement of zuko's NSF), all host threads."""
+    from mentflow_b200 import workloads
+    from oracle import hotpath as hp
+    from oracle.zuko_nsf import NSFOracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = workloads.isotropic_1d(ndim=args.ndim, num=args.num_proj, bins=args.bins, xmax=3.5, seed=0)
+    torch.manual_seed(0)
+    flow = NSFOracle(args.ndim)
+    trained_like_(flow)
+    screens = [[hp.Screen1D(edges=wl["edges"], bandwidth=0.5)] for _ in wl["matrices"]]
+    truth = workloads.gaussian_mixture(200_000, ndim=args.ndim, seed=1)
+    width = wl["edges"][1] - wl["edges"][0]
+    meas = []
+    for m in wl["matrices"]:
+        h = hp.hist_density_1d(hp.linear_map(truth, m)[:, 0], wl["edges"])
+        meas.append([h / h.sum() / width])
+    n = args.cpu_particles
+
+    def step():
+        with torch.no_grad():
+            x, logq = flow.sample_and_log_prob(n)
+            L, H, D = hp.mentflow_loss(x, logq, wl["matrices"], screens, meas, 3.0, 25.0)
+        return float(L)
+
+    return step, n
+
+
+def time_cpu(step, n, reps, warmup=1):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return n / min(ts), ts
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    step, n = cpu_step_factory(args)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{n} particles per step (reference batch size, experiments/rec_nd_1d/run_gmm.sh:21)"
+    line = {
+        "impl": "reference", "metric": "particles/sec/GPU for flow sample+log_prob+project+KDE (6D, 100 proj)",
+        "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rec_nd_1d C3: D={args.ndim}, K={args.num_proj} 1-D projections, B={args.bins}, "
+                               f"NSF 5x[64,64,64] bins=20; CPU oracle port on {cores} host threads",
+                   "particles_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mentflow_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    import torch.distributed as dist
+
+    import mentflow_b200 as mf
+    from mentflow_b200 import distributed as mfd
+    from mentflow_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    model, wl = build_model(args, device)
+    reducer = mfd.shard_model(model, equal_shards=True) if world > 1 else None
+    gen = model.generator
+    n, d = args.particles, args.ndim
+
+    # inputs resident in HBM: a distinct base-noise block per rank
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    z_dev = torch.randn(n, d, generator=g, device=device)
+    z_host = torch.empty(n, d, dtype=torch.float32).pin_memory()
+    z_host.copy_(z_dev.cpu())
+    z_in = torch.empty_like(z_dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MB > 126 MB L2
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    nsf_ms, kde_ms = [], []
+
+    def step(z, timers=None):
+        with torch.no_grad():
+            if timers:
+                timers[0].record()
+            x, logq = gen.forward_and_log_prob(z)
+            if timers:
+                timers[1].record()
+            H = model.entropy_estimator(x, logq)
+            if timers:
+                timers[2].record()
+            preds = mf.simulate.forward(x, model.transforms, model.diagnostics, reducer=reducer)
+            if timers:
+                timers[3].record()
+            D = model.discrepancy_vector(preds)
+            L = H + model.penalty_parameter * (sum(D) / len(D))
+        return L
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step(z_dev)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-resident timing -------------------------------------------------------
+    total_ms = 0.0
+    losses = []
+    for _ in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations
+        e0, e1 = ev(), ev()
+        tm = [ev() for _ in range(4)]
+        e0.record()
+        L = step(z_dev, tm)
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        nsf_ms.append(tm[0].elapsed_time(tm[1]))
+        kde_ms.append(tm[2].elapsed_time(tm[3]))
+        losses.append(L)
+    barrier()
+    # ---- end to end: z from pinned host memory, loss read back ----------------------------
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        z_in.copy_(z_host, non_blocking=True)
+        L = step(z_in)
+        lval = float(L.item())
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    clocks = sampler.finish()
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = n * world * args.steps / (total_ms * 1e-3)
+    e2e_value = n * world * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        nsf_step_ms = statistics.mean(nsf_ms)
+        flops = FLOP_MASK_AWARE.get(d, 0) * n
+        achieved = flops / (nsf_step_ms * 1e-3) / 1e12
+        layers = gen.transforms
+        line = {
+            "metric": "particles/sec/GPU for flow sample+log_prob+project+KDE (6D, 100 proj)",
+            "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"rec_nd_1d C3: D={d}, K={args.num_proj} random 1-D projections, B={args.bins}, "
+                                   f"NSF 5 layers x MaskedMLP[{d},64,64,64,{59 * d}] 20-bin RQ spline, forward "
+                                   f"(sample+log_prob+entropy+project+KDE+KL loss)",
+                       "particles_per_gpu_per_step": n, "parallelism": f"particles sharded x{world}",
+                       "l2": "256 MB flush write between timed iterations",
+                       "weights": "default init x3 (trained-like), seed 0", "value_per_gpu": value / world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": n * d * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()"},
+            "gpu_launches": args.steps * 2 * (layers + 2 + 3),
+            "gpu_launches_per_step": {"nsf_layer_fwd_kernel": layers, "moments": 2, "kde1d deposit+reduce+normalize": 3},
+            "roofline": {"bound": "tensor", "kernel": "nsf_layer_fwd_kernel<6> x5 (fp32 CUDA-core stage; no tensor-core MMA yet)",
+                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
+                         "algorithmic_flop_per_particle": FLOP_MASK_AWARE.get(d), "dense_equivalent_flop": FLOP_DENSE.get(d),
+                         "kernel_ms_per_step": nsf_step_ms, "share_of_step": nsf_step_ms / (total_ms / args.steps),
+                         "kde_ms_per_step": statistics.mean(kde_ms),
+                         "hbm_gbs_nsf": (n * (2 * d * 4 + 8) * layers) / (nsf_step_ms * 1e-3) / 1e9},
+            "loss": float(losses[-1]),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            stepf, ncpu = cpu_step_factory(args)
+            v, ts = time_cpu(stepf, ncpu, reps=5)
+            line["cpu_baseline"] = {"value": v, "unit": "particles/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{ncpu} particles per step, best of {len(ts)} after 1 warm-up "
+                                              f"({sum(ts):.1f} s of CPU work); flow = oracle restatement of zuko NSF"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,9 +39,11 @@ int mfb_sm_count(void);
 /* ------------------------------------------------------------------------------------
  * Screen geometry of one 1-D projection, 8 floats per projection (device array [K][8]):
  *   [0] c0        first bin centre            (diagnostics/diagnostics.py:111 `coords`)
- *   [1] delta     centre spacing c[1]-c[0]    (diagnostics/histogram.py:40)
+ *   [1] spacing   centre spacing, accurate: (c[B-1]-c[0])/(B-1) evaluated in float64
  *   [2] sigma     absolute kernel width       (diagnostics/diagnostics.py:113-114)
- *   [3..7]        reserved (0)
+ *   [3] delta     the reference's fp32 c[1]-c[0] used in the normalisation
+ *                 (diagnostics/histogram.py:40); differs from [1] by up to 1e-5 relative
+ *   [4..7]        reserved (0)
  * 2-D screens use two consecutive records (x axis, then y axis).
  * ------------------------------------------------------------------------------------ */
 #define MFB_GEOM_STRIDE 8
@@ -55,7 +57,7 @@ int mfb_sm_count(void);
  * x[n][d]; proj[K][d] (row `axis` of M_k, or M_k^T d_hat); out partial sums are reduced
  * deterministically into sums[K][B] = S_kb = sum_n K_nb (unnormalised; this is what ranks
  * all-reduce).  max_sigma_over_delta = largest sigma/delta of the K screens (host value; sets
- * the deposit window: bins further than ~6.4 sigma from a particle are skipped).         */
+ * the deposit window: bins further than ~8.9 sigma from a particle are skipped).         */
 int64_t mfb_kde1d_workspace_bytes(int64_t n, int d, int k, int b);
 int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
                           int k, int b, float max_sigma_over_delta, float* sums, void* workspace,
@@ -82,10 +84,11 @@ int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, cons
 /* ---- 2-D screens ------------------------------------------------------------------------
  * diagnostics/diagnostics.py:179-191 -> histogram.py:89-101, 47-74: P = Kx^T Ky.
  * proj[K][2][d], geom[K][2][8]; sums[K][bx][by] unnormalised.  Deposits are accumulated in
- * fixed point (2^-20 per deposit in shared memory, 64-bit integers globally) so the result
- * is independent of the atomics' order, the CTA decomposition and the rank count.
- * workspace = int64 accumulators [K][bx][by] (this is what ranks all-reduce exactly).    */
-#define MFB_KDE2D_FRAC_BITS 20
+ * fixed point (44 fractional bits; 64-bit integers globally) so the result is independent
+ * of the atomics' order, the CTA decomposition and the rank count.
+ * workspace = int64 accumulators [2][K][bx][by] (plane 0 in units of 2^-22, plane 1 in units
+ * of 2^-44; this is what ranks all-reduce exactly).                                      */
+#define MFB_KDE2D_FRAC_BITS 44
 int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by);
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
                           int k, int bx, int by, float max_sigma_over_delta, float* sums,

@@ -11,8 +11,8 @@
 // k = t % Kc and particle slice t / Kc, and a PRIVATE column of bins in shared memory
 // (bins[b][t]: bank = t % 32, conflict free), so deposits are plain LDS/FADD/STS -- no
 // atomics, and the accumulation order is fixed => run-to-run deterministic.  Each particle
-// touches only the 2R+1 bins within ~6.4 sigma of its projection (everything else is below
-// fp32 resolution of the sum), instead of all B.  Per-CTA partials are merged in a fixed
+// touches only the 2R+1 bins within ~8.9 sigma of its projection (everything else is below
+// 1e-17 of a central tap), instead of all B.  Per-CTA partials are merged in a fixed
 // order by a second tiny kernel.
 #include "common.cuh"
 
@@ -33,10 +33,12 @@ struct ProjLaunch {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// window radius in bins: taps further than (R+0.5) bins from the particle contribute
-// < exp(-0.5*6.44^2) ~ 1e-9 of a central tap.
+// Window radius in bins.  Dropped taps are further than (R+0.5) bins = 8.85 sigma from the
+// particle, i.e. below exp(-0.5*8.85^2) ~ 1e-17 of a central tap.  That is far below fp32
+// resolution of the *profile*, but the KL gradient divides by (p_b + 1e-12): a bin reached
+// only by tails must still see them, or dL/dx is off by 1e-4 (measured) -- hence 1e-17, not 1e-9.
 static inline int window_radius(double sigma_over_delta) {
-  double r = 6.44 * sigma_over_delta - 0.5;
+  double r = 8.85 * sigma_over_delta - 0.5;
   int ri = (int)r;
   if ((double)ri < r) ++ri;
   return ri < 1 ? 1 : ri;
@@ -225,7 +227,7 @@ kde1d_normalize_kernel(const float* __restrict__ sums, float inv_n, const float*
                        float* __restrict__ prof) {
   __shared__ float red[33];
   const int k = blockIdx.x;
-  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 1];
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 3];  // the reference's c[1]-c[0]
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) acc += sums[(size_t)k * B + b] * inv_n * delta;
   const float z = block_sum_256(acc, red) + 1.0e-10f;
@@ -237,7 +239,7 @@ kde1d_normalize_bwd_kernel(const float* __restrict__ sums, float inv_n, const fl
                            const float* __restrict__ gprof, float* __restrict__ gsums) {
   __shared__ float red[33];
   const int k = blockIdx.x;
-  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 1];
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 3];  // the reference's c[1]-c[0]
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) acc += sums[(size_t)k * B + b] * inv_n * delta;
   const float z = block_sum_256(acc, red) + 1.0e-10f;
@@ -406,9 +408,9 @@ static int launch_kde1d_deposit(int r, const ProjLaunch& L, const float* x, int6
                                   (int)L.smem));                                                           \
     kde1d_deposit_kernel<D, RR><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, partial); \
   }
-  if (r <= 3) MFB_LAUNCH_R(3)
-  else if (r <= 6) MFB_LAUNCH_R(6)
-  else if (r <= 12) MFB_LAUNCH_R(12)
+  if (r <= 4) MFB_LAUNCH_R(4)
+  else if (r <= 9) MFB_LAUNCH_R(9)
+  else if (r <= 13) MFB_LAUNCH_R(13)
   else return MFB_E_UNSUPPORTED;
 #undef MFB_LAUNCH_R
   return launch_status();
@@ -424,9 +426,9 @@ static int launch_kde1d_bwd(int r, int grid, size_t smem, const float* x, int64_
                                   (int)smem));                                                          \
     kde1d_bwd_kernel<D, RR><<<grid, 256, smem, st>>>(x, n, d, proj, geom, k, b, gsums, gx, acc);         \
   }
-  if (r <= 3) MFB_LAUNCH_R(3)
-  else if (r <= 6) MFB_LAUNCH_R(6)
-  else if (r <= 12) MFB_LAUNCH_R(12)
+  if (r <= 4) MFB_LAUNCH_R(4)
+  else if (r <= 9) MFB_LAUNCH_R(9)
+  else if (r <= 13) MFB_LAUNCH_R(13)
   else return MFB_E_UNSUPPORTED;
 #undef MFB_LAUNCH_R
   return launch_status();

@@ -8,18 +8,21 @@
 //
 // Design: one CTA = one screen x one contiguous block of particles; the screen's (Bx, By) bins
 // live in shared memory.  Each particle deposits the (2R+1)^2 window of Kx_a * Ky_b around its
-// image.  Deposits are accumulated as *fixed point* integers (scale 2^kFracBits) with native
-// shared-memory integer atomics: integer addition is associative, so the result does not depend
-// on the order of the atomics, the CTA decomposition, or the number of ranks (bit-reproducible).
-// The per-CTA bins are flushed to 64-bit global accumulators before they could overflow.
+// image.  Deposits are accumulated as *fixed point* integers (44 fractional bits, split into
+// two 22-bit halves held in two u32 tables) with native shared-memory integer atomics
+// (ATOMS.ADD; on sm_100a both fp32 and 64-bit shared atomicAdd compile to CAS spin loops):
+// integer addition is associative, so the result does not depend on the order of the atomics,
+// the CTA decomposition, or the number of ranks (bit-reproducible).  44 bits keep the far
+// Gaussian tails (6e-14 per deposit) that the KL's log(p + 1e-12) is sensitive to.  The per-CTA
+// tables are flushed to 64-bit global accumulators before they could overflow.
 #include "common.cuh"
 
 namespace mfb {
 
-constexpr int kFracBits = 20;                 // smem accumulators: u32, value * 2^20
-constexpr float kFixScale = 1048576.0f;       // 2^20
+constexpr int kHalfBits = MFB_KDE2D_FRAC_BITS / 2;  // 44 = 22 (high table) + 22 (low table)
+constexpr float kHalfScale = 4194304.0f;            // 2^22
 constexpr int k2dThreads = 256;
-constexpr int kFlushParticles = 3840;         // 3840 * 2^20 < 2^32: no overflow between flushes
+constexpr int kFlushParticles = 1024 - 256;         // 768 * 2^22 < 2^32, 768 * 2^21 < 2^31: no overflow
 
 struct Axis {
   float c0, inv_delta, alpha, beta;  // beta = -delta / sigma^2
@@ -55,12 +58,14 @@ template <int R>
 __global__ void __launch_bounds__(k2dThreads)
 kde2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
                      const float* __restrict__ geom, int BX, int BY, int64_t chunk,
-                     unsigned long long* __restrict__ acc /* [K][BX][BY] */) {
+                     unsigned long long* __restrict__ acc /* [2][K][BX][BY]: high, low */, int64_t acc_len) {
   extern __shared__ __align__(16) unsigned int s_bins[];
   __shared__ float s_w[2 * kMaxDim];
   const int k = blockIdx.y;
   const int nbins = BX * BY;
-  for (int i = threadIdx.x; i < nbins; i += k2dThreads) s_bins[i] = 0u;
+  unsigned int* s_hi = s_bins;                              // units of 2^-22
+  int* s_lo = reinterpret_cast<int*>(s_bins + nbins);       // signed, units of 2^-44
+  for (int i = threadIdx.x; i < 2 * nbins; i += k2dThreads) s_bins[i] = 0u;
   if (threadIdx.x < 2 * d) s_w[threadIdx.x] = proj[(size_t)k * 2 * d + threadIdx.x];
   const Axis ax = load_axis(geom + (size_t)(2 * k) * MFB_GEOM_STRIDE);
   const Axis ay = load_axis(geom + (size_t)(2 * k + 1) * MFB_GEOM_STRIDE);
@@ -89,23 +94,35 @@ kde2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float*
       for (int ja = 0; ja <= 2 * R; ++ja) {
         const int a = bx0 + ja - R;
         if ((unsigned)a < (unsigned)BX) {
-          const float sx = vx[ja] * kFixScale;
-          unsigned int* row = s_bins + a * BY;
+          const float sx = vx[ja] * kHalfScale;
+          const int rowoff = a * BY;
 #pragma unroll
           for (int jb = 0; jb <= 2 * R; ++jb) {
             const int b = by0 + jb - R;
-            const unsigned int q = __float2uint_rn(sx * vy[jb]);
-            if ((unsigned)b < (unsigned)BY && q) atomicAdd(row + b, q);
+            // v * 2^44 = hi * 2^22 + lo with hi = rint(v 2^22), lo = rint((v 2^22 - hi) 2^22)
+            const float v22 = sx * vy[jb];
+            const float hif = rintf(v22);
+            const int lo = __float2int_rn((v22 - hif) * kHalfScale);
+            const unsigned int hi = (unsigned int)hif;
+            if ((unsigned)b < (unsigned)BY) {
+              if (hi) atomicAdd(s_hi + rowoff + b, hi);
+              if (lo) atomicAdd(s_lo + rowoff + b, lo);
+            }
           }
         }
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += k2dThreads) {
-      const unsigned int v = s_bins[i];
-      if (v) {
-        atomicAdd(out + i, (unsigned long long)v);
-        s_bins[i] = 0u;
+      const unsigned int h = s_hi[i];
+      const int l = s_lo[i];
+      if (h) {
+        atomicAdd(out + i, (unsigned long long)h);
+        s_hi[i] = 0u;
+      }
+      if (l) {
+        atomicAdd(out + acc_len + i, (unsigned long long)(long long)l);
+        s_lo[i] = 0;
       }
     }
     __syncthreads();
@@ -114,8 +131,9 @@ kde2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float*
 
 __global__ void fixed_to_float_kernel(const unsigned long long* __restrict__ acc, int64_t len,
                                       float* __restrict__ sums) {
+  const double sh = 1.0 / (double)(1ull << kHalfBits);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-    sums[i] = (float)((double)acc[i] * (1.0 / (double)kFixScale));
+    sums[i] = (float)(((double)(long long)acc[i] + (double)(long long)acc[len + i] * sh) * sh);
 }
 
 // ---- normalisation P / (sum(P) dx dy + 1e-10) and its backward: one CTA per screen -------------
@@ -139,7 +157,7 @@ kde2d_normalize_kernel(const float* __restrict__ sums, const float* __restrict__
                        float* __restrict__ prof) {
   __shared__ float red[33];
   const int k = blockIdx.x;
-  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 1], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 1];
+  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 3], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 3];
   const float* s = sums + (size_t)k * nbins;
   float acc = 0.f;
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) acc += s[i] * dx * dy;
@@ -152,7 +170,7 @@ kde2d_normalize_bwd_kernel(const float* __restrict__ sums, const float* __restri
                            const float* __restrict__ gprof, float* __restrict__ gsums) {
   __shared__ float red[33];
   const int k = blockIdx.x;
-  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 1], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 1];
+  const float dx = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + 3], dy = geom[(size_t)(2 * k + 1) * MFB_GEOM_STRIDE + 3];
   const float* s = sums + (size_t)k * nbins;
   const float* gp = gprof + (size_t)k * nbins;
   float acc = 0.f;
@@ -312,7 +330,7 @@ static int64_t plan_chunk(int64_t n, int k, int* grid_x) {
 using namespace mfb;
 
 static int radius2d(float hint) {
-  double r = 6.44 * (hint > 0.f ? hint : 0.5) - 0.5;
+  double r = 8.85 * (hint > 0.f ? hint : 0.5) - 0.5;  // see kde1d.cu window_radius
   int ri = (int)r;
   if ((double)ri < r) ++ri;
   return ri < 1 ? 1 : ri;
@@ -324,7 +342,7 @@ int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by) {
   (void)n;
   (void)d;
   if (k < 1 || bx < 1 || by < 1) return 0;
-  return (int64_t)k * bx * by * 8;
+  return (int64_t)k * bx * by * 16;  // two int64 planes: units 2^-22 and 2^-44
 }
 
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx,
@@ -333,23 +351,23 @@ int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, c
   MFB_CHECK_ARG(x && proj && geom && sums && workspace);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 2 && by >= 2);
   const int64_t len = (int64_t)k * bx * by;
-  if (workspace_bytes < len * 8) return MFB_E_WORKSPACE;
-  const size_t smem = (size_t)bx * by * 4;
+  if (workspace_bytes < len * 16) return MFB_E_WORKSPACE;
+  const size_t smem = (size_t)bx * by * 8;  // two u32 tables
   if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* acc = (unsigned long long*)workspace;
-  MFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)len * 8, st));
+  MFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)len * 16, st));
   if (n > 0) {
     int gx;
     const int64_t chunk = plan_chunk(n, k, &gx);
     dim3 grid(gx, k);
     const int r = radius2d(max_sigma_over_delta);
-    if (r <= 3) {
-      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kde2d_deposit_kernel<3><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc);
-    } else if (r <= 6) {
-      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kde2d_deposit_kernel<6><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc);
+    if (r <= 4) {
+      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kde2d_deposit_kernel<4><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc, len);
+    } else if (r <= 9) {
+      MFB_CUDA(cudaFuncSetAttribute(kde2d_deposit_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kde2d_deposit_kernel<9><<<grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, bx, by, chunk, acc, len);
     } else {
       return MFB_E_UNSUPPORTED;
     }
@@ -391,12 +409,12 @@ int mfb_project_kde2d_bwd(const float* x, int64_t n, int d, const float* proj, c
   const int64_t blocks = (n + k2dThreads - 1) / k2dThreads;
   if (grid > blocks) grid = blocks;
   const int r = radius2d(max_sigma_over_delta);
-  if (r <= 3) {
-    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kde2d_bwd_kernel<3><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
-  } else if (r <= 6) {
-    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kde2d_bwd_kernel<6><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
+  if (r <= 4) {
+    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kde2d_bwd_kernel<4><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
+  } else if (r <= 9) {
+    MFB_CUDA(cudaFuncSetAttribute(kde2d_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kde2d_bwd_kernel<9><<<(int)grid, k2dThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, gsums, gx, accumulate);
   } else {
     return MFB_E_UNSUPPORTED;
   }

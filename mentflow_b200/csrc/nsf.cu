@@ -55,66 +55,69 @@ __device__ __forceinline__ void dense8(const float (&h)[kH], const float* __rest
 }
 
 // softmax over nb raw parameters held in a strided shared-memory column; leaves
-// exp(w - max) in place and returns 1/sum.
+// exp(w - max) in place and returns their sum.
 __device__ __forceinline__ float softmax_inplace(float* col, int stride, int nb) {
   float m = -INFINITY;
   for (int j = 0; j < nb; ++j) {
     float w = col[j * stride];
-    w = __fdividef(w, 1.0f + kClipW * fabsf(w));
+    w = w / (1.0f + kClipW * fabsf(w));
     col[j * stride] = w;
     m = fmaxf(m, w);
   }
   float sum = 0.f;
   for (int j = 0; j < nb; ++j) {
-    const float e = fast_exp2((col[j * stride] - m) * kLog2e);
+    const float e = expf(col[j * stride] - m);
     col[j * stride] = e;
     sum += e;
   }
-  return 1.0f / sum;
+  return sum;
 }
 
 // One univariate spline: parameters (3*nb-1 raw conditioner outputs) in col[j*stride].
 // Returns y and adds log dy/dv to ladj.
+//
+// Conditioning: zuko differences the cumulative knot arrays (x1 - x0, y1 - y0), which cancels
+// catastrophically in narrow bins (widths go down to 1e-3 of the mean).  Here the bin width and
+// height are taken directly from the softmax values (dx = 2B W_k, dy = 2B H_k), which is the same
+// number in exact arithmetic but accurate to an ulp; only the bin origin comes from the
+// cumulative sum.  This puts the kernel closer to the float64 truth than a plain fp32 evaluation.
 __device__ __forceinline__ float rq_spline_forward(float* col, int stride, int nb, float v, float& ladj) {
   // horizontal knots + bin search: k = #(knots < v) - 1
-  const float inv_w = softmax_inplace(col, stride, nb);
-  float cum = 0.f, xl = -kBound, x0 = 0.f, x1 = 0.f;
+  const float sum_w = softmax_inplace(col, stride, nb);
+  float cum = 0.f, xl = -kBound, x0 = 0.f, wk = 0.f;
   int kbin = -1;
   for (int j = 0; j < nb; ++j) {
-    cum += col[j * stride] * inv_w;
+    const float wj = col[j * stride] / sum_w;
+    cum += wj;
     const float xr = fmaf(2.0f * kBound, cum, -kBound);
     if (kbin < 0 && xl < v && v <= xr) {
       kbin = j;
       x0 = xl;
-      x1 = xr;
+      wk = wj;
     }
     xl = xr;
   }
   if (kbin < 0) return v;  // outside [-bound, bound]: identity, ladj += 0
   float* colh = col + nb * stride;
-  const float inv_h = softmax_inplace(colh, stride, nb);
+  const float sum_h = softmax_inplace(colh, stride, nb);
   cum = 0.f;
-  float yl = -kBound, y0 = 0.f, y1 = 0.f;
-  for (int j = 0; j <= kbin; ++j) {
-    cum += colh[j * stride] * inv_h;
-    const float yr = fmaf(2.0f * kBound, cum, -kBound);
-    y0 = yl;
-    y1 = yr;
-    yl = yr;
-  }
+  for (int j = 0; j < kbin; ++j) cum += colh[j * stride] / sum_h;
+  const float y0 = fmaf(2.0f * kBound, cum, -kBound);
+  const float hk = colh[kbin * stride] / sum_h;
   const float* cold = col + 2 * nb * stride;
   float d0 = 1.0f, d1 = 1.0f;
   if (kbin > 0) {
     const float r = cold[(kbin - 1) * stride];
-    d0 = fast_exp2(__fdividef(r, 1.0f + kClipD * fabsf(r)) * kLog2e);
+    d0 = expf(r / (1.0f + kClipD * fabsf(r)));
   }
   if (kbin < nb - 1) {
     const float r = cold[kbin * stride];
-    d1 = fast_exp2(__fdividef(r, 1.0f + kClipD * fabsf(r)) * kLog2e);
+    d1 = expf(r / (1.0f + kClipD * fabsf(r)));
   }
-  const float dx = x1 - x0, dy = y1 - y0;
-  const float s = dy / dx;
-  const float t = (v - x0) / dx;
+  const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hk;
+  const float s = hk / wk;
+  float t = (v - x0) / dx;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
   const float omt = 1.0f - t;
   const float tomt = t * omt;
   const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);

@@ -15,9 +15,13 @@ from .. import ops
 from ..utils import coords_from_edges
 
 
-def _uniform_geometry(edges: torch.Tensor, what: str) -> Tuple[float, float]:
-    """(first centre, centre spacing) in the fp32 arithmetic of the reference; raises if the
-    bins are not equally spaced (the KDE kernel deposits on a regular grid)."""
+def _uniform_geometry(edges: torch.Tensor, what: str) -> Tuple[float, float, float]:
+    """(first centre, accurate centre spacing, reference delta).  Centres are computed in the
+    reference's fp32 arithmetic; the spacing used to place deposits is the float64 mean
+    spacing of those centres, while ``delta`` = fp32 c[1]-c[0] is what the reference multiplies
+    by in its normalisation (it carries up to 1e-5 relative rounding error, which would shift
+    far bins by 1e-3 bin widths if it were used as the grid pitch).  Raises if the bins are not
+    equally spaced (the KDE kernel deposits on a regular grid)."""
     e = edges.detach().to("cpu", torch.float32)
     if e.ndim != 1 or e.numel() < 3:
         raise ValueError(f"{what}: need at least two bins")
@@ -26,7 +30,8 @@ def _uniform_geometry(edges: torch.Tensor, what: str) -> Tuple[float, float]:
     delta = float(c[1] - c[0])
     if delta <= 0 or float((w - delta).abs().max()) > 1.0e-4 * abs(delta):
         raise NotImplementedError(f"{what}: KDE screens need equally spaced bin edges")
-    return float(c[0]), delta
+    spacing = float((c[-1].double() - c[0].double()) / (c.numel() - 1))
+    return float(c[0]), spacing, delta
 
 
 class Diagnostic(torch.nn.Module):
@@ -98,10 +103,11 @@ class Histogram1D(Histogram):
     def nbins(self) -> int:
         return self.edges.shape[0] - 1
 
-    def geometry(self) -> Tuple[float, float, float]:
+    def geometry(self) -> Tuple[float, float, float, float]:
+        """(c0, spacing, sigma, delta): one geometry record of the C ABI."""
         if self._geom is None:
-            c0, delta = _uniform_geometry(self.edges, "Histogram1D")
-            self._geom = (c0, delta, float(self.bandwidth.detach().cpu()))
+            c0, spacing, delta = _uniform_geometry(self.edges, "Histogram1D")
+            self._geom = (c0, spacing, float(self.bandwidth.detach().cpu()), delta)
         return self._geom
 
     def projection_vector(self, matrix: Optional[torch.Tensor], ndim: int, device) -> torch.Tensor:
@@ -167,10 +173,10 @@ class Histogram2D(Histogram):
 
     def geometry(self):
         if self._geom is None:
-            cx, dx = _uniform_geometry(self.edges_x, "Histogram2D (x)")
-            cy, dy = _uniform_geometry(self.edges_y, "Histogram2D (y)")
-            self._geom = ((cx, dx, float(self.bandwidth_x.detach().cpu())),
-                          (cy, dy, float(self.bandwidth_y.detach().cpu())))
+            cx, sx, dx = _uniform_geometry(self.edges_x, "Histogram2D (x)")
+            cy, sy, dy = _uniform_geometry(self.edges_y, "Histogram2D (y)")
+            self._geom = ((cx, sx, float(self.bandwidth_x.detach().cpu()), dx),
+                          (cy, sy, float(self.bandwidth_y.detach().cpu()), dy))
         return self._geom
 
     def projection_vectors(self, matrix: Optional[torch.Tensor], ndim: int, device) -> torch.Tensor:

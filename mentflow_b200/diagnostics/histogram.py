@@ -12,10 +12,10 @@ def _geom_rows(edges_list, sigmas, device):
     from .diagnostics import _uniform_geometry
     rows, ratio = [], 0.0
     for e, s in zip(edges_list, sigmas):
-        c0, delta = _uniform_geometry(e, "kde_histogram")
+        c0, spacing, delta = _uniform_geometry(e, "kde_histogram")
         s = float(s)
-        rows.append([c0, delta, s, 0.0, 0.0, 0.0, 0.0, 0.0])
-        ratio = max(ratio, s / delta)
+        rows.append([c0, spacing, s, delta, 0.0, 0.0, 0.0, 0.0])
+        ratio = max(ratio, s / spacing)
     return torch.tensor(rows, dtype=torch.float32, device=device), ratio
 
 

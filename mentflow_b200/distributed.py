@@ -1,0 +1,84 @@
+"""Particle sharding across GPUs (one process per GPU, ``torch.distributed``).
+
+Particles are i.i.d. rows, so every op up to the per-bin sums is rank-local.  The only
+exchange on the forward path is ONE small all-reduce of the *unnormalised* profile sums
+(K*B floats, or exact 64-bit fixed-point integers for 2-D screens / histogram counts) and of
+the entropy partial sums -- it has to happen before the non-linear normalisation and KL
+(SURVEY.md 8e).  Gradients of the flow parameters are summed after backward
+(``allreduce_gradients``).  The reference has no distributed code at all.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_sizes(total: int, world_size: int):
+    """Split ``total`` particles as evenly as possible: the first ``total % world`` ranks get
+    one extra particle."""
+    base, extra = divmod(int(total), int(world_size))
+    return [base + (1 if r < extra else 0) for r in range(world_size)]
+
+
+def shard_slice(total: int, rank: int, world_size: int) -> slice:
+    sizes = shard_sizes(total, world_size)
+    start = sum(sizes[:rank])
+    return slice(start, start + sizes[rank])
+
+
+class ShardReducer:
+    """Callable handed to the fused ops: ``n_global = reducer(partial_sums, n_local)`` sums the
+    tensor in place over the group.  With ``equal_shards`` (every rank holds the same number of
+    particles, the weak-scaling layout) the global count needs no communication and no host
+    synchronisation."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, equal_shards: bool = True):
+        self.group = group
+        self.equal_shards = equal_shards
+        self.calls = 0
+        self.bytes = 0
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def __call__(self, tensor: torch.Tensor, n_local: float) -> float:
+        if self.world_size == 1:
+            return float(n_local)
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        self.bytes += tensor.numel() * tensor.element_size()
+        if self.equal_shards or n_local == 0.0:
+            return float(n_local) * self.world_size
+        count = torch.tensor([float(n_local)], dtype=torch.float64, device=tensor.device)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=self.group)
+        return float(count.item())
+
+
+def shard_model(model, group: Optional[dist.ProcessGroup] = None, equal_shards: bool = True) -> ShardReducer:
+    """Attach a reducer to a ``MENTFlow`` model (and its entropy estimator) so that
+    ``model.loss(n_local)`` returns the loss of the *global* batch on every rank."""
+    reducer = ShardReducer(group, equal_shards)
+    model.reducer = reducer
+    if getattr(model, "entropy_estimator", None) is not None and hasattr(model.entropy_estimator, "reducer"):
+        model.entropy_estimator.reducer = reducer
+    return reducer
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None) -> None:
+    """Sum parameter gradients over ranks in one flattened all-reduce (636 KB for the 6-D flow).
+    Every rank back-propagates the same replicated dL/dS through its own particles, so the
+    plain SUM is the gradient of the global loss."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    offset = 0
+    for g in grads:
+        g.copy_(flat[offset:offset + g.numel()].view_as(g))
+        offset += g.numel()

@@ -144,14 +144,14 @@ def project_hist1d(x: torch.Tensor, proj: torch.Tensor, edges: torch.Tensor,
 # 2-D screens
 # --------------------------------------------------------------------------------------
 def kde2d_sums(x, proj, geom, ratio, bx, by):
-    """(sums float32 [K,bx,by], acc int64 [K,bx,by]): acc holds the exact fixed-point
-    accumulators (value * 2^20) that ranks all-reduce."""
+    """(sums float32 [K,bx,by], acc int64 [2,K,bx,by]): acc holds the exact fixed-point
+    accumulators (plane 0: value * 2^22, plane 1: remainder * 2^44) that ranks all-reduce."""
     lib = _lib.load()
     x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
     n, d = x.shape
     k = proj.shape[0]
     sums = torch.empty((k, bx, by), dtype=torch.float32, device=x.device)
-    acc = torch.empty((k, bx, by), dtype=torch.int64, device=x.device)
+    acc = torch.empty((2, k, bx, by), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.mfb_project_kde2d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, bx, by, float(ratio),
                                              _ptr(sums), _ptr(acc), acc.numel() * 8, _stream()),
@@ -178,7 +178,7 @@ class ProjectKDE2D(torch.autograd.Function):
         sums, acc = kde2d_sums(x, proj, geom, ratio, bx, by)
         if reducer is not None:
             reducer(acc, float(x.shape[0]))          # exact integer all-reduce
-            sums = acc.to(torch.float64).mul_(2.0 ** -20).to(torch.float32)
+            sums = (acc[0].to(torch.float64) * 2.0 ** -22 + acc[1].to(torch.float64) * 2.0 ** -44).to(torch.float32)
         prof = kde2d_normalize(sums, geom)
         ctx.save_for_backward(x, proj, geom, sums)
         ctx.ratio = ratio

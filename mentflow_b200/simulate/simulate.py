@@ -32,7 +32,7 @@ def set_default_reducer(reducer: Optional[Callable]) -> None:
 
 
 def _geom_tensor(rows, device):
-    return torch.tensor([[c0, delta, sigma, 0.0, 0.0, 0.0, 0.0, 0.0] for c0, delta, sigma in rows],
+    return torch.tensor([[c0, spacing, sigma, delta, 0.0, 0.0, 0.0, 0.0] for c0, spacing, sigma, delta in rows],
                         dtype=torch.float32, device=device)
 
 
@@ -56,7 +56,7 @@ def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D
         if "geom" not in cache:
             rows = [d.geometry() for d in diags]
             cache["geom"] = _geom_tensor(rows, x.device)
-            cache["ratio"] = max(s / dl for _, dl, s in rows)
+            cache["ratio"] = max(s / sp for _, sp, s, _ in rows)
         return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer)
     if "edges" not in cache:
         cache["edges"] = torch.stack([d.edges.to(x.device) for d in diags]).contiguous()
@@ -80,7 +80,7 @@ def profiles_2d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram2D
                 gx, gy = d.geometry()
                 rows += [gx, gy]
             cache["geom"] = _geom_tensor(rows, x.device).reshape(len(diags), 2, -1)
-            cache["ratio"] = max(s / dl for _, dl, s in rows)
+            cache["ratio"] = max(s / sp for _, sp, s, _ in rows)
         return ops.project_kde2d(x, proj, cache["geom"], cache["ratio"], bx, by, reducer)
     if "ex" not in cache:
         cache["ex"] = torch.stack([d.edges_x.to(x.device) for d in diags]).contiguous()

@@ -50,3 +50,20 @@ def profile_err(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
     return float(((a - b).abs().max(dim=1).values / b.abs().max(dim=1).values).max())
+
+
+def geom_rows(edges, bandwidth, k):
+    """k identical C-ABI geometry records [c0, spacing, sigma, delta, 0...] for fp32 edges."""
+    e = edges.float()
+    c = 0.5 * (e[:-1] + e[1:])
+    delta = float(c[1] - c[0])
+    spacing = float((c[-1].double() - c[0].double()) / (c.numel() - 1))
+    sigma = float(bandwidth * (e[1] - e[0]))
+    return torch.tensor([[float(c[0]), spacing, sigma, delta, 0, 0, 0, 0]] * k, dtype=torch.float32), sigma
+
+
+def err_stats(a, b):
+    """elementwise |a-b| / max(1,|b|): (max, 99.9th percentile)."""
+    e = ((a.double().cpu() - b.double().cpu()).abs() / b.double().cpu().abs().clamp_min(1.0)).flatten()
+    k = max(1, int(e.numel() * 0.999))
+    return float(e.max()), float(e.kthvalue(k).values)

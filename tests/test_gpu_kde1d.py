@@ -7,7 +7,7 @@ import torch
 
 import mentflow_b200 as mf
 from mentflow_b200 import ops
-from mfb_testutil import cuda, profile_err, t32
+from mfb_testutil import cuda, geom_rows, profile_err, t32
 from oracle import hotpath as hp
 
 pytestmark = pytest.mark.gpu
@@ -105,10 +105,9 @@ def test_kde1d_vs_oracle_ragged_shapes(n, d, k, nb):
     w = torch.randn(k, d, generator=gen)
     w = w / w.norm(dim=1, keepdim=True)
     edges = torch.linspace(-3.5, 3.5, nb + 1)
-    delta = float(edges[1] - edges[0])
-    geom = torch.tensor([[float(0.5 * (edges[0] + edges[1])), delta, 0.5 * delta, 0, 0, 0, 0, 0]] * k)
+    geom, sigma = geom_rows(edges, 0.5, k)
     sums = ops.kde1d_sums(x.cuda(), w.cuda(), geom.cuda(), 0.5, nb).cpu().double()
-    ref = torch.stack([hp.kde_sums_1d(x @ w[i], edges, 0.5 * delta) for i in range(k)])
+    ref = torch.stack([hp.kde_sums_1d(x @ w[i], edges, sigma) for i in range(k)])
     assert float((sums - ref).abs().max() / ref.abs().max()) < 2e-5
     # deterministic: same launch twice gives the same bits
     again = ops.kde1d_sums(x.cuda(), w.cuda(), geom.cuda(), 0.5, nb).cpu().double()
@@ -132,7 +131,7 @@ def test_full_size_properties():
     w = w / w.norm(dim=1, keepdim=True)
     edges = torch.linspace(-3.5, 3.5, nb + 1)
     delta = float(edges[1] - edges[0])
-    geom = torch.tensor([[float(0.5 * (edges[0] + edges[1])), delta, 0.5 * delta, 0, 0, 0, 0, 0]] * k).cuda()
+    geom = geom_rows(edges, 0.5, k)[0].cuda()
     full = ops.kde1d_sums(x, w, geom, 0.5, nb).double()
     half = ops.kde1d_sums(x[: n // 2], w, geom, 0.5, nb).double() + ops.kde1d_sums(x[n // 2:], w, geom, 0.5, nb).double()
     assert float((full - half).abs().max() / full.max()) < 1e-5

@@ -4,7 +4,7 @@ import torch
 
 import mentflow_b200 as mf
 from mentflow_b200 import ops
-from mfb_testutil import cuda, profile_err, t32
+from mfb_testutil import cuda, geom_rows, profile_err, t32
 from oracle import hotpath as hp
 
 pytestmark = pytest.mark.gpu
@@ -70,13 +70,9 @@ def test_kde2d_vs_oracle_shapes(n, d, k, bx, by):
     w = torch.randn(k, 2, d, generator=gen)
     w = w / w.norm(dim=2, keepdim=True)
     ex, ey = torch.linspace(-3.5, 3.5, bx + 1), torch.linspace(-3.0, 3.0, by + 1)
-    dx, dy = float(ex[1] - ex[0]), float(ey[1] - ey[0])
-    rows = []
-    for _ in range(k):
-        rows += [[float(0.5 * (ex[0] + ex[1])), dx, 0.5 * dx, 0, 0, 0, 0, 0],
-                 [float(0.5 * (ey[0] + ey[1])), dy, 0.5 * dy, 0, 0, 0, 0, 0]]
-    geom = torch.tensor(rows).reshape(k, 2, 8)
+    (gx, sx), (gy, sy) = geom_rows(ex, 0.5, k), geom_rows(ey, 0.5, k)
+    geom = torch.stack([gx, gy], dim=1)
     prof = ops.project_kde2d(x.cuda(), w.cuda(), geom.cuda(), 0.5, bx, by).cpu()
-    ref = torch.stack([hp.kde_profile_2d(x @ w[i, 0], x @ w[i, 1], ex, ey, 0.5 * dx, 0.5 * dy, chunk=20000)
+    ref = torch.stack([hp.kde_profile_2d(x @ w[i, 0], x @ w[i, 1], ex, ey, sx, sy, chunk=20000)
                        for i in range(k)])
     assert profile_err(prof, ref) < TOL

@@ -101,8 +101,9 @@ def test_diagnostic_interface_and_no_cpu_fallback():
     d = mf.diagnostics.Histogram1D(axis=0, edges=e, bandwidth=0.5, noise=True, noise_scale=0.0, seed=1)
     assert d.ndim == 1 and d.kde and d.edges.shape == (65,) and d.coords.shape == (64,)
     assert abs(float(d.bandwidth) - 0.5 * float(e[1] - e[0])) < 1e-9
-    c0, delta, sigma = d.geometry()
-    assert abs(c0 - float(d.coords[0])) < 1e-7 and abs(delta - float(d.coords[1] - d.coords[0])) < 1e-7
+    c0, spacing, sigma, delta = d.geometry()
+    assert abs(c0 - float(d.coords[0])) < 1e-7 and delta == float(d.coords[1] - d.coords[0])
+    assert abs(spacing - 7.0 / 64) < 1e-9 and abs(spacing - delta) < 1e-5 * delta
     x = torch.randn(10, 6)
     assert torch.equal(d.project(x), x[:, 0])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
