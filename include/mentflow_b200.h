@@ -118,6 +118,20 @@ int mfb_nsf_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hi
                       int bins, const float* params, const int32_t* order_host, const float* logq_in,
                       int first_layer, float* y, float* logq_out, void* stream);
 
+/* Backward of one layer (replaces torch autograd through the zuko graph).  Activations are
+ * recomputed from the layer input v.  gy = dL/dy [n][d], glogq = dL/dlogq_out [n] (may be NULL);
+ * outputs gv = dL/dv [n][d] and gparams = dL/dparams in the packed forward layout (added to
+ * when accumulate != 0).  params_om: the same masked weights in out-major layout
+ * W1 [64][d] | Wl [64 out][64 in] x (L-1) | Wout [d*64 (59->64 padded rows)][64 in], no biases
+ * (mfb_nsf_layer_param_om_floats floats).  dL/dlogq_in = glogq (pass-through).           */
+int64_t mfb_nsf_layer_param_om_floats(int d, int hidden_units, int hidden_layers);
+int64_t mfb_nsf_layer_bwd_workspace_bytes(int64_t n, int d, int hidden_layers);
+int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d,
+                      int hidden_units, int hidden_layers, int bins, const float* params,
+                      const float* params_om, const int32_t* order_host, int first_layer, float* gv,
+                      float* gparams, int accumulate, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
 /* ---- Monte-Carlo entropy pieces (entropy.py:58-62, prior.py:25-26) ----------------------
  * out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j
  * (double precision, deterministic two-stage reduction; the x_i / x_i x_j block only when

@@ -116,6 +116,20 @@ class NSFGenerator(GenerativeModel):
         parts += [wo.reshape(T, -1), bo.reshape(T, -1)]
         return torch.cat(parts, dim=1).contiguous()
 
+    def packed_parameters_om(self) -> torch.Tensor:
+        """(T, floats) masked weights in out-major layout for the backward data-gradient kernels:
+        W1 [64][D] | Wl [64][64] x (L-1) | Wout [D*64 (59->64 padded rows)][64]; detached (the
+        parameter gradient flows through ``packed_parameters``)."""
+        T, H, D, P = self.transforms, self.hidden_units, self.features, self.total
+        with torch.no_grad():
+            parts = [(self.w_in * self.m_in).reshape(T, -1)]
+            if self.hidden_layers > 1:
+                parts.append((self.w_hid * self.m_hid).reshape(T, -1))
+            wo = (self.w_out * self.m_out).reshape(T, D, P, H)
+            wo = torch.nn.functional.pad(wo, (0, 0, 0, 64 - P))
+            parts.append(wo.reshape(T, -1))
+            return torch.cat(parts, dim=1).contiguous()
+
     # zuko-style names in checkpoints ------------------------------------------------
     def _zuko_items(self):
         for t in range(self.transforms):
@@ -158,8 +172,10 @@ class NSFGenerator(GenerativeModel):
         return torch.randn((int(n), self.features), dtype=torch.float32, device=self.w_in.device)
 
     def _run(self, z: torch.Tensor, want_logq: bool, want_steps: bool = False):
-        return ops.nsf_forward(z, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
-                               self.bins, want_logq, want_steps)
+        need_grad = torch.is_grad_enabled() and (z.requires_grad or self.w_in.requires_grad)
+        packed_om = self.packed_parameters_om() if need_grad else None
+        return ops.nsf_forward(z, self.packed_parameters(), packed_om, self._orders, self.hidden_units,
+                               self.hidden_layers, self.bins, want_logq, want_steps)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         return self._run(z, False)[0]

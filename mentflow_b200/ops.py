@@ -269,12 +269,12 @@ def moments(x: torch.Tensor, logq: Optional[torch.Tensor], with_cov: bool = Fals
 # whole flow (all layers), differentiable
 # --------------------------------------------------------------------------------------
 class NSFForward(torch.autograd.Function):
-    """x, log q = flow(z): one kernel launch per autoregressive layer.  The layer inputs are
-    kept (24 B / particle / layer) so that backward recomputes conditioner activations tile
-    by tile instead of storing them (10.9 KB / particle in the reference's autograd graph)."""
+    """x, log q = flow(z): one kernel launch per autoregressive layer.  Only the layer inputs are
+    kept (24 B / particle / layer); backward recomputes the conditioner activations instead of
+    storing them (10.9 KB / particle in the reference's autograd graph)."""
 
     @staticmethod
-    def forward(ctx, z, packed, meta):
+    def forward(ctx, z, packed, packed_om, meta):
         orders, hidden_units, hidden_layers, bins, want_logq = meta
         z = _check_f32("z", z)
         packed = _check_f32("packed", packed)
@@ -285,8 +285,7 @@ class NSFForward(torch.autograd.Function):
                                         first_layer=(t == 0), want_logq=want_logq)
             steps.append(y)
         ctx.meta = meta
-        ctx.save_for_backward(packed, *steps[:-1])
-        ctx.mark_non_differentiable(*[])
+        ctx.save_for_backward(packed, packed_om, *steps[:-1])
         if logq is None:
             logq = z.new_empty(0)
         return steps[-1], logq
@@ -294,17 +293,45 @@ class NSFForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gx, glogq):
         orders, hidden_units, hidden_layers, bins, want_logq = ctx.meta
-        packed, *inputs = ctx.saved_tensors
-        gx = _check_f32("gx", gx) if gx is not None else None
-        return nsf_backward(inputs, packed, orders, hidden_units, hidden_layers, bins, gx,
-                            glogq if want_logq else None) + (None,)
+        packed, packed_om, *inputs = ctx.saved_tensors
+        n, d = inputs[0].shape
+        gx = _check_f32("gx", gx) if gx is not None else torch.zeros_like(inputs[0])
+        gl = _check_f32("glogq", glogq) if (want_logq and glogq is not None and glogq.numel() == n) else None
+        gz, gpacked = nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, gl)
+        return gz, gpacked, None, None
 
 
-def nsf_backward(inputs, packed, orders, hidden_units, hidden_layers, bins, gx, glogq):
-    raise NotImplementedError("mentflow_b200: the NSF backward kernel is not built yet")
+NSF_BWD_CHUNK = 1 << 20   # particles per backward pass: bounds the recompute workspace (~2.9 KB/particle)
 
 
-def nsf_forward(z, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
+def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, glogq):
+    """(dL/dz, dL/dpacked) given the per-layer inputs saved by the forward pass."""
+    lib = _lib.load()
+    n, d = inputs[0].shape
+    dev = inputs[0].device
+    gpacked = torch.zeros_like(packed)
+    gz = torch.empty_like(inputs[0])
+    chunk = min(n, NSF_BWD_CHUNK)
+    with torch.cuda.device(dev):
+        wbytes = lib.mfb_nsf_layer_bwd_workspace_bytes(chunk, d, hidden_layers)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        for start in range(0, n, chunk):
+            m = min(chunk, n - start)
+            g = gx[start:start + m]
+            gl = None if glogq is None else glogq[start:start + m]
+            for t in range(len(orders) - 1, -1, -1):
+                order_arr = (ctypes.c_int32 * d)(*[int(o) for o in orders[t]])
+                out = gz[start:start + m] if t == 0 else torch.empty((m, d), dtype=torch.float32, device=dev)
+                _lib.check(lib.mfb_nsf_layer_bwd(_ptr(inputs[t][start:start + m]), _ptr(g), _ptr(gl), m, d, hidden_units,
+                                                 hidden_layers, bins, _ptr(packed[t]), _ptr(packed_om[t]),
+                                                 ctypes.cast(order_arr, ctypes.c_void_p), 1 if t == 0 else 0,
+                                                 _ptr(out), _ptr(gpacked[t]), 1 if start > 0 else 0, _ptr(work),
+                                                 wbytes, _stream()), "nsf_layer_bwd")
+                g = out
+    return gz, gpacked
+
+
+def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
     """Returns (x, logq or None, steps or None)."""
     if want_steps:
         z = _check_f32("z", z)
@@ -315,7 +342,7 @@ def nsf_forward(z, packed, orders, hidden_units, hidden_layers, bins, want_logq=
             steps.append(y)
         return steps[-1], logq, steps
     meta = (tuple(tuple(o) for o in orders), hidden_units, hidden_layers, bins, bool(want_logq))
-    x, logq = NSFForward.apply(z, packed, meta)
+    x, logq = NSFForward.apply(z, packed, packed_om, meta)
     return x, (logq if want_logq else None), None
 
 

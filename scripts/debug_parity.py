@@ -61,3 +61,14 @@ print("kde2d grad: cuda vs fp64", float((xx.grad.cpu().double() - x64.grad).abs(
       "cuda vs ref32", float((xx.grad.cpu() - ref).abs().max() / ref.abs().max()))
 prof = torch.stack([o[0] for o in out]).detach().cpu().double(); p64 = torch.stack([o[0] for o in o64]).detach()
 print("kde2d prof err vs fp64", float(((prof - p64).abs().amax(dim=(1, 2)) / p64.amax(dim=(1, 2))).max()), "min-bin ratio check", float((prof[p64 > 1e-14] / p64[p64 > 1e-14]).min()), float((prof[p64 > 1e-14] / p64[p64 > 1e-14]).max()))
+
+# ---- NSF backward diagnostics
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_gpu_nsf import _grads_case
+for args in [(6, 3000, 1.0, 3, 5, 20), (2, 1000, 1.5, 3, 5, 20), (3, 513, 1.0, 1, 2, 12)]:
+    gr = _grads_case(*args, seed=1)
+    print("nsf bwd", args)
+    for name, (got, want) in gr.items():
+        want = want.double(); e = (got.double().cpu() - want).abs()
+        if name.endswith("0") or name == "z" or name.endswith(".0"):
+            print(f"   {name:10s} max|g| {float(want.abs().max()):.3e} err/max {float(e.max() / want.abs().max()):.2e}")
