@@ -248,14 +248,22 @@ def main():
             x, logq = gen.forward_and_log_prob(z)
             if timers:
                 timers[1].record()
-            H = model.entropy_estimator(x, logq)
+            L, H, D = model.loss_from_particles(x, logq)
             if timers:
                 timers[2].record()
-            preds = mf.simulate.forward(x, model.transforms, model.diagnostics, reducer=reducer)
-            if timers:
-                timers[3].record()
-            D = model.discrepancy_vector(preds)
-            L = H + model.penalty_parameter * (sum(D) / len(D))
+        return L
+
+    params = list(model.parameters())
+
+    def train_step(z):
+        """forward + hand-written backward (+ gradient all-reduce): what one optimiser step costs"""
+        for p_ in params:
+            p_.grad = None
+        x, logq = gen.forward_and_log_prob(z)
+        L, H, D = model.loss_from_particles(x, logq)
+        L.backward()
+        if world > 1:
+            mfd.allreduce_gradients(params)
         return L
 
     def barrier():
@@ -276,14 +284,14 @@ def main():
     for _ in range(args.steps):
         flush.zero_()                      # evict L2 between timed iterations
         e0, e1 = ev(), ev()
-        tm = [ev() for _ in range(4)]
+        tm = [ev() for _ in range(3)]
         e0.record()
         L = step(z_dev, tm)
         e1.record()
         e1.synchronize()
         total_ms += e0.elapsed_time(e1)
         nsf_ms.append(tm[0].elapsed_time(tm[1]))
-        kde_ms.append(tm[2].elapsed_time(tm[3]))
+        kde_ms.append(tm[1].elapsed_time(tm[2]))
         losses.append(L)
     barrier()
     # ---- end to end: z from pinned host memory, loss read back ----------------------------
@@ -297,12 +305,26 @@ def main():
         lval = float(L.item())
         e2e_s += time.perf_counter() - t0
     barrier()
+    # ---- training step (forward + backward), reported beside the headline ----------------------
+    tsteps = max(2, args.steps // 4)
+    train_step(z_dev)
+    barrier()
+    train_ms = 0.0
+    for _ in range(tsteps):
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        e0.record()
+        train_step(z_dev)
+        e1.record()
+        e1.synchronize()
+        train_ms += e0.elapsed_time(e1)
+    barrier()
     clocks = sampler.finish()
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
     value = n * world * args.steps / (total_ms * 1e-3)
     e2e_value = n * world * args.steps / (e2e_ms * 1e-3)
 
@@ -327,7 +349,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": n * d * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()"},
-            "gpu_launches": args.steps * 2 * (layers + 2 + 3),
+            "gpu_launches": (2 * args.steps) * (layers + 2 + 3),
             "gpu_launches_per_step": {"nsf_layer_fwd_kernel": layers, "moments": 2, "kde1d deposit+reduce+normalize": 3},
             "roofline": {"bound": "tensor", "kernel": "nsf_layer_fwd_kernel<6> x5 (fp32 CUDA-core stage; no tensor-core MMA yet)",
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -335,9 +357,13 @@ def main():
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_particle": FLOP_MASK_AWARE.get(d), "dense_equivalent_flop": FLOP_DENSE.get(d),
                          "kernel_ms_per_step": nsf_step_ms, "share_of_step": nsf_step_ms / (total_ms / args.steps),
-                         "kde_ms_per_step": statistics.mean(kde_ms),
+                         "entropy_project_kde_loss_ms_per_step": statistics.mean(kde_ms),
                          "hbm_gbs_nsf": (n * (2 * d * 4 + 8) * layers) / (nsf_step_ms * 1e-3) / 1e9},
             "loss": float(losses[-1]),
+            "train_step": {"value": n * world * tsteps / (train_ms * 1e-3), "unit": "particles/s",
+                           "ms_per_step": train_ms / tsteps, "steps": tsteps,
+                           "what": "loss forward + hand-written backward to all flow parameters"
+                                   + (" + gradient all-reduce" if world > 1 else "")},
         }
         if world == 1 and not args.no_cpu_baseline:
             stepf, ncpu = cpu_step_factory(args)

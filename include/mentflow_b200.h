@@ -118,6 +118,15 @@ int mfb_nsf_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hi
                       int bins, const float* params, const int32_t* order_host, const float* logq_in,
                       int first_layer, float* y, float* logq_out, void* stream);
 
+/* Density direction of one layer: v = A^-1(y) (d conditioner sweeps per particle) and
+ * ladj_out = ladj_in + log|det dA/dv|(v).  Replaces generate/flows/zuko.py:21-22,31-32,43-50
+ * (log_prob / inverse / inverse_steps).  Call the layers in REVERSE order; with last_layer != 0
+ * (the flow's first layer) ladj_out receives log q(x) = log N(v;0,I) - sum ladj instead.
+ * ladj_in / ladj_out may be NULL.  order_host is required (HOST array of d ints).          */
+int mfb_nsf_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hidden_layers,
+                      int bins, const float* params, const int32_t* order_host, const float* ladj_in,
+                      int last_layer, float* v, float* ladj_out, void* stream);
+
 /* Backward of one layer (replaces torch autograd through the zuko graph).  Activations are
  * recomputed from the layer input v.  gy = dL/dy [n][d], glogq = dL/dlogq_out [n] (may be NULL);
  * outputs gv = dL/dv [n][d] and gparams = dL/dparams in the packed forward layout (added to
@@ -139,6 +148,42 @@ int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64
 int64_t mfb_moments_workspace_bytes(int64_t n, int d);
 int mfb_moments(const float* x, const float* logq, int64_t n, int d, int with_cov, double* out,
                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- classical MENT (ment.py, sample.py) --------------------------------------------------
+ * rho(x) = exp(log prior(x)) * prod_k clamp(h_k(proj_k . x), 0, 1e10); h_k = linear interpolation
+ * of tables[k][0..b) on the bin centres coords[k][0..b), 0 outside the first/last centre,
+ * evaluated in double like scipy's RegularGridInterpolator (ment.py:45-52, 227-249).
+ * prior: log p(x) = prior_neg_half_inv_s2 * |x|^2 + prior_log_norm (Gaussian prior.py:25-26;
+ * a flat prior passes 0 and its log constant).                                            */
+int mfb_ment_prob(const float* x, int64_t g, int d, const float* proj, const float* coords,
+                  const float* tables, int k, int b, float prior_neg_half_inv_s2,
+                  float prior_log_norm, float* out, void* stream);
+/* same on the cell centres of a regular grid generated from the index ('ij' order, last axis
+ * fastest) instead of res^D x D materialised points (sample.py:99-104 GridSampler).  shape /
+ * first_centre / step are HOST arrays of d entries.                                       */
+int mfb_ment_prob_grid(int d, const int32_t* shape_host, const float* first_centre_host,
+                       const float* step_host, const float* proj, const float* coords,
+                       const float* tables, int k, int b, float prior_neg_half_inv_s2,
+                       float prior_log_norm, float* out, void* stream);
+/* integrate mode for a 1-D screen (ment.py:267-317): pred[i] = sum over the integration grid of
+ * rho(Minv [meas_coords[i] on meas_axis ; grid point on the other axes]).                 */
+int mfb_ment_integrate(int d, const float* meas_coords, int nb_meas, int meas_axis, int n_int_axes,
+                       const int32_t* int_shape_host, const float* int_first_host,
+                       const float* int_step_host, const float* minv, const float* proj,
+                       const float* coords, const float* tables, int k, int b,
+                       float prior_neg_half_inv_s2, float prior_log_norm, float* pred, void* stream);
+/* sample.py:27-57: cdf of (rho + pad) over the cells in double, then `size` draws: cell by
+ * inverse-CDF search with a Philox4x32-10 stream (seed, offset), uniform position inside the
+ * cell (+ 0.5*U(-delta,delta) when jitter != 0).  workspace[0] (device double) = total mass. */
+int64_t mfb_cdf_workspace_bytes(int64_t g);
+int mfb_cdf_build(const float* rho, int64_t g, double pad, double* cdf, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+int mfb_cdf_sample(const double* cdf, int64_t g, const void* workspace, int d,
+                   const int32_t* shape_host, const float* first_edge_host, const float* cell_host,
+                   int jitter, uint64_t seed, uint64_t offset, int64_t size, float* out, void* stream);
+/* ment.py:360-367: pred[pred<thresh]=0; where meas!=0 and pred!=0: h *= 1 + lr*(meas/pred-1) */
+int mfb_gs_update(float* table, const float* meas, const float* pred, int n, float lr, float thresh,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ missing (or a symbol is), importing the ops fails loudly.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmentflow_b200.so")
@@ -31,10 +31,19 @@ SIGNATURES = {
     "mfb_project_hist2d": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_int, P, P]),
     "mfb_nsf_layer_param_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "mfb_nsf_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
+    "mfb_nsf_layer_inv": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_param_om_floats": (c_int64, [c_int, c_int, c_int]),
     "mfb_nsf_layer_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "mfb_nsf_layer_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P,
                                   c_int64, P]),
+    "mfb_ment_prob": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, c_float, P, P]),
+    "mfb_ment_prob_grid": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P, P]),
+    "mfb_ment_integrate": (c_int, [c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float,
+                                   c_float, P, P]),
+    "mfb_cdf_workspace_bytes": (c_int64, [c_int64]),
+    "mfb_cdf_build": (c_int, [P, c_int64, c_double, P, P, c_int64, P]),
+    "mfb_cdf_sample": (c_int, [P, c_int64, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int64, P, P]),
+    "mfb_gs_update": (c_int, [P, P, P, c_int, c_float, c_float, P]),
     "mfb_moments_workspace_bytes": (c_int64, [c_int64, c_int]),
     "mfb_moments": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
 }

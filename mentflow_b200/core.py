@@ -57,12 +57,54 @@ class MENTFlow(nn.Module):
         return [self.discrepancy_function(pred, meas)
                 for pred, meas in zip(unravel(predictions), unravel(self.measurements))]
 
+    _BATCHED = None
+
+    def _batched_discrepancy(self, stacked, n_slots):
+        """All D_k in a handful of kernels when the discrepancy is one of the library's (the
+        reference evaluates K small expressions in a Python loop, core.py:89-93)."""
+        from . import loss as _loss
+        table = {_loss.kl_divergence: _loss.kl_divergence_batched,
+                 _loss.mean_absolute_error: lambda p, t: (p - t).abs().reshape(p.shape[0], -1).mean(dim=1),
+                 _loss.mean_square_error: lambda p, t: (p - t).square().reshape(p.shape[0], -1).mean(dim=1)}
+        fn = table.get(self.discrepancy_function)
+        if fn is None or not stacked or sum(len(s) for s, _ in stacked) != n_slots:
+            return None
+        key = tuple(id(m) for row in self.measurements for m in row)
+        if self._BATCHED is None or self._BATCHED[0] != key:
+            offsets, base = [], 0
+            for row in self.measurements:
+                offsets.append(base)
+                base += len(row)
+            groups = []
+            for slots, prof in stacked:
+                meas = torch.stack([self.measurements[i][j] for i, j in slots]).to(prof.device)
+                index = torch.tensor([offsets[i] + j for i, j in slots], device=prof.device)
+                groups.append((meas, index))
+            self._BATCHED = (key, groups)
+        out = None
+        for (slots, prof), (meas, index) in zip(stacked, self._BATCHED[1]):
+            d = fn(prof, meas)
+            if len(stacked) == 1 and index.numel() == n_slots:
+                return d                      # single group in natural order (the usual case)
+            if out is None:
+                out = torch.zeros(n_slots, dtype=d.dtype, device=d.device)
+            out = out.index_copy(0, index, d)
+        return out
+
     def loss_from_particles(self, x: torch.Tensor, log_prob: torch.Tensor):
         """The part of ``loss`` after sampling (used by parity tests that fix the particles)."""
         H = self.entropy_estimator(x, log_prob)
-        predictions = simulate_forward(x, self.transforms, self.diagnostics, reducer=self.reducer)
-        D = self.discrepancy_vector(predictions)
-        L = H + self.penalty_parameter * (sum(D) / len(D))
+        stacked = []
+        predictions = simulate_forward(x, self.transforms, self.diagnostics, reducer=self.reducer, stacked=stacked)
+        n_slots = sum(len(row) for row in predictions)
+        dvec = self._batched_discrepancy(stacked, n_slots)
+        if dvec is not None:
+            D = list(dvec.unbind(0))
+            mean_d = dvec.mean()
+        else:
+            D = self.discrepancy_vector(predictions)
+            mean_d = sum(D) / len(D)
+        L = H + self.penalty_parameter * mean_d
         return L, H, D
 
     def loss(self, batch_size: int):

@@ -1,0 +1,470 @@
+// Classical MENT: density rho(x) = prior(x) * prod_k h_k(w_k . x), its integration / sampling
+// and the Gauss-Seidel update of the Lagrange tables.
+//
+// Replaces (reference file:line, relative to mentflow/):
+//   ment.py:239-249, 227-234, 45-52   MENT.prob: per measurement a full matmul, a device->numpy
+//                                     ->scipy RegularGridInterpolator (fp64, single thread)->device
+//                                     round trip, clamp, product; then * exp(prior.log_prob)
+//   sample.py:27-57, 99-104           GridSampler: prob on the full res^D grid, multinomial over
+//                                     cells (<= 2^24 categories), uniform jitter
+//   ment.py:267-317                   _simulate_integrate: Python loop over measured pixels
+//   ment.py:360-367                   Python per-bin loop of the Gauss-Seidel update
+#include "common.cuh"
+
+namespace mfb {
+
+constexpr int kMentThreads = 256;
+
+struct MentGrid {            // regular grid of cell centres (GridSampler) or an integration grid
+  int ndim;
+  int shape[kMaxDim];
+  float lo[kMaxDim];         // first centre
+  float step[kMaxDim];       // centre spacing
+};
+
+struct MentPrior {
+  float neg_half_inv_s2;     // -0.5 / scale^2 (0 for a flat prior)
+  float log_norm;            // -D log s - D/2 log 2pi (log of the constant for a flat prior)
+};
+
+// shared-memory tables: coords[K][B] (bin centres) and values[K][B] (h_k)
+__device__ __forceinline__ float lagrange_eval(const float* __restrict__ c, const float* __restrict__ h, int B,
+                                               float inv_step, float u) {
+  // scipy RegularGridInterpolator(method="linear", bounds_error=False, fill_value=0) on the bin
+  // centres, evaluated in double like the reference (ment.py:45-52), then cast to fp32 (:233)
+  if (!(u >= c[0] && u <= c[B - 1])) return 0.f;
+  int i = (int)((u - c[0]) * inv_step);
+  i = min(max(i, 0), B - 2);
+  while (i > 0 && u < c[i]) --i;
+  while (i < B - 2 && u > c[i + 1]) ++i;
+  const double x0 = (double)c[i], x1 = (double)c[i + 1];
+  const double w = ((double)u - x0) / (x1 - x0);
+  return (float)((double)h[i] * (1.0 - w) + (double)h[i + 1] * w);
+}
+
+template <int D>
+__device__ __forceinline__ float ment_density(const float (&x)[D], const float* __restrict__ s_proj,
+                                              const float* __restrict__ s_c, const float* __restrict__ s_h,
+                                              const float* __restrict__ s_inv, int K, int B, MentPrior prior) {
+  float prob = 1.0f;
+  for (int k = 0; k < K; ++k) {
+    float u = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) u = fmaf(s_proj[k * D + i], x[i], u);
+    float h = lagrange_eval(s_c + (size_t)k * B, s_h + (size_t)k * B, B, s_inv[k], u);
+    h = fminf(fmaxf(h, 0.0f), 1.0e10f);   // ment.py:246
+    prob *= h;
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) ss = fmaf(x[i], x[i], ss);
+  return prob * expf(fmaf(prior.neg_half_inv_s2, ss, prior.log_norm));
+}
+
+__device__ __forceinline__ void load_tables(float* s_proj, float* s_c, float* s_h, float* s_inv,
+                                            const float* __restrict__ proj, const float* __restrict__ coords,
+                                            const float* __restrict__ tables, int K, int B, int D) {
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) s_proj[i] = proj[i];
+  for (int i = threadIdx.x; i < K * B; i += blockDim.x) {
+    s_c[i] = coords[i];
+    s_h[i] = tables[i];
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    s_inv[k] = (float)(B - 1) / (coords[(size_t)k * B + B - 1] - coords[(size_t)k * B]);
+}
+
+// MODE 0: explicit points x[G][D];  MODE 1: points of a regular grid generated from the index
+template <int D, int MODE>
+__global__ void __launch_bounds__(kMentThreads)
+ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const float* __restrict__ proj,
+                 const float* __restrict__ coords, const float* __restrict__ tables, int K, int B,
+                 MentPrior prior, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_proj = sm;
+  float* s_c = s_proj + (((size_t)K * D + 3) & ~(size_t)3);
+  float* s_h = s_c + (size_t)K * B;
+  float* s_inv = s_h + (size_t)K * B;
+  load_tables(s_proj, s_c, s_h, s_inv, proj, coords, tables, K, B, D);
+  __syncthreads();
+  for (int64_t g = (int64_t)blockIdx.x * kMentThreads + threadIdx.x; g < G; g += (int64_t)gridDim.x * kMentThreads) {
+    float xr[D];
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) xr[i] = x[g * D + i];
+    } else {
+      int64_t rem = g;  // 'ij' ordering: last axis fastest (utils/grid.py:9-10)
+#pragma unroll
+      for (int i = D - 1; i >= 0; --i) {
+        const int idx = (int)(rem % grid.shape[i]);
+        rem /= grid.shape[i];
+        xr[i] = fmaf((float)idx, grid.step[i], grid.lo[i]);
+      }
+    }
+    out[g] = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+  }
+}
+
+// integrate mode (ment.py:267-317) for a 1-D screen: pred[b] = sum_q rho(Minv [c_b ; t_q])
+// one CTA per measured pixel, deterministic block reduction
+template <int D>
+__global__ void __launch_bounds__(kMentThreads)
+ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int meas_axis, MentGrid igrid,
+                      const float* __restrict__ minv /* [D][D] */, const float* __restrict__ proj,
+                      const float* __restrict__ coords, const float* __restrict__ tables, int K, int B,
+                      MentPrior prior, float* __restrict__ pred) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_proj = sm;
+  float* s_c = s_proj + (((size_t)K * D + 3) & ~(size_t)3);
+  float* s_h = s_c + (size_t)K * B;
+  float* s_inv = s_h + (size_t)K * B;
+  __shared__ float s_minv[D * D];
+  __shared__ double red[kMentThreads / 32];
+  load_tables(s_proj, s_c, s_h, s_inv, proj, coords, tables, K, B, D);
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_minv[i] = minv[i];
+  __syncthreads();
+  int64_t Q = 1;
+  for (int i = 0; i < igrid.ndim; ++i) Q *= igrid.shape[i];
+  const int b = blockIdx.x;
+  const float cm = meas_coords[b];
+  float acc = 0.f;  // the reference sums fp32 densities with torch.sum
+  double dacc = 0.0;
+  for (int64_t q = threadIdx.x; q < Q; q += kMentThreads) {
+    float u[D];
+    int64_t rem = q;
+    int ia = igrid.ndim - 1;
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) {
+      if (i == meas_axis) {
+        u[i] = cm;
+      } else {
+        const int idx = (int)(rem % igrid.shape[ia]);
+        rem /= igrid.shape[ia];
+        u[i] = fmaf((float)idx, igrid.step[ia], igrid.lo[ia]);
+        --ia;
+      }
+    }
+    float xr[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(u[j], s_minv[i * D + j], s);
+      xr[i] = s;
+    }
+    dacc += (double)ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+  }
+  (void)acc;
+  dacc = warp_sum(dacc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kMentThreads / 32; ++i) t += red[i];
+    pred[b] = (float)t;
+  }
+}
+
+// ---- inclusive scan of (rho + pad) in double: 3 passes -----------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums_kernel(const float* __restrict__ rho, int64_t G, double pad, double* __restrict__ tile_sums) {
+  __shared__ double red[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < G) s += (double)rho[base + i] + pad;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kScanThreads / 32; ++i) t += red[i];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_tile_offsets_kernel(double* __restrict__ tile_sums, int64_t ntiles, double* __restrict__ total) {
+  // single thread block, serial over tiles in chunks: ntiles <= G/4096 (4096 for 2^24 cells)
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double run = 0.0;
+    for (int64_t i = 0; i < ntiles; ++i) {
+      const double v = tile_sums[i];
+      tile_sums[i] = run;
+      run += v;
+    }
+    *total = run;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const float* __restrict__ rho, int64_t G, double pad, const double* __restrict__ tile_offsets,
+                  double* __restrict__ cdf) {
+  __shared__ double s_thread[kScanThreads];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  double loc[kScanItems];
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < G) s += (double)rho[base + i] + pad;
+    loc[i] = s;
+  }
+  s_thread[threadIdx.x] = s;
+  __syncthreads();
+  // exclusive prefix over the 256 thread sums (serial per thread over <= 255 values: tiny)
+  double off = tile_offsets[blockIdx.x];
+  for (int t = 0; t < (int)threadIdx.x; ++t) off += s_thread[t];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < G) cdf[base + i] = off + loc[i];
+}
+
+// ---- Philox4x32-10 -------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t c[4];
+};
+__device__ __forceinline__ Philox philox4x32(uint64_t counter, uint32_t stream, uint64_t seed) {
+  uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = stream, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox p;
+  p.c[0] = c0; p.c[1] = c1; p.c[2] = c2; p.c[3] = c3;
+  return p;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+
+// draw `size` particles: cell ~ pmf (binary search in the CDF), then uniform inside the cell
+// (sample.py:34-57).  jitter != 0 adds 0.5*U(-delta, delta) per axis (:53-55).
+template <int D>
+__global__ void __launch_bounds__(kMentThreads)
+cdf_sample_kernel(const double* __restrict__ cdf, int64_t G, const double* __restrict__ total, MentGrid grid,
+                  int jitter, uint64_t seed, uint64_t offset, int64_t size, float* __restrict__ out) {
+  const double tot = *total;
+  for (int64_t s = (int64_t)blockIdx.x * kMentThreads + threadIdx.x; s < size; s += (int64_t)gridDim.x * kMentThreads) {
+    const Philox r0 = philox4x32(offset + (uint64_t)s, 0u, seed);
+    // 53-bit uniform for the cell choice
+    const double uu = ((double)(((uint64_t)r0.c[0] << 21) ^ (uint64_t)(r0.c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double target = uu * tot;
+    int64_t lo = 0, hi = G - 1;
+    while (lo < hi) {  // first index with cdf > target
+      const int64_t mid = (lo + hi) >> 1;
+      if (cdf[mid] > target) hi = mid;
+      else lo = mid + 1;
+    }
+    int64_t rem = lo;
+    uint32_t rnd[2 * kMaxDim];
+    rnd[0] = r0.c[2];
+    rnd[1] = r0.c[3];
+#pragma unroll
+    for (int b = 0; b < (2 * D + 1) / 4 + 1; ++b) {
+      const Philox rb = philox4x32(offset + (uint64_t)s, 1u + b, seed);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (2 + 4 * b + q < 2 * kMaxDim) rnd[2 + 4 * b + q] = rb.c[q];
+    }
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) {
+      const int idx = (int)(rem % grid.shape[i]);
+      rem /= grid.shape[i];
+      // grid.lo / grid.step here describe cell EDGES: lb = lo + idx*step
+      const float lb = fmaf((float)idx, grid.step[i], grid.lo[i]);
+      float v = fmaf(grid.step[i], u01(rnd[2 * i]), lb);
+      if (jitter) v += 0.5f * grid.step[i] * (2.0f * u01(rnd[2 * i + 1]) - 1.0f);
+      out[s * D + i] = v;
+    }
+  }
+}
+
+// Gauss-Seidel update of one table (ment.py:360-367)
+__global__ void gs_update_kernel(float* __restrict__ table, const float* __restrict__ meas,
+                                 const float* __restrict__ pred, int n, float lr, float thresh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p = pred[i];
+  if (p < thresh) p = 0.f;
+  const float g = meas[i];
+  if (g != 0.f && p != 0.f) table[i] *= 1.0f + lr * (g / p - 1.0f);
+}
+
+static size_t ment_smem(int K, int B, int d) {
+  return ((((size_t)K * d + 3) & ~(size_t)3) + 2 * (size_t)K * B + K) * 4 + 16;
+}
+
+static MentGrid make_grid(int ndim, const int32_t* shape, const float* lo, const float* step) {
+  MentGrid g;
+  g.ndim = ndim;
+  for (int i = 0; i < kMaxDim; ++i) {
+    g.shape[i] = i < ndim ? shape[i] : 1;
+    g.lo[i] = i < ndim ? lo[i] : 0.f;
+    g.step[i] = i < ndim ? step[i] : 0.f;
+  }
+  return g;
+}
+
+template <int D>
+static int launch_prob(int mode, const float* x, int64_t G, const MentGrid& grid, const float* proj,
+                       const float* coords, const float* tables, int K, int B, MentPrior prior, float* out,
+                       cudaStream_t st) {
+  const size_t smem = ment_smem(K, B, D);
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  int64_t blocks = (G + kMentThreads - 1) / kMentThreads;
+  int64_t cap = (int64_t)sm_count() * 8;
+  const int gridx = (int)(blocks < cap ? blocks : cap);
+  if (mode == 0) {
+    MFB_CUDA(cudaFuncSetAttribute(ment_prob_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ment_prob_kernel<D, 0><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, out);
+  } else {
+    MFB_CUDA(cudaFuncSetAttribute(ment_prob_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ment_prob_kernel<D, 1><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, out);
+  }
+  return launch_status();
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" {
+
+int mfb_ment_prob(const float* x, int64_t g, int d, const float* proj, const float* coords, const float* tables,
+                  int k, int b, float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(x && proj && coords && tables && out && g >= 0 && k >= 0 && b >= 2 && d >= 1 && d <= kMaxDim);
+  if (g == 0) return 0;
+  MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
+  MentGrid grid = make_grid(0, nullptr, nullptr, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 1: return launch_prob<1>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 2: return launch_prob<2>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 3: return launch_prob<3>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 4: return launch_prob<4>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 5: return launch_prob<5>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 6: return launch_prob<6>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 7: return launch_prob<7>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+    default: return launch_prob<8>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
+  }
+}
+
+int mfb_ment_prob_grid(int d, const int32_t* shape_host, const float* first_centre_host, const float* step_host,
+                       const float* proj, const float* coords, const float* tables, int k, int b,
+                       float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(shape_host && first_centre_host && step_host && proj && coords && tables && out);
+  MFB_CHECK_ARG(k >= 0 && b >= 2 && d >= 1 && d <= kMaxDim);
+  int64_t g = 1;
+  for (int i = 0; i < d; ++i) {
+    MFB_CHECK_ARG(shape_host[i] >= 1);
+    g *= shape_host[i];
+  }
+  MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
+  MentGrid grid = make_grid(d, shape_host, first_centre_host, step_host);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 1: return launch_prob<1>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 2: return launch_prob<2>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 3: return launch_prob<3>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 4: return launch_prob<4>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 5: return launch_prob<5>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 6: return launch_prob<6>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 7: return launch_prob<7>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    default: return launch_prob<8>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+  }
+}
+
+int mfb_ment_integrate(int d, const float* meas_coords, int nb_meas, int meas_axis, int n_int_axes,
+                       const int32_t* int_shape_host, const float* int_first_host, const float* int_step_host,
+                       const float* minv, const float* proj, const float* coords, const float* tables, int k,
+                       int b, float prior_neg_half_inv_s2, float prior_log_norm, float* pred, void* stream) {
+  MFB_CHECK_ARG(meas_coords && minv && proj && coords && tables && pred && int_shape_host && int_first_host &&
+                int_step_host);
+  MFB_CHECK_ARG(d >= 2 && d <= kMaxDim && n_int_axes == d - 1 && meas_axis >= 0 && meas_axis < d && nb_meas >= 1);
+  MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
+  MentGrid grid = make_grid(n_int_axes, int_shape_host, int_first_host, int_step_host);
+  const size_t smem = ment_smem(k, b, d);
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MFB_INT(DD)                                                                                                \
+  {                                                                                                                \
+    MFB_CUDA(cudaFuncSetAttribute(ment_integrate_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ment_integrate_kernel<DD><<<nb_meas, kMentThreads, smem, st>>>(meas_coords, nb_meas, meas_axis, grid, minv, proj, \
+                                                                  coords, tables, k, b, pr, pred);                 \
+  }
+  switch (d) {
+    case 2: MFB_INT(2) break;
+    case 3: MFB_INT(3) break;
+    case 4: MFB_INT(4) break;
+    case 5: MFB_INT(5) break;
+    case 6: MFB_INT(6) break;
+    case 7: MFB_INT(7) break;
+    default: MFB_INT(8) break;
+  }
+#undef MFB_INT
+  return launch_status();
+}
+
+int64_t mfb_cdf_workspace_bytes(int64_t g) {
+  if (g < 1) return 0;
+  const int64_t ntiles = (g + kScanTile - 1) / kScanTile;
+  return (ntiles + 2) * 8;
+}
+
+/* cdf[i] = sum_{j<=i} (rho[j] + pad) in double; total written to workspace[0] (device) */
+int mfb_cdf_build(const float* rho, int64_t g, double pad, double* cdf, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+  MFB_CHECK_ARG(rho && cdf && workspace && g >= 1);
+  if (workspace_bytes < mfb_cdf_workspace_bytes(g)) return MFB_E_WORKSPACE;
+  const int64_t ntiles = (g + kScanTile - 1) / kScanTile;
+  double* total = (double*)workspace;
+  double* tiles = total + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_tile_sums_kernel<<<(int)ntiles, kScanThreads, 0, st>>>(rho, g, pad, tiles);
+  scan_tile_offsets_kernel<<<1, 32, 0, st>>>(tiles, ntiles, total);
+  scan_apply_kernel<<<(int)ntiles, kScanThreads, 0, st>>>(rho, g, pad, tiles, cdf);
+  return launch_status();
+}
+
+int mfb_cdf_sample(const double* cdf, int64_t g, const void* workspace, int d, const int32_t* shape_host,
+                   const float* first_edge_host, const float* cell_host, int jitter, uint64_t seed, uint64_t offset,
+                   int64_t size, float* out, void* stream) {
+  MFB_CHECK_ARG(cdf && workspace && shape_host && first_edge_host && cell_host && out && g >= 1 && size >= 0);
+  MFB_CHECK_ARG(d >= 1 && d <= kMaxDim);
+  if (size == 0) return 0;
+  MentGrid grid = make_grid(d, shape_host, first_edge_host, cell_host);
+  const double* total = (const double*)workspace;
+  int64_t blocks = (size + kMentThreads - 1) / kMentThreads;
+  int64_t cap = (int64_t)sm_count() * 8;
+  const int gridx = (int)(blocks < cap ? blocks : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MFB_SAMPLE(DD) \
+  cdf_sample_kernel<DD><<<gridx, kMentThreads, 0, st>>>(cdf, g, total, grid, jitter, seed, offset, size, out)
+  switch (d) {
+    case 1: MFB_SAMPLE(1); break;
+    case 2: MFB_SAMPLE(2); break;
+    case 3: MFB_SAMPLE(3); break;
+    case 4: MFB_SAMPLE(4); break;
+    case 5: MFB_SAMPLE(5); break;
+    case 6: MFB_SAMPLE(6); break;
+    case 7: MFB_SAMPLE(7); break;
+    default: MFB_SAMPLE(8); break;
+  }
+#undef MFB_SAMPLE
+  return launch_status();
+}
+
+int mfb_gs_update(float* table, const float* meas, const float* pred, int n, float lr, float thresh, void* stream) {
+  MFB_CHECK_ARG(table && meas && pred && n >= 1);
+  gs_update_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table, meas, pred, n, lr, thresh);
+  return launch_status();
+}
+
+}  // extern "C"

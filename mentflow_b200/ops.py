@@ -347,4 +347,122 @@ def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins,
 
 
 def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
-    raise NotImplementedError("mentflow_b200: the NSF inverse (density of given x) kernel is not built yet")
+    """Density direction: returns (z, log q(x) or None, steps or None).  Not differentiable (no
+    experiment of the reference trains through log_prob(x))."""
+    lib = _lib.load()
+    x = _check_f32("x", x.detach())
+    packed = _check_f32("packed", packed.detach())
+    n, d = x.shape
+    steps = [x]
+    acc = None
+    with torch.cuda.device(x.device):
+        for t in range(len(orders) - 1, -1, -1):
+            v = torch.empty_like(x)
+            out = torch.empty(n, dtype=torch.float32, device=x.device) if want_logq else None
+            order_arr = (ctypes.c_int32 * d)(*[int(o) for o in orders[t]])
+            _lib.check(lib.mfb_nsf_layer_inv(_ptr(steps[-1]), n, d, hidden_units, hidden_layers, bins, _ptr(packed[t]),
+                                             ctypes.cast(order_arr, ctypes.c_void_p), _ptr(acc), 1 if t == 0 else 0,
+                                             _ptr(v), _ptr(out), _stream()), "nsf_layer_inv")
+            acc = out
+            steps.append(v)
+    return steps[-1], acc, (steps if want_steps else None)
+
+
+# --------------------------------------------------------------------------------------
+# classical MENT
+# --------------------------------------------------------------------------------------
+def _host_i32(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def _host_f32(values):
+    arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def ment_prob(x, proj, coords, tables, neg_half_inv_s2: float, log_norm: float) -> torch.Tensor:
+    """rho at explicit points x (G, D); proj (K, D), coords / tables (K, B)."""
+    lib = _lib.load()
+    x, proj = _check_f32("x", x), _check_f32("proj", proj)
+    coords, tables = _check_f32("coords", coords), _check_f32("tables", tables)
+    g, d = x.shape
+    k, b = tables.shape
+    out = torch.empty(g, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_ment_prob(_ptr(x), g, d, _ptr(proj), _ptr(coords), _ptr(tables), k, b,
+                                     float(neg_half_inv_s2), float(log_norm), _ptr(out), _stream()), "ment_prob")
+    return out
+
+
+def ment_prob_grid(shape, first_centre, step, proj, coords, tables, neg_half_inv_s2, log_norm) -> torch.Tensor:
+    """rho on the centres of a regular grid (flattened, 'ij' order) without materialising the points."""
+    lib = _lib.load()
+    proj, coords, tables = _check_f32("proj", proj), _check_f32("coords", coords), _check_f32("tables", tables)
+    d = len(shape)
+    k, b = tables.shape
+    g = 1
+    for s in shape:
+        g *= int(s)
+    out = torch.empty(g, dtype=torch.float32, device=proj.device)
+    a1, p1 = _host_i32(shape)
+    a2, p2 = _host_f32(first_centre)
+    a3, p3 = _host_f32(step)
+    with torch.cuda.device(proj.device):
+        _lib.check(lib.mfb_ment_prob_grid(d, p1, p2, p3, _ptr(proj), _ptr(coords), _ptr(tables), k, b,
+                                          float(neg_half_inv_s2), float(log_norm), _ptr(out), _stream()),
+                   "ment_prob_grid")
+    return out
+
+
+def ment_integrate(d, meas_coords, meas_axis, int_shape, int_first, int_step, minv, proj, coords, tables,
+                   neg_half_inv_s2, log_norm) -> torch.Tensor:
+    lib = _lib.load()
+    meas_coords, minv = _check_f32("meas_coords", meas_coords), _check_f32("minv", minv)
+    proj, coords, tables = _check_f32("proj", proj), _check_f32("coords", coords), _check_f32("tables", tables)
+    k, b = tables.shape
+    nb = meas_coords.shape[0]
+    pred = torch.empty(nb, dtype=torch.float32, device=proj.device)
+    a1, p1 = _host_i32(int_shape)
+    a2, p2 = _host_f32(int_first)
+    a3, p3 = _host_f32(int_step)
+    with torch.cuda.device(proj.device):
+        _lib.check(lib.mfb_ment_integrate(d, _ptr(meas_coords), nb, int(meas_axis), len(int_shape), p1, p2, p3,
+                                          _ptr(minv), _ptr(proj), _ptr(coords), _ptr(tables), k, b,
+                                          float(neg_half_inv_s2), float(log_norm), _ptr(pred), _stream()),
+                   "ment_integrate")
+    return pred
+
+
+def cdf_sample(rho: torch.Tensor, shape, first_edge, cell, size: int, seed: int, offset: int = 0,
+               jitter: bool = False, pad: float = 1.0e-15) -> torch.Tensor:
+    """`size` particles from the piecewise-constant density rho (flattened grid, 'ij' order)."""
+    lib = _lib.load()
+    rho = _check_f32("rho", rho.reshape(-1))
+    g = rho.numel()
+    d = len(shape)
+    cdf = torch.empty(g, dtype=torch.float64, device=rho.device)
+    out = torch.empty((int(size), d), dtype=torch.float32, device=rho.device)
+    a1, p1 = _host_i32(shape)
+    a2, p2 = _host_f32(first_edge)
+    a3, p3 = _host_f32(cell)
+    with torch.cuda.device(rho.device):
+        wbytes = lib.mfb_cdf_workspace_bytes(g)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=rho.device)
+        _lib.check(lib.mfb_cdf_build(_ptr(rho), g, float(pad), _ptr(cdf), _ptr(work), wbytes, _stream()), "cdf_build")
+        _lib.check(lib.mfb_cdf_sample(_ptr(cdf), g, _ptr(work), d, p1, p2, p3, 1 if jitter else 0,
+                                      int(seed) & (2 ** 64 - 1), int(offset), int(size), _ptr(out), _stream()),
+                   "cdf_sample")
+    return out
+
+
+def gs_update(table: torch.Tensor, meas: torch.Tensor, pred: torch.Tensor, lr: float, thresh: float) -> None:
+    """In-place Gauss-Seidel update of one Lagrange table."""
+    lib = _lib.load()
+    n = table.numel()
+    meas, pred = _check_f32("meas", meas), _check_f32("pred", pred)
+    if not (table.is_cuda and table.is_contiguous() and table.dtype == torch.float32):
+        raise RuntimeError("gs_update: table must be a contiguous CUDA float32 tensor (no CPU fallback)")
+    with torch.cuda.device(table.device):
+        _lib.check(lib.mfb_gs_update(_ptr(table), _ptr(meas), _ptr(pred), n, float(lr), float(thresh), _stream()),
+                   "gs_update")

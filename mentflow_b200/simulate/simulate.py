@@ -163,8 +163,13 @@ def _build_plan(x, transforms, diagnostics) -> _Plan:
 
 
 def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List[nn.Module]],
-            reducer: Optional[Callable] = None) -> List[List[torch.Tensor]]:
-    """Predicted profiles for every transform / diagnostic pair (simulate/simulate.py:8-33)."""
+            reducer: Optional[Callable] = None, stacked: Optional[list] = None) -> List[List[torch.Tensor]]:
+    """Predicted profiles for every transform / diagnostic pair (simulate/simulate.py:8-33).
+
+    ``stacked`` (optional list) receives one ``(slots, profiles)`` pair per fused group, where
+    ``profiles`` is the (K, ...) tensor the returned rows are views of and ``slots`` the (i, j)
+    positions they fill -- callers that reduce all profiles at once (MENTFlow.loss) use it to
+    avoid K small kernels.  It is left empty if any pair needed the object-by-object path."""
     key = (_plan_key(transforms, diagnostics), x.shape[1], str(x.device))
     plan = _plan_cache.get(key)
     if plan is None:
@@ -178,8 +183,11 @@ def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List
     for grp in plan.groups.values():
         fn = profiles_1d if grp.kind == "1d" else profiles_2d
         prof = fn(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache)
+        noisy = any(d.noise and d.noise_scale > 0.0 for d in grp.diags)
+        if stacked is not None and not noisy and not plan.fallback:
+            stacked.append((grp.slots, prof))
         for row, (i, j), d in zip(prof.unbind(0), grp.slots, grp.diags):
-            out[i][j] = d.apply_noise(row)
+            out[i][j] = d.apply_noise(row) if noisy else row
     if plan.fallback:
         cache = {}
         for i, j in plan.fallback:

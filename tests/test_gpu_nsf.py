@@ -165,3 +165,36 @@ def test_backward_matches_oracle_autograd(d, n, scale, hl, tr, bins):
         assert float(e.median()) < 2e-5, f"{name}: median {float(e.median()):.2e}"
     got, want = grads["w_out0"]
     assert float(got.cpu()[want == 0].abs().max()) == 0.0      # masked weights: exactly zero gradient
+
+
+@pytest.mark.parametrize("d,n,scale", [(2, 2000, 1.5), (6, 20000, 1.0), (4, 999, 2.0)])
+def test_inverse_and_log_prob(d, n, scale):
+    """Density direction (generate/flows/zuko.py:21-22,31-32,43-50): round trip through the CUDA
+    forward, and log_prob(x) / inverse(x) / inverse_steps(x) vs the float64 oracle."""
+    torch.manual_seed(100 + d)
+    gen = mf.generate.NSFGenerator(d)
+    with torch.no_grad():
+        for p in gen.parameters():
+            p.mul_(scale)
+    ref, ref32 = oracle_from_generator(gen), oracle_from_generator(gen, torch.float32)
+    gen = gen.to("cuda")
+    z = torch.randn(n, d)
+    z[: max(1, n // 200)] *= 4.0
+    with torch.no_grad():
+        x, lq = gen.forward_and_log_prob(z.cuda())
+        zi = gen.inverse(x)
+        lp = gen.log_prob(x)
+        steps = gen.inverse_steps(x)
+        x64 = x.cpu().double()
+        z64 = ref.inverse(x64)
+        lp64 = ref.log_prob(x64)
+        z32 = ref32.inverse(x.cpu())
+        lp32 = ref32.log_prob(x.cpu())
+    assert len(steps) == gen.transforms + 1 and torch.equal(steps[-1], zi)
+    assert_parity(zi, z64, z32)
+    assert_parity(lp, lp64, lp32)
+    # round trip: inverse(forward(z)) ~ z and log_prob(forward(z)) ~ log q from the sampling pass
+    e = ((zi.cpu() - z).abs() / z.abs().clamp_min(1.0)).flatten()
+    assert float(e.median()) < 1e-5 and float((e > 1e-3).float().mean()) < 2e-3
+    el = ((lp - lq).abs() / lq.abs().clamp_min(1.0)).flatten()
+    assert float(el.median()) < 1e-5 and float((el > 1e-3).float().mean()) < 5e-3
