@@ -44,10 +44,11 @@ def test_prob_matches_reference(golden):
     assert (prob[:4] == 0).all() or torch.allclose(prob[:4], ref[:4], rtol=1e-4, atol=1e-12)
     grid = model.prob_on_grid(model.sampler).cpu()
     refg = t32(g["prob_grid"])
-    assert torch.allclose(grid, refg, rtol=1e-4, atol=1e-9 * float(refg.max()))
+    # grid points come from the index (lo + i*step) instead of fp32 linspace centres: 1-ulp shifts
+    assert torch.allclose(grid, refg, rtol=1e-4, atol=2e-6 * float(refg.max()))
     # generic prob_func path of the sampler (materialised grid points) gives the same density
     pts = model.sampler.get_grid_points()
-    assert torch.allclose(model.prob(pts).cpu(), grid, rtol=1e-6, atol=1e-12)
+    assert torch.allclose(model.prob(pts).cpu(), grid, rtol=1e-4, atol=2e-6 * float(refg.max()))
     # a single Lagrange function called like the reference's interpolator
     u = torch.linspace(-4.5, 4.5, 1001)
     h = model.lagrange_functions[1][0](u.cuda()).cpu()
@@ -93,13 +94,34 @@ def test_sample_mode_update_is_statistically_consistent(golden):
     assert (pred - ref).abs().max() < 0.06 * ref.max()
     width = float(t32(g["edges"])[1] - t32(g["edges"])[0])
     assert abs(float(pred.sum()) * width - 1.0) < 1e-5
+    # one full Gauss-Seidel sweep at high statistics on both sides: the oracle (pinned to the
+    # reference's sweep by tests/test_oracle_golden.py) with torch's CPU generator, the CUDA path with
+    # its Philox stream.  Sampling noise ~ sqrt(32 bins / 1e6) = 0.6 %, compounded over 6 updates.
+    n = 1_000_000
+    model.n_samples = n
     model.gauss_seidel_update(lr=float(g["lr"]), thresh=float(g["thresh"]))
     got = torch.stack([model.lagrange_functions[i][0].values.cpu() for i in range(6)])
-    ref1 = t32(g["tables1"])
-    # the reference's update used 30000 noisy samples per projection; agree within that noise
-    big = ref1 > 0.3 * ref1.max()
-    assert float(((got - ref1).abs() / ref1)[big].median()) < 0.05
-    assert torch.equal(got == 0, ref1 == 0)
+    mats, edges, meas = t32(g["matrices"]), t32(g["edges"]), t32(g["meas"])
+    res, xmax, s = int(g["grid_res"]), float(g["grid_xmax"]), float(g["prior_scale"])
+    scr = [[hp.Screen1D(edges=edges)] for _ in mats]
+    gedges = [torch.linspace(-xmax, xmax, res + 1) for _ in range(4)]
+    pts = hp.grid_points([hp.centres(e) for e in gedges])
+    cur = [t.clone() for t in t32(g["tables0"])]
+    gen = torch.Generator().manual_seed(5)
+    preds = []
+    for i in range(6):
+        pgi = hp.ment_prob(pts, list(mats), scr, [[t] for t in cur], s)
+        xs = hp.sample_grid(pgi.reshape(4 * [res]), gedges, n, generator=gen)
+        pr = hp.kde_profile_1d(hp.linear_map(xs, mats[i])[:, 0], edges, scr[i][0].sigma, chunk=100000)
+        pr = hp.normalize_projection(pr, edges[1] - edges[0])
+        preds.append(pr)
+        cur[i] = hp.gauss_seidel_table(cur[i], meas[i], pr, float(g["lr"]), float(g["thresh"]))
+    want = torch.stack(cur)
+    preds = torch.stack(preds)
+    solid = (meas > 0) & (preds > 0.02 * preds.max(dim=1, keepdim=True).values)
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-12))[solid]
+    assert float(rel.median()) < 0.02 and float(rel.max()) < 0.25
+    assert torch.equal(got == 0, want == 0)
     assert model.epoch == 1
 
 
