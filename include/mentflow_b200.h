@@ -185,6 +185,12 @@ int mfb_cdf_sample(const double* cdf, int64_t g, const void* workspace, int d,
 int mfb_gs_update(float* table, const float* meas, const float* pred, int n, float lr, float thresh,
                   void* stream);
 
+/* ---- diagnostics --------------------------------------------------------------------------
+ * Self-test of the tcgen05/TMEM building blocks: d[128][n] = a[128][64] * b[n][64]^T through
+ * fp16 (hi,lo)-split kind::f16 MMAs with TMEM accumulators (n = 64, 128 or 256).  *err != 0
+ * if the MMA never completed.                                                              */
+int mfb_selftest_umma(const float* a, const float* b, int n, float* d, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

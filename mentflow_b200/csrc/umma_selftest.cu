@@ -1,0 +1,94 @@
+// Self-test of the tcgen05 building blocks used by the tensor-core conditioner:
+// D[128 x N] = A[128 x 64] * B[N x 64]^T with fp32 inputs split into fp16 (hi, lo) pairs and
+// three kind::f16 MMAs per K step (hi*hi + hi*lo + lo*hi), accumulators in TMEM.
+#include "umma.cuh"
+
+namespace mfb {
+
+constexpr int kSelfWaitLimit = 1 << 22;
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, float* __restrict__ D,
+                     int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // [A_hi 16K][A_lo 16K][B_hi N*128][B_lo N*128]
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + 16384;
+  unsigned char* b_hi = smem + 32768;
+  unsigned char* b_lo = b_hi + (size_t)N * 128;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) umma::tmem_alloc(&tmem_base, 256);
+  // operands: thread r handles row r of A; rows r (and r+128 for N = 256...) of B
+  for (int r = tid; r < 128 + N; r += 128) {
+    const bool isA = r < 128;
+    const int row = isA ? r : r - 128;
+    const float* src = isA ? A + (size_t)row * 64 : B + (size_t)row * 64;
+    unsigned char* dhi = isA ? a_hi : b_hi;
+    unsigned char* dlo = isA ? a_lo : b_lo;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      __align__(16) __half hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) umma::split_f16(src[c * 8 + e], hi[e], lo[e]);
+      const uint32_t off = umma::sw128_offset(row, c);
+      *reinterpret_cast<uint4*>(dhi + off) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(dlo + off) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+  fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_base;
+
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    const uint64_t da_hi = umma::make_desc_sw128(smem_u32(a_hi)), da_lo = umma::make_desc_sw128(smem_u32(a_lo));
+    const uint64_t db_hi = umma::make_desc_sw128(smem_u32(b_hi)), db_lo = umma::make_desc_sw128(smem_u32(b_lo));
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      umma::mma_f16_ss(tbase, umma::desc_advance_k(da_hi, k), umma::desc_advance_k(db_hi, k), idesc, acc);
+      acc = 1;
+      umma::mma_f16_ss(tbase, umma::desc_advance_k(da_hi, k), umma::desc_advance_k(db_lo, k), idesc, 1);
+      umma::mma_f16_ss(tbase, umma::desc_advance_k(da_lo, k), umma::desc_advance_k(db_hi, k), idesc, 1);
+    }
+    umma::commit(&bar);
+  }
+  // everyone waits for the accumulator
+  int spins = 0;
+  while (!mbar_try_wait(&bar, 0)) {
+    if (++spins > kSelfWaitLimit) {
+      if (tid == 0) *err = 1;
+      break;
+    }
+  }
+  umma::fence_after_sync();
+  const int warp = tid >> 5;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    umma::tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t)tid * N + c0 + i] = v[i];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tbase, 256);
+}
+
+}  // namespace mfb
+
+extern "C" int mfb_selftest_umma(const float* a, const float* b, int n, float* d, int* err, void* stream) {
+  MFB_CHECK_ARG(a && b && d && err && (n == 64 || n == 128 || n == 256));
+  const size_t smem = 32768 + (size_t)n * 256 + 1024;
+  MFB_CUDA(cudaFuncSetAttribute(mfb::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mfb::umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, n, d, err);
+  return mfb::launch_status();
+}

@@ -1,0 +1,30 @@
+"""tcgen05 building blocks: fp16 (hi,lo)-split MMA with TMEM accumulators vs float64 matmul."""
+import ctypes
+
+import pytest
+import torch
+
+from mentflow_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_umma_split_gemm(n):
+    lib = _lib.load()
+    torch.manual_seed(n)
+    a = (torch.randn(128, 64) * 3).cuda()
+    b = (torch.randn(n, 64) * 0.2).cuda()
+    a[:, 5] = 0.0
+    d = torch.zeros(128, n, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.mfb_selftest_umma(a.data_ptr(), b.data_ptr(), n, d.data_ptr(), err.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    want = a.double() @ b.double().T
+    scale = (a.double().abs() @ b.double().abs().T)
+    e = ((d.double() - want).abs() / scale).max()
+    e32 = (((a @ b.T).double() - want).abs() / scale).max()
+    assert float(e) < 2e-6, f"split-fp16 error {float(e):.2e} (fp32 matmul: {float(e32):.2e})"
