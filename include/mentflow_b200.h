@@ -118,6 +118,25 @@ int mfb_nsf_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hi
                       int bins, const float* params, const int32_t* order_host, const float* logq_in,
                       int first_layer, float* y, float* logq_out, void* stream);
 
+/* Tensor-core version of mfb_nsf_layer_fwd (same reference lines): the conditioner's masked GEMMs
+ * run as tcgen05.mma tiles over fp16 (hi, lo) splits of the fp32 operands with fp32 accumulators
+ * in TMEM, the spline is the epilogue.  Compiled for hidden_units = 64, hidden_layers = 3,
+ * bins = 20, d = 2..6 (mfb_nsf_tc_supported); other shapes use mfb_nsf_layer_fwd.
+ * mfb_nsf_tc_prepare turns the packed fp32 parameters of n_layers layers (layer l at
+ * params + l * layer_stride_floats; they MUST be pre-masked: all-zero blocks are skipped) into
+ * n_layers operand images of mfb_nsf_tc_image_bytes bytes each; orders_host = HOST array
+ * [n_layers][d].  mfb_nsf_tc_layer_fwd then runs one layer from its image.                  */
+int mfb_nsf_tc_supported(int d, int hidden_units, int hidden_layers, int bins);
+int64_t mfb_nsf_tc_image_bytes(int d, int hidden_layers);
+int64_t mfb_nsf_tc_prepare_workspace_bytes(int n_layers);
+int mfb_nsf_tc_prepare(const float* params, int64_t layer_stride_floats, int n_layers, int d,
+                       int hidden_units, int hidden_layers, int bins, const int32_t* orders_host,
+                       void* images, void* workspace, int64_t workspace_bytes, void* stream);
+int mfb_nsf_tc_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hidden_layers,
+                         int bins, const void* image, const int32_t* order_host,
+                         const float* logq_in, int first_layer, float* y, float* logq_out,
+                         void* stream);
+
 /* Density direction of one layer: v = A^-1(y) (d conditioner sweeps per particle) and
  * ladj_out = ladj_in + log|det dA/dv|(v).  Replaces generate/flows/zuko.py:21-22,31-32,43-50
  * (log_prob / inverse / inverse_steps).  Call the layers in REVERSE order; with last_layer != 0

@@ -31,6 +31,11 @@ SIGNATURES = {
     "mfb_project_hist2d": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_int, P, P]),
     "mfb_nsf_layer_param_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "mfb_nsf_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
+    "mfb_nsf_tc_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "mfb_nsf_tc_image_bytes": (c_int64, [c_int, c_int]),
+    "mfb_nsf_tc_prepare_workspace_bytes": (c_int64, [c_int]),
+    "mfb_nsf_tc_prepare": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int64, P]),
+    "mfb_nsf_tc_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_inv": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_param_om_floats": (c_int64, [c_int, c_int, c_int]),
     "mfb_nsf_layer_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),

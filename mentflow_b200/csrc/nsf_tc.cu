@@ -1,0 +1,720 @@
+// Neural spline flow layer on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces, per autoregressive layer, the same reference work as nsf.cu (generate/flows/zuko.py:24-29
+// -> zuko 1.3.1 MaskedMLP + MonotonicRQSTransform.call_and_ladj): the four masked
+// GEMMs of the conditioner run as tcgen05.mma tiles (M = 128 particles, fp32 inputs split into fp16
+// (hi, lo) pairs, three MMAs per K step, fp32 accumulators in TMEM), and the rational-quadratic spline
+// with its log|det J| is the epilogue of the output-layer tile: parameters go TMEM -> registers and
+// never touch shared memory or HBM.
+//
+// CTA = 3 warpgroups (384 threads), persistent, one CTA per SM.  The layer's weights live in shared
+// memory as ready-made K-major SWIZZLE_128B fp16 operand tiles (an "image" built once per call by
+// nsf_tc_prepare_kernel, loaded with one TMA bulk copy).  Every warpgroup owns one 128-particle tile
+// at a time, its own A-operand buffer (activations, hi|lo) and its own 128 TMEM columns, and walks
+//   v -> [L1 MMA] -> relu/split -> [L2 MMA] -> relu/split -> [L3 MMA] -> relu/split ->
+//        per feature: [output MMA, N = 64] -> spline epilogue          (double buffered in TMEM)
+// on its own; the three warpgroups interleave on the SM so that the tensor pipe works on one tile
+// while the CUDA cores run the epilogues of the other two.
+//
+// Mask awareness: hidden units are re-ordered by autoregressive class (a permutation of the hidden
+// layer, applied when the image is built), which makes every masked weight matrix block lower
+// triangular; K steps whose weights are all zero for a block of outputs are not issued (14 of 20
+// output-layer K steps at D = 6).  The feature that is first in the layer's order has a bias-only
+// spline: its knots are precomputed into a table in the image.
+#include "nsf_common.cuh"
+#include "umma.cuh"
+
+namespace mfb {
+namespace tc {
+
+constexpr int kWG = 3;
+constexpr int kThreads = kWG * 128;
+constexpr int kTileBytes = 8192;     // 64 rows x 128 B (one fp16 operand tile, K = 64)
+constexpr int kABytes = 32768;       // 128 rows x 128 B, hi then lo
+constexpr int kCT = 24;              // stride of the constant-feature tables (floats)
+constexpr int kConstFloats = 6 * kCT;
+
+struct Meta {
+  int slot_feature[kMaxDim];  // feature handled by output slot s (order > 0, ascending order)
+  int slot_ksteps[kMaxDim];   // K steps (of 16 hidden units) with non-zero weights for slot s
+  int hid_n0[4];              // hidden->hidden: first output row that reads K step s (multiple of 16)
+  int const_feature;          // feature with order 0 (bias-only spline)
+  int nslots;
+};
+
+struct PrepMeta {
+  int perm[kH];               // perm[p] = original hidden unit stored at sorted position p
+  int slot_feature[kMaxDim];
+  int const_feature;
+  int nslots;
+};
+
+// ---- image layout (bytes) -------------------------------------------------------------------
+//  [B1 8K] [hid l: hi 8K | lo 8K] x (L-1) [out hi: S x 8K] [out lo: S x 8K] [f32 block]
+//  f32 block: bhid [(L-1)][64] | bout [S][64] (x log2 e) | const tables [6][kCT]
+__host__ __device__ inline int off_hid(int l) { return kTileBytes + l * 2 * kTileBytes; }
+__host__ __device__ inline int off_out_hi(int L, int s) { return kTileBytes + (L - 1) * 2 * kTileBytes + s * kTileBytes; }
+__host__ __device__ inline int off_out_lo(int L, int S, int s) { return off_out_hi(L, S) + s * kTileBytes; }
+__host__ __device__ inline int off_f32(int L, int S) { return off_out_hi(L, S) + S * kTileBytes; }
+__host__ __device__ inline int f32_floats(int L, int S) { return (L - 1) * kH + S * kH + kConstFloats; }
+__host__ __device__ inline int image_bytes(int D, int L) {
+  const int S = D - 1;
+  const int raw = off_f32(L, S) + 4 * f32_floats(L, S);
+  return (raw + 1023) & ~1023;
+}
+
+// =============================================================================================
+// image builder
+// =============================================================================================
+__device__ __forceinline__ void store_split8(unsigned char* hi_tile, unsigned char* lo_tile, int row, int chunk,
+                                             const float (&x)[8]) {
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) umma::split_f16(x[e], hi[e], lo[e]);
+  const uint32_t off = umma::sw128_offset(row, chunk);
+  *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(hi);
+  if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// one block per layer; params = packed fp32 block of nsf_common.cuh (pre-masked, [in][out])
+__global__ void __launch_bounds__(256)
+nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride, int D, int L, int nb,
+                      const PrepMeta* __restrict__ metas, unsigned char* __restrict__ images, int img_bytes) {
+  const int layer = blockIdx.x;
+  const float* par = params_all + (size_t)layer * layer_stride;
+  const PrepMeta& pm = metas[layer];
+  unsigned char* img = images + (size_t)layer * img_bytes;
+  const int S = pm.nslots;
+  const float* W1t = par;
+  const float* b1 = W1t + D * kH;
+  const float* hid = b1 + kH;
+  const float* Wout = hid + (size_t)(L - 1) * (kH * kH + kH);
+  const float* bout = Wout + (size_t)D * kH * kPP;
+  float* f32 = reinterpret_cast<float*>(img + off_f32(L, S));
+
+  // zero everything first (padding rows / columns must be exact zeros)
+  for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const int ntask = kH + (L - 1) * kH * 8 + S * kH * 8;
+  for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+    if (task < kH) {
+      // B1 row n: K step 0 = [W1hi (D) | W1hi (D) | b1hi | b1lo | 0], K step 1 = [W1lo (D) | 0]
+      const int n = task, o = pm.perm[n];
+      __align__(16) __half k0[16], k1[16];
+      for (int e = 0; e < 16; ++e) k0[e] = k1[e] = __float2half_rn(0.f);
+      for (int i = 0; i < D; ++i) {
+        __half hi, lo;
+        umma::split_f16(W1t[i * kH + o], hi, lo);
+        k0[i] = hi;
+        k0[D + i] = hi;
+        k1[i] = lo;
+      }
+      __half bh, bl;
+      umma::split_f16(b1[o], bh, bl);
+      k0[2 * D] = bh;
+      k0[2 * D + 1] = bl;
+      for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<uint4*>(img + umma::sw128_offset(n, c)) = reinterpret_cast<const uint4*>(k0)[c];
+        *reinterpret_cast<uint4*>(img + umma::sw128_offset(n, 2 + c)) = reinterpret_cast<const uint4*>(k1)[c];
+      }
+    } else if (task < kH + (L - 1) * kH * 8) {
+      const int t2 = task - kH;
+      const int l = t2 / (kH * 8), n = (t2 / 8) % kH, c = t2 % 8;
+      const float* wt = hid + (size_t)l * (kH * kH + kH);
+      float x[8];
+      for (int e = 0; e < 8; ++e) x[e] = wt[pm.perm[c * 8 + e] * kH + pm.perm[n]];
+      store_split8(img + off_hid(l), img + off_hid(l) + kTileBytes, n, c, x);
+    } else {
+      const int t2 = task - kH - (L - 1) * kH * 8;
+      const int s = t2 / (kH * 8), q = (t2 / 8) % kH, c = t2 % 8;
+      const int f = pm.slot_feature[s];
+      const float* wf = Wout + (size_t)f * kH * kPP;
+      float x[8];
+      for (int e = 0; e < 8; ++e) x[e] = (q < 3 * nb - 1) ? wf[pm.perm[c * 8 + e] * kPP + q] * kLog2e : 0.f;
+      store_split8(img + off_out_hi(L, s), img + off_out_lo(L, S, s), q, c, x);
+    }
+  }
+  // fp32 block
+  for (int i = threadIdx.x; i < (L - 1) * kH; i += blockDim.x) {
+    const int l = i / kH, n = i % kH;
+    f32[i] = hid[(size_t)l * (kH * kH + kH) + kH * kH + pm.perm[n]];
+  }
+  for (int i = threadIdx.x; i < S * kH; i += blockDim.x) {
+    const int s = i / kH, q = i % kH;
+    f32[(L - 1) * kH + i] = (q < 3 * nb - 1) ? bout[pm.slot_feature[s] * kPP + q] * kLog2e : 0.f;
+  }
+  // constant feature: knots of its bias-only spline (same formulas as the epilogue)
+  if (threadIdx.x == 0) {
+    float* ct = f32 + (L - 1) * kH + S * kH;
+    const float* bf = bout + pm.const_feature * kPP;
+    float ew[32], eh[32];
+    float sw = 0.f, sh = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const float w = bf[j], h = bf[nb + j];
+      ew[j] = expf(w / (1.0f + kClipW * fabsf(w)));
+      eh[j] = expf(h / (1.0f + kClipW * fabsf(h)));
+      sw += ew[j];
+      sh += eh[j];
+    }
+    float cw = 0.f, ch = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const float wj = ew[j] / sw, hj = eh[j] / sh;
+      float dl = 1.f, dr = 1.f;
+      if (j > 0) {
+        const float r = bf[2 * nb + j - 1];
+        dl = expf(r / (1.0f + kClipD * fabsf(r)));
+      }
+      if (j < nb - 1) {
+        const float r = bf[2 * nb + j];
+        dr = expf(r / (1.0f + kClipD * fabsf(r)));
+      }
+      ct[0 * kCT + j] = fmaf(2.0f * kBound, cw, -kBound);  // left knot x
+      ct[1 * kCT + j] = 2.0f * kBound * wj;                // bin width
+      ct[2 * kCT + j] = fmaf(2.0f * kBound, ch, -kBound);  // left knot y
+      ct[3 * kCT + j] = 2.0f * kBound * hj;                // bin height
+      ct[4 * kCT + j] = dl;
+      ct[5 * kCT + j] = dr;
+      cw += wj;
+      ch += hj;
+    }
+  }
+}
+
+// =============================================================================================
+// device helpers
+// =============================================================================================
+// mbarrier wait that traps instead of hanging the device if an MMA / TMA never arrives
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (int spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1 << 24)) __trap();
+}
+
+__device__ __forceinline__ void wg_barrier(int wg) {
+  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// soft clip + exp of two raw (log2e-scaled) parameters with one reciprocal:
+//   e = 2^(t / (1 + c |t|))
+__device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, float& e0, float& e1) {
+  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
+  const float r = fast_rcp(d0 * d1);
+  e0 = fast_exp2(t0 * (r * d1));
+  e1 = fast_exp2(t1 * (r * d0));
+}
+
+// Rational-quadratic spline of one feature from the raw conditioner outputs a[0..3NB-2] (already
+// multiplied by log2 e through the weights; bias, equally scaled, in shared memory).  Works in
+// un-normalised softmax units: the bin is searched on the running sum of e_j against
+// (v + B) / 2B * sum, and bin width / height come from e_k directly (no differencing of knots).
+// Multiplies jac by dy/dv (1 outside [-B, B]) and returns y.
+template <int NB>
+__device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const float* __restrict__ bias, float v,
+                                                float& jac) {
+  constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+  // ---- widths
+  float e[NB];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; j += 4) {
+    const float4 b = b4[j >> 2];
+    clip_exp2_pair(a[j] + b.x, a[j + 1] + b.y, cW, e[j], e[j + 1]);
+    clip_exp2_pair(a[j + 2] + b.z, a[j + 3] + b.w, cW, e[j + 2], e[j + 3]);
+    sum += (e[j] + e[j + 1]) + (e[j + 2] + e[j + 3]);
+  }
+  const float target = (v + kBound) * (0.5f / kBound) * sum;
+  // m[j] = 1 if bin j lies entirely left of v; ind[j] = 1 for the bin that holds v
+  float m[NB], ind[NB];
+  float cum = 0.f, x0c = 0.f, ek = 0.f, mprev = 1.0f;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    cum += e[j];
+    m[j] = (j < NB - 1 && cum < target) ? 1.0f : 0.0f;
+    ind[j] = mprev - m[j];
+    x0c = fmaf(m[j], e[j], x0c);
+    ek = fmaf(ind[j], e[j], ek);
+    mprev = m[j];
+  }
+  // ---- heights
+  float sumh = 0.f, y0c = 0.f, hk = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; j += 4) {
+    const float4 b = b4[(NB + j) >> 2];
+    float h0, h1, h2, h3;
+    clip_exp2_pair(a[NB + j] + b.x, a[NB + j + 1] + b.y, cW, h0, h1);
+    clip_exp2_pair(a[NB + j + 2] + b.z, a[NB + j + 3] + b.w, cW, h2, h3);
+    sumh += (h0 + h1) + (h2 + h3);
+    y0c = fmaf(m[j], h0, y0c);
+    y0c = fmaf(m[j + 1], h1, y0c);
+    y0c = fmaf(m[j + 2], h2, y0c);
+    y0c = fmaf(m[j + 3], h3, y0c);
+    hk = fmaf(ind[j], h0, hk);
+    hk = fmaf(ind[j + 1], h1, hk);
+    hk = fmaf(ind[j + 2], h2, hk);
+    hk = fmaf(ind[j + 3], h3, hk);
+  }
+  // ---- derivatives at the two knots of the bin (raw 0 -> slope 1 at the outer knots)
+  float tl = 0.f, tr = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; j += 4) {
+    const float4 b = b4[(2 * NB + j) >> 2];
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j + q < NB - 1) {
+        const float t = a[2 * NB + j + q] + bb[q];
+        tl = fmaf(ind[j + q + 1], t, tl);
+        tr = fmaf(ind[j + q], t, tr);
+      }
+    }
+  }
+  float d0, d1;
+  clip_exp2_pair(tl, tr, cD, d0, d1);
+  // ---- rational quadratic
+  const float r_e = fast_rcp(ek), r_sh = fast_rcp(sumh);
+  float t = (target - x0c) * r_e;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float hn = hk * r_sh;                 // normalised bin height / 2B
+  const float s = hn * sum * r_e;             // dy / dx
+  const float omt = 1.0f - t, tomt = t * omt;
+  const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
+  const float r_den = fast_rcp(den);
+  const float y0 = fmaf(2.0f * kBound, y0c * r_sh, -kBound);
+  const float y = fmaf(2.0f * kBound * hn * (s * t * t + d0 * tomt), r_den, y0);
+  const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
+  const bool inside = (v > -kBound) && (v <= kBound);
+  jac *= inside ? j1 : 1.0f;
+  return inside ? y : v;
+}
+
+// bias-only spline from the precomputed knot tables (shared memory, broadcast reads)
+template <int NB>
+__device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, float v, float& jac) {
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j < NB; ++j) k += (ct[j] < v) ? 1 : 0;
+  const float x0 = ct[k], dx = ct[kCT + k], y0 = ct[2 * kCT + k], dy = ct[3 * kCT + k];
+  const float d0 = ct[4 * kCT + k], d1 = ct[5 * kCT + k];
+  const float r_dx = fast_rcp(dx);
+  const float s = dy * r_dx;
+  float t = (v - x0) * r_dx;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float omt = 1.0f - t, tomt = t * omt;
+  const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
+  const float r_den = fast_rcp(den);
+  const float y = fmaf(dy * (s * t * t + d0 * tomt), r_den, y0);
+  const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
+  const bool inside = (v > -kBound) && (v <= kBound);
+  jac *= inside ? j1 : 1.0f;
+  return inside ? y : v;
+}
+
+// relu(acc + bias) -> (hi, lo) fp16 rows of the A operand tile (row = particle)
+template <bool kBias>
+__device__ __forceinline__ void store_hidden(const float (&acc)[64], const float* __restrict__ bias,
+                                             unsigned char* a_hi, unsigned char* a_lo, int row) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float x[8];
+    if (kBias) {
+      const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * c];
+      const float4 b1 = reinterpret_cast<const float4*>(bias)[2 * c + 1];
+      x[0] = acc[8 * c + 0] + b0.x; x[1] = acc[8 * c + 1] + b0.y; x[2] = acc[8 * c + 2] + b0.z;
+      x[3] = acc[8 * c + 3] + b0.w; x[4] = acc[8 * c + 4] + b1.x; x[5] = acc[8 * c + 5] + b1.y;
+      x[6] = acc[8 * c + 6] + b1.z; x[7] = acc[8 * c + 7] + b1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = acc[8 * c + e];
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = fmaxf(x[2 * e], 0.f), x1 = fmaxf(x[2 * e + 1], 0.f);
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint32_t off = umma::sw128_offset(row, c);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// three split MMAs of one K step: hi*hi + hi*lo + lo*hi
+__device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                           int kstep, uint32_t idesc, uint32_t accumulate) {
+  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_hi, kstep), idesc, accumulate);
+  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_lo, kstep), idesc, 1);
+  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_lo, kstep), umma::desc_advance_k(b_hi, kstep), idesc, 1);
+}
+
+// =============================================================================================
+// the layer kernel
+// =============================================================================================
+template <int D, int L, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char* __restrict__ image,
+                    const __grid_constant__ Meta meta,
+                    const float* __restrict__ logq_in, int first_layer, float* __restrict__ y,
+                    float* __restrict__ logq_out) {
+  constexpr int S = D - 1;
+  constexpr int kImg = ((kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes +
+                         4 * ((L - 1) * kH + S * kH + kConstFloats)) + 1023) & ~1023;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* img = smem;
+  unsigned char* a_all = smem + kImg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);  // [0] image, [1 + 2*wg + b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kWG);
+
+  const int tid = threadIdx.x;
+  const int wg = tid >> 7, t = tid & 127;
+  if (tid == 0) {
+    for (int i = 0; i < 1 + 2 * kWG; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) umma::tmem_alloc(tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (uint32_t)kImg);
+    tma_load_1d(img, image, (uint32_t)kImg, &bars[0]);
+  }
+  const uint32_t tmem_base = *tmem_slot;
+  mbar_wait_bounded(&bars[0], 0);
+
+  unsigned char* a_hi = a_all + wg * kABytes;
+  unsigned char* a_lo = a_hi + kABytes / 2;
+  uint64_t* bar0 = &bars[1 + 2 * wg];
+  uint64_t* bar1 = bar0 + 1;
+  uint32_t ph0 = 0, ph1 = 0;
+  const uint32_t lane_sel = (uint32_t)((t >> 5) * 32) << 16;
+  const uint32_t col0 = tmem_base + (uint32_t)(wg * 128);
+  const float* f32 = reinterpret_cast<const float*>(img + kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes);
+  const float* bhid = f32;
+  const float* bout = f32 + (L - 1) * kH;
+  const float* ctab = bout + S * kH;
+
+  const uint32_t idesc64 = umma::make_idesc_f16(128, 64);
+  const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(a_hi)), dA_lo = umma::make_desc_sw128(smem_u32(a_lo));
+  const uint64_t dB1 = umma::make_desc_sw128(smem_u32(img));
+
+  const int64_t ntiles = (n + 127) / 128;
+  const int64_t tstride = (int64_t)gridDim.x * kWG;
+  int64_t tile = (int64_t)blockIdx.x * kWG + wg;
+  float vin[D];
+  {
+    const int64_t p = tile * 128 + t;
+#pragma unroll
+    for (int i = 0; i < D; ++i) vin[i] = (tile < ntiles && p < n) ? v[p * D + i] : 0.f;
+  }
+  for (; tile < ntiles; tile += tstride) {
+    const int64_t p = tile * 128 + t;
+    const bool valid = p < n;
+    // ---- first masked layer: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16)
+    {
+      __align__(16) __half row[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < D; ++i) umma::split_f16(vin[i], row[i], row[D + i]);
+      row[2 * D] = __float2half_rn(1.0f);
+      row[2 * D + 1] = __float2half_rn(1.0f);
+      *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 0)) = reinterpret_cast<const uint4*>(row)[0];
+      *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 1)) = reinterpret_cast<const uint4*>(row)[1];
+    }
+    fence_proxy_async();
+    umma::fence_before_sync();
+    wg_barrier(wg);
+    if (t == 0) {
+      umma::fence_after_sync();
+      umma::mma_f16_ss(col0, dA_hi, dB1, idesc64, 0);
+      umma::mma_f16_ss(col0, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
+      umma::commit(bar0);
+    }
+    // prefetch the next tile's particle while the tensor pipe works
+    float vnext[D];
+    {
+      const int64_t tn = tile + tstride;
+      const int64_t pn = tn * 128 + t;
+#pragma unroll
+      for (int i = 0; i < D; ++i) vnext[i] = (tn < ntiles && pn < n) ? v[pn * D + i] : 0.f;
+    }
+    // ---- hidden epilogues: relu + split into the A tile, then the next masked GEMM
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      mbar_wait_bounded(bar0, ph0);
+      ph0 ^= 1;
+      umma::fence_after_sync();
+      float acc[64];
+      tmem_ld64(col0 + lane_sel, acc);
+      if (l == 0)
+        store_hidden<false>(acc, nullptr, a_hi, a_lo, t);
+      else
+        store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
+      fence_proxy_async();
+      umma::fence_before_sync();
+      wg_barrier(wg);
+      if (t == 0) {
+        umma::fence_after_sync();
+        if (l < L - 1) {
+          const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
+          const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
+            const int n0 = meta.hid_n0[ks];
+            const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
+            const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
+            mma_split3(col0 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+          }
+          umma::commit(bar0);
+        } else {
+          // output layer: slots 0 and 1 into the two TMEM buffers
+#pragma unroll
+          for (int s = 0; s < 2 && s < S; ++s) {
+            const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + s * kTileBytes));
+            const uint64_t dBl = umma::make_desc_sw128(
+                smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s) * kTileBytes));
+            const int nk = meta.slot_ksteps[s];
+            for (int ks = 0; ks < nk; ++ks) mma_split3(col0 + s * 64, dA_hi, dA_lo, dBh, dBl, ks, idesc64, ks > 0);
+            umma::commit(s == 0 ? bar0 : bar1);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- splines
+    float jac = 1.0f;
+    float yout[D];
+    {
+      float vf = vin[0];
+#pragma unroll
+      for (int i = 1; i < D; ++i) vf = (meta.const_feature == i) ? vin[i] : vf;
+      const float yf = rq_spline_const<NB>(ctab, vf, jac);
+#pragma unroll
+      for (int i = 0; i < D; ++i) yout[i] = yf;  // every other entry is overwritten below
+    }
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) {
+      const int b = s & 1;
+      if (b == 0) {
+        mbar_wait_bounded(bar0, ph0);
+        ph0 ^= 1;
+      } else {
+        mbar_wait_bounded(bar1, ph1);
+        ph1 ^= 1;
+      }
+      umma::fence_after_sync();
+      float acc[64];
+      tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
+      umma::fence_before_sync();
+      wg_barrier(wg);
+      if (t == 0 && s + 2 < S) {
+        umma::fence_after_sync();
+        const int s2 = s + 2;
+        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + s2 * kTileBytes));
+        const uint64_t dBl = umma::make_desc_sw128(
+            smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s2) * kTileBytes));
+        const int nk = meta.slot_ksteps[s2];
+        for (int ks = 0; ks < nk; ++ks) mma_split3(col0 + b * 64, dA_hi, dA_lo, dBh, dBl, ks, idesc64, ks > 0);
+        umma::commit(b == 0 ? bar0 : bar1);
+      }
+      __syncwarp();
+      const int f = meta.slot_feature[s];
+      float vf = vin[0];
+#pragma unroll
+      for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
+      const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
+#pragma unroll
+      for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[p * D + i] = yout[i];
+      if (logq_out) {
+        float base;
+        if (first_layer) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < D; ++i) ss = fmaf(vin[i], vin[i], ss);
+          base = -0.5f * ss - (float)D * kHalfLog2Pi;
+        } else {
+          base = logq_in[p];
+        }
+        logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) vin[i] = vnext[i];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side ----------------------------------------------------------------------------
+static void hidden_classes(int d, int* cls, int* perm) {
+  for (int h = 0; h < kH; ++h) cls[h] = 1 + h % (d - 1);
+  int p = 0;
+  for (int c = 1; c <= d - 1; ++c)
+    for (int h = 0; h < kH; ++h)
+      if (cls[h] == c) perm[p++] = h;
+}
+
+static void make_meta(int d, const int32_t* order, Meta* m, PrepMeta* pm) {
+  int cls[kH], perm[kH];
+  hidden_classes(d, cls, perm);
+  int cnt_le[kMaxDim + 2] = {0};  // cnt_le[c] = #hidden units with class <= c
+  for (int c = 1; c <= d; ++c) {
+    cnt_le[c] = cnt_le[c - 1];
+    for (int h = 0; h < kH; ++h) cnt_le[c] += (cls[h] == c);
+  }
+  int slots = 0, cfeat = 0;
+  int feat_of_order[kMaxDim];
+  for (int i = 0; i < d; ++i) feat_of_order[order[i]] = i;
+  cfeat = feat_of_order[0];
+  Meta mm = {};
+  PrepMeta pp = {};
+  for (int o = 1; o < d; ++o) {
+    const int f = feat_of_order[o];
+    const int cnt = cnt_le[o < d - 1 ? o : d - 1];
+    mm.slot_feature[slots] = f;
+    mm.slot_ksteps[slots] = (cnt + 15) / 16;
+    pp.slot_feature[slots] = f;
+    ++slots;
+  }
+  for (int ks = 0; ks < 4; ++ks) {
+    const int cmin = cls[perm[16 * ks]];   // smallest class among the inputs of this K step
+    const int first = cnt_le[cmin - 1];    // outputs with class >= cmin start here (sorted order)
+    mm.hid_n0[ks] = (first / 16) * 16;
+  }
+  mm.const_feature = cfeat;
+  mm.nslots = slots;
+  pp.const_feature = cfeat;
+  pp.nslots = slots;
+  for (int h = 0; h < kH; ++h) pp.perm[h] = perm[h];
+  if (m) *m = mm;
+  if (pm) *pm = pp;
+}
+
+static bool valid_order(int d, const int32_t* order) {
+  int seen = 0;
+  for (int i = 0; i < d; ++i) {
+    if (order[i] < 0 || order[i] >= d) return false;
+    seen |= 1 << order[i];
+  }
+  return seen == (1 << d) - 1;
+}
+
+template <int D>
+static int launch_layer(const float* v, int64_t n, const unsigned char* image, const Meta& meta, const float* logq_in,
+                        int first, float* y, float* logq_out, cudaStream_t st) {
+  constexpr int L = 3, NB = 20;
+  const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 128 + 1024;
+  auto kern = nsf_tc_layer_kernel<D, L, NB>;
+  MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + 127) / 128;
+  int64_t grid = sm_count();
+  if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
+  kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, logq_in, first, y, logq_out);
+  return launch_status();
+}
+
+}  // namespace tc
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" {
+
+int mfb_nsf_tc_supported(int d, int hidden_units, int hidden_layers, int bins) {
+  return (d >= 2 && d <= 6 && hidden_units == kH && hidden_layers == 3 && bins == 20) ? 1 : 0;
+}
+
+int64_t mfb_nsf_tc_image_bytes(int d, int hidden_layers) {
+  if (d < 2 || d > 6 || hidden_layers < 1 || hidden_layers > 3) return 0;
+  return tc::image_bytes(d, hidden_layers);
+}
+
+int64_t mfb_nsf_tc_prepare_workspace_bytes(int n_layers) { return (int64_t)n_layers * sizeof(tc::PrepMeta); }
+
+int mfb_nsf_tc_prepare(const float* params, int64_t layer_stride_floats, int n_layers, int d, int hidden_units,
+                       int hidden_layers, int bins, const int32_t* orders_host, void* images, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  MFB_CHECK_ARG(params && orders_host && images && workspace && n_layers > 0);
+  if (!mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins)) return MFB_E_UNSUPPORTED;
+  if (workspace_bytes < mfb_nsf_tc_prepare_workspace_bytes(n_layers)) return MFB_E_WORKSPACE;
+  if (n_layers > 64) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  tc::PrepMeta pm[64];
+  for (int l = 0; l < n_layers; ++l) {
+    if (!tc::valid_order(d, orders_host + (size_t)l * d)) return MFB_E_BADARG;
+    tc::make_meta(d, orders_host + (size_t)l * d, nullptr, &pm[l]);
+  }
+  // pageable-host -> device copy of a stack buffer: cudaMemcpyAsync stages it before returning
+  MFB_CUDA(cudaMemcpyAsync(workspace, pm, sizeof(tc::PrepMeta) * n_layers, cudaMemcpyHostToDevice, st));
+  tc::nsf_tc_prepare_kernel<<<n_layers, 256, 0, st>>>(params, layer_stride_floats, d, hidden_layers, bins,
+                                                      reinterpret_cast<const tc::PrepMeta*>(workspace),
+                                                      reinterpret_cast<unsigned char*>(images),
+                                                      tc::image_bytes(d, hidden_layers));
+  return launch_status();
+}
+
+int mfb_nsf_tc_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hidden_layers, int bins,
+                         const void* image, const int32_t* order_host, const float* logq_in, int first_layer,
+                         float* y, float* logq_out, void* stream) {
+  MFB_CHECK_ARG(v && image && y && order_host && n >= 0);
+  if (!mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins)) return MFB_E_UNSUPPORTED;
+  MFB_CHECK_ARG(first_layer || !logq_out || logq_in);
+  if (!tc::valid_order(d, order_host)) return MFB_E_BADARG;
+  if (n == 0) return 0;
+  tc::Meta meta;
+  tc::make_meta(d, order_host, &meta, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(image);
+  switch (d) {
+    case 2: return tc::launch_layer<2>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    case 3: return tc::launch_layer<3>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    case 4: return tc::launch_layer<4>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    case 5: return tc::launch_layer<5>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    case 6: return tc::launch_layer<6>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    default: return MFB_E_UNSUPPORTED;
+  }
+}
+
+}  // extern "C"

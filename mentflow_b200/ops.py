@@ -228,21 +228,69 @@ def nsf_layer_param_floats(d: int, hidden_units: int, hidden_layers: int, bins: 
     return int(_lib.load().mfb_nsf_layer_param_floats(d, hidden_units, hidden_layers, bins))
 
 
-def nsf_layer_forward(v, params, order, hidden_units, hidden_layers, bins, logq_in, first_layer,
-                      want_logq=True):
-    """One autoregressive spline layer: returns (y, logq_out)."""
+NSF_USE_TENSOR_CORES = True   # tcgen05 conditioner where the configuration is compiled; False = fp32 CUDA-core kernel
+
+
+def nsf_tc_supported(d: int, hidden_units: int, hidden_layers: int, bins: int) -> bool:
+    return bool(NSF_USE_TENSOR_CORES and _lib.load().mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins))
+
+
+def nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins):
+    """fp16 (hi, lo) SWIZZLE_128B operand images of every layer's masked weights, (T, bytes) uint8;
+    built on the device from the packed fp32 parameters (one small launch per forward call)."""
     lib = _lib.load()
-    v, params = _check_f32("v", v), _check_f32("params", params)
+    packed = _check_f32("packed", packed)
+    t_layers, d = len(orders), len(orders[0])
+    nbytes = int(lib.mfb_nsf_tc_image_bytes(d, hidden_layers))
+    images = torch.empty((t_layers, nbytes), dtype=torch.uint8, device=packed.device)
+    order_arr = (ctypes.c_int32 * (t_layers * d))(*[int(o) for order in orders for o in order])
+    with torch.cuda.device(packed.device):
+        wbytes = int(lib.mfb_nsf_tc_prepare_workspace_bytes(t_layers))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=packed.device)
+        _lib.check(lib.mfb_nsf_tc_prepare(_ptr(packed), packed.stride(0), t_layers, d, hidden_units, hidden_layers,
+                                          bins, ctypes.cast(order_arr, ctypes.c_void_p), _ptr(images), _ptr(work),
+                                          wbytes, _stream()), "nsf_tc_prepare")
+    return images
+
+
+def nsf_layer_forward(v, params, order, hidden_units, hidden_layers, bins, logq_in, first_layer,
+                      want_logq=True, image=None):
+    """One autoregressive spline layer: returns (y, logq_out).  With ``image`` (one row of
+    ``nsf_tc_images``) the tensor-core kernel runs, otherwise the fp32 CUDA-core kernel."""
+    lib = _lib.load()
+    v = _check_f32("v", v)
     n, d = v.shape
     y = torch.empty_like(v)
     logq_out = torch.empty(n, dtype=torch.float32, device=v.device) if want_logq else None
     order_arr = (ctypes.c_int32 * d)(*[int(o) for o in order])
     with torch.cuda.device(v.device):
-        _lib.check(lib.mfb_nsf_layer_fwd(_ptr(v), n, d, hidden_units, hidden_layers, bins, _ptr(params),
-                                         ctypes.cast(order_arr, ctypes.c_void_p), _ptr(logq_in),
-                                         1 if first_layer else 0, _ptr(y), _ptr(logq_out), _stream()),
-                   "nsf_layer_fwd")
+        if image is not None:
+            _lib.check(lib.mfb_nsf_tc_layer_fwd(_ptr(v), n, d, hidden_units, hidden_layers, bins, _ptr(image),
+                                                ctypes.cast(order_arr, ctypes.c_void_p), _ptr(logq_in),
+                                                1 if first_layer else 0, _ptr(y), _ptr(logq_out), _stream()),
+                       "nsf_tc_layer_fwd")
+        else:
+            params = _check_f32("params", params)
+            _lib.check(lib.mfb_nsf_layer_fwd(_ptr(v), n, d, hidden_units, hidden_layers, bins, _ptr(params),
+                                             ctypes.cast(order_arr, ctypes.c_void_p), _ptr(logq_in),
+                                             1 if first_layer else 0, _ptr(y), _ptr(logq_out), _stream()),
+                       "nsf_layer_fwd")
     return y, logq_out
+
+
+def _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq):
+    """All layers in sampling order; returns ([z, y_1, ..., x], log q)."""
+    d = z.shape[1]
+    images = None
+    if nsf_tc_supported(d, hidden_units, hidden_layers, bins):
+        images = nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins)
+    steps, logq = [z], None
+    for t, order in enumerate(orders):
+        y, logq = nsf_layer_forward(steps[-1], packed[t], order, hidden_units, hidden_layers, bins, logq,
+                                    first_layer=(t == 0), want_logq=want_logq,
+                                    image=None if images is None else images[t])
+        steps.append(y)
+    return steps, logq
 
 
 # --------------------------------------------------------------------------------------
@@ -278,12 +326,7 @@ class NSFForward(torch.autograd.Function):
         orders, hidden_units, hidden_layers, bins, want_logq = meta
         z = _check_f32("z", z)
         packed = _check_f32("packed", packed)
-        steps = [z]
-        logq = None
-        for t, order in enumerate(orders):
-            y, logq = nsf_layer_forward(steps[-1], packed[t], order, hidden_units, hidden_layers, bins, logq,
-                                        first_layer=(t == 0), want_logq=want_logq)
-            steps.append(y)
+        steps, logq = _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq)
         ctx.meta = meta
         ctx.save_for_backward(packed, packed_om, *steps[:-1])
         if logq is None:
@@ -335,11 +378,8 @@ def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins,
     """Returns (x, logq or None, steps or None)."""
     if want_steps:
         z = _check_f32("z", z)
-        steps, logq = [z], None
-        for t, order in enumerate(orders):
-            y, logq = nsf_layer_forward(steps[-1], packed[t].contiguous(), order, hidden_units, hidden_layers, bins,
-                                        logq, first_layer=(t == 0), want_logq=want_logq)
-            steps.append(y)
+        steps, logq = _nsf_run_layers(z, _check_f32("packed", packed.detach()), orders, hidden_units, hidden_layers,
+                                      bins, want_logq)
         return steps[-1], logq, steps
     meta = (tuple(tuple(o) for o in orders), hidden_units, hidden_layers, bins, bool(want_logq))
     x, logq = NSFForward.apply(z, packed, packed_om, meta)
