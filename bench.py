@@ -334,6 +334,11 @@ def main():
         flops = FLOP_MASK_AWARE.get(d, 0) * n
         achieved = flops / (nsf_step_ms * 1e-3) / 1e12
         layers = gen.transforms
+        tc = ops.nsf_tc_supported(d, gen.hidden_units, gen.hidden_layers, gen.bins)
+        nsf_kernel = (f"nsf_tc_layer_kernel<{d},3,20> x{layers} (tcgen05 split-fp16 conditioner, TMEM accumulators, "
+                      f"register-resident spline epilogue) + nsf_tc_prepare_kernel x1" if tc else
+                      f"nsf_layer_fwd_kernel<{d}> x{layers} (fp32 CUDA-core kernel)")
+        nsf_launches = {"nsf_tc_layer_kernel": layers, "nsf_tc_prepare_kernel": 1} if tc else {"nsf_layer_fwd_kernel": layers}
         line = {
             "metric": "particles/sec/GPU for flow sample+log_prob+project+KDE (6D, 100 proj)",
             "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -349,9 +354,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": n * d * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "api": "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()"},
-            "gpu_launches": (2 * args.steps) * (layers + 2 + 3),
-            "gpu_launches_per_step": {"nsf_layer_fwd_kernel": layers, "moments": 2, "kde1d deposit+reduce+normalize": 3},
-            "roofline": {"bound": "tensor", "kernel": "nsf_layer_fwd_kernel<6> x5 (fp32 CUDA-core stage; no tensor-core MMA yet)",
+            "gpu_launches": (2 * args.steps) * (sum(nsf_launches.values()) + 2 + 3),
+            "gpu_launches_per_step": {**nsf_launches, "moments": 2, "kde1d deposit+reduce+normalize": 3},
+            "roofline": {"bound": "tensor", "kernel": nsf_kernel,
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",

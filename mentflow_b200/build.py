@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+               "-Xcompiler", "-fPIC", "-c", src, "-o", obj] + os.environ.get("MFB_NVCC_FLAGS", "").split()
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

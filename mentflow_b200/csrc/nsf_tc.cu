@@ -191,8 +191,16 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (spins > (1 << 24)) __trap();
 }
 
-__device__ __forceinline__ void wg_barrier(int wg) {
-  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+// Warpgroup rendezvous without a barrier: every warp bumps a shared counter when its part is done
+// (A rows written / TMEM buffer read); the warp that arrives last gets `true` in lane 0 and issues
+// the next MMAs, the other three carry on immediately.  acq_rel at CTA scope orders the earlier
+// shared-memory / TMEM traffic of all four warps before the issue.
+__device__ __forceinline__ bool arrive_is_last(uint32_t* cnt) {
+  __syncwarp();
+  uint32_t old = 0;
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+  return ((threadIdx.x & 31) == 0) && ((old & 3u) == 3u);
 }
 
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
@@ -224,13 +232,25 @@ __device__ __forceinline__ float fast_lg2(float x) {
   return y;
 }
 
+// MUFU reciprocal + one Newton step (the raw approximation's 1 ulp is amplified by the
+// ill-conditioned knot sums; with the step the spline is as accurate as a divide)
+__device__ __forceinline__ float rcp_nr(float x) {
+  const float r = fast_rcp(x);
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
 // soft clip + exp of two raw (log2e-scaled) parameters with one reciprocal:
 //   e = 2^(t / (1 + c |t|))
 __device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, float& e0, float& e1) {
   const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
-  const float r = fast_rcp(d0 * d1);
+#ifdef MFB_TC_EXACT
+  e0 = exp2f(t0 / d0);
+  e1 = exp2f(t1 / d1);
+#else
+  const float r = rcp_nr(d0 * d1);
   e0 = fast_exp2(t0 * (r * d1));
   e1 = fast_exp2(t1 * (r * d0));
+#endif
 }
 
 // Rational-quadratic spline of one feature from the raw conditioner outputs a[0..3NB-2] (already
@@ -243,26 +263,28 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
                                                 float& jac) {
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
   const float4* b4 = reinterpret_cast<const float4*>(bias);
-  // ---- widths
-  float e[NB];
-  float sum = 0.f;
+  // ---- widths: e_j, running sums c_j = e_0 + ... + e_j (the same sums give the total, so
+  //      bin origin + bin width + remainder add up consistently)
+  float e[NB], c[NB];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
     const float4 b = b4[j >> 2];
     clip_exp2_pair(a[j] + b.x, a[j + 1] + b.y, cW, e[j], e[j + 1]);
     clip_exp2_pair(a[j + 2] + b.z, a[j + 3] + b.w, cW, e[j + 2], e[j + 3]);
-    sum += (e[j] + e[j + 1]) + (e[j + 2] + e[j + 3]);
   }
+  c[0] = e[0];
+#pragma unroll
+  for (int j = 1; j < NB; ++j) c[j] = c[j - 1] + e[j];
+  const float sum = c[NB - 1];
   const float target = (v + kBound) * (0.5f / kBound) * sum;
   // m[j] = 1 if bin j lies entirely left of v; ind[j] = 1 for the bin that holds v
   float m[NB], ind[NB];
-  float cum = 0.f, x0c = 0.f, ek = 0.f, mprev = 1.0f;
+  float x0c = 0.f, ek = 0.f, mprev = 1.0f;
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    cum += e[j];
-    m[j] = (j < NB - 1 && cum < target) ? 1.0f : 0.0f;
+    m[j] = (j < NB - 1 && c[j] < target) ? 1.0f : 0.0f;
     ind[j] = mprev - m[j];
-    x0c = fmaf(m[j], e[j], x0c);
+    if (j > 0) x0c = fmaf(ind[j], c[j - 1], x0c);
     ek = fmaf(ind[j], e[j], ek);
     mprev = m[j];
   }
@@ -302,14 +324,14 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
   float d0, d1;
   clip_exp2_pair(tl, tr, cD, d0, d1);
   // ---- rational quadratic
-  const float r_e = fast_rcp(ek), r_sh = fast_rcp(sumh);
+  const float r_e = rcp_nr(ek), r_sh = rcp_nr(sumh);
   float t = (target - x0c) * r_e;
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   const float hn = hk * r_sh;                 // normalised bin height / 2B
   const float s = hn * sum * r_e;             // dy / dx
   const float omt = 1.0f - t, tomt = t * omt;
   const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
-  const float r_den = fast_rcp(den);
+  const float r_den = rcp_nr(den);
   const float y0 = fmaf(2.0f * kBound, y0c * r_sh, -kBound);
   const float y = fmaf(2.0f * kBound * hn * (s * t * t + d0 * tomt), r_den, y0);
   const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
@@ -326,13 +348,13 @@ __device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, f
   for (int j = 1; j < NB; ++j) k += (ct[j] < v) ? 1 : 0;
   const float x0 = ct[k], dx = ct[kCT + k], y0 = ct[2 * kCT + k], dy = ct[3 * kCT + k];
   const float d0 = ct[4 * kCT + k], d1 = ct[5 * kCT + k];
-  const float r_dx = fast_rcp(dx);
+  const float r_dx = rcp_nr(dx);
   const float s = dy * r_dx;
   float t = (v - x0) * r_dx;
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   const float omt = 1.0f - t, tomt = t * omt;
   const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
-  const float r_den = fast_rcp(den);
+  const float r_den = rcp_nr(den);
   const float y = fmaf(dy * (s * t * t + d0 * tomt), r_den, y0);
   const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
   const bool inside = (v > -kBound) && (v <= kBound);
@@ -373,12 +395,22 @@ __device__ __forceinline__ void store_hidden(const float (&acc)[64], const float
   }
 }
 
-// three split MMAs of one K step: hi*hi + hi*lo + lo*hi
-__device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                           int kstep, uint32_t idesc, uint32_t accumulate) {
-  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_hi, kstep), idesc, accumulate);
-  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_lo, kstep), idesc, 1);
+// Split MMAs of one K step.  The cross terms (hi*lo + lo*hi, 2^-11 of the result) of ALL K steps
+// are accumulated first, the hi*hi terms last: the tensor core rounds the fp32 accumulator once per
+// MMA, so only the last few MMAs round at the full magnitude of the result.
+__device__ __forceinline__ void mma_cross(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                          int kstep, uint32_t idesc, uint32_t accumulate) {
+  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_lo, kstep), idesc, accumulate);
   umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_lo, kstep), umma::desc_advance_k(b_hi, kstep), idesc, 1);
+}
+__device__ __forceinline__ void mma_main(uint32_t tmem_d, uint64_t a_hi, uint64_t b_hi, int kstep, uint32_t idesc) {
+  umma::mma_f16_ss(tmem_d, umma::desc_advance_k(a_hi, kstep), umma::desc_advance_k(b_hi, kstep), idesc, 1);
+}
+// output-layer tile of one feature: nk K steps, N = 64
+__device__ __forceinline__ void mma_slot(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                         int nk, uint32_t idesc) {
+  for (int ks = 0; ks < nk; ++ks) mma_cross(tmem_d, a_hi, a_lo, b_hi, b_lo, ks, idesc, ks > 0);
+  for (int ks = 0; ks < nk; ++ks) mma_main(tmem_d, a_hi, b_hi, ks, idesc);
 }
 
 // =============================================================================================
@@ -394,16 +426,18 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   constexpr int kImg = ((kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes +
                          4 * ((L - 1) * kH + S * kH + kConstFloats)) + 1023) & ~1023;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   unsigned char* img = smem;
   unsigned char* a_all = smem + kImg;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);  // [0] image, [1 + 2*wg + b]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kWG);
+  uint32_t* counters = tmem_slot + 1;  // [wg][3]: hidden chain, slot buffer 0, slot buffer 1
 
   const int tid = threadIdx.x;
   const int wg = tid >> 7, t = tid & 127;
   if (tid == 0) {
     for (int i = 0; i < 1 + 2 * kWG; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3 * kWG; ++i) counters[i] = 0;
     fence_mbar_init();
   }
   if (tid < 32) umma::tmem_alloc(tmem_slot, 512);
@@ -422,6 +456,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   uint64_t* bar0 = &bars[1 + 2 * wg];
   uint64_t* bar1 = bar0 + 1;
   uint32_t ph0 = 0, ph1 = 0;
+  uint32_t* cnt_h = counters + 3 * wg;
+  uint32_t* cnt_q = cnt_h + 1;
   const uint32_t lane_sel = (uint32_t)((t >> 5) * 32) << 16;
   const uint32_t col0 = tmem_base + (uint32_t)(wg * 128);
   const float* f32 = reinterpret_cast<const float*>(img + kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes);
@@ -459,8 +495,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     }
     fence_proxy_async();
     umma::fence_before_sync();
-    wg_barrier(wg);
-    if (t == 0) {
+    if (arrive_is_last(cnt_h)) {
       umma::fence_after_sync();
       umma::mma_f16_ss(col0, dA_hi, dB1, idesc64, 0);
       umma::mma_f16_ss(col0, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
@@ -488,19 +523,24 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
       fence_proxy_async();
       umma::fence_before_sync();
-      wg_barrier(wg);
-      if (t == 0) {
+      if (arrive_is_last(cnt_h)) {
         umma::fence_after_sync();
         if (l < L - 1) {
           const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
           const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
-            const int n0 = meta.hid_n0[ks];
-            const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
-            const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
-            mma_split3(col0 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
+              const int n0 = meta.hid_n0[ks];
+              const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
+              const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
+              if (pass == 0)
+                mma_cross(col0 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+              else
+                mma_main(col0 + n0, dA_hi, dBh + boff, ks, idesc);
+            }
           }
           umma::commit(bar0);
         } else {
@@ -511,7 +551,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
             const uint64_t dBl = umma::make_desc_sw128(
                 smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s) * kTileBytes));
             const int nk = meta.slot_ksteps[s];
-            for (int ks = 0; ks < nk; ++ks) mma_split3(col0 + s * 64, dA_hi, dA_lo, dBh, dBl, ks, idesc64, ks > 0);
+            mma_slot(col0 + s * 64, dA_hi, dA_lo, dBh, dBl, nk, idesc64);
             umma::commit(s == 0 ? bar0 : bar1);
           }
         }
@@ -543,15 +583,14 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       float acc[64];
       tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
       umma::fence_before_sync();
-      wg_barrier(wg);
-      if (t == 0 && s + 2 < S) {
+      if (s + 2 < S && arrive_is_last(cnt_q + b)) {
         umma::fence_after_sync();
         const int s2 = s + 2;
         const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + s2 * kTileBytes));
         const uint64_t dBl = umma::make_desc_sw128(
             smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s2) * kTileBytes));
         const int nk = meta.slot_ksteps[s2];
-        for (int ks = 0; ks < nk; ++ks) mma_split3(col0 + b * 64, dA_hi, dA_lo, dBh, dBl, ks, idesc64, ks > 0);
+        mma_slot(col0 + b * 64, dA_hi, dA_lo, dBh, dBl, nk, idesc64);
         umma::commit(b == 0 ? bar0 : bar1);
       }
       __syncwarp();
@@ -559,7 +598,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       float vf = vin[0];
 #pragma unroll
       for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
+#ifdef MFB_TC_REFSPLINE
+      float colr[64];
+      for (int j = 0; j < 3 * NB - 1; ++j) colr[j] = (acc[j] + bout[s * kH + j]) * 0.69314718055994531f;
+      float ladj_r = 0.f;
+      const float yf = rq_spline_forward(colr, 1, NB, vf, ladj_r);
+      jac *= expf(ladj_r);
+#else
       const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
+#endif
 #pragma unroll
       for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
     }
