@@ -186,9 +186,24 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
 // device helpers
 // =============================================================================================
 // mbarrier wait that traps instead of hanging the device if an MMA / TMA never arrives
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of spinning on the issue port it shares with the other warpgroups
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  for (int spins = 0; !mbar_try_wait(bar, parity); ++spins)
-    if (spins > (1 << 24)) __trap();
+  for (int spins = 0; !mbar_try_wait_hint(bar, parity); ++spins)
+    if (spins > (1 << 22)) __trap();
 }
 
 // Warpgroup rendezvous without a barrier: every warp bumps a shared counter when its part is done
@@ -247,7 +262,7 @@ __device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, floa
   e0 = exp2f(t0 / d0);
   e1 = exp2f(t1 / d1);
 #else
-  const float r = rcp_nr(d0 * d1);
+  const float r = fast_rcp(d0 * d1);
   e0 = fast_exp2(t0 * (r * d1));
   e1 = fast_exp2(t1 * (r * d0));
 #endif
@@ -362,6 +377,16 @@ __device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, f
   return inside ? y : v;
 }
 
+// relu + (hi, lo) fp16 split of two activations with the ReLU folded into the conversions:
+// hi = rz(max(x, 0)) (truncated, so the residual of a positive x is never negative),
+// lo = rn(max(x - hi, 0)) (x < 0: hi = 0 and the residual x is clamped to 0).  hi + lo = relu(x) to 2^-22.
+__device__ __forceinline__ void split_relu_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float2 hf = __half22float2(h);
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+}
+
 // relu(acc + bias) -> (hi, lo) fp16 rows of the A operand tile (row = particle)
 template <bool kBias>
 __device__ __forceinline__ void store_hidden(const float (&acc)[64], const float* __restrict__ bias,
@@ -381,14 +406,7 @@ __device__ __forceinline__ void store_hidden(const float (&acc)[64], const float
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = fmaxf(x[2 * e], 0.f), x1 = fmaxf(x[2 * e + 1], 0.f);
-      const __half2 h = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-    }
+    for (int e = 0; e < 4; ++e) split_relu_pair(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
     const uint32_t off = umma::sw128_offset(row, c);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -434,7 +452,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   uint32_t* counters = tmem_slot + 1;  // [wg][3]: hidden chain, slot buffer 0, slot buffer 1
 
   const int tid = threadIdx.x;
-  const int wg = tid >> 7, t = tid & 127;
+  // warp-uniform by construction (shuffle from lane 0): lets the MMA descriptors live in uniform registers
+  const int wg = __shfl_sync(0xffffffffu, tid >> 7, 0);
+  const int t = tid & 127;
   if (tid == 0) {
     for (int i = 0; i < 1 + 2 * kWG; ++i) mbar_init(&bars[i], 1);
     for (int i = 0; i < 3 * kWG; ++i) counters[i] = 0;
@@ -448,7 +468,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     mbar_expect_tx(&bars[0], (uint32_t)kImg);
     tma_load_1d(img, image, (uint32_t)kImg, &bars[0]);
   }
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   mbar_wait_bounded(&bars[0], 0);
 
   unsigned char* a_hi = a_all + wg * kABytes;
@@ -469,6 +489,90 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(a_hi)), dA_lo = umma::make_desc_sw128(smem_u32(a_lo));
   const uint64_t dB1 = umma::make_desc_sw128(smem_u32(img));
 
+  // TMEM buffers of this warpgroup: slot s lands in buffer s & 1; the hidden chain of the NEXT tile
+  // runs in the buffer that frees first (the one of slot S-2) while the last splines are computed.
+  constexpr int kHB = (S >= 2) ? ((S - 2) & 1) : 1;
+  constexpr int kFork = (S >= 2) ? S - 2 : 0;   // slot after whose TMEM load the next tile starts
+
+  auto wait_buf = [&](int bsel) {
+    if (bsel == 0) {
+      mbar_wait_bounded(bar0, ph0);
+      ph0 ^= 1;
+    } else {
+      mbar_wait_bounded(bar1, ph1);
+      ph1 ^= 1;
+    }
+    umma::fence_after_sync();
+  };
+  auto commit_buf = [&](int bsel) { umma::commit(bsel == 0 ? bar0 : bar1); };
+  auto issue_slot = [&](int slot, int bsel) {  // single thread
+    const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + slot * kTileBytes));
+    const uint64_t dBl =
+        umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + slot) * kTileBytes));
+    mma_slot(col0 + bsel * 64, dA_hi, dA_lo, dBh, dBl, meta.slot_ksteps[slot], idesc64);
+    commit_buf(bsel);
+  };
+  // first masked layer of a tile: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16), two MMAs
+  auto start_tile = [&](const float (&vv)[D]) {
+    __align__(16) __half row[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
+#pragma unroll
+    for (int i = 0; i < D; ++i) umma::split_f16(vv[i], row[i], row[D + i]);
+    row[2 * D] = __float2half_rn(1.0f);
+    row[2 * D + 1] = __float2half_rn(1.0f);
+    *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 0)) = reinterpret_cast<const uint4*>(row)[0];
+    *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 1)) = reinterpret_cast<const uint4*>(row)[1];
+    fence_proxy_async();
+    umma::fence_before_sync();
+    if (arrive_is_last(cnt_h)) {
+      umma::fence_after_sync();
+      umma::mma_f16_ss(col0 + kHB * 64, dA_hi, dB1, idesc64, 0);
+      umma::mma_f16_ss(col0 + kHB * 64, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
+      commit_buf(kHB);
+    }
+    __syncwarp();
+  };
+  // hidden step l (0..L-1): accumulator -> relu -> (hi, lo) rows of A, then the next masked GEMM
+  // (l < L-1) or the first two output-layer tiles (l == L-1)
+  auto hidden_step = [&](int l) {
+    wait_buf(kHB);
+    float acc[64];
+    tmem_ld64(col0 + (uint32_t)(kHB * 64) + lane_sel, acc);
+    if (l == 0)
+      store_hidden<false>(acc, nullptr, a_hi, a_lo, t);
+    else
+      store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
+    fence_proxy_async();
+    umma::fence_before_sync();
+    if (arrive_is_last(cnt_h)) {
+      umma::fence_after_sync();
+      if (l < L - 1) {
+        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
+        const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
+            const int n0 = meta.hid_n0[ks];
+            const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
+            const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
+            if (pass == 0)
+              mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+            else
+              mma_main(col0 + kHB * 64 + n0, dA_hi, dBh + boff, ks, idesc);
+          }
+        }
+        commit_buf(kHB);
+      } else {
+        issue_slot(0, 0);
+        if (S > 1) issue_slot(1, 1);
+      }
+    }
+    __syncwarp();
+  };
+
   const int64_t ntiles = (n + 127) / 128;
   const int64_t tstride = (int64_t)gridDim.x * kWG;
   int64_t tile = (int64_t)blockIdx.x * kWG + wg;
@@ -478,138 +582,71 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
 #pragma unroll
     for (int i = 0; i < D; ++i) vin[i] = (tile < ntiles && p < n) ? v[p * D + i] : 0.f;
   }
-  for (; tile < ntiles; tile += tstride) {
+  // Software-pipelined over the tiles of this warpgroup: iteration i computes the splines of tile i
+  // ("cur") and, interleaved with its last splines, the conditioner chain of tile i+1 ("next"), so
+  // every MMA has a spline's worth of CUDA-core work to hide behind.  The first iteration has no
+  // current tile (cur = false): it only runs the chain of the first tile, through the same code.
+  bool cur = false;
+  bool has_next = tile < ntiles;   // uniform over the warpgroup
+  float vnext[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) vnext[i] = vin[i];
+  tile -= tstride;
+  while (cur || has_next) {
     const int64_t p = tile * 128 + t;
-    const bool valid = p < n;
-    // ---- first masked layer: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16)
-    {
-      __align__(16) __half row[16];
+    const bool valid = cur && p < n;
+    if (cur) {
+      has_next = tile + tstride < ntiles;
+      const int64_t pn = (tile + tstride) * 128 + t;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
-#pragma unroll
-      for (int i = 0; i < D; ++i) umma::split_f16(vin[i], row[i], row[D + i]);
-      row[2 * D] = __float2half_rn(1.0f);
-      row[2 * D + 1] = __float2half_rn(1.0f);
-      *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 0)) = reinterpret_cast<const uint4*>(row)[0];
-      *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 1)) = reinterpret_cast<const uint4*>(row)[1];
+      for (int i = 0; i < D; ++i) vnext[i] = (has_next && pn < n) ? v[pn * D + i] : 0.f;
     }
-    fence_proxy_async();
-    umma::fence_before_sync();
-    if (arrive_is_last(cnt_h)) {
-      umma::fence_after_sync();
-      umma::mma_f16_ss(col0, dA_hi, dB1, idesc64, 0);
-      umma::mma_f16_ss(col0, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
-      umma::commit(bar0);
-    }
-    // prefetch the next tile's particle while the tensor pipe works
-    float vnext[D];
-    {
-      const int64_t tn = tile + tstride;
-      const int64_t pn = tn * 128 + t;
-#pragma unroll
-      for (int i = 0; i < D; ++i) vnext[i] = (tn < ntiles && pn < n) ? v[pn * D + i] : 0.f;
-    }
-    // ---- hidden epilogues: relu + split into the A tile, then the next masked GEMM
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      mbar_wait_bounded(bar0, ph0);
-      ph0 ^= 1;
-      umma::fence_after_sync();
-      float acc[64];
-      tmem_ld64(col0 + lane_sel, acc);
-      if (l == 0)
-        store_hidden<false>(acc, nullptr, a_hi, a_lo, t);
-      else
-        store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
-      fence_proxy_async();
-      umma::fence_before_sync();
-      if (arrive_is_last(cnt_h)) {
-        umma::fence_after_sync();
-        if (l < L - 1) {
-          const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
-          const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
-              const int n0 = meta.hid_n0[ks];
-              const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
-              const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
-              if (pass == 0)
-                mma_cross(col0 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
-              else
-                mma_main(col0 + n0, dA_hi, dBh + boff, ks, idesc);
-            }
-          }
-          umma::commit(bar0);
-        } else {
-          // output layer: slots 0 and 1 into the two TMEM buffers
-#pragma unroll
-          for (int s = 0; s < 2 && s < S; ++s) {
-            const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + s * kTileBytes));
-            const uint64_t dBl = umma::make_desc_sw128(
-                smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s) * kTileBytes));
-            const int nk = meta.slot_ksteps[s];
-            mma_slot(col0 + s * 64, dA_hi, dA_lo, dBh, dBl, nk, idesc64);
-            umma::commit(s == 0 ? bar0 : bar1);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    // ---- splines
     float jac = 1.0f;
     float yout[D];
-    {
+    if (cur) {
       float vf = vin[0];
 #pragma unroll
       for (int i = 1; i < D; ++i) vf = (meta.const_feature == i) ? vin[i] : vf;
       const float yf = rq_spline_const<NB>(ctab, vf, jac);
 #pragma unroll
       for (int i = 0; i < D; ++i) yout[i] = yf;  // every other entry is overwritten below
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) yout[i] = 0.f;
     }
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
       const int b = s & 1;
-      if (b == 0) {
-        mbar_wait_bounded(bar0, ph0);
-        ph0 ^= 1;
-      } else {
-        mbar_wait_bounded(bar1, ph1);
-        ph1 ^= 1;
-      }
-      umma::fence_after_sync();
       float acc[64];
-      tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
-      umma::fence_before_sync();
-      if (s + 2 < S && arrive_is_last(cnt_q + b)) {
-        umma::fence_after_sync();
-        const int s2 = s + 2;
-        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + s2 * kTileBytes));
-        const uint64_t dBl = umma::make_desc_sw128(
-            smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + s2) * kTileBytes));
-        const int nk = meta.slot_ksteps[s2];
-        mma_slot(col0 + b * 64, dA_hi, dA_lo, dBh, dBl, nk, idesc64);
-        umma::commit(b == 0 ? bar0 : bar1);
+      if (cur) {
+        if (!(S >= 2 && s == S - 1)) wait_buf(b);   // the last slot was already waited for at kFork
+        tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
+        umma::fence_before_sync();
+        if (s + 2 < S && arrive_is_last(cnt_q + b)) {
+          umma::fence_after_sync();
+          issue_slot(s + 2, b);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      const int f = meta.slot_feature[s];
-      float vf = vin[0];
+      if (s == kFork) {
+        if (cur && S >= 2) wait_buf((S - 1) & 1);   // every output-layer MMA of this tile is done: A is free
+        if (has_next) start_tile(vnext);
+      }
+      if (cur) {
+        const int f = meta.slot_feature[s];
+        float vf = vin[0];
 #pragma unroll
-      for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
-#ifdef MFB_TC_REFSPLINE
-      float colr[64];
-      for (int j = 0; j < 3 * NB - 1; ++j) colr[j] = (acc[j] + bout[s * kH + j]) * 0.69314718055994531f;
-      float ladj_r = 0.f;
-      const float yf = rq_spline_forward(colr, 1, NB, vf, ladj_r);
-      jac *= expf(ladj_r);
-#else
-      const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
-#endif
+        for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
+        const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
 #pragma unroll
-      for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
+        for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
+      }
+      if (has_next) {
+        if (s == kFork) hidden_step(0);
+        if (S >= 2 && s == S - 1) hidden_step(1);
+      }
     }
+    if (S == 1 && has_next) hidden_step(1);
     if (valid) {
 #pragma unroll
       for (int i = 0; i < D; ++i) y[p * D + i] = yout[i];
@@ -626,8 +663,12 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
       }
     }
+    if (has_next) hidden_step(2);
 #pragma unroll
     for (int i = 0; i < D; ++i) vin[i] = vnext[i];
+    cur = has_next;
+    has_next = false;   // recomputed at the top of the next iteration
+    tile += tstride;
   }
   umma::fence_before_sync();
   __syncthreads();
