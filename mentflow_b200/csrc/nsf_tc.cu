@@ -28,7 +28,8 @@ namespace mfb {
 namespace tc {
 
 constexpr int kWG = 3;
-constexpr int kThreads = kWG * 128;
+constexpr int kThreads = (kWG + 1) * 128;   // 3 compute warpgroups + the warpgroup of the MMA-issuer warp
+constexpr int kRegsCompute = 160, kRegsIssuer = 32;   // setmaxnreg: 3*128*160 + 128*32 = 64 K registers
 constexpr int kTileBytes = 8192;     // 64 rows x 128 B (one fp16 operand tile, K = 64)
 constexpr int kABytes = 32768;       // 128 rows x 128 B, hi then lo
 constexpr int kCT = 24;              // stride of the constant-feature tables (floats)
@@ -185,37 +186,71 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
 // =============================================================================================
 // device helpers
 // =============================================================================================
+#ifdef MFB_TC_TRACE
+__device__ long long g_trace[4 * 1024];
+__device__ __forceinline__ void trace_event(int& pos, int warp, int id) {
+  if ((threadIdx.x & 31) == 0 && blockIdx.x == 0 && pos < 1024) {
+    g_trace[warp * 1024 + pos] = ((long long)id << 48) | (clock64() & 0xFFFFFFFFFFFFll);
+    ++pos;
+  }
+}
+#define TRACE(id) trace_event(trace_pos, (int)(threadIdx.x >> 5), id)
+#else
+#define TRACE(id)
+#endif
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity);
+
 // mbarrier wait that traps instead of hanging the device if an MMA / TMA never arrives
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
-// hint expires) instead of spinning on the issue port it shares with the other warpgroups
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+// mbarrier wait that traps instead of hanging the device if an MMA / TMA never arrives.  Plain
+// try_wait polling: the suspend-time-hint form sleeps in coarse quanta (measured: 2-4 thousand
+// cycles from arrival to wake-up), which is longer than the MMAs being waited for.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (int spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1 << 24)) __trap();
+}
+// issuer side: poll without occupying the issue port of the compute warps on the same scheduler
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
+  for (int spins = 0; !mbar_test_wait(bar, parity); ++spins) {
+    __nanosleep(40);
+    if (spins > (1 << 24)) __trap();
+  }
+}
+
+// Warpgroup -> issuer hand-off: every compute warp arrives (lane 0, after __syncwarp) on a request
+// mbarrier of count 4 when its part is done (A rows written / TMEM buffer read) and carries on; the
+// issuer warp sees the phase complete and issues the MMAs.  Nobody in the warpgroup waits, and the
+// issue work does not land on one of the four compute warps (a warp that issues falls behind the
+// others, arrives last again and keeps the duty: measured as 20 % of warp time lost).
+// one lane of a fully converged warp (the idiom ptxas recognises: MMAs issued under it take their
+// operands from uniform registers without a per-instruction election loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void request_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  for (int spins = 0; !mbar_try_wait_hint(bar, parity); ++spins)
-    if (spins > (1 << 22)) __trap();
-}
-
-// Warpgroup rendezvous without a barrier: every warp bumps a shared counter when its part is done
-// (A rows written / TMEM buffer read); the warp that arrives last gets `true` in lane 0 and issues
-// the next MMAs, the other three carry on immediately.  acq_rel at CTA scope orders the earlier
-// shared-memory / TMEM traffic of all four warps before the issue.
-__device__ __forceinline__ bool arrive_is_last(uint32_t* cnt) {
-  __syncwarp();
-  uint32_t old = 0;
-  if ((threadIdx.x & 31) == 0)
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
-  return ((threadIdx.x & 31) == 0) && ((old & 3u) == 3u);
 }
 
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
@@ -447,17 +482,20 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   unsigned char* img = smem;
   unsigned char* a_all = smem + kImg;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);  // [0] image, [1 + 2*wg + b]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kWG);
-  uint32_t* counters = tmem_slot + 1;  // [wg][3]: hidden chain, slot buffer 0, slot buffer 1
+  // mbarriers: [0] image; [1 + 2*wg + b] "MMA into TMEM buffer b of wg complete" (count 1, tcgen05.commit);
+  // [1 + 2*kWG + 3*wg + r] requests of wg to the issuer (count 4): r = 0 conditioner chain, 1 / 2 = slot
+  // buffer 0 / 1 has been read
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);
+  uint64_t* reqs = bars + 1 + 2 * kWG;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reqs + 3 * kWG);
 
   const int tid = threadIdx.x;
   // warp-uniform by construction (shuffle from lane 0): lets the MMA descriptors live in uniform registers
-  const int wg = __shfl_sync(0xffffffffu, tid >> 7, 0);
+  const int wg = __shfl_sync(0xffffffffu, tid >> 7, 0);   // kWG = the issuer warp
   const int t = tid & 127;
   if (tid == 0) {
     for (int i = 0; i < 1 + 2 * kWG; ++i) mbar_init(&bars[i], 1);
-    for (int i = 0; i < 3 * kWG; ++i) counters[i] = 0;
+    for (int i = 0; i < 3 * kWG; ++i) mbar_init(&reqs[i], 4);
     fence_mbar_init();
   }
   if (tid < 32) umma::tmem_alloc(tmem_slot, 512);
@@ -471,30 +509,132 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   mbar_wait_bounded(&bars[0], 0);
 
+  constexpr int kOutOff = kTileBytes + (L - 1) * 2 * kTileBytes;   // first output-layer tile in the image
+  // TMEM buffers of a warpgroup: slot s lands in buffer s & 1; the hidden chain of the NEXT tile
+  // runs in the buffer that frees first (the one of slot S-2) while the last splines are computed.
+  constexpr int kHB = (S >= 2) ? ((S - 2) & 1) : 1;
+  constexpr int kFork = (S >= 2) ? S - 2 : 0;   // slot after whose TMEM load the next tile starts
+  const int64_t ntiles = (n + 127) / 128;
+  const int64_t tstride = (int64_t)gridDim.x * kWG;
+  const uint32_t idesc64 = umma::make_idesc_f16(128, 64);
+
+  if (wg == kWG) {
+    // =========================================================================================
+    // MMA issuers: warp i of this warpgroup (one thread of it) serves compute warpgroup i.  The
+    // requests of a warpgroup come in a fixed order -- per tile: slots 2..S-1 as the TMEM buffers are
+    // read, then the conditioner chain of the next tile (first layer, two hidden GEMMs, output slots
+    // 0 and 1) -- so the issuer simply sleeps on the next request barrier (try_wait with a hint).
+    // =========================================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
+    const int w = __shfl_sync(0xffffffffu, (tid - kWG * 128) >> 5, 0);
+    if (w < kWG) {   // the whole warp walks the schedule; one elected lane issues
+      const int64_t first = (int64_t)blockIdx.x * kWG + w;
+      const int cnt = first < ntiles ? (int)((ntiles - first + tstride - 1) / tstride) : 0;
+      uint64_t* req_chain = &reqs[3 * w];
+      uint64_t* wbar = &bars[1 + 2 * w];
+      uint32_t rp = 0, rq0 = 0, rq1 = 0;
+      unsigned char* wa_hi = a_all + w * kABytes;
+      const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(wa_hi));
+      const uint64_t dA_lo = umma::make_desc_sw128(smem_u32(wa_hi + kABytes / 2));
+      const uint64_t dB1 = umma::make_desc_sw128(smem_u32(img));
+      const uint32_t col0 = tmem_base + (uint32_t)(w * 128);
+      auto issue_slot = [&](int slot) {
+        const int bsel = slot & 1;
+        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kOutOff + slot * kTileBytes));
+        const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kOutOff + (S + slot) * kTileBytes));
+        if (elect_one()) {
+          mma_slot(col0 + bsel * 64, dA_hi, dA_lo, dBh, dBl, meta.slot_ksteps[slot], idesc64);
+          umma::commit(wbar + bsel);
+        }
+        __syncwarp();
+      };
+      auto chain = [&]() {
+        // first masked layer (K = 16, bias folded in)
+        mbar_wait_polite(req_chain, rp);
+        rp ^= 1;
+        umma::fence_after_sync();
+        if (elect_one()) {
+          umma::mma_f16_ss(col0 + kHB * 64, dA_hi, dB1, idesc64, 0);
+          umma::mma_f16_ss(col0 + kHB * 64, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
+          umma::commit(wbar + kHB);
+        }
+        __syncwarp();
+        // hidden -> hidden
+#pragma unroll 1
+        for (int l = 0; l < L - 1; ++l) {
+          mbar_wait_polite(req_chain, rp);
+          rp ^= 1;
+          umma::fence_after_sync();
+          const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
+          const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
+          if (elect_one()) {
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
+              const int n0 = meta.hid_n0[ks];
+              const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
+              const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
+              if (pass == 0)
+                mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+              else
+                mma_main(col0 + kHB * 64 + n0, dA_hi, dBh + boff, ks, idesc);
+            }
+          }
+          umma::commit(wbar + kHB);
+          }
+          __syncwarp();
+        }
+        // output layer: slots 0 and 1 into the two TMEM buffers
+        mbar_wait_polite(req_chain, rp);
+        rp ^= 1;
+        umma::fence_after_sync();
+        issue_slot(0);
+        if (S > 1) issue_slot(1);
+      };
+      if (cnt > 0) chain();
+#pragma unroll 1
+      for (int i = 0; i < cnt; ++i) {
+#pragma unroll 1
+        for (int sq = 0; sq + 2 < S; ++sq) {
+          if ((sq & 1) == 0) {
+            mbar_wait_polite(req_chain + 1, rq0);
+            rq0 ^= 1;
+          } else {
+            mbar_wait_polite(req_chain + 2, rq1);
+            rq1 ^= 1;
+          }
+          umma::fence_after_sync();
+          issue_slot(sq + 2);
+        }
+        if (i + 1 < cnt) chain();
+      }
+    }
+    __syncwarp();
+  } else {
+  // ===========================================================================================
+  // compute warpgroups
+  // ===========================================================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
   unsigned char* a_hi = a_all + wg * kABytes;
   unsigned char* a_lo = a_hi + kABytes / 2;
   uint64_t* bar0 = &bars[1 + 2 * wg];
   uint64_t* bar1 = bar0 + 1;
+  uint64_t* req_chain = &reqs[3 * wg];
   uint32_t ph0 = 0, ph1 = 0;
-  uint32_t* cnt_h = counters + 3 * wg;
-  uint32_t* cnt_q = cnt_h + 1;
   const uint32_t lane_sel = (uint32_t)((t >> 5) * 32) << 16;
   const uint32_t col0 = tmem_base + (uint32_t)(wg * 128);
-  const float* f32 = reinterpret_cast<const float*>(img + kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes);
+  const float* f32 = reinterpret_cast<const float*>(img + kOutOff + 2 * S * kTileBytes);
   const float* bhid = f32;
   const float* bout = f32 + (L - 1) * kH;
   const float* ctab = bout + S * kH;
 
-  const uint32_t idesc64 = umma::make_idesc_f16(128, 64);
-  const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(a_hi)), dA_lo = umma::make_desc_sw128(smem_u32(a_lo));
-  const uint64_t dB1 = umma::make_desc_sw128(smem_u32(img));
-
-  // TMEM buffers of this warpgroup: slot s lands in buffer s & 1; the hidden chain of the NEXT tile
-  // runs in the buffer that frees first (the one of slot S-2) while the last splines are computed.
-  constexpr int kHB = (S >= 2) ? ((S - 2) & 1) : 1;
-  constexpr int kFork = (S >= 2) ? S - 2 : 0;   // slot after whose TMEM load the next tile starts
-
+#ifdef MFB_TC_TRACE
+  int trace_pos = 0;
+#endif
   auto wait_buf = [&](int bsel) {
+    TRACE(1);
     if (bsel == 0) {
       mbar_wait_bounded(bar0, ph0);
       ph0 ^= 1;
@@ -503,16 +643,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       ph1 ^= 1;
     }
     umma::fence_after_sync();
+    TRACE(2);
   };
-  auto commit_buf = [&](int bsel) { umma::commit(bsel == 0 ? bar0 : bar1); };
-  auto issue_slot = [&](int slot, int bsel) {  // single thread
-    const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + slot * kTileBytes));
-    const uint64_t dBl =
-        umma::make_desc_sw128(smem_u32(img + kTileBytes + (L - 1) * 2 * kTileBytes + (S + slot) * kTileBytes));
-    mma_slot(col0 + bsel * 64, dA_hi, dA_lo, dBh, dBl, meta.slot_ksteps[slot], idesc64);
-    commit_buf(bsel);
-  };
-  // first masked layer of a tile: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16), two MMAs
+  // first masked layer of a tile: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16)
   auto start_tile = [&](const float (&vv)[D]) {
     __align__(16) __half row[16];
 #pragma unroll
@@ -524,17 +657,11 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 0)) = reinterpret_cast<const uint4*>(row)[0];
     *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 1)) = reinterpret_cast<const uint4*>(row)[1];
     fence_proxy_async();
-    umma::fence_before_sync();
-    if (arrive_is_last(cnt_h)) {
-      umma::fence_after_sync();
-      umma::mma_f16_ss(col0 + kHB * 64, dA_hi, dB1, idesc64, 0);
-      umma::mma_f16_ss(col0 + kHB * 64, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
-      commit_buf(kHB);
-    }
-    __syncwarp();
+    request_arrive(req_chain);
+    TRACE(3);
   };
-  // hidden step l (0..L-1): accumulator -> relu -> (hi, lo) rows of A, then the next masked GEMM
-  // (l < L-1) or the first two output-layer tiles (l == L-1)
+  // hidden step l (0..L-1): accumulator -> relu -> (hi, lo) rows of A, then ask for the next masked
+  // GEMM (l < L-1) or the first two output-layer tiles (l == L-1)
   auto hidden_step = [&](int l) {
     wait_buf(kHB);
     float acc[64];
@@ -545,36 +672,10 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
     fence_proxy_async();
     umma::fence_before_sync();
-    if (arrive_is_last(cnt_h)) {
-      umma::fence_after_sync();
-      if (l < L - 1) {
-        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
-        const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            // outputs below hid_n0[ks] have all-zero weights for this K step: skip those rows
-            const int n0 = meta.hid_n0[ks];
-            const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
-            const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
-            if (pass == 0)
-              mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
-            else
-              mma_main(col0 + kHB * 64 + n0, dA_hi, dBh + boff, ks, idesc);
-          }
-        }
-        commit_buf(kHB);
-      } else {
-        issue_slot(0, 0);
-        if (S > 1) issue_slot(1, 1);
-      }
-    }
-    __syncwarp();
+    request_arrive(req_chain);
+    TRACE(4 + l);
   };
 
-  const int64_t ntiles = (n + 127) / 128;
-  const int64_t tstride = (int64_t)gridDim.x * kWG;
   int64_t tile = (int64_t)blockIdx.x * kWG + wg;
   float vin[D];
   {
@@ -622,11 +723,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         if (!(S >= 2 && s == S - 1)) wait_buf(b);   // the last slot was already waited for at kFork
         tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
         umma::fence_before_sync();
-        if (s + 2 < S && arrive_is_last(cnt_q + b)) {
-          umma::fence_after_sync();
-          issue_slot(s + 2, b);
-        }
-        __syncwarp();
+        if (s + 2 < S) request_arrive(req_chain + 1 + b);
+        TRACE(10 + s);
       }
       if (s == kFork) {
         if (cur && S >= 2) wait_buf((S - 1) & 1);   // every output-layer MMA of this tile is done: A is free
@@ -640,6 +738,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
 #pragma unroll
         for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
+        TRACE(20 + s);
       }
       if (has_next) {
         if (s == kFork) hidden_step(0);
@@ -670,6 +769,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     has_next = false;   // recomputed at the top of the next iteration
     tile += tstride;
   }
+  }  // compute warpgroups
   umma::fence_before_sync();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(tmem_base, 512);
@@ -749,6 +849,12 @@ static int launch_layer(const float* v, int64_t n, const unsigned char* image, c
 using namespace mfb;
 
 extern "C" {
+
+#ifdef MFB_TC_TRACE
+int mfb_debug_copy_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(long long) * 4 * 1024);
+}
+#endif
 
 int mfb_nsf_tc_supported(int d, int hidden_units, int hidden_layers, int bins) {
   return (d >= 2 && d <= 6 && hidden_units == kH && hidden_layers == 3 && bins == 20) ? 1 : 0;
