@@ -108,10 +108,67 @@ __device__ __forceinline__ float project_row(const float* __restrict__ xr, const
 }
 
 // ---- forward: KDE deposit --------------------------------------------------------------------
+// Launch plan of the deposit kernel: up to 512 threads (= projections x particle slices) per CTA,
+// one private column of B + 2G bins per thread (G = 2R+1 guard rows on either side, so that no tap
+// needs a bounds check: particles beyond the screen are clamped to a position whose whole window
+// lies in the guard rows).
+constexpr int kDepThreads = 512;
+struct KdePlan {
+  int kc, slices, threads, ld, kchunks, grid_x, tile, rows, guard;   // ld = row stride of the bins (threads rounded up to 32)
+  size_t smem;
+};
+static KdePlan plan_kde(int64_t n, int d, int k, int b, int r) {
+  KdePlan P;
+  P.guard = 2 * r + 1;
+  P.rows = b + 2 * P.guard;
+  P.kchunks = (k + kDepThreads - 1) / kDepThreads;
+  P.kc = (k + P.kchunks - 1) / P.kchunks;
+  int sms = sm_count();
+  int tile = 512;
+  while (tile > 128 && ceil_div64(n, tile) < 2 * sms) tile >>= 1;
+  P.tile = tile;
+  const size_t budget = 222 * 1024;
+  int slices = kDepThreads / P.kc;
+  while (slices > 1 && (size_t)P.rows * ((slices * P.kc + 31) & ~31) * 4 + 2ull * tile * d * 4 + 64 > budget) --slices;
+  if (slices < 1) slices = 1;
+  P.slices = slices;
+  P.threads = slices * P.kc;
+  P.ld = (P.threads + 31) & ~31;   // bank = thread % 32 whatever bin a lane hits: conflict free
+  P.smem = (size_t)P.rows * P.ld * 4 + 2ull * tile * d * 4 + 64;
+  int ctas_per_sm = (int)((226 * 1024) / (P.smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm * P.threads > 1024) ctas_per_sm = 1024 / P.threads > 0 ? 1024 / P.threads : 1;
+  int64_t gx = (int64_t)sms * ctas_per_sm;
+  const int64_t tiles = ceil_div64(n, tile);
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  P.grid_x = (int)gx;
+  return P;
+}
+
+// Gaussian taps of one particle at fractional offset f from its nearest bin centre:
+//   tap[R + j] = 2^(alpha (f - j)^2) = E0 * q^j * c_j,  E0 = 2^(alpha f^2), q = 2^(-2 alpha f),
+// c_j / c_(j-1) = 2^(alpha (2j-1)) (rj[j-1], per projection).  Three MUFU instead of 2R+1.
+template <int R>
+__device__ __forceinline__ void gauss_taps(float f, float alpha, const float (&rj)[R], float (&tap)[2 * R + 1]) {
+  const float af = alpha * f;
+  const float e0 = fast_exp2(af * f);
+  const float q = fast_exp2(-2.0f * af), qi = fast_exp2(2.0f * af);
+  tap[R] = e0;
+  float up = e0, dn = e0;
+#pragma unroll
+  for (int j = 1; j <= R; ++j) {
+    up *= q * rj[j - 1];
+    dn *= qi * rj[j - 1];
+    tap[R + j] = up;
+    tap[R - j] = dn;
+  }
+}
+
 template <int D, int R>
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __launch_bounds__(kDepThreads)
 kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
-                     const float* __restrict__ geom, int K, int B, int kc, int tile,
+                     const float* __restrict__ geom, int K, int B, int kc, int tile, int guard, int ld,
                      float* __restrict__ partial /* [gridDim.x][K][B] */) {
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -122,6 +179,7 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
   float* bins = reinterpret_cast<float*>(tp.bar + 8);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int rows_total = B + 2 * guard;
   const int kbase = blockIdx.y * kc;
   const int kloc = tid % kc;
   const int slice = tid / kc;
@@ -129,7 +187,7 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
   const int k = kbase + kloc;
   const bool active = k < K;
 
-  for (int i = tid; i < B * nthreads; i += nthreads) bins[i] = 0.f;
+  for (int i = tid; i < rows_total * ld; i += nthreads) bins[i] = 0.f;
   if (tid == 0) {
     mbar_init(&tp.bar[0], 1);
     mbar_init(&tp.bar[1], 1);
@@ -138,21 +196,27 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
   __syncthreads();
 
   float w[kMaxDim];
-  float c0 = 0.f, inv_delta = 0.f, alpha = 0.f;
+  float c0s = 0.f, inv_delta = 0.f, alpha = 0.f;
+  float rj[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) rj[j] = 0.f;
   if (active) {
 #pragma unroll
     for (int i = 0; i < kMaxDim; ++i) w[i] = i < d ? proj[(size_t)k * d + i] : 0.f;
     const float* g = geom + (size_t)k * MFB_GEOM_STRIDE;
-    c0 = g[0];
     inv_delta = 1.0f / g[1];
+    c0s = g[0] * inv_delta;
     float r = g[1] / g[2];
     alpha = -0.5f * r * r * kLog2e;
+#pragma unroll
+    for (int j = 0; j < R; ++j) rj[j] = exp2f(alpha * (float)(2 * j + 1));
   }
 
   const int64_t ntiles = (n + tile - 1) / tile;
   if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
-  float* mybins = bins + tid;
-  const float lo = -(float)(R + 2), hi = (float)(B + R + 1);
+  // window origin of a particle at bin b0 is row b0 + guard - R of this thread's column
+  float* mybins = bins + tid + (size_t)(guard - R) * ld;
+  const float lo = -(float)(R + 1), hi = (float)(B + R);
 
   int it = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -164,20 +228,24 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     const int rows = rows64 > tile ? tile : (int)rows64;
     const float* xs = tp.buf[stage];
     if (active) {
-      for (int p = slice; p < rows; p += slices) {
-        const float u = project_row<D>(xs + (size_t)p * d, w, d);
-        float a = (u - c0) * inv_delta;
-        a = fminf(fmaxf(a, lo), hi);
-        const float fb = rintf(a);
-        const int b0 = (int)fb;
-        const float f = a - fb;
+      // two particles per trip: their taps are independent, only the deposits are ordered
+      for (int p = slice; p < rows; p += 2 * slices) {
+        const int p2 = p + slices;
+        const float ua = project_row<D>(xs + (size_t)p * d, w, d);
+        const float ub = project_row<D>(xs + (size_t)(p2 < rows ? p2 : p) * d, w, d);
+        float aa = fmaf(ua, inv_delta, -c0s), ab = fmaf(ub, inv_delta, -c0s);
+        aa = fminf(fmaxf(aa, lo), hi);
+        ab = (p2 < rows) ? fminf(fmaxf(ab, lo), hi) : lo;   // a missing second particle goes to the guard rows
+        const float fba = rintf(aa), fbb = rintf(ab);
+        float ta[2 * R + 1], tb[2 * R + 1];
+        gauss_taps<R>(aa - fba, alpha, rj, ta);
+        gauss_taps<R>(ab - fbb, alpha, rj, tb);
+        float* ca = mybins + (int)fba * ld;
+        float* cb = mybins + (int)fbb * ld;
 #pragma unroll
-        for (int j = -R; j <= R; ++j) {
-          const int b = b0 + j;
-          const float tt = f - (float)j;
-          const float val = fast_exp2(alpha * tt * tt);
-          if ((unsigned)b < (unsigned)B) mybins[(size_t)b * nthreads] += val;
-        }
+        for (int j = 0; j <= 2 * R; ++j) ca[j * ld] += ta[j];
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) cb[j * ld] += tb[j];
       }
     }
     __syncthreads();  // everyone is done with buf[stage] before it is refilled
@@ -189,7 +257,7 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     const int kk = idx % kc, b = idx / kc;
     if (kbase + kk < K) {
       float s = 0.f;
-      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)b * nthreads + sl * kc + kk];
+      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)(b + guard) * ld + sl * kc + kk];
       out[(size_t)(kbase + kk) * B + b] = s;
     }
   }
@@ -399,14 +467,14 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
 
 // ---- host-side dispatch -----------------------------------------------------------------------------
 template <int D>
-static int launch_kde1d_deposit(int r, const ProjLaunch& L, const float* x, int64_t n, int d, const float* proj,
+static int launch_kde1d_deposit(int r, const KdePlan& L, const float* x, int64_t n, int d, const float* proj,
                                 const float* geom, int k, int b, float* partial, cudaStream_t st) {
   dim3 grid(L.grid_x, L.kchunks), block(L.threads);
 #define MFB_LAUNCH_R(RR)                                                                                   \
   {                                                                                                        \
     MFB_CUDA(cudaFuncSetAttribute(kde1d_deposit_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)L.smem));                                                           \
-    kde1d_deposit_kernel<D, RR><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, partial); \
+    kde1d_deposit_kernel<D, RR><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, L.guard, L.ld, partial); \
   }
   if (r <= 4) MFB_LAUNCH_R(4)
   else if (r <= 9) MFB_LAUNCH_R(9)
@@ -446,8 +514,11 @@ extern "C" {
 
 int64_t mfb_kde1d_workspace_bytes(int64_t n, int d, int k, int b) {
   if (n < 0 || d < 1 || d > kMaxDim || k < 1 || b < 1) return 0;
-  ProjLaunch L = plan_launch(n > 0 ? n : 1, d, k, b, 4, 0);
-  return (int64_t)L.grid_x * k * b * 4;
+  // upper bound over every deposit plan (the window radius is not known here)
+  const int64_t tiles = ceil_div64(n > 0 ? n : 1, 128);
+  int64_t gx = (int64_t)sm_count() * 4;
+  if (gx > tiles) gx = tiles;
+  return gx * k * b * 4;
 }
 
 int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
@@ -457,10 +528,11 @@ int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, c
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2);
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return (int)cudaMemsetAsync(sums, 0, (size_t)k * b * 4, st);
-  ProjLaunch L = plan_launch(n, d, k, b, 4, 0);
+  const int r = radius_from_hint(max_sigma_over_delta);
+  const int rr = r <= 4 ? 4 : (r <= 9 ? 9 : 13);   // compiled window radii
+  KdePlan L = plan_kde(n, d, k, b, rr);
   if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
   if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
-  const int r = radius_from_hint(max_sigma_over_delta);
   float* partial = (float*)workspace;
   int rc;
   switch (d) {

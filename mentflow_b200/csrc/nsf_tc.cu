@@ -416,6 +416,16 @@ __device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, f
 // hi = rz(max(x, 0)) (truncated, so the residual of a positive x is never negative),
 // lo = rn(max(x - hi, 0)) (x < 0: hi = 0 and the residual x is clamped to 0).  hi + lo = relu(x) to 2^-22.
 __device__ __forceinline__ void split_relu_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+#ifdef MFB_TC_RNSPLIT
+  x0 = fmaxf(x0, 0.f);
+  x1 = fmaxf(x1, 0.f);
+  const __half2 h2 = __floats2half2_rn(x0, x1);
+  const float2 h2f = __half22float2(h2);
+  const __half2 l2 = __floats2half2_rn(x0 - h2f.x, x1 - h2f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+  return;
+#endif
   asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const __half2 h = *reinterpret_cast<const __half2*>(&hi);
   const float2 hf = __half22float2(h);
