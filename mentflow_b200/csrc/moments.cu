@@ -51,11 +51,13 @@ moments_kernel(const float* __restrict__ x, const float* __restrict__ logq, int6
 }
 
 __global__ void moments_finish_kernel(const double* __restrict__ partial, int nparts, int m, double* __restrict__ out) {
-  const int i = threadIdx.x;
-  if (i < m) {
+  // one warp per output: lanes stride over the partials, fixed shuffle tree => deterministic
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x >> 5; i < m; i += nwarps) {
     double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * m + i];
-    out[i] = s;
+    for (int c = lane; c < nparts; c += 32) s += partial[(size_t)c * m + i];
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
   }
 }
 
@@ -75,7 +77,7 @@ static int launch_moments(const float* x, const float* logq, int64_t n, int cov,
   else moments_kernel<D, false><<<grid, kMomThreads, 0, st>>>(x, logq, n, partial);
   int rc = launch_status();
   if (rc) return rc;
-  moments_finish_kernel<<<1, 128, 0, st>>>(partial, grid, m, out);
+  moments_finish_kernel<<<1, 256, 0, st>>>(partial, grid, m, out);
   return launch_status();
 }
 

@@ -307,14 +307,18 @@ __device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, floa
 // multiplied by log2 e through the weights; bias, equally scaled, in shared memory).  Works in
 // un-normalised softmax units: the bin is searched on the running sum of e_j against
 // (v + B) / 2B * sum, and bin width / height come from e_k directly (no differencing of knots).
+// The search is two-level -- which group of four bins, then which bin of the group -- with
+// predicated selects, so that nothing is indexed dynamically and everything stays in registers.
 // Multiplies jac by dy/dv (1 outside [-B, B]) and returns y.
 template <int NB>
 __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const float* __restrict__ bias, float v,
                                                 float& jac) {
+  static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
+  constexpr int G = NB / 4;
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
   const float4* b4 = reinterpret_cast<const float4*>(bias);
-  // ---- widths: e_j, running sums c_j = e_0 + ... + e_j (the same sums give the total, so
-  //      bin origin + bin width + remainder add up consistently)
+  // ---- widths: e_j and running sums c_j = e_0 + ... + e_j (the same sums give the total, so bin
+  //      origin + bin width + remainder add up consistently)
   float e[NB], c[NB];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
@@ -327,50 +331,62 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
   for (int j = 1; j < NB; ++j) c[j] = c[j - 1] + e[j];
   const float sum = c[NB - 1];
   const float target = (v + kBound) * (0.5f / kBound) * sum;
-  // m[j] = 1 if bin j lies entirely left of v; ind[j] = 1 for the bin that holds v
-  float m[NB], ind[NB];
-  float x0c = 0.f, ek = 0.f, mprev = 1.0f;
+  // level 1: pg[g] <=> the bin of v lies beyond group g (monotone in g)
+  bool pg[G - 1];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    m[j] = (j < NB - 1 && c[j] < target) ? 1.0f : 0.0f;
-    ind[j] = mprev - m[j];
-    if (j > 0) x0c = fmaf(ind[j], c[j - 1], x0c);
-    ek = fmaf(ind[j], e[j], ek);
-    mprev = m[j];
+  for (int g = 0; g < G - 1; ++g) pg[g] = c[4 * g + 3] < target;
+  float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
+#pragma unroll
+  for (int g = 1; g < G; ++g) {
+    q0 = pg[g - 1] ? e[4 * g] : q0;
+    q1 = pg[g - 1] ? e[4 * g + 1] : q1;
+    q2 = pg[g - 1] ? e[4 * g + 2] : q2;
+    q3 = pg[g - 1] ? e[4 * g + 3] : q3;
+    xg = pg[g - 1] ? c[4 * g - 1] : xg;
   }
-  // ---- heights
-  float sumh = 0.f, y0c = 0.f, hk = 0.f;
+  // level 2: the same partial sums as c[] (same operands, same order), then the bin of the group
+  const float c0 = xg + q0, c1 = c0 + q1, c2 = c1 + q2;
+  const bool r0 = c0 < target, r1 = c1 < target, r2 = c2 < target;
+  const float x0c = r2 ? c2 : (r1 ? c1 : (r0 ? c0 : xg));
+  const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
+  // ---- heights, one group at a time
+  float run = 0.f, yg = 0.f, h0s = 0.f, h1s = 0.f, h2s = 0.f, h3s = 0.f;
 #pragma unroll
-  for (int j = 0; j < NB; j += 4) {
-    const float4 b = b4[(NB + j) >> 2];
+  for (int g = 0; g < G; ++g) {
+    const float4 b = b4[(NB + 4 * g) >> 2];
     float h0, h1, h2, h3;
-    clip_exp2_pair(a[NB + j] + b.x, a[NB + j + 1] + b.y, cW, h0, h1);
-    clip_exp2_pair(a[NB + j + 2] + b.z, a[NB + j + 3] + b.w, cW, h2, h3);
-    sumh += (h0 + h1) + (h2 + h3);
-    y0c = fmaf(m[j], h0, y0c);
-    y0c = fmaf(m[j + 1], h1, y0c);
-    y0c = fmaf(m[j + 2], h2, y0c);
-    y0c = fmaf(m[j + 3], h3, y0c);
-    hk = fmaf(ind[j], h0, hk);
-    hk = fmaf(ind[j + 1], h1, hk);
-    hk = fmaf(ind[j + 2], h2, hk);
-    hk = fmaf(ind[j + 3], h3, hk);
+    clip_exp2_pair(a[NB + 4 * g] + b.x, a[NB + 4 * g + 1] + b.y, cW, h0, h1);
+    clip_exp2_pair(a[NB + 4 * g + 2] + b.z, a[NB + 4 * g + 3] + b.w, cW, h2, h3);
+    const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
+    h0s = take ? h0 : h0s;
+    h1s = take ? h1 : h1s;
+    h2s = take ? h2 : h2s;
+    h3s = take ? h3 : h3s;
+    yg = take ? run : yg;
+    run += (h0 + h1) + (h2 + h3);
   }
-  // ---- derivatives at the two knots of the bin (raw 0 -> slope 1 at the outer knots)
-  float tl = 0.f, tr = 0.f;
+  const float sumh = run;
+  const float p0 = yg + h0s, p1 = p0 + h1s, p2 = p1 + h2s;
+  const float y0c = r2 ? p2 : (r1 ? p1 : (r0 ? p0 : yg));
+  const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
+  // ---- derivatives at the two knots of the bin (raw 0 -> slope 1 at the outer knots):
+  //      u[-1..3] = raw parameters of the knots around the group's four bins
+  float um = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, prev = 0.f;
 #pragma unroll
-  for (int j = 0; j < NB; j += 4) {
-    const float4 b = b4[(2 * NB + j) >> 2];
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (j + q < NB - 1) {
-        const float t = a[2 * NB + j + q] + bb[q];
-        tl = fmaf(ind[j + q + 1], t, tl);
-        tr = fmaf(ind[j + q], t, tr);
-      }
-    }
+  for (int g = 0; g < G; ++g) {
+    const float4 b = b4[(2 * NB + 4 * g) >> 2];
+    const float t0 = a[2 * NB + 4 * g] + b.x, t1 = a[2 * NB + 4 * g + 1] + b.y, t2 = a[2 * NB + 4 * g + 2] + b.z;
+    const float t3 = (4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] + b.w : 0.f;
+    const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
+    um = take ? prev : um;
+    u0 = take ? t0 : u0;
+    u1 = take ? t1 : u1;
+    u2 = take ? t2 : u2;
+    u3 = take ? t3 : u3;
+    prev = t3;
   }
+  const float tl = r2 ? u2 : (r1 ? u1 : (r0 ? u0 : um));
+  const float tr = r2 ? u3 : (r1 ? u2 : (r0 ? u1 : u0));
   float d0, d1;
   clip_exp2_pair(tl, tr, cD, d0, d1);
   // ---- rational quadratic
@@ -714,6 +730,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     }
     float jac = 1.0f;
     float yout[D];
+    float lq_in = 0.f;   // loaded a tile's worth of work before it is needed
+    if (cur && valid && logq_out && !first_layer) lq_in = logq_in[p];
     if (cur) {
       float vf = vin[0];
 #pragma unroll
@@ -767,7 +785,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
           for (int i = 0; i < D; ++i) ss = fmaf(vin[i], vin[i], ss);
           base = -0.5f * ss - (float)D * kHalfLog2Pi;
         } else {
-          base = logq_in[p];
+          base = lq_in;
         }
         logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
       }
