@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--bins", type=int, default=64)
     ap.add_argument("--cpu-particles", type=int, default=25_000, help="sample size of the CPU baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -271,28 +272,54 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # One step = one replay of the captured CUDA graph of the public forward pass
+    # (mentflow_b200.graphs.GraphedLoss: generator.forward_and_log_prob + MENTFlow.loss_from_particles);
+    # multi-rank runs launch eagerly (the collective stays outside any capture).
+    use_graph = (world == 1) and not args.no_graph
+    graphed = None
+    if use_graph:
+        from mentflow_b200.graphs import GraphedLoss
+        graphed = GraphedLoss(model, n, warmup=2)
+
+    def run_step(z):
+        if graphed is not None:
+            return graphed(z)[0]
+        return step(z)
+
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
+        run_step(z_dev)
         step(z_dev)
     barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # ---- per-section timing (eager launches): the NSF layer kernels vs the rest of the step --------
+    for _ in range(args.steps):
+        flush.zero_()
+        tm = [ev() for _ in range(3)]
+        step(z_dev, tm)
+        tm[2].synchronize()
+        nsf_ms.append(tm[0].elapsed_time(tm[1]))
+        kde_ms.append(tm[1].elapsed_time(tm[2]))
+    barrier()
     # ---- device-resident timing -------------------------------------------------------
     total_ms = 0.0
     losses = []
+    z_res = z_dev
+    if graphed is not None:
+        graphed.z.copy_(z_dev)             # the graph's own input buffer: z is resident, nothing is copied
+        z_res = graphed.z
+    barrier()
     for _ in range(args.steps):
         flush.zero_()                      # evict L2 between timed iterations
         e0, e1 = ev(), ev()
-        tm = [ev() for _ in range(3)]
         e0.record()
-        L = step(z_dev, tm)
+        L = run_step(z_res)
         e1.record()
         e1.synchronize()
         total_ms += e0.elapsed_time(e1)
-        nsf_ms.append(tm[0].elapsed_time(tm[1]))
-        kde_ms.append(tm[1].elapsed_time(tm[2]))
-        losses.append(L)
+        losses.append(L.clone())
     barrier()
     # ---- end to end: z from pinned host memory, loss read back ----------------------------
     e2e_s = 0.0
@@ -300,8 +327,11 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        z_in.copy_(z_host, non_blocking=True)
-        L = step(z_in)
+        if graphed is not None:
+            L = run_step(z_host)           # pinned host -> device copy, then the replay
+        else:
+            z_in.copy_(z_host, non_blocking=True)
+            L = step(z_in)
         lval = float(L.item())
         e2e_s += time.perf_counter() - t0
     barrier()
@@ -336,9 +366,10 @@ def main():
         layers = gen.transforms
         tc = ops.nsf_tc_supported(d, gen.hidden_units, gen.hidden_layers, gen.bins)
         nsf_kernel = (f"nsf_tc_layer_kernel<{d},3,20> x{layers} (tcgen05 split-fp16 conditioner, TMEM accumulators, "
-                      f"register-resident spline epilogue) + nsf_tc_prepare_kernel x1" if tc else
+                      f"register-resident spline epilogue)" if tc else
                       f"nsf_layer_fwd_kernel<{d}> x{layers} (fp32 CUDA-core kernel)")
-        nsf_launches = {"nsf_tc_layer_kernel": layers, "nsf_tc_prepare_kernel": 1} if tc else {"nsf_layer_fwd_kernel": layers}
+        # the operand images are cached while the weights do not change: no prepare kernel in a forward-only step
+        nsf_launches = {"nsf_tc_layer_kernel": layers} if tc else {"nsf_layer_fwd_kernel": layers}
         line = {
             "metric": "particles/sec/GPU for flow sample+log_prob+project+KDE (6D, 100 proj)",
             "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -349,12 +380,16 @@ def main():
                                    f"(sample+log_prob+entropy+project+KDE+KL loss)",
                        "particles_per_gpu_per_step": n, "parallelism": f"particles sharded x{world}",
                        "l2": "256 MB flush write between timed iterations",
+                       "launch": ("CUDA graph replay of the forward step (mentflow_b200.graphs.GraphedLoss)"
+                                  if use_graph else "eager launches"),
                        "weights": "default init x3 (trained-like), seed 0", "value_per_gpu": value / world},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": n * d * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()"},
-            "gpu_launches": (2 * args.steps) * (sum(nsf_launches.values()) + 2 + 3),
+                    "api": ("GraphedLoss(model, n)(z_pinned_host): H2D copy + graph replay of generator.forward_and_log_prob "
+                            "+ MENTFlow.loss_from_particles; loss.item()" if use_graph else
+                            "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()")},
+            "gpu_launches": (3 * args.steps) * (sum(nsf_launches.values()) + 2 + 3),
             "gpu_launches_per_step": {**nsf_launches, "moments": 2, "kde1d deposit+reduce+normalize": 3},
             "roofline": {"bound": "tensor", "kernel": nsf_kernel,
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",

@@ -43,11 +43,15 @@ struct Meta {
   int nslots;
 };
 
-struct PrepMeta {
-  int perm[kH];               // perm[p] = original hidden unit stored at sorted position p
+struct PrepMeta {             // per layer: which feature each output slot serves
   int slot_feature[kMaxDim];
   int const_feature;
   int nslots;
+};
+constexpr int kMaxPrepLayers = 16;
+struct PrepArgs {             // by-value kernel argument (no host->device copy, graph-capturable)
+  int perm[kH];               // perm[p] = original hidden unit stored at sorted position p (same for every layer)
+  PrepMeta layer[kMaxPrepLayers];
 };
 
 // ---- image layout (bytes) -------------------------------------------------------------------
@@ -80,10 +84,12 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_tile, unsigned ch
 // one block per layer; params = packed fp32 block of nsf_common.cuh (pre-masked, [in][out])
 __global__ void __launch_bounds__(256)
 nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride, int D, int L, int nb,
-                      const PrepMeta* __restrict__ metas, unsigned char* __restrict__ images, int img_bytes) {
-  const int layer = blockIdx.x;
+                      const __grid_constant__ PrepArgs args, int layer0, unsigned char* __restrict__ images,
+                      int img_bytes) {
+  const int layer = layer0 + blockIdx.x;
   const float* par = params_all + (size_t)layer * layer_stride;
-  const PrepMeta& pm = metas[layer];
+  const PrepMeta& pm = args.layer[blockIdx.x];
+  const int* perm = args.perm;
   unsigned char* img = images + (size_t)layer * img_bytes;
   const int S = pm.nslots;
   const float* W1t = par;
@@ -102,7 +108,7 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
   for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
     if (task < kH) {
       // B1 row n: K step 0 = [W1hi (D) | W1hi (D) | b1hi | b1lo | 0], K step 1 = [W1lo (D) | 0]
-      const int n = task, o = pm.perm[n];
+      const int n = task, o = perm[n];
       __align__(16) __half k0[16], k1[16];
       for (int e = 0; e < 16; ++e) k0[e] = k1[e] = __float2half_rn(0.f);
       for (int i = 0; i < D; ++i) {
@@ -125,7 +131,7 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
       const int l = t2 / (kH * 8), n = (t2 / 8) % kH, c = t2 % 8;
       const float* wt = hid + (size_t)l * (kH * kH + kH);
       float x[8];
-      for (int e = 0; e < 8; ++e) x[e] = wt[pm.perm[c * 8 + e] * kH + pm.perm[n]];
+      for (int e = 0; e < 8; ++e) x[e] = wt[perm[c * 8 + e] * kH + perm[n]];
       store_split8(img + off_hid(l), img + off_hid(l) + kTileBytes, n, c, x);
     } else {
       const int t2 = task - kH - (L - 1) * kH * 8;
@@ -133,14 +139,14 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
       const int f = pm.slot_feature[s];
       const float* wf = Wout + (size_t)f * kH * kPP;
       float x[8];
-      for (int e = 0; e < 8; ++e) x[e] = (q < 3 * nb - 1) ? wf[pm.perm[c * 8 + e] * kPP + q] * kLog2e : 0.f;
+      for (int e = 0; e < 8; ++e) x[e] = (q < 3 * nb - 1) ? wf[perm[c * 8 + e] * kPP + q] * kLog2e : 0.f;
       store_split8(img + off_out_hi(L, s), img + off_out_lo(L, S, s), q, c, x);
     }
   }
   // fp32 block
   for (int i = threadIdx.x; i < (L - 1) * kH; i += blockDim.x) {
     const int l = i / kH, n = i % kH;
-    f32[i] = hid[(size_t)l * (kH * kH + kH) + kH * kH + pm.perm[n]];
+    f32[i] = hid[(size_t)l * (kH * kH + kH) + kH * kH + perm[n]];
   }
   for (int i = threadIdx.x; i < S * kH; i += blockDim.x) {
     const int s = i / kH, q = i % kH;
@@ -843,7 +849,6 @@ static void make_meta(int d, const int32_t* order, Meta* m, PrepMeta* pm) {
   mm.nslots = slots;
   pp.const_feature = cfeat;
   pp.nslots = slots;
-  for (int h = 0; h < kH; ++h) pp.perm[h] = perm[h];
   if (m) *m = mm;
   if (pm) *pm = pp;
 }
@@ -893,28 +898,32 @@ int64_t mfb_nsf_tc_image_bytes(int d, int hidden_layers) {
   return tc::image_bytes(d, hidden_layers);
 }
 
-int64_t mfb_nsf_tc_prepare_workspace_bytes(int n_layers) { return (int64_t)n_layers * sizeof(tc::PrepMeta); }
+int64_t mfb_nsf_tc_prepare_workspace_bytes(int n_layers) { (void)n_layers; return 0; }   /* kept for ABI stability */
 
 int mfb_nsf_tc_prepare(const float* params, int64_t layer_stride_floats, int n_layers, int d, int hidden_units,
                        int hidden_layers, int bins, const int32_t* orders_host, void* images, void* workspace,
                        int64_t workspace_bytes, void* stream) {
-  MFB_CHECK_ARG(params && orders_host && images && workspace && n_layers > 0);
+  (void)workspace;
+  (void)workspace_bytes;
+  MFB_CHECK_ARG(params && orders_host && images && n_layers > 0);
   if (!mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins)) return MFB_E_UNSUPPORTED;
-  if (workspace_bytes < mfb_nsf_tc_prepare_workspace_bytes(n_layers)) return MFB_E_WORKSPACE;
-  if (n_layers > 64) return MFB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  tc::PrepMeta pm[64];
-  for (int l = 0; l < n_layers; ++l) {
-    if (!tc::valid_order(d, orders_host + (size_t)l * d)) return MFB_E_BADARG;
-    tc::make_meta(d, orders_host + (size_t)l * d, nullptr, &pm[l]);
+  const int img_bytes = tc::image_bytes(d, hidden_layers);
+  for (int l0 = 0; l0 < n_layers; l0 += tc::kMaxPrepLayers) {
+    const int nl = n_layers - l0 < tc::kMaxPrepLayers ? n_layers - l0 : tc::kMaxPrepLayers;
+    tc::PrepArgs args = {};
+    int cls[kH];
+    tc::hidden_classes(d, cls, args.perm);
+    for (int l = 0; l < nl; ++l) {
+      if (!tc::valid_order(d, orders_host + (size_t)(l0 + l) * d)) return MFB_E_BADARG;
+      tc::make_meta(d, orders_host + (size_t)(l0 + l) * d, nullptr, &args.layer[l]);
+    }
+    tc::nsf_tc_prepare_kernel<<<nl, 256, 0, st>>>(params, layer_stride_floats, d, hidden_layers, bins, args, l0,
+                                                  reinterpret_cast<unsigned char*>(images), img_bytes);
+    const int rc = launch_status();
+    if (rc) return rc;
   }
-  // pageable-host -> device copy of a stack buffer: cudaMemcpyAsync stages it before returning
-  MFB_CUDA(cudaMemcpyAsync(workspace, pm, sizeof(tc::PrepMeta) * n_layers, cudaMemcpyHostToDevice, st));
-  tc::nsf_tc_prepare_kernel<<<n_layers, 256, 0, st>>>(params, layer_stride_floats, d, hidden_layers, bins,
-                                                      reinterpret_cast<const tc::PrepMeta*>(workspace),
-                                                      reinterpret_cast<unsigned char*>(images),
-                                                      tc::image_bytes(d, hidden_layers));
-  return launch_status();
+  return 0;
 }
 
 int mfb_nsf_tc_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int hidden_layers, int bins,

@@ -94,6 +94,7 @@ class NSFGenerator(GenerativeModel):
         self.register_buffer("m_hid", torch.stack(m_hid).float(), persistent=False)
         self.register_buffer("m_out", torch.stack(m_out).float(), persistent=False)
         self._orders = [layer_order(D, t) for t in range(T)]
+        self._pack_key, self._pack_cache = None, None
         if device is not None:
             self.to(device)
 
@@ -171,8 +172,27 @@ class NSFGenerator(GenerativeModel):
     def sample_base(self, n: int) -> torch.Tensor:
         return torch.randn((int(n), self.features), dtype=torch.float32, device=self.w_in.device)
 
+    def _packed_cached(self):
+        """(packed parameters, tensor-core operand images) for the current weights, rebuilt only when a
+        parameter tensor was modified (in-place version counters) or moved -- sampling / evaluation
+        loops with fixed weights skip a dozen small kernels per call."""
+        params = (self.w_in, self.b_in, self.w_hid, self.b_hid, self.w_out, self.b_out)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (ops.NSF_USE_TENSOR_CORES,)
+        if self._pack_key != key:
+            with torch.no_grad():
+                packed = self.packed_parameters()
+                images = None
+                if ops.nsf_tc_supported(self.features, self.hidden_units, self.hidden_layers, self.bins):
+                    images = ops.nsf_tc_images(packed, self._orders, self.hidden_units, self.hidden_layers, self.bins)
+            self._pack_key, self._pack_cache = key, (packed, images)
+        return self._pack_cache
+
     def _run(self, z: torch.Tensor, want_logq: bool, want_steps: bool = False):
         need_grad = torch.is_grad_enabled() and (z.requires_grad or self.w_in.requires_grad)
+        if not need_grad and z.is_cuda:
+            packed, images = self._packed_cached()
+            return ops.nsf_forward(z, packed, None, self._orders, self.hidden_units, self.hidden_layers, self.bins,
+                                   want_logq, want_steps, images=images)
         packed_om = self.packed_parameters_om() if need_grad else None
         return ops.nsf_forward(z, self.packed_parameters(), packed_om, self._orders, self.hidden_units,
                                self.hidden_layers, self.bins, want_logq, want_steps)

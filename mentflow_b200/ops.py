@@ -245,11 +245,9 @@ def nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins):
     images = torch.empty((t_layers, nbytes), dtype=torch.uint8, device=packed.device)
     order_arr = (ctypes.c_int32 * (t_layers * d))(*[int(o) for order in orders for o in order])
     with torch.cuda.device(packed.device):
-        wbytes = int(lib.mfb_nsf_tc_prepare_workspace_bytes(t_layers))
-        work = torch.empty(wbytes, dtype=torch.uint8, device=packed.device)
         _lib.check(lib.mfb_nsf_tc_prepare(_ptr(packed), packed.stride(0), t_layers, d, hidden_units, hidden_layers,
-                                          bins, ctypes.cast(order_arr, ctypes.c_void_p), _ptr(images), _ptr(work),
-                                          wbytes, _stream()), "nsf_tc_prepare")
+                                          bins, ctypes.cast(order_arr, ctypes.c_void_p), _ptr(images), None, 0,
+                                          _stream()), "nsf_tc_prepare")
     return images
 
 
@@ -278,11 +276,13 @@ def nsf_layer_forward(v, params, order, hidden_units, hidden_layers, bins, logq_
     return y, logq_out
 
 
-def _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq):
-    """All layers in sampling order; returns ([z, y_1, ..., x], log q)."""
+def _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq, images=None):
+    """All layers in sampling order; returns ([z, y_1, ..., x], log q).  ``images``: operand images
+    of the tensor-core kernel when the caller has them cached for these weights."""
     d = z.shape[1]
-    images = None
-    if nsf_tc_supported(d, hidden_units, hidden_layers, bins):
+    if not nsf_tc_supported(d, hidden_units, hidden_layers, bins):
+        images = None
+    elif images is None:
         images = nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins)
     steps, logq = [z], None
     for t, order in enumerate(orders):
@@ -323,10 +323,10 @@ class NSFForward(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, packed, packed_om, meta):
-        orders, hidden_units, hidden_layers, bins, want_logq = meta
+        orders, hidden_units, hidden_layers, bins, want_logq, images = meta
         z = _check_f32("z", z)
         packed = _check_f32("packed", packed)
-        steps, logq = _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq)
+        steps, logq = _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq, images)
         ctx.meta = meta
         ctx.save_for_backward(packed, packed_om, *steps[:-1])
         if logq is None:
@@ -335,7 +335,7 @@ class NSFForward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gx, glogq):
-        orders, hidden_units, hidden_layers, bins, want_logq = ctx.meta
+        orders, hidden_units, hidden_layers, bins, want_logq, _ = ctx.meta
         packed, packed_om, *inputs = ctx.saved_tensors
         n, d = inputs[0].shape
         gx = _check_f32("gx", gx) if gx is not None else torch.zeros_like(inputs[0])
@@ -374,14 +374,16 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
     return gz, gpacked
 
 
-def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
+def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False,
+                images=None):
     """Returns (x, logq or None, steps or None)."""
-    if want_steps:
-        z = _check_f32("z", z)
+    if want_steps or not (torch.is_grad_enabled() and (z.requires_grad or packed.requires_grad)):
+        # nothing to differentiate: skip the autograd.Function bookkeeping
+        z = _check_f32("z", z.detach())
         steps, logq = _nsf_run_layers(z, _check_f32("packed", packed.detach()), orders, hidden_units, hidden_layers,
-                                      bins, want_logq)
-        return steps[-1], logq, steps
-    meta = (tuple(tuple(o) for o in orders), hidden_units, hidden_layers, bins, bool(want_logq))
+                                      bins, want_logq, images)
+        return steps[-1], logq, (steps if want_steps else None)
+    meta = (tuple(tuple(o) for o in orders), hidden_units, hidden_layers, bins, bool(want_logq), images)
     x, logq = NSFForward.apply(z, packed, packed_om, meta)
     return x, (logq if want_logq else None), None
 

@@ -59,3 +59,48 @@ def test_mentflow_loss_matches_reference(golden):
     assert abs(float(L) - float(g["loss_L"])) <= TOL * abs(float(g["loss_L"]))
     assert abs(float(H) - float(g["loss_H"])) <= TOL * abs(float(g["loss_H"]))
     assert torch.allclose(torch.stack(D).cpu(), t32(g["loss_D"]), rtol=TOL, atol=1e-8)
+
+
+def test_graphed_loss_matches_eager_and_tracks_weight_updates():
+    """CUDA-graph replay of the forward pass (mentflow_b200.graphs.GraphedLoss) gives the eager
+    result bit for bit, accepts pinned host noise, and re-captures after the weights change."""
+    import torch
+    import mentflow_b200 as mf
+    from mentflow_b200 import workloads
+    from mentflow_b200.graphs import GraphedLoss
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    wl = workloads.isotropic_1d(ndim=6, num=12, bins=64, xmax=3.5, seed=0)
+    gen = mf.generate.NSFGenerator(6).to(dev)
+    tfs = [mf.simulate.LinearTransform(m.to(dev)) for m in wl["matrices"]]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(dev)
+    diags = [[diag] for _ in tfs]
+    truth = workloads.gaussian_mixture(20_000, ndim=6, seed=1, device=dev)
+    diag.kde = False
+    meas = mf.simulate.forward(truth, tfs, diags)
+    diag.kde = True
+    width = float(wl["edges"][1] - wl["edges"][0])
+    meas = [[m[0] / m[0].sum() / width] for m in meas]
+    prior = mf.prior.Gaussian(ndim=6, scale=3.0)
+    model = mf.MENTFlow(transforms=tfs, diagnostics=diags, measurements=meas, generator=gen, prior=prior,
+                        entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                        discrepancy_function=mf.loss.kl_divergence, penalty_parameter=10.0)
+    n = 20_000
+    g = GraphedLoss(model, n)
+    z = torch.randn(n, 6)
+    zp = z.pin_memory()
+
+    def eager(zz):
+        with torch.no_grad():
+            x, lq = gen.forward_and_log_prob(zz.to(dev))
+            return model.loss_from_particles(x, lq)
+
+    L, H, D = g(zp)
+    Le, He, De = eager(z)
+    assert torch.equal(L, Le) and torch.equal(H, He) and torch.equal(torch.stack(D), torch.stack(De))
+    with torch.no_grad():
+        gen.w_out.mul_(1.5)        # "optimiser step": the next call must see the new weights
+    L2 = g(zp)[0].clone()
+    assert torch.equal(L2, eager(z)[0]) and not torch.equal(L2, Le)
+    L3 = g(None)[0]                # noise drawn on the device
+    assert torch.isfinite(L3)
