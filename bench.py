@@ -225,6 +225,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings: not on stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=device)
     model, wl = build_model(args, device)
     reducer = mfd.shard_model(model, equal_shards=True) if world > 1 else None
@@ -274,8 +275,9 @@ def main():
 
     # One step = one replay of the captured CUDA graph of the public forward pass
     # (mentflow_b200.graphs.GraphedLoss: generator.forward_and_log_prob + MENTFlow.loss_from_particles);
-    # multi-rank runs launch eagerly (the collective stays outside any capture).
-    use_graph = (world == 1) and not args.no_graph
+    # at N > 1 the NCCL all-reduce of the unnormalised profile sums is one node of the graph.  The timed
+    # loop does not synchronise between steps, so the host runs ahead of the device in either mode.
+    use_graph = not args.no_graph
     graphed = None
     if use_graph:
         from mentflow_b200.graphs import GraphedLoss
@@ -312,16 +314,17 @@ def main():
         graphed.z.copy_(z_dev)             # the graph's own input buffer: z is resident, nothing is copied
         z_res = graphed.z
     barrier()
+    marks = []
     for _ in range(args.steps):
-        flush.zero_()                      # evict L2 between timed iterations
+        flush.zero_()                      # evict L2 between timed iterations (outside the [e0, e1] bracket)
         e0, e1 = ev(), ev()
         e0.record()
         L = run_step(z_res)
         e1.record()
-        e1.synchronize()
-        total_ms += e0.elapsed_time(e1)
+        marks.append((e0, e1))
         losses.append(L.clone())
     barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in marks)
     # ---- end to end: z from pinned host memory, loss read back ----------------------------
     e2e_s = 0.0
     for it in range(-2, args.steps):       # two untimed passes of this very loop first
@@ -418,7 +421,15 @@ def main():
                                               f"({sum(ts):.1f} s of CPU work); flow = oracle restatement of zuko NSF"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them before the communicator goes away, and leave without
+        # the (blocking) communicator teardown -- every rank is past its last collective here
+        if graphed is not None:
+            graphed.graph = graphed._host_graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
