@@ -62,7 +62,8 @@ static ProjLaunch plan_launch(int64_t n, int d, int k, int b, int bytes_per_bin,
   while (tile > 128 && ceil_div64(n, tile) < 2 * sms) tile >>= 1;
   L.tile = tile;
   int64_t tiles = ceil_div64(n, tile);
-  size_t smem = 2ull * tile * d * 4 + 64 + (size_t)b * L.threads * bytes_per_bin + extra_smem;
+  // bins are stored with a row stride of threads rounded up to 32: bank = thread % 32 for any bin
+  size_t smem = 2ull * tile * d * 4 + 64 + (size_t)b * ((L.threads + 31) & ~31) * bytes_per_bin + extra_smem;
   int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;
@@ -396,7 +397,8 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
   unsigned int* bins = reinterpret_cast<unsigned int*>(tp.bar + 8);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  float* s_edges = reinterpret_cast<float*>(bins + (size_t)B * nthreads);  // [kc][B+1]
+  const int ld = (nthreads + 31) & ~31;   // row stride of the private bins: conflict free for any bin pattern
+  float* s_edges = reinterpret_cast<float*>(bins + (size_t)B * ld);  // [kc][B+1]
   const int kbase = blockIdx.y * kc;
   const int kloc = tid % kc;
   const int slice = tid / kc;
@@ -404,7 +406,7 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
   const int k = kbase + kloc;
   const bool active = k < K;
 
-  for (int i = tid; i < B * nthreads; i += nthreads) bins[i] = 0u;
+  for (int i = tid; i < B * ld; i += nthreads) bins[i] = 0u;
   for (int i = tid; i < kc * (B + 1); i += nthreads) {
     const int kk = kbase + i / (B + 1);
     s_edges[i] = kk < K ? edges[(size_t)kk * (B + 1) + i % (B + 1)] : 0.f;
@@ -448,7 +450,7 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
           b = min(max(b, 0), B - 1);
           while (b > 0 && u < E[b]) --b;
           while (b < B - 1 && u >= E[b + 1]) ++b;
-          mybins[(size_t)b * nthreads] += 1u;
+          mybins[(size_t)b * ld] += 1u;
         }
       }
     }
@@ -459,7 +461,7 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
     const int kk = idx % kc, b = idx / kc;
     if (kbase + kk < K) {
       unsigned long long s = 0ull;
-      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)b * nthreads + sl * kc + kk];
+      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)b * ld + sl * kc + kk];
       if (s) atomicAdd(&counts[(size_t)(kbase + kk) * B + b], s);
     }
   }
