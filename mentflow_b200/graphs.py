@@ -21,7 +21,7 @@ import torch
 
 
 class GraphedLoss:
-    def __init__(self, model, batch_size: int, warmup: int = 2, host_chunks: int = 3) -> None:
+    def __init__(self, model, batch_size: int, warmup: int = 2, host_chunks: int = 2) -> None:
         self.model = model
         self.batch_size = int(batch_size)
         self.warmup = max(1, int(warmup))
@@ -71,9 +71,20 @@ class GraphedLoss:
 
     # ---- pinned host input: chunked copies overlapped with the flow -------------------------------
     def _chunk_bounds(self):
+        """Pieces of growing size (1 : 3 : 4 : 4 ...): only the first copy is exposed, so it is the
+        small one; tile-aligned boundaries keep every slice 16-byte aligned."""
         n, c = self.batch_size, self.host_chunks
-        step = max(128, ((n + c - 1) // c + 127) // 128 * 128)   # tile-aligned pieces keep slices 16-B aligned
-        return [(a, min(a + step, n)) for a in range(0, n, step)]
+        if c == 1 or n < 8 * 128:
+            return [(0, n)]
+        weights = ([1, 3] + [4] * (c - 2))[:c]
+        total = sum(weights)
+        bounds, a = [], 0
+        for i, w in enumerate(weights):
+            b = n if i == len(weights) - 1 else min(n, (a + n * w // total + 127) // 128 * 128)
+            if b > a:
+                bounds.append((a, b))
+            a = b
+        return bounds
 
     def _step_from_host(self, z_host):
         gen = self.model.generator
