@@ -323,24 +323,24 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
   constexpr int G = NB / 4;
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
   const float4* b4 = reinterpret_cast<const float4*>(bias);
-  // ---- widths: e_j and running sums c_j = e_0 + ... + e_j (the same sums give the total, so bin
-  //      origin + bin width + remainder add up consistently)
-  float e[NB], c[NB];
+  // ---- widths: e_j, sums of the groups of four and their prefixes P_g (short dependency chains;
+  //      P_G is the total, so bin origin + bin width + remainder add up consistently)
+  float e[NB], pre[G + 1];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
     const float4 b = b4[j >> 2];
     clip_exp2_pair(a[j] + b.x, a[j + 1] + b.y, cW, e[j], e[j + 1]);
     clip_exp2_pair(a[j + 2] + b.z, a[j + 3] + b.w, cW, e[j + 2], e[j + 3]);
   }
-  c[0] = e[0];
+  pre[0] = 0.f;
 #pragma unroll
-  for (int j = 1; j < NB; ++j) c[j] = c[j - 1] + e[j];
-  const float sum = c[NB - 1];
+  for (int g = 0; g < G; ++g) pre[g + 1] = pre[g] + ((e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]));
+  const float sum = pre[G];
   const float target = (v + kBound) * (0.5f / kBound) * sum;
   // level 1: pg[g] <=> the bin of v lies beyond group g (monotone in g)
   bool pg[G - 1];
 #pragma unroll
-  for (int g = 0; g < G - 1; ++g) pg[g] = c[4 * g + 3] < target;
+  for (int g = 0; g < G - 1; ++g) pg[g] = pre[g + 1] < target;
   float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
 #pragma unroll
   for (int g = 1; g < G; ++g) {
@@ -348,9 +348,9 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
     q1 = pg[g - 1] ? e[4 * g + 1] : q1;
     q2 = pg[g - 1] ? e[4 * g + 2] : q2;
     q3 = pg[g - 1] ? e[4 * g + 3] : q3;
-    xg = pg[g - 1] ? c[4 * g - 1] : xg;
+    xg = pg[g - 1] ? pre[g] : xg;
   }
-  // level 2: the same partial sums as c[] (same operands, same order), then the bin of the group
+  // level 2: running sums inside the group, then the bin of the group
   const float c0 = xg + q0, c1 = c0 + q1, c2 = c1 + q2;
   const bool r0 = c0 < target, r1 = c1 < target, r2 = c2 < target;
   const float x0c = r2 ? c2 : (r1 ? c1 : (r0 ? c0 : xg));
