@@ -55,22 +55,36 @@ struct PrepArgs {             // by-value kernel argument (no host->device copy,
 };
 
 // ---- image layout (bytes) -------------------------------------------------------------------
-//  [B1 8K] [hid l: hi 8K | lo 8K] x (L-1) [out hi: S x 8K] [out lo: S x 8K] [f32 block]
-//  f32 block: bhid [(L-1)][64] | bout [S][64] (x log2 e) | const tables [6][kCT]
-__host__ __device__ inline int off_hid(int l) { return kTileBytes + l * 2 * kTileBytes; }
-__host__ __device__ inline int off_out_hi(int L, int s) { return kTileBytes + (L - 1) * 2 * kTileBytes + s * kTileBytes; }
-__host__ __device__ inline int off_out_lo(int L, int S, int s) { return off_out_hi(L, S) + s * kTileBytes; }
-__host__ __device__ inline int off_f32(int L, int S) { return off_out_hi(L, S) + S * kTileBytes; }
-__host__ __device__ inline int f32_floats(int L, int S) { return (L - 1) * kH + S * kH + kConstFloats; }
-__host__ __device__ inline int image_bytes(int D, int L) {
-  const int S = D - 1;
-  const int raw = off_f32(L, S) + 4 * f32_floats(L, S);
-  return (raw + 1023) & ~1023;
+// "k tile" = one MMA K step of an operand: rows x 32 B, SWIZZLE_32B (umma::sw32_offset), 2 KB for 64 rows.
+//   [ones: 128-row k tile, row = (1, 1, 0...)]                                   A operand of the bias MMAs
+//   [B1: k tile (W1hi | W1hi | b1hi | b1lo), k tile (W1lo)]                      first layer, bias folded in
+//   [hid l: hi 8K | lo 8K] x (L-1)                                               64 x 64, SWIZZLE_128B
+//   [bias k tiles: (L-1) hidden, S slots: row n = (b_hi, b_lo, 0...)]            B operand of the bias MMAs
+//   [slot s: (hi, lo) k tiles of its slot_nk(D, s) non-zero K steps]             output layer, x log2 e
+//   [const tables [6][kCT] fp32]
+// Hidden units of class c = 1 + h % (D-1) may feed outputs of order >= c; sorted by class, the first
+// cnt_le(o) units are the ones an output of order o reads.
+constexpr int kKTile = 2048;
+__host__ __device__ constexpr int cnt_le(int D, int o) {   // hidden units with class <= o
+  return o >= D - 1 ? kH : o * (kH / (D - 1)) + (o < kH % (D - 1) ? o : kH % (D - 1));
 }
+__host__ __device__ constexpr int slot_nk(int D, int s) { return (cnt_le(D, s + 1) + 15) / 16; }   // slot s has order s+1
+__host__ __device__ constexpr int slot_koff(int D, int s) {
+  int k = 0;
+  for (int i = 0; i < s; ++i) k += slot_nk(D, i);
+  return k;
+}
+__host__ __device__ constexpr int off_ones() { return 0; }
+__host__ __device__ constexpr int off_b1() { return 2 * kKTile; }
+__host__ __device__ constexpr int off_hid(int l) { return 4 * kKTile + l * 2 * kTileBytes; }
+__host__ __device__ constexpr int off_bias(int L, int i) { return off_hid(L - 1) + i * kKTile; }   // i < L-1: hidden, then slots
+__host__ __device__ constexpr int off_slot(int D, int L, int s, int ks, int half) {
+  return off_bias(L, (L - 1) + (D - 1)) + ((slot_koff(D, s) + ks) * 2 + half) * kKTile;
+}
+__host__ __device__ constexpr int off_f32(int D, int L) { return off_slot(D, L, D - 1, 0, 0); }
+__host__ __device__ constexpr int image_bytes(int D, int L) { return (off_f32(D, L) + 4 * kConstFloats + 1023) & ~1023; }
 
-// =============================================================================================
-// image builder
-// =============================================================================================
+// eight fp32 values -> (hi, lo) fp16 chunks of a 64-wide SWIZZLE_128B tile
 __device__ __forceinline__ void store_split8(unsigned char* hi_tile, unsigned char* lo_tile, int row, int chunk,
                                              const float (&x)[8]) {
   __align__(16) __half hi[8], lo[8];
@@ -78,7 +92,11 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_tile, unsigned ch
   for (int e = 0; e < 8; ++e) umma::split_f16(x[e], hi[e], lo[e]);
   const uint32_t off = umma::sw128_offset(row, chunk);
   *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(hi);
-  if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(lo);
+}
+__device__ __forceinline__ void store_ktile_row(unsigned char* tile, int row, const __half (&v)[16]) {
+  *reinterpret_cast<uint4*>(tile + umma::sw32_offset(row, 0)) = reinterpret_cast<const uint4*>(v)[0];
+  *reinterpret_cast<uint4*>(tile + umma::sw32_offset(row, 1)) = reinterpret_cast<const uint4*>(v)[1];
 }
 
 // one block per layer; params = packed fp32 block of nsf_common.cuh (pre-masked, [in][out])
@@ -97,20 +115,33 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
   const float* hid = b1 + kH;
   const float* Wout = hid + (size_t)(L - 1) * (kH * kH + kH);
   const float* bout = Wout + (size_t)D * kH * kPP;
-  float* f32 = reinterpret_cast<float*>(img + off_f32(L, S));
+  float* f32 = reinterpret_cast<float*>(img + off_f32(D, L));
+  const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.0f);
 
   // zero everything first (padding rows / columns must be exact zeros)
   for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
-  const int ntask = kH + (L - 1) * kH * 8 + S * kH * 8;
+  // tasks: 128 ones rows | 64 first-layer rows | (L-1) x 64 x 8 hidden chunks | (L-1+S) x 64 bias rows |
+  //        sum_s nk(s) x 64 slot rows
+  const int n_ones = 128, n_b1 = kH, n_hid = (L - 1) * kH * 8, n_bias = (L - 1 + S) * kH;
+  const int n_slot = slot_koff(D, S) * kH;
+  const int ntask = n_ones + n_b1 + n_hid + n_bias + n_slot;
   for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-    if (task < kH) {
-      // B1 row n: K step 0 = [W1hi (D) | W1hi (D) | b1hi | b1lo | 0], K step 1 = [W1lo (D) | 0]
-      const int n = task, o = perm[n];
+    int t2 = task;
+    if (t2 < n_ones) {
+      __align__(16) __half v[16];
+      for (int e = 0; e < 16; ++e) v[e] = e < 2 ? one : zero;
+      store_ktile_row(img + off_ones(), t2, v);
+      continue;
+    }
+    t2 -= n_ones;
+    if (t2 < n_b1) {
+      // first layer, row n: K step 0 = [W1hi (D) | W1hi (D) | b1hi | b1lo | 0], K step 1 = [W1lo (D) | 0]
+      const int n = t2, o = perm[n];
       __align__(16) __half k0[16], k1[16];
-      for (int e = 0; e < 16; ++e) k0[e] = k1[e] = __float2half_rn(0.f);
+      for (int e = 0; e < 16; ++e) k0[e] = k1[e] = zero;
       for (int i = 0; i < D; ++i) {
         __half hi, lo;
         umma::split_f16(W1t[i * kH + o], hi, lo);
@@ -118,43 +149,55 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
         k0[D + i] = hi;
         k1[i] = lo;
       }
-      __half bh, bl;
-      umma::split_f16(b1[o], bh, bl);
-      k0[2 * D] = bh;
-      k0[2 * D + 1] = bl;
-      for (int c = 0; c < 2; ++c) {
-        *reinterpret_cast<uint4*>(img + umma::sw128_offset(n, c)) = reinterpret_cast<const uint4*>(k0)[c];
-        *reinterpret_cast<uint4*>(img + umma::sw128_offset(n, 2 + c)) = reinterpret_cast<const uint4*>(k1)[c];
-      }
-    } else if (task < kH + (L - 1) * kH * 8) {
-      const int t2 = task - kH;
+      umma::split_f16(b1[o], k0[2 * D], k0[2 * D + 1]);
+      store_ktile_row(img + off_b1(), n, k0);
+      store_ktile_row(img + off_b1() + kKTile, n, k1);
+      continue;
+    }
+    t2 -= n_b1;
+    if (t2 < n_hid) {
       const int l = t2 / (kH * 8), n = (t2 / 8) % kH, c = t2 % 8;
       const float* wt = hid + (size_t)l * (kH * kH + kH);
       float x[8];
       for (int e = 0; e < 8; ++e) x[e] = wt[perm[c * 8 + e] * kH + perm[n]];
       store_split8(img + off_hid(l), img + off_hid(l) + kTileBytes, n, c, x);
-    } else {
-      const int t2 = task - kH - (L - 1) * kH * 8;
-      const int s = t2 / (kH * 8), q = (t2 / 8) % kH, c = t2 % 8;
-      const int f = pm.slot_feature[s];
-      const float* wf = Wout + (size_t)f * kH * kPP;
-      float x[8];
-      for (int e = 0; e < 8; ++e) x[e] = (q < 3 * nb - 1) ? wf[perm[c * 8 + e] * kPP + q] * kLog2e : 0.f;
-      store_split8(img + off_out_hi(L, s), img + off_out_lo(L, S, s), q, c, x);
+      continue;
     }
-  }
-  // fp32 block
-  for (int i = threadIdx.x; i < (L - 1) * kH; i += blockDim.x) {
-    const int l = i / kH, n = i % kH;
-    f32[i] = hid[(size_t)l * (kH * kH + kH) + kH * kH + perm[n]];
-  }
-  for (int i = threadIdx.x; i < S * kH; i += blockDim.x) {
-    const int s = i / kH, q = i % kH;
-    f32[(L - 1) * kH + i] = (q < 3 * nb - 1) ? bout[pm.slot_feature[s] * kPP + q] * kLog2e : 0.f;
+    t2 -= n_hid;
+    if (t2 < n_bias) {
+      const int i = t2 / kH, n = t2 % kH;
+      float bv;
+      if (i < L - 1) {
+        bv = hid[(size_t)i * (kH * kH + kH) + kH * kH + perm[n]];
+      } else {
+        bv = (n < 3 * nb - 1) ? bout[pm.slot_feature[i - (L - 1)] * kPP + n] * kLog2e : 0.f;
+      }
+      __align__(16) __half v[16];
+      for (int e = 0; e < 16; ++e) v[e] = zero;
+      umma::split_f16(bv, v[0], v[1]);
+      store_ktile_row(img + off_bias(L, i), n, v);
+      continue;
+    }
+    t2 -= n_bias;
+    {
+      // slot rows: find (slot, K step) of this row
+      const int kk = t2 / kH, q = t2 % kH;
+      int sl = 0;
+      while (sl + 1 < S && slot_koff(D, sl + 1) <= kk) ++sl;
+      const int ks = kk - slot_koff(D, sl);
+      const float* wf = Wout + (size_t)pm.slot_feature[sl] * kH * kPP;
+      __align__(16) __half hi[16], lo[16];
+      for (int e = 0; e < 16; ++e) {
+        const float w = (q < 3 * nb - 1) ? wf[perm[16 * ks + e] * kPP + q] * kLog2e : 0.f;
+        umma::split_f16(w, hi[e], lo[e]);
+      }
+      store_ktile_row(img + off_slot(D, L, sl, ks, 0), q, hi);
+      store_ktile_row(img + off_slot(D, L, sl, ks, 1), q, lo);
+    }
   }
   // constant feature: knots of its bias-only spline (same formulas as the epilogue)
   if (threadIdx.x == 0) {
-    float* ct = f32 + (L - 1) * kH + S * kH;
+    float* ct = f32;
     const float* bf = bout + pm.const_feature * kPP;
     float ew[32], eh[32];
     float sw = 0.f, sh = 0.f;
@@ -310,27 +353,24 @@ __device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, floa
 }
 
 // Rational-quadratic spline of one feature from the raw conditioner outputs a[0..3NB-2] (already
-// multiplied by log2 e through the weights; bias, equally scaled, in shared memory).  Works in
+// multiplied by log2 e through the weights, bias included by the bias MMA).  Works in
 // un-normalised softmax units: the bin is searched on the running sum of e_j against
 // (v + B) / 2B * sum, and bin width / height come from e_k directly (no differencing of knots).
 // The search is two-level -- which group of four bins, then which bin of the group -- with
 // predicated selects, so that nothing is indexed dynamically and everything stays in registers.
 // Multiplies jac by dy/dv (1 outside [-B, B]) and returns y.
 template <int NB>
-__device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const float* __restrict__ bias, float v,
-                                                float& jac) {
+__device__ __forceinline__ float rq_spline_regs(const float (&a)[64], float v, float& jac) {
   static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
   constexpr int G = NB / 4;
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
   // ---- widths: e_j, sums of the groups of four and their prefixes P_g (short dependency chains;
   //      P_G is the total, so bin origin + bin width + remainder add up consistently)
   float e[NB], pre[G + 1];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
-    const float4 b = b4[j >> 2];
-    clip_exp2_pair(a[j] + b.x, a[j + 1] + b.y, cW, e[j], e[j + 1]);
-    clip_exp2_pair(a[j + 2] + b.z, a[j + 3] + b.w, cW, e[j + 2], e[j + 3]);
+    clip_exp2_pair(a[j], a[j + 1], cW, e[j], e[j + 1]);
+    clip_exp2_pair(a[j + 2], a[j + 3], cW, e[j + 2], e[j + 3]);
   }
   pre[0] = 0.f;
 #pragma unroll
@@ -359,10 +399,9 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
   float run = 0.f, yg = 0.f, h0s = 0.f, h1s = 0.f, h2s = 0.f, h3s = 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const float4 b = b4[(NB + 4 * g) >> 2];
     float h0, h1, h2, h3;
-    clip_exp2_pair(a[NB + 4 * g] + b.x, a[NB + 4 * g + 1] + b.y, cW, h0, h1);
-    clip_exp2_pair(a[NB + 4 * g + 2] + b.z, a[NB + 4 * g + 3] + b.w, cW, h2, h3);
+    clip_exp2_pair(a[NB + 4 * g], a[NB + 4 * g + 1], cW, h0, h1);
+    clip_exp2_pair(a[NB + 4 * g + 2], a[NB + 4 * g + 3], cW, h2, h3);
     const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
     h0s = take ? h0 : h0s;
     h1s = take ? h1 : h1s;
@@ -380,9 +419,8 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], const floa
   float um = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, prev = 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const float4 b = b4[(2 * NB + 4 * g) >> 2];
-    const float t0 = a[2 * NB + 4 * g] + b.x, t1 = a[2 * NB + 4 * g + 1] + b.y, t2 = a[2 * NB + 4 * g + 2] + b.z;
-    const float t3 = (4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] + b.w : 0.f;
+    const float t0 = a[2 * NB + 4 * g], t1 = a[2 * NB + 4 * g + 1], t2 = a[2 * NB + 4 * g + 2];
+    const float t3 = (4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f;
     const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
     um = take ? prev : um;
     u0 = take ? t0 : u0;
@@ -454,26 +492,13 @@ __device__ __forceinline__ void split_relu_pair(float x0, float x1, uint32_t& hi
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
 
-// relu(acc + bias) -> (hi, lo) fp16 rows of the A operand tile (row = particle)
-template <bool kBias>
-__device__ __forceinline__ void store_hidden(const float (&acc)[64], const float* __restrict__ bias,
-                                             unsigned char* a_hi, unsigned char* a_lo, int row) {
+// relu(acc) -> (hi, lo) fp16 rows of the A operand tile (row = particle); the bias is already in acc
+__device__ __forceinline__ void store_hidden(const float (&acc)[64], unsigned char* a_hi, unsigned char* a_lo, int row) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float x[8];
-    if (kBias) {
-      const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * c];
-      const float4 b1 = reinterpret_cast<const float4*>(bias)[2 * c + 1];
-      x[0] = acc[8 * c + 0] + b0.x; x[1] = acc[8 * c + 1] + b0.y; x[2] = acc[8 * c + 2] + b0.z;
-      x[3] = acc[8 * c + 3] + b0.w; x[4] = acc[8 * c + 4] + b1.x; x[5] = acc[8 * c + 5] + b1.y;
-      x[6] = acc[8 * c + 6] + b1.z; x[7] = acc[8 * c + 7] + b1.w;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = acc[8 * c + e];
-    }
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split_relu_pair(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+    for (int e = 0; e < 4; ++e) split_relu_pair(acc[8 * c + 2 * e], acc[8 * c + 2 * e + 1], hi[e], lo[e]);
     const uint32_t off = umma::sw128_offset(row, c);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -508,8 +533,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
                     const float* __restrict__ logq_in, int first_layer, float* __restrict__ y,
                     float* __restrict__ logq_out) {
   constexpr int S = D - 1;
-  constexpr int kImg = ((kTileBytes + (L - 1) * 2 * kTileBytes + 2 * S * kTileBytes +
-                         4 * ((L - 1) * kH + S * kH + kConstFloats)) + 1023) & ~1023;
+  constexpr int kImg = image_bytes(D, L);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   unsigned char* img = smem;
@@ -541,7 +565,6 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   mbar_wait_bounded(&bars[0], 0);
 
-  constexpr int kOutOff = kTileBytes + (L - 1) * 2 * kTileBytes;   // first output-layer tile in the image
   // TMEM buffers of a warpgroup: slot s lands in buffer s & 1; the hidden chain of the NEXT tile
   // runs in the buffer that frees first (the one of slot S-2) while the last splines are computed.
   constexpr int kHB = (S >= 2) ? ((S - 2) & 1) : 1;
@@ -568,26 +591,41 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       unsigned char* wa_hi = a_all + w * kABytes;
       const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(wa_hi));
       const uint64_t dA_lo = umma::make_desc_sw128(smem_u32(wa_hi + kABytes / 2));
-      const uint64_t dB1 = umma::make_desc_sw128(smem_u32(img));
+      const uint64_t dOnes = umma::make_desc_sw32(smem_u32(img + off_ones()));
+      const uint64_t dB1 = umma::make_desc_sw32(smem_u32(img + off_b1()));
       const uint32_t col0 = tmem_base + (uint32_t)(w * 128);
+      // output-layer tile of slot `slot`: bias (ones x bias tile), then the cross terms of all its
+      // non-zero K steps, then the hi*hi terms (see mma_cross)
       auto issue_slot = [&](int slot) {
         const int bsel = slot & 1;
-        const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kOutOff + slot * kTileBytes));
-        const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kOutOff + (S + slot) * kTileBytes));
         if (elect_one()) {
-          mma_slot(col0 + bsel * 64, dA_hi, dA_lo, dBh, dBl, meta.slot_ksteps[slot], idesc64);
+          const uint32_t dcol = col0 + bsel * 64;
+          int koff = 0;
+          for (int i = 0; i < slot; ++i) koff += meta.slot_ksteps[i];
+          const uint32_t tiles = smem_u32(img + off_slot(D, L, 0, 0, 0)) + (uint32_t)(koff * 2 * kKTile);
+          const int nk = meta.slot_ksteps[slot];
+          umma::mma_f16_ss(dcol, dOnes, umma::make_desc_sw32(smem_u32(img + off_bias(L, (L - 1) + slot))), idesc64, 0);
+          for (int ks = 0; ks < nk; ++ks) {
+            const uint64_t dBh = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile));
+            const uint64_t dBl = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile + kKTile));
+            umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), dBl, idesc64, 1);
+            umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_lo, ks), dBh, idesc64, 1);
+          }
+          for (int ks = 0; ks < nk; ++ks)
+            umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks),
+                             umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile)), idesc64, 1);
           umma::commit(wbar + bsel);
         }
         __syncwarp();
       };
       auto chain = [&]() {
-        // first masked layer (K = 16, bias folded in)
+        // first masked layer (K = 16, bias folded into the weights' spare K columns)
         mbar_wait_polite(req_chain, rp);
         rp ^= 1;
         umma::fence_after_sync();
         if (elect_one()) {
           umma::mma_f16_ss(col0 + kHB * 64, dA_hi, dB1, idesc64, 0);
-          umma::mma_f16_ss(col0 + kHB * 64, dA_hi, umma::desc_advance_k(dB1, 1), idesc64, 1);
+          umma::mma_f16_ss(col0 + kHB * 64, dA_hi, dB1 + (uint64_t)(kKTile >> 4), idesc64, 1);
           umma::commit(wbar + kHB);
         }
         __syncwarp();
@@ -597,9 +635,11 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
           mbar_wait_polite(req_chain, rp);
           rp ^= 1;
           umma::fence_after_sync();
-          const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes));
-          const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + kTileBytes + l * 2 * kTileBytes + kTileBytes));
+          const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + off_hid(0) + l * 2 * kTileBytes));
+          const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + off_hid(0) + l * 2 * kTileBytes + kTileBytes));
           if (elect_one()) {
+          umma::mma_f16_ss(col0 + kHB * 64, dOnes, umma::make_desc_sw32(smem_u32(img + off_bias(L, 0) + l * kKTile)),
+                           idesc64, 0);
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -609,7 +649,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
               const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
               const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
               if (pass == 0)
-                mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, ks > 0);
+                mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, 1);
               else
                 mma_main(col0 + kHB * 64 + n0, dA_hi, dBh + boff, ks, idesc);
             }
@@ -657,10 +697,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   uint32_t ph0 = 0, ph1 = 0;
   const uint32_t lane_sel = (uint32_t)((t >> 5) * 32) << 16;
   const uint32_t col0 = tmem_base + (uint32_t)(wg * 128);
-  const float* f32 = reinterpret_cast<const float*>(img + kOutOff + 2 * S * kTileBytes);
-  const float* bhid = f32;
-  const float* bout = f32 + (L - 1) * kH;
-  const float* ctab = bout + S * kH;
+  const float* ctab = reinterpret_cast<const float*>(img + off_f32(D, L));
 
 #ifdef MFB_TC_TRACE
   int trace_pos = 0;
@@ -698,10 +735,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     wait_buf(kHB);
     float acc[64];
     tmem_ld64(col0 + (uint32_t)(kHB * 64) + lane_sel, acc);
-    if (l == 0)
-      store_hidden<false>(acc, nullptr, a_hi, a_lo, t);
-    else
-      store_hidden<true>(acc, bhid + (l - 1) * kH, a_hi, a_lo, t);
+    store_hidden(acc, a_hi, a_lo, t);   // biases are already in the accumulator (bias MMA)
     fence_proxy_async();
     umma::fence_before_sync();
     request_arrive(req_chain);
@@ -769,7 +803,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         float vf = vin[0];
 #pragma unroll
         for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
-        const float yf = rq_spline_regs<NB>(acc, bout + s * kH, vf, jac);
+        const float yf = rq_spline_regs<NB>(acc, vf, jac);
 #pragma unroll
         for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
         TRACE(20 + s);
@@ -834,9 +868,8 @@ static void make_meta(int d, const int32_t* order, Meta* m, PrepMeta* pm) {
   PrepMeta pp = {};
   for (int o = 1; o < d; ++o) {
     const int f = feat_of_order[o];
-    const int cnt = cnt_le[o < d - 1 ? o : d - 1];
     mm.slot_feature[slots] = f;
-    mm.slot_ksteps[slots] = (cnt + 15) / 16;
+    mm.slot_ksteps[slots] = slot_nk(d, slots);
     pp.slot_feature[slots] = f;
     ++slots;
   }

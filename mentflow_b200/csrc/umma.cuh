@@ -28,6 +28,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 // advance along K by one UMMA_K (=16 fp16 = 32 bytes) inside the 128-byte swizzle span
 __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, int kstep) { return desc + (uint64_t)(kstep * 2); }
 
+// K-major tile with 32-byte rows (16 fp16 = ONE MMA K step), SWIZZLE_32B: rows stored back to back,
+// swizzle atoms of 8 rows x 32 B = 256 bytes; the swizzle XORs address bit 4 with bit 7, i.e. the
+// 16-byte chunk c in {0,1} of row r lands at chunk c ^ ((r >> 2) & 1).
+__device__ __forceinline__ uint32_t sw32_offset(int r, int c) {
+  return (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4));
+}
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(256 >> 4) << 32;   // stride byte offset: 8 rows * 32 B between swizzle atoms
+  d |= (uint64_t)1 << 46;            // descriptor version for sm_100
+  d |= (uint64_t)6 << 61;            // SWIZZLE_32B
+  return d;
+}
+
 // InstrDescriptor for kind::f16: fp16 A/B (K-major), fp32 accumulate, shape M x N x 16
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

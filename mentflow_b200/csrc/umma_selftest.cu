@@ -83,7 +83,85 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, i
   if (tid < 32) umma::tmem_dealloc(tbase, 256);
 }
 
+// Second self-test: one K step (K = 16) with 32-byte-row SWIZZLE_32B operand tiles (the packed
+// weight / bias tiles of the flow kernel) against a SWIZZLE_128B A operand, as issued there:
+//   mode 0: A sw32 x B sw32      mode 1: A sw128 (K step `kstep` of a 64-wide tile) x B sw32
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_sw32_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int mode, int kstep,
+                          float* __restrict__ D, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a32 = smem;               // 128 x 32 B
+  unsigned char* a128 = smem + 4096;       // 128 x 128 B (1024-aligned)
+  unsigned char* b32 = smem + 4096 + 16384;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) umma::tmem_alloc(&tmem_base, 256);
+  for (int i = tid; i < 16384 / 16; i += 128) reinterpret_cast<uint4*>(a128)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int r = tid; r < 128 + N; r += 128) {
+    const bool isA = r < 128;
+    const int row = isA ? r : r - 128;
+    const float* src = isA ? A + (size_t)row * 16 : B + (size_t)row * 16;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(src[c * 8 + e]);
+      if (isA) {
+        *reinterpret_cast<uint4*>(a32 + umma::sw32_offset(row, c)) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(a128 + umma::sw128_offset(row, 2 * kstep + c)) = *reinterpret_cast<const uint4*>(h);
+      } else {
+        *reinterpret_cast<uint4*>(b32 + umma::sw32_offset(row, c)) = *reinterpret_cast<const uint4*>(h);
+      }
+    }
+  }
+  fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    const uint64_t da = mode == 0 ? umma::make_desc_sw32(smem_u32(a32))
+                                  : umma::desc_advance_k(umma::make_desc_sw128(smem_u32(a128)), kstep);
+    umma::mma_f16_ss(tbase, da, umma::make_desc_sw32(smem_u32(b32)), idesc, 0);
+    umma::commit(&bar);
+  }
+  int spins = 0;
+  while (!mbar_try_wait(&bar, 0)) {
+    if (++spins > kSelfWaitLimit) {
+      if (tid == 0) *err = 1;
+      break;
+    }
+  }
+  umma::fence_after_sync();
+  const int warp = tid >> 5;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    umma::tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t)tid * N + c0 + i] = v[i];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tbase, 256);
+}
+
 }  // namespace mfb
+
+extern "C" int mfb_selftest_umma_sw32(const float* a, const float* b, int n, int mode, int kstep, float* d, int* err,
+                                      void* stream) {
+  MFB_CHECK_ARG(a && b && d && err && (n == 64 || n == 128) && (mode == 0 || mode == 1) && kstep >= 0 && kstep < 4);
+  const size_t smem = 4096 + 16384 + (size_t)n * 32 + 1024;
+  MFB_CUDA(cudaFuncSetAttribute(mfb::umma_selftest_sw32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mfb::umma_selftest_sw32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, n, mode, kstep, d, err);
+  return mfb::launch_status();
+}
 
 extern "C" int mfb_selftest_umma(const float* a, const float* b, int n, float* d, int* err, void* stream) {
   MFB_CHECK_ARG(a && b && d && err && (n == 64 || n == 128 || n == 256));
