@@ -259,10 +259,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 // issuer side: poll without occupying the issue port of the compute warps on the same scheduler
 __device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
-  for (int spins = 0; !mbar_test_wait(bar, parity); ++spins) {
-    __nanosleep(40);
-    if (spins > (1 << 24)) __trap();
-  }
+  while (!mbar_test_wait(bar, parity)) __nanosleep(40);
 }
 
 // Warpgroup -> issuer hand-off: every compute warp arrives (lane 0, after __syncwarp) on a request
@@ -543,7 +540,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   // buffer 0 / 1 has been read
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);
   uint64_t* reqs = bars + 1 + 2 * kWG;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reqs + 3 * kWG);
+  uint64_t* sbars = reqs + 3 * kWG;            // [wg][2]: particle rows of a tile have landed (TMA, count 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbars + 2 * kWG);
+  float* stage_all = reinterpret_cast<float*>(a_all + kWG * kABytes + 256);   // [wg][2][128][D]
 
   const int tid = threadIdx.x;
   // warp-uniform by construction (shuffle from lane 0): lets the MMA descriptors live in uniform registers
@@ -552,6 +551,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   if (tid == 0) {
     for (int i = 0; i < 1 + 2 * kWG; ++i) mbar_init(&bars[i], 1);
     for (int i = 0; i < 3 * kWG; ++i) mbar_init(&reqs[i], 4);
+    for (int i = 0; i < 2 * kWG; ++i) mbar_init(&sbars[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) umma::tmem_alloc(tmem_slot, 512);
@@ -715,7 +715,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     TRACE(2);
   };
   // first masked layer of a tile: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16)
-  auto start_tile = [&](const float (&vv)[D]) {
+  auto start_tile = [&](const float* vv, uint64_t* landed, uint32_t parity) {
+    mbar_wait_bounded(landed, parity);   // the TMA copy of this tile's particle rows has landed
     __align__(16) __half row[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
@@ -742,46 +743,50 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     TRACE(4 + l);
   };
 
+  // Particles are staged through shared memory ([128][D] per tile, two buffers per warpgroup): the
+  // rows of the NEXT tile come in with one TMA bulk copy issued a few splines ahead (no registers
+  // held, no exposed global-load latency), each spline reads its v_f from the thread's row and writes
+  // y_f back in place, and the finished row goes out from there.
+  float* stage0 = stage_all + ((size_t)(wg * 2) * 128 + t) * D;
+  float* stage1 = stage0 + 128 * D;
+  uint64_t* sbar = sbars + 2 * wg;
+  auto prefetch = [&](int64_t tl, int buf) {   // one thread of the warpgroup
+    if (tl >= ntiles) return;
+    int64_t rows = n - tl * 128;
+    if (rows > 128) rows = 128;
+    float* dst = stage_all + (size_t)(wg * 2 + buf) * 128 * D;
+    const float* src = v + tl * 128 * D;
+    const uint32_t bytes = (uint32_t)(rows * D * 4), bulk = bytes & ~15u;
+    for (uint32_t i = bulk / 4; i < bytes / 4; ++i) dst[i] = src[i];   // ragged tail (< 16 B)
+    mbar_expect_tx(&sbar[buf], bulk);
+    if (bulk) tma_load_1d(dst, src, bulk, &sbar[buf]);
+  };
+
   int64_t tile = (int64_t)blockIdx.x * kWG + wg;
-  float vin[D];
-  {
-    const int64_t p = tile * 128 + t;
-#pragma unroll
-    for (int i = 0; i < D; ++i) vin[i] = (tile < ntiles && p < n) ? v[p * D + i] : 0.f;
-  }
   // Software-pipelined over the tiles of this warpgroup: iteration i computes the splines of tile i
   // ("cur") and, interleaved with its last splines, the conditioner chain of tile i+1 ("next"), so
   // every MMA has a spline's worth of CUDA-core work to hide behind.  The first iteration has no
   // current tile (cur = false): it only runs the chain of the first tile, through the same code.
   bool cur = false;
   bool has_next = tile < ntiles;   // uniform over the warpgroup
-  float vnext[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) vnext[i] = vin[i];
+  float* sc = stage0;              // this thread's row of the current tile
+  float* sn = stage1;              // ... of the next tile
+  int nbuf = 1;                    // staging buffer of the next tile
+  uint32_t sph0 = 0, sph1 = 0;     // phases of the two "landed" barriers
+  if (t == 0) prefetch(tile, nbuf);
   tile -= tstride;
   while (cur || has_next) {
     const int64_t p = tile * 128 + t;
     const bool valid = cur && p < n;
-    if (cur) {
-      has_next = tile + tstride < ntiles;
-      const int64_t pn = (tile + tstride) * 128 + t;
-#pragma unroll
-      for (int i = 0; i < D; ++i) vnext[i] = (has_next && pn < n) ? v[pn * D + i] : 0.f;
-    }
+    if (cur) has_next = tile + tstride < ntiles;
     float jac = 1.0f;
-    float yout[D];
+    float ss = 0.f;      // |v|^2 for the base density of the first layer
     float lq_in = 0.f;   // loaded a tile's worth of work before it is needed
     if (cur && valid && logq_out && !first_layer) lq_in = logq_in[p];
     if (cur) {
-      float vf = vin[0];
-#pragma unroll
-      for (int i = 1; i < D; ++i) vf = (meta.const_feature == i) ? vin[i] : vf;
-      const float yf = rq_spline_const<NB>(ctab, vf, jac);
-#pragma unroll
-      for (int i = 0; i < D; ++i) yout[i] = yf;  // every other entry is overwritten below
-    } else {
-#pragma unroll
-      for (int i = 0; i < D; ++i) yout[i] = 0.f;
+      const float vf = sc[meta.const_feature];
+      ss = vf * vf;
+      sc[meta.const_feature] = rq_spline_const<NB>(ctab, vf, jac);
     }
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
@@ -792,20 +797,27 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
         umma::fence_before_sync();
         if (s + 2 < S) request_arrive(req_chain + 1 + b);
+        // slot 0 is complete => every warp is past its last read of the other staging buffer
+        if (s == 0 && t == 0 && has_next) prefetch(tile + tstride, nbuf);
         TRACE(10 + s);
       }
       if (s == kFork) {
         if (cur && S >= 2) wait_buf((S - 1) & 1);   // every output-layer MMA of this tile is done: A is free
-        if (has_next) start_tile(vnext);
+        if (has_next) {
+          if (nbuf == 0) {
+            start_tile(sn, &sbar[0], sph0);
+            sph0 ^= 1;
+          } else {
+            start_tile(sn, &sbar[1], sph1);
+            sph1 ^= 1;
+          }
+        }
       }
       if (cur) {
         const int f = meta.slot_feature[s];
-        float vf = vin[0];
-#pragma unroll
-        for (int i = 1; i < D; ++i) vf = (f == i) ? vin[i] : vf;
-        const float yf = rq_spline_regs<NB>(acc, vf, jac);
-#pragma unroll
-        for (int i = 0; i < D; ++i) yout[i] = (f == i) ? yf : yout[i];
+        const float vf = sc[f];
+        ss = fmaf(vf, vf, ss);
+        sc[f] = rq_spline_regs<NB>(acc, vf, jac);
         TRACE(20 + s);
       }
       if (has_next) {
@@ -816,23 +828,17 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     if (S == 1 && has_next) hidden_step(1);
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) y[p * D + i] = yout[i];
+      for (int i = 0; i < D; ++i) y[p * D + i] = sc[i];
       if (logq_out) {
-        float base;
-        if (first_layer) {
-          float ss = 0.f;
-#pragma unroll
-          for (int i = 0; i < D; ++i) ss = fmaf(vin[i], vin[i], ss);
-          base = -0.5f * ss - (float)D * kHalfLog2Pi;
-        } else {
-          base = lq_in;
-        }
+        const float base = first_layer ? -0.5f * ss - (float)D * kHalfLog2Pi : lq_in;
         logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
       }
     }
     if (has_next) hidden_step(2);
-#pragma unroll
-    for (int i = 0; i < D; ++i) vin[i] = vnext[i];
+    float* tmp = sc;
+    sc = sn;
+    sn = tmp;
+    nbuf ^= 1;
     cur = has_next;
     has_next = false;   // recomputed at the top of the next iteration
     tile += tstride;
@@ -899,7 +905,7 @@ template <int D>
 static int launch_layer(const float* v, int64_t n, const unsigned char* image, const Meta& meta, const float* logq_in,
                         int first, float* y, float* logq_out, cudaStream_t st) {
   constexpr int L = 3, NB = 20;
-  const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 128 + 1024;
+  const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 256 + (size_t)kWG * 2 * 128 * D * 4 + 1024;
   auto kern = nsf_tc_layer_kernel<D, L, NB>;
   MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (n + 127) / 128;
