@@ -349,6 +349,21 @@ __device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, floa
 #endif
 }
 
+// the same for four parameters with ONE reciprocal (the spline phases are bound by the MUFU pipe:
+// 8 issue slots per MUFU instruction, so three extra multiplies per quad are the cheaper side)
+__device__ __forceinline__ void clip_exp2_quad(float t0, float t1, float t2, float t3, float c, float& e0, float& e1,
+                                               float& e2, float& e3) {
+  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
+  const float d2 = fmaf(fabsf(t2), c, 1.0f), d3 = fmaf(fabsf(t3), c, 1.0f);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = fast_rcp(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
+  e0 = fast_exp2(t0 * (r01 * d1));
+  e1 = fast_exp2(t1 * (r01 * d0));
+  e2 = fast_exp2(t2 * (r23 * d3));
+  e3 = fast_exp2(t3 * (r23 * d2));
+}
+
 // Rational-quadratic spline of one feature from the raw conditioner outputs a[0..3NB-2] (already
 // multiplied by log2 e through the weights, bias included by the bias MMA).  Works in
 // un-normalised softmax units: the bin is searched on the running sum of e_j against
@@ -366,8 +381,7 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], float v, f
   float e[NB], pre[G + 1];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
-    clip_exp2_pair(a[j], a[j + 1], cW, e[j], e[j + 1]);
-    clip_exp2_pair(a[j + 2], a[j + 3], cW, e[j + 2], e[j + 3]);
+    clip_exp2_quad(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
   }
   pre[0] = 0.f;
 #pragma unroll
@@ -397,8 +411,7 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], float v, f
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     float h0, h1, h2, h3;
-    clip_exp2_pair(a[NB + 4 * g], a[NB + 4 * g + 1], cW, h0, h1);
-    clip_exp2_pair(a[NB + 4 * g + 2], a[NB + 4 * g + 3], cW, h2, h3);
+    clip_exp2_quad(a[NB + 4 * g], a[NB + 4 * g + 1], a[NB + 4 * g + 2], a[NB + 4 * g + 3], cW, h0, h1, h2, h3);
     const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
     h0s = take ? h0 : h0s;
     h1s = take ? h1 : h1s;
