@@ -142,3 +142,61 @@ class GraphedLoss:
             self.z.copy_(z, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class GraphedTrainStep:
+    """``zero_grad(); loss, H, D = model.loss(n); loss.backward(); optimizer.step()`` -- the body of
+    the reference's training loop (train/train.py:164-169) -- as ONE CUDA-graph replay.
+
+    The optimiser must be capturable (``torch.optim.AdamW(..., capturable=True)``): its step counter
+    and the learning rate then live on the device, so LR schedulers keep working between replays.
+    One difference from the reference loop: a non-finite loss cannot skip the update from inside a
+    graph; ``step.finite`` (a device flag refreshed by every replay) lets the caller notice.
+    """
+
+    def __init__(self, model, optimizer, batch_size: int, warmup: int = 3) -> None:
+        self.model, self.optimizer = model, optimizer
+        self.batch_size = int(batch_size)
+        dev = next(model.generator.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs a CUDA model; mentflow_b200 has no CPU fallback")
+        for group in optimizer.param_groups:
+            if not group.get("capturable", False):
+                raise ValueError("GraphedTrainStep needs an optimizer constructed with capturable=True")
+        self.device = dev
+        self._penalty = None
+        self.graph = None
+        self.out = None
+        self.finite = None
+        self.warmup = max(3, int(warmup))
+
+    def _body(self):
+        L, H, D = self.model.loss(self.batch_size)
+        L.backward()
+        self.optimizer.step()
+        return L.detach(), H.detach() if torch.is_tensor(H) else H, [d.detach() for d in D]
+
+    def _capture(self) -> None:
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self.out = self._body()
+                self.finite = torch.isfinite(self.out[0])
+        self._penalty = float(self.model.penalty_parameter)
+
+    def __call__(self):
+        """One optimisation step; returns (L, H, [D_k]) of the batch it was taken on (static tensors,
+        overwritten by the next call)."""
+        if self.graph is None or self._penalty != float(self.model.penalty_parameter):
+            self._capture()     # the penalty parameter is a host scalar baked into the graph
+        self.graph.replay()
+        return self.out
