@@ -229,24 +229,28 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     const int rows = rows64 > tile ? tile : (int)rows64;
     const float* xs = tp.buf[stage];
     if (active) {
-      // two particles per trip: their taps are independent, only the deposits are ordered
-      for (int p = slice; p < rows; p += 2 * slices) {
-        const int p2 = p + slices;
-        const float ua = project_row<D>(xs + (size_t)p * d, w, d);
-        const float ub = project_row<D>(xs + (size_t)(p2 < rows ? p2 : p) * d, w, d);
-        float aa = fmaf(ua, inv_delta, -c0s), ab = fmaf(ub, inv_delta, -c0s);
-        aa = fminf(fmaxf(aa, lo), hi);
-        ab = (p2 < rows) ? fminf(fmaxf(ab, lo), hi) : lo;   // a missing second particle goes to the guard rows
-        const float fba = rintf(aa), fbb = rintf(ab);
-        float ta[2 * R + 1], tb[2 * R + 1];
-        gauss_taps<R>(aa - fba, alpha, rj, ta);
-        gauss_taps<R>(ab - fbb, alpha, rj, tb);
-        float* ca = mybins + (int)fba * ld;
-        float* cb = mybins + (int)fbb * ld;
+      // kPer particles per trip: their taps are independent (ILP for the MUFU / FMA work), only the
+      // deposits into this thread's private bins are ordered
+      constexpr int kPer = 4;
+      for (int p = slice; p < rows; p += kPer * slices) {
+        float taps[kPer][2 * R + 1];
+        float* dstp[kPer];
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) ca[j * ld] += ta[j];
+        for (int q = 0; q < kPer; ++q) {
+          const int pq = p + q * slices;
+          const bool have = pq < rows;
+          const float u = project_row<D>(xs + (size_t)(have ? pq : p) * d, w, d);
+          float a = fmaf(u, inv_delta, -c0s);
+          a = have ? fminf(fmaxf(a, lo), hi) : lo;   // a missing particle goes to the guard rows
+          const float fb = rintf(a);
+          gauss_taps<R>(a - fb, alpha, rj, taps[q]);
+          dstp[q] = mybins + (int)fb * ld;
+        }
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) cb[j * ld] += tb[j];
+        for (int q = 0; q < kPer; ++q) {
+#pragma unroll
+          for (int j = 0; j <= 2 * R; ++j) dstp[q][j * ld] += taps[q][j];
+        }
       }
     }
     __syncthreads();  // everyone is done with buf[stage] before it is refilled

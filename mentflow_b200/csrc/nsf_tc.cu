@@ -786,21 +786,17 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   float* sn = stage1;              // ... of the next tile
   int nbuf = 1;                    // staging buffer of the next tile
   uint32_t sph0 = 0, sph1 = 0;     // phases of the two "landed" barriers
+  float jac_carry = 1.0f, ss_carry = 0.f;
   if (t == 0) prefetch(tile, nbuf);
   tile -= tstride;
   while (cur || has_next) {
     const int64_t p = tile * 128 + t;
     const bool valid = cur && p < n;
     if (cur) has_next = tile + tstride < ntiles;
-    float jac = 1.0f;
-    float ss = 0.f;      // |v|^2 for the base density of the first layer
-    float lq_in = 0.f;   // loaded a tile's worth of work before it is needed
+    float jac = jac_carry;   // Jacobian of the bias-only feature, computed at the end of the previous iteration
+    float ss = ss_carry;     // |v|^2 for the base density of the first layer
+    float lq_in = 0.f;       // loaded a tile's worth of work before it is needed
     if (cur && valid && logq_out && !first_layer) lq_in = logq_in[p];
-    if (cur) {
-      const float vf = sc[meta.const_feature];
-      ss = vf * vf;
-      sc[meta.const_feature] = rq_spline_const<NB>(ctab, vf, jac);
-    }
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
       const int b = s & 1;
@@ -847,7 +843,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
       }
     }
-    if (has_next) hidden_step(2);
+    if (has_next) {
+      // bias-only feature of the NEXT tile here: CUDA-core work between the request for the third
+      // GEMM of its chain and the wait for it
+      const float vf = sn[meta.const_feature];
+      ss_carry = vf * vf;
+      jac_carry = 1.0f;
+      sn[meta.const_feature] = rq_spline_const<NB>(ctab, vf, jac_carry);
+      hidden_step(2);
+    }
     float* tmp = sc;
     sc = sn;
     sn = tmp;
