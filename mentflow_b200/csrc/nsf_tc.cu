@@ -7,14 +7,16 @@
 // with its log|det J| is the epilogue of the output-layer tile: parameters go TMEM -> registers and
 // never touch shared memory or HBM.
 //
-// CTA = 3 warpgroups (384 threads), persistent, one CTA per SM.  The layer's weights live in shared
-// memory as ready-made K-major SWIZZLE_128B fp16 operand tiles (an "image" built once per call by
-// nsf_tc_prepare_kernel, loaded with one TMA bulk copy).  Every warpgroup owns one 128-particle tile
-// at a time, its own A-operand buffer (activations, hi|lo) and its own 128 TMEM columns, and walks
+// CTA = 3 compute warpgroups + 1 MMA-issuer warpgroup (setmaxnreg: 160 / 32 registers), persistent,
+// one CTA per SM.  The layer's weights live in shared memory as ready-made fp16 operand tiles (an
+// "image" built by nsf_tc_prepare_kernel, loaded with one TMA bulk copy).  Every compute warpgroup owns
+// one 128-particle tile at a time, its own A-operand buffer (activations, hi|lo) and its own 128 TMEM
+// columns, and walks
 //   v -> [L1 MMA] -> relu/split -> [L2 MMA] -> relu/split -> [L3 MMA] -> relu/split ->
 //        per feature: [output MMA, N = 64] -> spline epilogue          (double buffered in TMEM)
-// on its own; the three warpgroups interleave on the SM so that the tensor pipe works on one tile
-// while the CUDA cores run the epilogues of the other two.
+// software-pipelined over its tiles (the chain of tile i+1 runs between the last splines of tile i);
+// warp i of the issuer warpgroup issues the MMAs that compute warpgroup i requests through
+// mbarriers.  Biases enter the accumulators through an extra "ones x bias" MMA.
 //
 // Mask awareness: hidden units are re-ordered by autoregressive class (a permutation of the hidden
 // layer, applied when the image is built), which makes every masked weight matrix block lower
@@ -591,7 +593,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     // MMA issuers: warp i of this warpgroup (one thread of it) serves compute warpgroup i.  The
     // requests of a warpgroup come in a fixed order -- per tile: slots 2..S-1 as the TMEM buffers are
     // read, then the conditioner chain of the next tile (first layer, two hidden GEMMs, output slots
-    // 0 and 1) -- so the issuer simply sleeps on the next request barrier (try_wait with a hint).
+    // 0 and 1) -- so the issuer simply polls the next request barrier (test_wait + a short nanosleep,
+    // which keeps it off the issue port of the compute warps on its scheduler).
     // =========================================================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
     const int w = __shfl_sync(0xffffffffu, (tid - kWG * 128) >> 5, 0);

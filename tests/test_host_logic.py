@@ -142,3 +142,39 @@ def test_kl_matches_torch_kl_div():
     want = torch.stack([torch.nn.functional.kl_div(torch.log(a + 1e-12), b, reduction="batchmean")
                         for a, b in zip(P, T)])
     assert torch.allclose(mf.loss.kl_divergence_batched(P, T), want, rtol=1e-6)
+
+
+def test_tensor_core_flow_host_side_contract():
+    """Host-only parts of the tcgen05 flow entry points (no kernel is launched): which shapes are
+    compiled, the operand-image size, argument checking."""
+    import ctypes
+    from mentflow_b200 import _lib
+    lib = _lib.load()
+    assert lib.mfb_nsf_tc_supported(6, 64, 3, 20) == 1 and lib.mfb_nsf_tc_supported(2, 64, 3, 20) == 1
+    assert lib.mfb_nsf_tc_supported(6, 64, 2, 20) == 0 and lib.mfb_nsf_tc_supported(6, 64, 3, 16) == 0
+    assert lib.mfb_nsf_tc_supported(7, 64, 3, 20) == 0 and lib.mfb_nsf_tc_supported(6, 32, 3, 20) == 0
+    sizes = [lib.mfb_nsf_tc_image_bytes(d, 3) for d in range(2, 7)]
+    assert all(s % 1024 == 0 for s in sizes) and sizes == sorted(sizes)
+    # image + three 32 KB activation buffers + particle staging + barriers must fit one SM (227 KB)
+    assert sizes[-1] + 3 * 32768 + 3 * 2 * 128 * 6 * 4 + 256 + 1024 <= 227 * 1024
+    assert lib.mfb_nsf_tc_image_bytes(7, 3) == 0
+    bad_order = (ctypes.c_int32 * 6)(0, 1, 2, 3, 4, 4)          # not a permutation
+    dummy = ctypes.c_void_p(16)
+    rc = lib.mfb_nsf_tc_prepare(dummy, 1, 1, 6, 64, 3, 20, ctypes.cast(bad_order, ctypes.c_void_p), dummy, None, 0, None)
+    assert rc == -1 and b"bad argument" in lib.mfb_error_string(rc)
+    rc = lib.mfb_nsf_tc_layer_fwd(dummy, 10, 6, 64, 2, 20, dummy, ctypes.cast(bad_order, ctypes.c_void_p), None, 1,
+                                  dummy, None, None)
+    assert rc == -2                                             # hidden_layers = 2 is not compiled for tcgen05
+
+
+def test_graphed_loss_chunk_plan():
+    """Pieces of the pinned-host input: tile aligned, growing, covering the batch exactly."""
+    from mentflow_b200.graphs import GraphedLoss
+    g = GraphedLoss.__new__(GraphedLoss)
+    for n, c in [(1_000_000, 1), (1_000_000, 2), (1_000_000, 4), (20_000, 3), (1000, 3), (129, 2)]:
+        g.batch_size, g.host_chunks = n, c
+        b = g._chunk_bounds()
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(a % 128 == 0 for a, _ in b) and len(b) <= c
+        if len(b) > 1:
+            assert b[0][1] - b[0][0] <= b[1][1] - b[1][0]
