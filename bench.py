@@ -225,8 +225,19 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings: not on stdout (ONE JSON line)
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the communicator comes up; rank 0 must print ONE
+        # JSON line there, so stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.all_reduce(torch.zeros(1, device=device))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     model, wl = build_model(args, device)
     reducer = mfd.shard_model(model, equal_shards=True) if world > 1 else None
     gen = model.generator
