@@ -166,11 +166,12 @@ def cpu_step_factory(args):
     return step, n
 
 
-def time_cpu(step, n, reps, warmup=1):
+def time_cpu(step, n, reps, warmup=1, budget_s=12.0):
+    """Best step time over at least `reps` steps and about `budget_s` seconds of CPU work."""
     for _ in range(warmup):
         step()
     ts = []
-    for _ in range(reps):
+    while len(ts) < reps or (sum(ts) < budget_s and len(ts) < 200):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
@@ -412,7 +413,12 @@ def main():
             "gpu_launches_per_step": {**nsf_launches, "moments": 2, "kde1d deposit+reduce+normalize": 3},
             "roofline": {"bound": "tensor", "kernel": nsf_kernel,
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                         "frac": achieved / pk["bf16_tflops_sustained"],
+                         # ncu --set full of one layer launch at this workload (profiles/r1c_full_metrics.txt):
+                         # dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic 56 B/particle is read z +
+                         # log q in, write y + log q out (the writes are still in L2 when the launch ends)
+                         "traffic": 24.3e6 if (tc and d == 6 and n == 1_000_000) else None,
+                         "traffic_unit": "bytes per layer launch (ncu)",
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_particle": FLOP_MASK_AWARE.get(d), "dense_equivalent_flop": FLOP_DENSE.get(d),
                          "kernel_ms_per_step": nsf_step_ms, "share_of_step": nsf_step_ms / (total_ms / args.steps),
