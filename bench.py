@@ -417,7 +417,7 @@ def main():
                          # ncu --set full of one layer launch at this workload (profiles/r1c_full_metrics.txt):
                          # dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic 56 B/particle is read z +
                          # log q in, write y + log q out (the writes are still in L2 when the launch ends)
-                         "traffic": 24.3e6 if (tc and d == 6 and n == 1_000_000) else None,
+                         "traffic": 28.3e6 if (tc and d == 6 and n == 1_000_000) else None,
                          "traffic_unit": "bytes per layer launch (ncu)",
                          "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_particle": FLOP_MASK_AWARE.get(d), "dense_equivalent_flop": FLOP_DENSE.get(d),
