@@ -153,6 +153,10 @@ int mfb_nsf_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hi
  * W1 [64][d] | Wl [64 out][64 in] x (L-1) | Wout [d*64 (59->64 padded rows)][64 in], no biases
  * (mfb_nsf_layer_param_om_floats floats).  dL/dlogq_in = glogq (pass-through).           */
 int64_t mfb_nsf_layer_param_om_floats(int d, int hidden_units, int hidden_layers);
+/* The data-gradient chain of mfb_nsf_layer_bwd (three dgrad GEMMs + the input gradient) runs on the
+ * tensor cores for hidden_layers = 3 (nsf_tc_bwd.cu).  enable: 1 / 0 switches it, < 0 only queries;
+ * returns the previous setting (process-wide; meant for A/B tests).                              */
+int mfb_nsf_bwd_use_tensor_cores(int enable);
 int64_t mfb_nsf_layer_bwd_workspace_bytes(int64_t n, int d, int hidden_layers);
 int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d,
                       int hidden_units, int hidden_layers, int bins, const float* params,

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(kNsfThreads, 1)
 nsf_bwd_spline_kernel(const float* __restrict__ v, const float* __restrict__ gy, const float* __restrict__ glogq,
                       int64_t n, int hidden_layers, int nb, const float* __restrict__ params, int64_t nparams,
                       FeatureOrder order, int first_layer, float* __restrict__ acts /* [L][64][n] */,
-                      float* __restrict__ gphi /* [D*64][n] */, float* __restrict__ gvd /* [n][D] */) {
+                      float* __restrict__ gphi /* [D*64][n] */, float* __restrict__ gvd /* [n][D] */,
+                      float* __restrict__ gmax /* [n]: max |gphi| of the particle (row scale of the tcgen05 dgrad) */) {
   extern __shared__ __align__(16) float smem[];
   float* s_par = smem;
   float* s_scr = smem + ((nparams + 3) & ~(int64_t)3);
@@ -218,6 +219,7 @@ nsf_bwd_spline_kernel(const float* __restrict__ v, const float* __restrict__ gy,
       }
     }
     float gvo[D];
+    float amax = 0.f;
 #pragma unroll 1
     for (int f = 0; f < D; ++f) {
       const float* bf = bout + f * kPP;
@@ -248,13 +250,18 @@ nsf_bwd_spline_kernel(const float* __restrict__ v, const float* __restrict__ gy,
         if (f == i) gvo[i] = g;
       if (valid) {
         float* gp = gphi + (size_t)f * kPP * n + p;
-        for (int j = 0; j < ptotal; ++j) gp[(size_t)j * n] = col[j * kNsfThreads];
+        for (int j = 0; j < ptotal; ++j) {
+          const float gj = col[j * kNsfThreads];
+          gp[(size_t)j * n] = gj;
+          amax = fmaxf(amax, fabsf(gj));
+        }
         for (int j = ptotal; j < kPP; ++j) gp[(size_t)j * n] = 0.f;
       }
     }
     if (valid) {
 #pragma unroll
       for (int i = 0; i < D; ++i) gvd[p * D + i] = gvo[i];
+      if (gmax) gmax[p] = amax;
     }
   }
 }
@@ -456,9 +463,18 @@ nsf_bwd_input_kernel(const float* __restrict__ gvd, const float* __restrict__ g1
   }
 }
 
+// switch for A/B tests: 0 = CUDA-core dgrad kernels only (mfb_nsf_bwd_use_tensor_cores)
+static int g_use_tc_dgrad = 1;
+
 // ---- host-side orchestration of one layer ----------------------------------------------------------------
+// tcgen05 data-gradient chain (nsf_tc_bwd.cu); MFB_E_UNSUPPORTED for shapes it is not compiled for
+int64_t nsf_tc_dgrad_image_bytes(int d);
+int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
+                 int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
+                 cudaStream_t st);
+
 struct BwdPlan {
-  int64_t acts, gphi, ga, gb, gvd, partial, total;  // float offsets
+  int64_t acts, gphi, ga, gb, gvd, gmax, image, partial, total;  // float offsets (ga: [L][64][n] when the tcgen05 chain runs)
   int nsplit;
   int64_t per_split;
 };
@@ -473,9 +489,11 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
   };
   P.acts = take((int64_t)hidden_layers * kH * n);
   P.gphi = take((int64_t)d * kPP * n);
-  P.ga = take((int64_t)kH * n);
+  P.ga = take((int64_t)hidden_layers * kH * n);
   P.gb = take((int64_t)kH * n);
   P.gvd = take(n * d);
+  P.gmax = take(n);
+  P.image = take((nsf_tc_dgrad_image_bytes(d) + 3) / 4 + 256);   // + slack to align the image to 1 KB
   const int sms = sm_count();
   int nsplit = (4 * sms + d - 1) / d;
   int64_t tiles = (n + kWgTileP - 1) / kWgTileP;
@@ -510,9 +528,20 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     int64_t tiles = (n + kNsfThreads - 1) / kNsfThreads;
     int grid = (int)(tiles < sms ? tiles : sms);
     nsf_bwd_spline_kernel<D><<<grid, kNsfThreads, smem, st>>>(v, gy, glogq, n, hidden_layers, nb, params, np, order,
-                                                              first, acts, gphi, gvd);
+                                                              first, acts, gphi, gvd, ws + P.gmax);
     int rc = launch_status();
     if (rc) return rc;
+  }
+  // 1b. data gradients of the whole conditioner on the tensor cores (three hidden layers):
+  //     ga[l] = dL/d(pre-activation) of hidden layer l, gv = dL/dv
+  bool tc_chain = false;
+  if (hidden_layers == 3 && g_use_tc_dgrad) {
+    int32_t ord[kMaxDim];
+    for (int i = 0; i < D; ++i) ord[i] = order.v[i];
+    unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
+    int rc = nsf_tc_dgrad(gphi, ws + P.gmax, acts, gvd, n, D, hidden_layers, params, ord, ga, gv, image, st);
+    if (rc == 0) tc_chain = true;
+    else if (rc != MFB_E_UNSUPPORTED) return rc;
   }
   // packed (forward) layout offsets
   const int64_t off_w1 = 0, off_b1 = (int64_t)D * kH, off_hid = off_b1 + kH;
@@ -531,12 +560,13 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     nsf_wgrad_reduce_kernel<<<(D * kH * kH + 255) / 256, 256, 0, st>>>(partial, P.nsplit, D, (int64_t)kH * kPP,
                                                                         gparams + off_wout, accumulate);
     nsf_rowsum_kernel<<<D * kPP, 256, 0, st>>>(gphi, n, gparams + off_bout, 0, kPP, 0, accumulate);
-    nsf_dgrad_kernel<<<dgrid, kBwdThreads, dsmem, st>>>(gphi, D * kPP, n, params_om + om_wout, h_last, ga);
+    if (!tc_chain)
+      nsf_dgrad_kernel<<<dgrid, kBwdThreads, dsmem, st>>>(gphi, D * kPP, n, params_om + om_wout, h_last, ga);
     int rc = launch_status();
     if (rc) return rc;
   }
-  // hidden layers, last to first: ga holds dL/d(pre-activation) of hidden layer l+1 (index l+1 in acts)
-  float* gcur = ga;
+  // hidden layers, last to first: gcur holds dL/d(pre-activation) of hidden layer l+1 (index l+1 in acts)
+  float* gcur = tc_chain ? ga + (size_t)(hidden_layers - 1) * kH * n : ga;
   float* gnext = gb;
   for (int l = hidden_layers - 2; l >= 0; --l) {
     const float* h_prev = acts + (size_t)l * kH * n;
@@ -545,6 +575,10 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     nsf_wgrad_kernel<<<grid, 256, 0, st>>>(h_prev, gcur, n, P.per_split, partial);
     nsf_wgrad_reduce_kernel<<<(kH * kH + 255) / 256, 256, 0, st>>>(partial, P.nsplit, 1, 0, gw, accumulate);
     nsf_rowsum_kernel<<<kH, 256, 0, st>>>(gcur, n, gw + kH * kH, 0, kH, 0, accumulate);
+    if (tc_chain) {
+      gcur = ga + (size_t)l * kH * n;   // already computed by the tcgen05 chain
+      continue;
+    }
     nsf_dgrad_kernel<<<dgrid, kBwdThreads, dsmem, st>>>(gcur, kH, n, params_om + om_hid + (int64_t)l * kH * kH,
                                                          h_prev, gnext);
     int rc = launch_status();
@@ -560,7 +594,7 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     nsf_wgrad_in_kernel<D><<<gridw, 256, 0, st>>>(v, gcur, n, per_cta, partial);
     nsf_sum_partials_kernel<<<(D * kH + 255) / 256, 256, 0, st>>>(partial, gridw, D * kH, gparams + off_w1, accumulate);
     nsf_rowsum_kernel<<<kH, 256, 0, st>>>(gcur, n, gparams + off_b1, 0, kH, 0, accumulate);
-    nsf_bwd_input_kernel<D><<<dgrid, 256, 0, st>>>(gvd, gcur, n, params_om + om_w1, gv);
+    if (!tc_chain) nsf_bwd_input_kernel<D><<<dgrid, 256, 0, st>>>(gvd, gcur, n, params_om + om_w1, gv);
   }
   return launch_status();
 }
@@ -570,6 +604,12 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
 using namespace mfb;
 
 extern "C" {
+
+int mfb_nsf_bwd_use_tensor_cores(int enable) {
+  const int old = g_use_tc_dgrad;
+  if (enable >= 0) g_use_tc_dgrad = enable ? 1 : 0;
+  return old;
+}
 
 int64_t mfb_nsf_layer_bwd_workspace_bytes(int64_t n, int d, int hidden_layers) {
   if (n < 1 || d < 2 || d > 6 || hidden_layers < 1) return 0;
