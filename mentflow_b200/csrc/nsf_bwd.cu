@@ -152,7 +152,8 @@ nsf_bwd_spline_kernel(const float* __restrict__ v, const float* __restrict__ gy,
                       int64_t n, int hidden_layers, int nb, const float* __restrict__ params, int64_t nparams,
                       FeatureOrder order, int first_layer, float* __restrict__ acts /* [L][64][n] */,
                       float* __restrict__ gphi /* [D*64][n] */, float* __restrict__ gvd /* [n][D] */,
-                      float* __restrict__ gmax /* [n]: max |gphi| of the particle (row scale of the tcgen05 dgrad) */) {
+                      float* __restrict__ gmax /* [n]: max |gphi| of the particle (row scale of the tcgen05 dgrad) */,
+                      int* __restrict__ gmaxes /* [0]: batch maximum of |gphi| as float bits (atomicMax) */) {
   extern __shared__ __align__(16) float smem[];
   float* s_par = smem;
   float* s_scr = smem + ((nparams + 3) & ~(int64_t)3);
@@ -262,6 +263,12 @@ nsf_bwd_spline_kernel(const float* __restrict__ v, const float* __restrict__ gy,
 #pragma unroll
       for (int i = 0; i < D; ++i) gvd[p * D + i] = gvo[i];
       if (gmax) gmax[p] = amax;
+    }
+    if (gmaxes) {
+      float wm = valid ? amax : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      if ((tid & 31) == 0) atomicMax(gmaxes, __float_as_int(wm));
     }
   }
 }
@@ -471,10 +478,15 @@ static int g_use_tc_dgrad = 1;
 int64_t nsf_tc_dgrad_image_bytes(int d);
 int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
-                 cudaStream_t st);
+                 int* gmaxes, cudaStream_t st);
+// tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu); needs n % 4 == 0
+int64_t nsf_tc_wgrad_partial_floats(int d);
+int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
+                 int hidden_layers, const int32_t* order, const int* gmaxes, float* partial, float* gparams,
+                 int accumulate, cudaStream_t st);
 
 struct BwdPlan {
-  int64_t acts, gphi, ga, gb, gvd, gmax, image, partial, total;  // float offsets (ga: [L][64][n] when the tcgen05 chain runs)
+  int64_t acts, gphi, ga, gb, gvd, gmax, gmaxes, image, partial, total;  // float offsets (ga: [L][64][n] when the tcgen05 chain runs)
   int nsplit;
   int64_t per_split;
 };
@@ -493,6 +505,7 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
   P.gb = take((int64_t)kH * n);
   P.gvd = take(n * d);
   P.gmax = take(n);
+  P.gmaxes = take(8);
   P.image = take((nsf_tc_dgrad_image_bytes(d) + 3) / 4 + 256);   // + slack to align the image to 1 KB
   const int sms = sm_count();
   int nsplit = (4 * sms + d - 1) / d;
@@ -502,7 +515,10 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
   int64_t per = ((tiles + nsplit - 1) / nsplit) * kWgTileP;
   P.nsplit = (int)((n + per - 1) / per);
   P.per_split = per;
-  P.partial = take((int64_t)P.nsplit * d * kH * kH);
+  {
+    int64_t pf = (int64_t)P.nsplit * d * kH * kH, tcf = nsf_tc_wgrad_partial_floats(d);
+    P.partial = take(pf > tcf ? pf : tcf);
+  }
   P.total = off;
   return P;
 }
@@ -520,6 +536,8 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
   float* gvd = ws + P.gvd;
   float* partial = ws + P.partial;
   const int sms = sm_count();
+  int* gmaxes = reinterpret_cast<int*>(ws + P.gmaxes);
+  MFB_CUDA(cudaMemsetAsync(gmaxes, 0, 8 * sizeof(int), st));
   // 1. recompute + spline backward
   {
     const size_t smem = (size_t)((np + 3) & ~(int64_t)3) * 4 + (size_t)kPP * kNsfThreads * 4;
@@ -528,7 +546,8 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     int64_t tiles = (n + kNsfThreads - 1) / kNsfThreads;
     int grid = (int)(tiles < sms ? tiles : sms);
     nsf_bwd_spline_kernel<D><<<grid, kNsfThreads, smem, st>>>(v, gy, glogq, n, hidden_layers, nb, params, np, order,
-                                                              first, acts, gphi, gvd, ws + P.gmax);
+                                                              first, acts, gphi, gvd, ws + P.gmax,
+                                                              reinterpret_cast<int*>(ws + P.gmaxes));
     int rc = launch_status();
     if (rc) return rc;
   }
@@ -539,9 +558,15 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     int32_t ord[kMaxDim];
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
-    int rc = nsf_tc_dgrad(gphi, ws + P.gmax, acts, gvd, n, D, hidden_layers, params, ord, ga, gv, image, st);
+    int rc = nsf_tc_dgrad(gphi, ws + P.gmax, acts, gvd, n, D, hidden_layers, params, ord, ga, gv, image, gmaxes, st);
     if (rc == 0) tc_chain = true;
     else if (rc != MFB_E_UNSUPPORTED) return rc;
+    // 1c. every weight and bias gradient of the layer in one tensor-core kernel
+    if (tc_chain && (n & 3) == 0) {
+      rc = nsf_tc_wgrad(gphi, ga, acts, v, n, D, hidden_layers, ord, gmaxes, partial, gparams, accumulate, st);
+      if (rc == 0) return launch_status();
+      if (rc != MFB_E_UNSUPPORTED) return rc;
+    }
   }
   // packed (forward) layout offsets
   const int64_t off_w1 = 0, off_b1 = (int64_t)D * kH, off_hid = off_b1 + kH;

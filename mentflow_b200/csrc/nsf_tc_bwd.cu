@@ -111,7 +111,8 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
                     const float* __restrict__ acts /* [L][64][n] */, const float* __restrict__ gvd /* [n][D] */,
                     int64_t n, const unsigned char* __restrict__ image, const __grid_constant__ DgradMeta meta,
                     float* __restrict__ gz /* [L][64][n]: dL/d(pre-activation) of hidden layer l */,
-                    float* __restrict__ gv /* [n][D] */) {
+                    float* __restrict__ gv /* [n][D] */,
+                    int* __restrict__ gmaxes /* [1 + L] float bits: batch maxima of |gphi|, |gz[l]| (atomicMax) */) {
   static_assert(L == 3, "compiled for three hidden layers");
   constexpr int S = D - 1;
   constexpr int kImg = dgrad_image_bytes(D, L);
@@ -271,6 +272,12 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
         store_row_split(acc, sc, a_hi, a_lo, t);
         unscale = inv;
         publish();
+        {   // batch maximum of |gz[l]|: one atomic per warp (non-negative floats order like ints)
+          float wm = amax;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+          if ((t & 31) == 0) atomicMax(gmaxes + 1 + l, __float_as_int(wm));
+        }
         if (valid) {
           float* gl = gz + (size_t)l * kH * n + p;
 #pragma unroll
@@ -299,7 +306,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
 template <int D>
 static int launch_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n,
                         const float* params, const int32_t* order, float* gz, float* gv, unsigned char* image,
-                        cudaStream_t st) {
+                        int* gmaxes, cudaStream_t st) {
   constexpr int L = 3;
   DgradMeta meta = {};
   int cls[kH];
@@ -323,7 +330,295 @@ static int launch_dgrad(const float* gphi, const float* gmax, const float* acts,
   const int64_t ntiles = (n + 127) / 128;
   int64_t grid = sm_count();
   if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
-  kern<<<(int)grid, kThreads, smem, st>>>(gphi, gmax, acts, gvd, n, image, meta, gz, gv);
+  kern<<<(int)grid, kThreads, smem, st>>>(gphi, gmax, acts, gvd, n, image, meta, gz, gv, gmaxes);
+  return launch_status();
+}
+
+// =============================================================================================
+// weight + bias gradients of one layer: dW[i][j] = sum_p H[i][p] G[j][p] for the eight (G, H) pairs
+//   (dL/dphi_f, h3) x S,  (g3, h2),  (g2, h1),  (g1, v^T)
+// as tcgen05 GEMMs whose K dimension is the particle axis.  The workspace rows are feature-major
+// ([row][n]), so 128 consecutive particles of a row are contiguous: exactly a K-major operand row.
+// Loader warps turn such rows into (hi, lo) fp16 SWIZZLE_128B tiles (64 rows x 128 K, two 64-wide
+// halves), the issuer warp multiplies them into accumulators that stay in TMEM for the whole
+// launch (464 columns: 5 x 64 + 64 + 64 + 16), bias gradients are row sums taken on the way.  G is
+// scaled by a power of two from the batch maximum (fp16 has no range for 1/N-sized gradients).
+// =============================================================================================
+constexpr int kWgTile = 32768;                 // one operand tile: hi (2 halves x 8 KB) | lo (2 x 8 KB)
+constexpr int kWgG = 3, kWgH = 2;              // ring depths
+constexpr int kWgLoaders = 12;                 // loader warps
+constexpr int kWgCols = 464;                   // accumulator columns
+
+struct WgradMeta {
+  int slot_feature[kMaxDim];
+  int const_feature;
+  int nslots;
+};
+
+__host__ __device__ constexpr int wgrad_rows(int D) { return kWgCols + D + 3; }   // + bias rows: D features, 3 hidden
+
+template <int D>
+__global__ void __launch_bounds__(512, 1)
+nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float* __restrict__ gz /* [3][64][n] */,
+                    const float* __restrict__ acts /* [3][64][n] */, const float* __restrict__ v /* [n][D] */,
+                    int64_t n, const int* __restrict__ gmaxes, const __grid_constant__ WgradMeta meta,
+                    float* __restrict__ partial /* [grid][wgrad_rows][64] */) {
+  constexpr int S = D - 1;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* g_ring = smem;
+  unsigned char* h_ring = smem + kWgG * kWgTile;
+  // 8 KB of slack after the rings: an M = 128 MMA reads 64 rows past a 64-row tile half
+  float* bias = reinterpret_cast<float*>(smem + (kWgG + kWgH) * kWgTile + 8192);   // [D + 3][64]
+  uint64_t* g_full = reinterpret_cast<uint64_t*>(bias + (D + 3) * 64);
+  uint64_t* g_empty = g_full + kWgG;
+  uint64_t* h_full = g_empty + kWgG;
+  uint64_t* h_empty = h_full + kWgH;
+  uint64_t* all_done = h_empty + kWgH;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (D + 3) * 64; i += 512) bias[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < kWgG; ++i) {
+      mbar_init(&g_full[i], kWgLoaders);
+      mbar_init(&g_empty[i], 1);
+    }
+    for (int i = 0; i < kWgH; ++i) {
+      mbar_init(&h_full[i], kWgLoaders);
+      mbar_init(&h_empty[i], 1);
+    }
+    mbar_init(all_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int64_t ntiles = (n + 127) / 128;
+  // scales of the G operands from the batch maxima: [0] dL/dphi, [1 + l] gz[l]
+  float gsc[4], ginv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) gsc[i] = pow2_scale(__int_as_float(gmaxes[i]), ginv[i]);
+
+  if (warp < kWgLoaders) {
+    // ===== loaders: rows w, w + 12, ... of every tile =====
+    uint32_t gi = 0, hi_ = 0;   // running use counters of the rings
+    auto fill = [&](unsigned char* tile, const float* rows, int nrows, int64_t p0, float scale, float* bsum, bool strided_v) {
+      for (int r = warp; r < nrows; r += kWgLoaders) {
+        float x[4];
+        if (!strided_v) {
+          const float* src = rows + (size_t)r * n + p0 + 4 * lane;
+          if (p0 + 4 * lane + 3 < n) {
+            const float4 q = *reinterpret_cast<const float4*>(src);
+            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (p0 + 4 * lane + e < n) ? src[e] : 0.f;
+          }
+        } else {   // v is particle-major: row r of v^T is feature r
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = (p0 + 4 * lane + e < n) ? rows[(p0 + 4 * lane + e) * D + r] : 0.f;
+        }
+        if (bsum) {
+          float sacc = (x[0] + x[1]) + (x[2] + x[3]);
+          sacc = warp_sum(sacc);
+          if (lane == 0) bsum[r] += sacc;
+        }
+        if (tile) {
+          const float x0 = x[0] * scale, x1 = x[1] * scale, x2 = x[2] * scale, x3 = x[3] * scale;
+          const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+          // K index 4*lane: half = lane / 16, 16-byte chunk (lane % 16) / 2, upper or lower 8 bytes of it
+          unsigned char* dst = tile + (lane >> 4) * 8192 + umma::sw128_offset(r, (lane & 15) >> 1) + (lane & 1) * 8;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(dst + 16384) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        }
+      }
+    };
+    auto fill_g = [&](const float* rows, int64_t p0, float scale, float* bsum) {
+      const uint32_t slot = gi % kWgG, par = (gi / kWgG) & 1;
+      mbar_wait_bounded(&g_empty[slot], par ^ 1);
+      fill(g_ring + slot * kWgTile, rows, 64, p0, scale, bsum, false);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&g_full[slot])) : "memory");
+      ++gi;
+    };
+    auto fill_h = [&](const float* rows, int nrows, int64_t p0, bool strided_v) {
+      const uint32_t slot = hi_ % kWgH, par = (hi_ / kWgH) & 1;
+      mbar_wait_bounded(&h_empty[slot], par ^ 1);
+      fill(h_ring + slot * kWgTile, rows, nrows, p0, 1.0f, nullptr, strided_v);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_full[slot])) : "memory");
+      ++hi_;
+    };
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t p0 = tile * 128;
+      fill_h(acts + (size_t)2 * kH * n, 64, p0, false);                                   // h3
+      for (int s = 0; s < S; ++s)
+        fill_g(gphi + (size_t)meta.slot_feature[s] * kPP * n, p0, gsc[0], bias + meta.slot_feature[s] * 64);
+      fill(nullptr, gphi + (size_t)meta.const_feature * kPP * n, 64, p0, 1.0f, bias + meta.const_feature * 64, false);
+      fill_h(acts + (size_t)1 * kH * n, 64, p0, false);                                   // h2
+      fill_g(gz + (size_t)2 * kH * n, p0, gsc[3], bias + (D + 0) * 64);                   // g3
+      fill_h(acts, 64, p0, false);                                                        // h1
+      fill_g(gz + (size_t)1 * kH * n, p0, gsc[2], bias + (D + 1) * 64);                   // g2
+      fill_h(v, D, p0, true);                                                             // v^T
+      fill_g(gz, p0, gsc[1], bias + (D + 2) * 64);                                        // g1
+    }
+  } else if (warp == kWgLoaders) {
+    // ===== issuer =====
+    uint32_t gi = 0, hi_ = 0;
+    const uint32_t idesc64 = umma::make_idesc_f16(128, 64), idesc16 = umma::make_idesc_f16(128, 16);
+    bool first = true;
+    auto job = [&](uint32_t dcol, uint32_t hslot, uint32_t idesc) {   // one (G, H) pair: K = 128 particles
+      const uint32_t slot = gi % kWgG, par = (gi / kWgG) & 1;
+      mbar_wait_polite(&g_full[slot], par);
+      umma::fence_after_sync();
+      const uint32_t ga = smem_u32(g_ring + slot * kWgTile), ha = smem_u32(h_ring + hslot * kWgTile);
+      if (elect_one()) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), aL = umma::make_desc_sw128(ga + 16384 + half * 8192);
+          const uint64_t bH = umma::make_desc_sw128(ha + half * 8192), bL = umma::make_desc_sw128(ha + 16384 + half * 8192);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_cross(dcol, aH, aL, bH, bL, ks, idesc, (first && half == 0 && ks == 0) ? 0u : 1u);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), bH = umma::make_desc_sw128(ha + half * 8192);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_main(dcol, aH, bH, ks, idesc);
+        }
+        umma::commit(&g_empty[slot]);
+      }
+      __syncwarp();
+      ++gi;
+    };
+    auto take_h = [&]() {
+      const uint32_t slot = hi_ % kWgH, par = (hi_ / kWgH) & 1;
+      mbar_wait_polite(&h_full[slot], par);
+      ++hi_;
+      return slot;
+    };
+    auto release_h = [&](uint32_t slot) {
+      if (elect_one()) umma::commit(&h_empty[slot]);
+      __syncwarp();
+    };
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      uint32_t hs = take_h();                                   // h3
+      for (int s = 0; s < S; ++s) job(tmem_base + 64 * s, hs, idesc64);
+      release_h(hs);
+      hs = take_h();                                            // h2
+      job(tmem_base + 320, hs, idesc64);
+      release_h(hs);
+      hs = take_h();                                            // h1
+      job(tmem_base + 384, hs, idesc64);
+      release_h(hs);
+      hs = take_h();                                            // v^T
+      job(tmem_base + 448, hs, idesc16);
+      release_h(hs);
+      first = false;
+    }
+    if (elect_one()) umma::commit(all_done);
+    __syncwarp();
+  }
+  // ===== epilogue: accumulators (lanes 0..63 = G row j) and bias sums -> this CTA's partial block
+  __syncthreads();   // every loader has added its last bias sums
+  float* out = partial + (size_t)blockIdx.x * wgrad_rows(D) * 64;
+  if (warp < 2) {
+    mbar_wait_bounded(all_done, 0);
+    umma::fence_after_sync();
+    const bool any = (int64_t)blockIdx.x < ntiles;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int j = warp * 32 + lane;
+    for (int c0 = 0; c0 < kWgCols; c0 += 32) {
+      float acc[32];
+      umma::tmem_ld32(taddr + c0, acc);
+      const float unscale = c0 < 320 ? ginv[0] : (c0 < 384 ? ginv[3] : (c0 < 448 ? ginv[2] : ginv[1]));
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < kWgCols) out[(size_t)(c0 + i) * 64 + j] = any ? acc[i] * unscale : 0.f;
+    }
+    umma::fence_before_sync();
+  } else if (warp >= 2 && warp < 4) {
+    for (int i = (warp - 2) * 32 + lane; i < (D + 3) * 64; i += 64) out[(size_t)kWgCols * 64 + i] = bias[i];
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// gparams (packed forward layout) (+)= sum over CTAs of the partial blocks
+__global__ void nsf_tc_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int D, int L,
+                                           const __grid_constant__ WgradMeta meta, float* __restrict__ gparams,
+                                           int accumulate) {
+  const int rows = wgrad_rows(D);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over rows * 64 partial entries
+  if (idx >= rows * 64) return;
+  const int c = idx / 64, j = idx % 64;
+  float sacc = 0.f;
+  for (int k = 0; k < nparts; ++k) sacc += partial[(size_t)k * rows * 64 + idx];
+  const int64_t off_w1 = 0, off_b1 = (int64_t)D * kH, off_hid = off_b1 + kH;
+  const int64_t off_wout = off_hid + (int64_t)(L - 1) * (kH * kH + kH);
+  const int64_t off_bout = off_wout + (int64_t)D * kH * kPP;
+  int64_t dst = -1;
+  if (c < 320) {                                  // dWout_t[f][i][q]: column block s, i = c % 64, q = j
+    const int sl = c / 64;
+    if (sl < meta.nslots) dst = off_wout + ((int64_t)meta.slot_feature[sl] * kH + (c % 64)) * kPP + j;
+  } else if (c < 384) {                           // W3: hidden block l = 1, Wt[in i][out j]
+    dst = off_hid + 1 * (kH * kH + kH) + (int64_t)(c - 320) * kH + j;
+  } else if (c < 448) {                           // W2: hidden block l = 0
+    dst = off_hid + (int64_t)(c - 384) * kH + j;
+  } else if (c < kWgCols) {                       // W1t[i][j]
+    if (c - 448 < D) dst = off_w1 + (int64_t)(c - 448) * kH + j;
+  } else {
+    const int kind = c - kWgCols;                 // bias rows: features 0..D-1, then g3, g2, g1
+    if (kind < D) dst = off_bout + (int64_t)kind * kPP + j;
+    else if (kind == D) dst = off_hid + 1 * (kH * kH + kH) + kH * kH + j;
+    else if (kind == D + 1) dst = off_hid + kH * kH + j;
+    else dst = off_b1 + j;
+  }
+  if (dst >= 0) gparams[dst] = accumulate ? gparams[dst] + sacc : sacc;
+}
+
+// the output-layer weights of the bias-only feature are masked: their gradient block is defined as zero
+__global__ void nsf_tc_wgrad_zero_const_kernel(float* __restrict__ gparams, int64_t off, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) gparams[off + i] = 0.f;
+}
+
+template <int D>
+static int launch_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n,
+                        const int32_t* order, const int* gmaxes, float* partial, float* gparams, int accumulate,
+                        cudaStream_t st) {
+  constexpr int L = 3;
+  WgradMeta meta = {};
+  int feat_of_order[kMaxDim];
+  for (int i = 0; i < D; ++i) feat_of_order[order[i]] = i;
+  meta.nslots = D - 1;
+  meta.const_feature = feat_of_order[0];
+  for (int s = 0; s < D - 1; ++s) meta.slot_feature[s] = feat_of_order[s + 1];
+  const size_t smem = (size_t)(kWgG + kWgH) * kWgTile + 8192 + (size_t)(D + 3) * 64 * 4 + 256 + 1024;
+  auto kern = nsf_tc_wgrad_kernel<D>;
+  MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + 127) / 128;
+  int grid = sm_count();
+  if (grid > ntiles) grid = (int)ntiles;
+  kern<<<grid, 512, smem, st>>>(gphi, gz, acts, v, n, gmaxes, meta, partial);
+  int rc = launch_status();
+  if (rc) return rc;
+  const int entries = wgrad_rows(D) * 64;
+  nsf_tc_wgrad_reduce_kernel<<<(entries + 255) / 256, 256, 0, st>>>(partial, grid, D, L, meta, gparams, accumulate);
+  if (!accumulate) {
+    const int64_t off_wout = (int64_t)D * kH + kH + (int64_t)(L - 1) * (kH * kH + kH);
+    nsf_tc_wgrad_zero_const_kernel<<<(kH * kPP + 255) / 256, 256, 0, st>>>(
+        gparams, off_wout + (int64_t)meta.const_feature * kH * kPP, kH * kPP);
+  }
   return launch_status();
 }
 
@@ -337,15 +632,33 @@ int64_t nsf_tc_dgrad_image_bytes(int d) { return (d >= 2 && d <= 6) ? tc::dgrad_
 
 int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
-                 cudaStream_t st) {
+                 int* gmaxes, cudaStream_t st) {
   if (hidden_layers != 3 || d < 2 || d > 6) return MFB_E_UNSUPPORTED;
   unsigned char* img = reinterpret_cast<unsigned char*>(image);
   switch (d) {
-    case 2: return tc::launch_dgrad<2>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, st);
-    case 3: return tc::launch_dgrad<3>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, st);
-    case 4: return tc::launch_dgrad<4>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, st);
-    case 5: return tc::launch_dgrad<5>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, st);
-    case 6: return tc::launch_dgrad<6>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, st);
+    case 2: return tc::launch_dgrad<2>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 3: return tc::launch_dgrad<3>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 4: return tc::launch_dgrad<4>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 5: return tc::launch_dgrad<5>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 6: return tc::launch_dgrad<6>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    default: return MFB_E_UNSUPPORTED;
+  }
+}
+
+int64_t nsf_tc_wgrad_partial_floats(int d) {
+  return (d >= 2 && d <= 6) ? (int64_t)sm_count() * tc::wgrad_rows(d) * 64 : 0;
+}
+
+int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
+                 int hidden_layers, const int32_t* order, const int* gmaxes, float* partial, float* gparams,
+                 int accumulate, cudaStream_t st) {
+  if (hidden_layers != 3 || d < 2 || d > 6 || (n & 3)) return MFB_E_UNSUPPORTED;
+  switch (d) {
+    case 2: return tc::launch_wgrad<2>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
+    case 3: return tc::launch_wgrad<3>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
+    case 4: return tc::launch_wgrad<4>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
+    case 5: return tc::launch_wgrad<5>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
+    case 6: return tc::launch_wgrad<6>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
     default: return MFB_E_UNSUPPORTED;
   }
 }
