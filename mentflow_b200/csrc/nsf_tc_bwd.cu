@@ -407,28 +407,40 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
     // ===== loaders: rows w, w + 12, ... of every tile =====
     uint32_t gi = 0, hi_ = 0;   // running use counters of the rings
     auto fill = [&](unsigned char* tile, const float* rows, int nrows, int64_t p0, float scale, float* bsum, bool strided_v) {
-      for (int r = warp; r < nrows; r += kWgLoaders) {
-        float x[4];
-        if (!strided_v) {
-          const float* src = rows + (size_t)r * n + p0 + 4 * lane;
-          if (p0 + 4 * lane + 3 < n) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
-            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-          } else {
+      // all rows of this warp are loaded before any is converted: 6 x 512 B in flight per warp
+      constexpr int kRows = (64 + kWgLoaders - 1) / kWgLoaders;
+      float x[kRows][4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = (p0 + 4 * lane + e < n) ? src[e] : 0.f;
+      for (int i = 0; i < kRows; ++i) {
+        const int r = warp + i * kWgLoaders;
+        x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
+        if (r < nrows) {
+          if (!strided_v) {
+            const float* src = rows + (size_t)r * n + p0 + 4 * lane;
+            if (p0 + 4 * lane + 3 < n) {
+              const float4 q = *reinterpret_cast<const float4*>(src);
+              x[i][0] = q.x; x[i][1] = q.y; x[i][2] = q.z; x[i][3] = q.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[i][e] = (p0 + 4 * lane + e < n) ? src[e] : 0.f;
+            }
+          } else {   // v is particle-major: row r of v^T is feature r
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[i][e] = (p0 + 4 * lane + e < n) ? rows[(p0 + 4 * lane + e) * D + r] : 0.f;
           }
-        } else {   // v is particle-major: row r of v^T is feature r
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = (p0 + 4 * lane + e < n) ? rows[(p0 + 4 * lane + e) * D + r] : 0.f;
         }
+      }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) {
+        const int r = warp + i * kWgLoaders;
+        if (r >= nrows) break;
         if (bsum) {
-          float sacc = (x[0] + x[1]) + (x[2] + x[3]);
+          float sacc = (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
           sacc = warp_sum(sacc);
           if (lane == 0) bsum[r] += sacc;
         }
         if (tile) {
-          const float x0 = x[0] * scale, x1 = x[1] * scale, x2 = x[2] * scale, x3 = x[3] * scale;
+          const float x0 = x[i][0] * scale, x1 = x[i][1] * scale, x2 = x[i][2] * scale, x3 = x[i][3] * scale;
           const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
           const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
