@@ -479,6 +479,10 @@ int64_t nsf_tc_dgrad_image_bytes(int d);
 int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
                  int* gmaxes, cudaStream_t st);
+// tcgen05 recompute + spline forward/backward (nsf_tc.cu); image: mfb_nsf_tc_image_bytes scratch
+int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
+                      int bins, const float* params, const int32_t* order, int first_layer, float* acts,
+                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, cudaStream_t st);
 // tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu); needs n % 4 == 0
 int64_t nsf_tc_wgrad_partial_floats(int d);
 int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
@@ -506,7 +510,10 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
   P.gvd = take(n * d);
   P.gmax = take(n);
   P.gmaxes = take(8);
-  P.image = take((nsf_tc_dgrad_image_bytes(d) + 3) / 4 + 256);   // + slack to align the image to 1 KB
+  {
+    int64_t ib = nsf_tc_dgrad_image_bytes(d), fb = mfb_nsf_tc_image_bytes(d, 3);
+    P.image = take(((ib > fb ? ib : fb) + 3) / 4 + 256);   // operand image scratch (+ slack to align it to 1 KB)
+  }
   const int sms = sm_count();
   int nsplit = (4 * sms + d - 1) / d;
   int64_t tiles = (n + kWgTileP - 1) / kWgTileP;
@@ -538,8 +545,18 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
   const int sms = sm_count();
   int* gmaxes = reinterpret_cast<int*>(ws + P.gmaxes);
   MFB_CUDA(cudaMemsetAsync(gmaxes, 0, 8 * sizeof(int), st));
-  // 1. recompute + spline backward
-  {
+  // 1. recompute + spline backward: on the tensor cores where compiled, else the CUDA-core kernel
+  bool tc_spline = false;
+  if (hidden_layers == 3 && g_use_tc_dgrad) {
+    int32_t ord[kMaxDim];
+    for (int i = 0; i < D; ++i) ord[i] = order.v[i];
+    unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
+    int rc = nsf_tc_spline_bwd(v, gy, glogq, n, D, hidden_layers, nb, params, ord, first, acts, gphi, gvd, ws + P.gmax,
+                               gmaxes, image, st);
+    if (rc == 0) tc_spline = true;
+    else if (rc != MFB_E_UNSUPPORTED) return rc;
+  }
+  if (!tc_spline) {
     const size_t smem = (size_t)((np + 3) & ~(int64_t)3) * 4 + (size_t)kPP * kNsfThreads * 4;
     if (smem > 227 * 1024) return MFB_E_UNSUPPORTED;
     MFB_CUDA(cudaFuncSetAttribute(nsf_bwd_spline_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -29,7 +29,7 @@ namespace mfb {
 namespace tc {
 
 constexpr int kCT = 24;              // stride of the constant-feature tables (floats)
-constexpr int kConstFloats = 6 * kCT;
+constexpr int kConstFloats = 6 * kCT + kPP;   // knot tables + the raw parameters (x log2 e) of the bias-only feature
 
 struct Meta {
   int slot_feature[kMaxDim];  // feature handled by output slot s (order > 0, ascending order)
@@ -37,6 +37,18 @@ struct Meta {
   int hid_n0[4];              // hidden->hidden: first output row that reads K step s (multiple of 16)
   int const_feature;          // feature with order 0 (bias-only spline)
   int nslots;
+  int perm[kH];               // original hidden unit at sorted position c (backward: global rows of the activations)
+};
+
+// pointers of the backward variant (recompute + spline backward): workspace rows are feature-major [row][n]
+struct BwdIO {
+  const float* gy;      // [n][D] dL/dy
+  const float* glogq;   // [n] dL/dlogq_out or null
+  float* acts;          // [3][64][n] post-ReLU activations (original unit order)
+  float* gphi;          // [D*64][n] dL/d(raw conditioner output)
+  float* gvd;           // [n][D] direct dL/dv through the spline (+ base density term)
+  float* gmax;          // [n] max |gphi| of the particle
+  int* gmaxes;          // [0]: batch maximum of |gphi| (float bits, atomicMax)
 };
 
 struct PrepMeta {             // per layer: which feature each output slot serves
@@ -215,6 +227,7 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
       cw += wj;
       ch += hj;
     }
+    for (int j = 0; j < kPP; ++j) ct[6 * kCT + j] = (j < 3 * nb - 1) ? bf[j] * kLog2e : 0.f;   // backward only
   }
 }
 
@@ -371,6 +384,140 @@ __device__ __forceinline__ float rq_spline_regs(const float (&a)[64], float v, f
   return inside ? y : v;
 }
 
+// soft clip + exp of four parameters like clip_exp2_quad; additionally returns 1 / (1 + c |t_j|) in place
+// of t_j: the derivative of the clip is its square
+__device__ __forceinline__ void clip_exp2_quad_bwd(float& t0, float& t1, float& t2, float& t3, float c, float& e0,
+                                                   float& e1, float& e2, float& e3) {
+  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
+  const float d2 = fmaf(fabsf(t2), c, 1.0f), d3 = fmaf(fabsf(t3), c, 1.0f);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = fast_rcp(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  const float i0 = r01 * d1, i1 = r01 * d0, i2 = r23 * d3, i3 = r23 * d2;
+  e0 = fast_exp2(t0 * i0);
+  e1 = fast_exp2(t1 * i1);
+  e2 = fast_exp2(t2 * i2);
+  e3 = fast_exp2(t3 * i3);
+  t0 = i0; t1 = i1; t2 = i2; t3 = i3;
+}
+
+// Spline forward + backward of one feature in registers (backward variant of rq_spline_regs; the
+// formulas are those of rq_spline_backward in nsf_bwd.cu, prototype scripts/proto_spline_bwd.py).
+// a[]: raw parameters (x log2 e) in, dL/d(raw natural parameter) out (j < 3NB-1).  gy = dL/dy,
+// gl = dL/d(log dy/dv).  Returns the direct dL/dv.
+template <int NB>
+__device__ __forceinline__ float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl) {
+  static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
+  constexpr int G = NB / 4;
+  constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
+  float e[NB], h[NB], pre[G + 1], preh[G + 1];
+#pragma unroll
+  for (int j = 0; j < NB; j += 4) {
+    clip_exp2_quad_bwd(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
+    clip_exp2_quad_bwd(a[NB + j], a[NB + j + 1], a[NB + j + 2], a[NB + j + 3], cW, h[j], h[j + 1], h[j + 2], h[j + 3]);
+  }
+  pre[0] = 0.f;
+  preh[0] = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    pre[g + 1] = pre[g] + ((e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]));
+    preh[g + 1] = preh[g] + ((h[4 * g] + h[4 * g + 1]) + (h[4 * g + 2] + h[4 * g + 3]));
+  }
+  const float sum = pre[G], sumh = preh[G];
+  const float target = (v + kBound) * (0.5f / kBound) * sum;
+  // two-level search as in the forward pass, plus the integer bin index for the scatter below
+  int gsel = 0;
+  float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
+  float h0s = h[0], h1s = h[1], h2s = h[2], h3s = h[3], yg = 0.f;
+#pragma unroll
+  for (int g = 1; g < G; ++g) {
+    const bool pgm = pre[g] < target;
+    gsel += pgm ? 1 : 0;
+    q0 = pgm ? e[4 * g] : q0;
+    q1 = pgm ? e[4 * g + 1] : q1;
+    q2 = pgm ? e[4 * g + 2] : q2;
+    q3 = pgm ? e[4 * g + 3] : q3;
+    xg = pgm ? pre[g] : xg;
+    h0s = pgm ? h[4 * g] : h0s;
+    h1s = pgm ? h[4 * g + 1] : h1s;
+    h2s = pgm ? h[4 * g + 2] : h2s;
+    h3s = pgm ? h[4 * g + 3] : h3s;
+    yg = pgm ? preh[g] : yg;
+  }
+  const float c0 = xg + q0, c1 = c0 + q1, c2 = c1 + q2;
+  const bool r0 = c0 < target, r1 = c1 < target, r2 = c2 < target;
+  const int k = 4 * gsel + (r0 ? 1 : 0) + (r1 ? 1 : 0) + (r2 ? 1 : 0);
+  const float x0c = r2 ? c2 : (r1 ? c1 : (r0 ? c0 : xg));
+  const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
+  const float p0 = yg + h0s, p1 = p0 + h1s, p2 = p1 + h2s;
+  const float y0c = r2 ? p2 : (r1 ? p1 : (r0 ? p0 : yg));
+  const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
+  // derivative parameters at the two knots of bin k (raw 0 at the outer knots)
+  float tl = 0.f, tr = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB - 1; ++j) {
+    tl = (j == k - 1) ? a[2 * NB + j] : tl;
+    tr = (j == k) ? a[2 * NB + j] : tr;
+  }
+  const float dd0 = fmaf(fabsf(tl), cD, 1.0f), dd1 = fmaf(fabsf(tr), cD, 1.0f);
+  const float rdd = fast_rcp(dd0 * dd1);
+  const float ri0 = rdd * dd1, ri1 = rdd * dd0;
+  const float d0 = fast_exp2(tl * ri0), d1 = fast_exp2(tr * ri1);
+  // forward quantities in natural units
+  const float inv_s = rcp_nr(sum), inv_sh = rcp_nr(sumh);
+  const float wk = ek * inv_s, hn = hk * inv_sh;
+  const float cumw = x0c * inv_s, cumh = y0c * inv_sh;
+  const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hn;
+  const float r_wk = rcp_nr(wk), r_dx = rcp_nr(dx);
+  const float s = hn * r_wk;
+  float t = (target - x0c) * rcp_nr(ek);
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float omt = 1.0f - t, q = t * omt;
+  const float A = d0 + d1 - 2.0f * s;
+  const float den = fmaf(A, q, s);
+  const float n1 = s * t * t + d0 * q;
+  const float n2 = 2.0f * s * q + d0 * omt * omt + d1 * t * t;
+  const float dq_dt = 1.0f - 2.0f * t;
+  const float dden_dt = A * dq_dt, dden_ds = 1.0f - 2.0f * q, dden_dd = q;
+  const float inv_den = rcp_nr(den), inv_n2 = rcp_nr(n2);
+  const float r1q = n1 * inv_den;
+  const float dy_dt = dy * (2.0f * s * t + d0 * dq_dt - r1q * dden_dt) * inv_den;
+  const float dy_ds = dy * (t * t - r1q * dden_ds) * inv_den;
+  const float dy_dd0 = dy * (q - r1q * dden_dd) * inv_den;
+  const float dy_dd1 = dy * (-r1q * dden_dd) * inv_den;
+  const float dl_dt = (2.0f * s * dq_dt - 2.0f * d0 * omt + 2.0f * d1 * t) * inv_n2 - 2.0f * dden_dt * inv_den;
+  const float dl_ds = 2.0f * rcp_nr(s) + 2.0f * q * inv_n2 - 2.0f * dden_ds * inv_den;
+  const float dl_dd0 = omt * omt * inv_n2 - 2.0f * dden_dd * inv_den;
+  const float dl_dd1 = t * t * inv_n2 - 2.0f * dden_dd * inv_den;
+  const float g_t = gy * dy_dt + gl * dl_dt;
+  const float g_s = gy * dy_ds + gl * dl_ds;
+  const float g_d0 = gy * dy_dd0 + gl * dl_dd0;
+  const float g_d1 = gy * dy_dd1 + gl * dl_dd1;
+  const float g_dy = gy * r1q;
+  const float gv = g_t * r_dx;
+  const float g_dx = -g_t * t * r_dx;
+  const float gW_lo = -2.0f * kBound * gv;
+  const float gW_k = 2.0f * kBound * g_dx - g_s * s * r_wk;
+  const float gH_lo = 2.0f * kBound * gy;
+  const float gH_k = 2.0f * kBound * g_dy + g_s * r_wk;
+  const float dotW = gW_lo * cumw + gW_k * wk;
+  const float dotH = gH_lo * cumh + gH_k * hn;
+  const bool inside = (v > -kBound) && (v <= kBound);
+  const float live = inside ? 1.0f : 0.0f;   // identity outside the spline box: no parameter gradient
+  const float ws = inv_s * live, hs = inv_sh * live;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float gw = (j < k ? gW_lo : (j == k ? gW_k : 0.f)) - dotW;
+    const float gh = (j < k ? gH_lo : (j == k ? gH_k : 0.f)) - dotH;
+    a[j] = (e[j] * ws) * gw * (a[j] * a[j]);                  // softmax Jacobian, then the clip derivative
+    a[NB + j] = (h[j] * hs) * gh * (a[NB + j] * a[NB + j]);
+  }
+  const float gd0 = g_d0 * d0 * ri0 * ri0 * live, gd1 = g_d1 * d1 * ri1 * ri1 * live;
+#pragma unroll
+  for (int j = 0; j < NB - 1; ++j) a[2 * NB + j] = (j == k - 1) ? gd0 : ((j == k) ? gd1 : 0.f);
+  return inside ? gv : gy;
+}
+
 // bias-only spline from the precomputed knot tables (shared memory, broadcast reads)
 template <int NB>
 __device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, float v, float& jac) {
@@ -436,12 +583,15 @@ __device__ __forceinline__ void mma_slot(uint32_t tmem_d, uint64_t a_hi, uint64_
 // =============================================================================================
 // the layer kernel
 // =============================================================================================
-template <int D, int L, int NB>
+// kBwd = false: forward layer (y, log q).  kBwd = true: the first stage of the backward of the same
+// layer -- conditioner recomputed, then spline forward + backward per feature: writes the post-ReLU
+// activations, dL/dphi, the direct dL/dv and the gradient maxima of BwdIO; y / log q are not written.
+template <int D, int L, int NB, bool kBwd>
 __global__ void __launch_bounds__(kThreads, 1)
 nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char* __restrict__ image,
                     const __grid_constant__ Meta meta,
                     const float* __restrict__ logq_in, int first_layer, float* __restrict__ y,
-                    float* __restrict__ logq_out) {
+                    float* __restrict__ logq_out, const __grid_constant__ BwdIO bio) {
   constexpr int S = D - 1;
   constexpr int kImg = image_bytes(D, L);
   extern __shared__ unsigned char smem_raw[];
@@ -644,6 +794,8 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     request_arrive(req_chain);
     TRACE(3);
   };
+  int64_t next_p = 0;        // particle of this thread in the tile whose chain is running (backward variant)
+  bool next_valid = false;
   // hidden step l (0..L-1): accumulator -> relu -> (hi, lo) rows of A, then ask for the next masked
   // GEMM (l < L-1) or the first two output-layer tiles (l == L-1)
   auto hidden_step = [&](int l) {
@@ -654,6 +806,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     fence_proxy_async();
     umma::fence_before_sync();
     request_arrive(req_chain);
+    if constexpr (kBwd) {
+      // post-ReLU activations of the tile being started (= next tile), feature-major, original unit order;
+      // after the hand-off so that the stores overlap the GEMM
+      if (next_valid) {
+        float* al = bio.acts + (size_t)l * kH * n + next_p;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) al[(size_t)meta.perm[c] * n] = fmaxf(acc[c], 0.f);
+      }
+    }
     TRACE(4 + l);
   };
 
@@ -694,10 +855,53 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     const int64_t p = tile * 128 + t;
     const bool valid = cur && p < n;
     if (cur) has_next = tile + tstride < ntiles;
+    next_p = (tile + tstride) * 128 + t;
+    next_valid = has_next && next_p < n;
     float jac = jac_carry;   // Jacobian of the bias-only feature, computed at the end of the previous iteration
     float ss = ss_carry;     // |v|^2 for the base density of the first layer
     float lq_in = 0.f;       // loaded a tile's worth of work before it is needed
-    if (cur && valid && logq_out && !first_layer) lq_in = logq_in[p];
+    if (!kBwd && cur && valid && logq_out && !first_layer) lq_in = logq_in[p];
+    // backward variant: upstream gradients of this particle, running maximum of |dL/dphi|
+    float gyr[D], glq = 0.f, amax = 0.f;
+    if constexpr (kBwd) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) gyr[i] = valid ? bio.gy[p * D + i] : 0.f;
+      glq = (valid && bio.glogq) ? bio.glogq[p] : 0.f;
+    }
+    // one feature of the backward variant: spline forward + backward from the raw parameters in acc,
+    // dL/dphi rows out, direct dL/dv into the staging row in place of v_f
+    auto feature_bwd = [&](float (&acc)[64], int f) {
+      const float vf = sc[f];
+      float gyf = gyr[0];
+#pragma unroll
+      for (int i = 1; i < D; ++i) gyf = (f == i) ? gyr[i] : gyf;
+      // logq_out = logq_in - ladj  =>  dL/d(ladj) = -dL/dlogq
+      float gvf = rq_spline_regs_bwd<NB>(acc, vf, gyf, -glq);
+      if (first_layer) gvf -= glq * vf;   // d/dv of log N(v; 0, I)
+      sc[f] = gvf;
+      if (valid) {
+        float* gp = bio.gphi + (size_t)f * kPP * n + p;
+#pragma unroll
+        for (int j = 0; j < 3 * NB - 1; ++j) {
+          gp[(size_t)j * n] = acc[j];
+          amax = fmaxf(amax, fabsf(acc[j]));
+        }
+#pragma unroll
+        for (int j = 3 * NB - 1; j < kPP; ++j) gp[(size_t)j * n] = 0.f;
+      }
+    };
+    if constexpr (kBwd) {
+      if (cur) {   // bias-only feature: its raw parameters are the same for every particle
+        float acc[64];
+        const float4* cb = reinterpret_cast<const float4*>(ctab + 6 * kCT);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 q4 = cb[i];
+          acc[4 * i] = q4.x; acc[4 * i + 1] = q4.y; acc[4 * i + 2] = q4.z; acc[4 * i + 3] = q4.w;
+        }
+        feature_bwd(acc, meta.const_feature);
+      }
+    }
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
       const int b = s & 1;
@@ -725,9 +929,13 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       }
       if (cur) {
         const int f = meta.slot_feature[s];
-        const float vf = sc[f];
-        ss = fmaf(vf, vf, ss);
-        sc[f] = rq_spline_regs<NB>(acc, vf, jac);
+        if constexpr (kBwd) {
+          feature_bwd(acc, f);
+        } else {
+          const float vf = sc[f];
+          ss = fmaf(vf, vf, ss);
+          sc[f] = rq_spline_regs<NB>(acc, vf, jac);
+        }
         TRACE(20 + s);
       }
       if (has_next) {
@@ -736,22 +944,37 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       }
     }
     if (S == 1 && has_next) hidden_step(1);
-    if (valid) {
+    if constexpr (kBwd) {
+      if (valid) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) y[p * D + i] = sc[i];
-      if (logq_out) {
-        const float base = first_layer ? -0.5f * ss - (float)D * kHalfLog2Pi : lq_in;
-        logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
+        for (int i = 0; i < D; ++i) bio.gvd[p * D + i] = sc[i];
+        bio.gmax[p] = amax;
       }
-    }
-    if (has_next) {
-      // bias-only feature of the NEXT tile here: CUDA-core work between the request for the third
-      // GEMM of its chain and the wait for it
-      const float vf = sn[meta.const_feature];
-      ss_carry = vf * vf;
-      jac_carry = 1.0f;
-      sn[meta.const_feature] = rq_spline_const<NB>(ctab, vf, jac_carry);
-      hidden_step(2);
+      if (cur) {   // batch maximum of |dL/dphi|: one atomic per warp (non-negative floats order like ints)
+        float wm = valid ? amax : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        if ((t & 31) == 0) atomicMax(bio.gmaxes, __float_as_int(wm));
+      }
+      if (has_next) hidden_step(2);
+    } else {
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) y[p * D + i] = sc[i];
+        if (logq_out) {
+          const float base = first_layer ? -0.5f * ss - (float)D * kHalfLog2Pi : lq_in;
+          logq_out[p] = fmaf(-0.69314718055994531f, fast_lg2(jac), base);
+        }
+      }
+      if (has_next) {
+        // bias-only feature of the NEXT tile here: CUDA-core work between the request for the third
+        // GEMM of its chain and the wait for it
+        const float vf = sn[meta.const_feature];
+        ss_carry = vf * vf;
+        jac_carry = 1.0f;
+        sn[meta.const_feature] = rq_spline_const<NB>(ctab, vf, jac_carry);
+        hidden_step(2);
+      }
     }
     float* tmp = sc;
     sc = sn;
@@ -796,6 +1019,7 @@ static void make_meta(int d, const int32_t* order, Meta* m, PrepMeta* pm) {
   }
   mm.const_feature = cfeat;
   mm.nslots = slots;
+  for (int h = 0; h < kH; ++h) mm.perm[h] = perm[h];
   pp.const_feature = cfeat;
   pp.nslots = slots;
   if (m) *m = mm;
@@ -816,16 +1040,60 @@ static int launch_layer(const float* v, int64_t n, const unsigned char* image, c
                         int first, float* y, float* logq_out, cudaStream_t st) {
   constexpr int L = 3, NB = 20;
   const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 256 + (size_t)kWG * 2 * 128 * D * 4 + 1024;
-  auto kern = nsf_tc_layer_kernel<D, L, NB>;
+  auto kern = nsf_tc_layer_kernel<D, L, NB, false>;
   MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (n + 127) / 128;
   int64_t grid = sm_count();
   if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
-  kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, logq_in, first, y, logq_out);
+  kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, logq_in, first, y, logq_out, BwdIO{});
+  return launch_status();
+}
+
+template <int D>
+static int launch_layer_bwd(const float* v, int64_t n, const unsigned char* image, const Meta& meta, int first,
+                            const BwdIO& bio, cudaStream_t st) {
+  constexpr int L = 3, NB = 20;
+  const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 256 + (size_t)kWG * 2 * 128 * D * 4 + 1024;
+  auto kern = nsf_tc_layer_kernel<D, L, NB, true>;
+  MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + 127) / 128;
+  int64_t grid = sm_count();
+  if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
+  kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, nullptr, first, nullptr, nullptr, bio);
   return launch_status();
 }
 
 }  // namespace tc
+
+// First stage of the layer backward on the tensor cores (called from nsf_bwd.cu): builds the operand
+// image of the layer into `image` (mfb_nsf_tc_image_bytes bytes, 1 KB aligned), then recompute + spline
+// forward/backward.  MFB_E_UNSUPPORTED for shapes the tcgen05 kernels are not compiled for.
+int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
+                      int bins, const float* params, const int32_t* order, int first_layer, float* acts,
+                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, cudaStream_t st) {
+  if (!(d >= 2 && d <= 6 && hidden_layers == 3 && bins == 20)) return MFB_E_UNSUPPORTED;
+  if (!tc::valid_order(d, order)) return MFB_E_BADARG;
+  tc::PrepArgs args = {};
+  int cls[kH];
+  tc::hidden_classes(d, cls, args.perm);
+  tc::Meta meta;
+  tc::make_meta(d, order, &meta, &args.layer[0]);
+  unsigned char* img = reinterpret_cast<unsigned char*>(image);
+  tc::nsf_tc_prepare_kernel<<<1, 256, 0, st>>>(params, 0, d, hidden_layers, bins, args, 0, img,
+                                               tc::image_bytes(d, hidden_layers));
+  int rc = launch_status();
+  if (rc) return rc;
+  const tc::BwdIO bio = {gy, glogq, acts, gphi, gvd, gmax, gmaxes};
+  switch (d) {
+    case 2: return tc::launch_layer_bwd<2>(v, n, img, meta, first_layer, bio, st);
+    case 3: return tc::launch_layer_bwd<3>(v, n, img, meta, first_layer, bio, st);
+    case 4: return tc::launch_layer_bwd<4>(v, n, img, meta, first_layer, bio, st);
+    case 5: return tc::launch_layer_bwd<5>(v, n, img, meta, first_layer, bio, st);
+    case 6: return tc::launch_layer_bwd<6>(v, n, img, meta, first_layer, bio, st);
+    default: return MFB_E_UNSUPPORTED;
+  }
+}
+
 }  // namespace mfb
 
 using namespace mfb;
