@@ -223,6 +223,50 @@ def test_backward_matches_oracle_autograd(d, n, scale, hl, tr, bins):
     assert float(got.cpu()[want == 0].abs().max()) == 0.0      # masked weights: exactly zero gradient
 
 
+@pytest.fixture
+def cuda_core_backward():
+    """Run a test with the fp32 CUDA-core backward kernels (the tcgen05 backward is the default)."""
+    from mentflow_b200 import _lib
+    lib = _lib.load()
+    old = lib.mfb_nsf_bwd_use_tensor_cores(0)
+    yield
+    lib.mfb_nsf_bwd_use_tensor_cores(old)
+
+
+def test_backward_cuda_core_kernels_match_oracle(cuda_core_backward):
+    """The CUDA-core backward (shapes the tensor-core kernels are not compiled for use it) on a shape
+    both support."""
+    test_backward_matches_oracle_autograd(6, 3000, 1.0, 3, 5, 20)
+
+
+def test_backward_tensor_core_and_cuda_core_agree():
+    """Same weights, inputs and upstream gradients through both backward implementations, with a
+    1/N-sized loss (gradients far below fp16's range: exercises the operand scaling)."""
+    from mentflow_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(11)
+    d, n = 6, 20_000
+    gen = mf.generate.NSFGenerator(d).to("cuda")
+    z = torch.randn(n, d, device="cuda")
+    a, b = torch.randn(n, d, device="cuda"), torch.randn(n, device="cuda")
+    out = {}
+    for flag in (1, 0):
+        old = lib.mfb_nsf_bwd_use_tensor_cores(flag)
+        try:
+            for p in gen.parameters():
+                p.grad = None
+            zc = z.clone().requires_grad_(True)
+            x, lq = gen.forward_and_log_prob(zc)
+            (((x * a).sum() + (lq * b).sum()) * 1e-7).backward()
+            out[flag] = [zc.grad.clone()] + [p.grad.clone() for p in gen.parameters()]
+        finally:
+            lib.mfb_nsf_bwd_use_tensor_cores(old)
+    for g1, g0 in zip(out[1], out[0]):
+        e = (g1 - g0).abs() / g0.abs().max().clamp_min(1e-30)
+        assert float(e.median()) < 1e-6 and float(e.max()) < 1e-3, (float(e.median()), float(e.max()))
+        assert float(g0.abs().max()) < 1e-3        # the gradients really are tiny
+
+
 @pytest.mark.parametrize("d,n,scale", [(2, 2000, 1.5), (6, 20000, 1.0), (4, 999, 2.0)])
 def test_inverse_and_log_prob(d, n, scale):
     """Density direction (generate/flows/zuko.py:21-22,31-32,43-50): round trip through the CUDA
