@@ -483,7 +483,7 @@ int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const 
 int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
                       int bins, const float* params, const int32_t* order, int first_layer, float* acts,
                       float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, cudaStream_t st);
-// tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu); needs n % 4 == 0
+// tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu)
 int64_t nsf_tc_wgrad_partial_floats(int d);
 int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
                  int hidden_layers, const int32_t* order, const int* gmaxes, float* partial, float* gparams,
@@ -503,9 +503,10 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
     off += (floats + 3) & ~(int64_t)3;
     return o;
   };
-  P.acts = take((int64_t)hidden_layers * kH * n);
-  P.gphi = take((int64_t)d * kPP * n);
-  P.ga = take((int64_t)hidden_layers * kH * n);
+  const int64_t npad = (n + 127) / 128 * 128;   // the tensor-core kernels store these matrices tile-major
+  P.acts = take((int64_t)hidden_layers * kH * npad);
+  P.gphi = take((int64_t)d * kPP * npad);
+  P.ga = take((int64_t)hidden_layers * kH * npad);
   P.gb = take((int64_t)kH * n);
   P.gvd = take(n * d);
   P.gmax = take(n);
@@ -571,19 +572,16 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
   // 1b. data gradients of the whole conditioner on the tensor cores (three hidden layers):
   //     ga[l] = dL/d(pre-activation) of hidden layer l, gv = dL/dv
   bool tc_chain = false;
-  if (hidden_layers == 3 && g_use_tc_dgrad) {
+  if (tc_spline) {   // the three tensor-core kernels share the tile-major workspace layout: all or none
     int32_t ord[kMaxDim];
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
     int rc = nsf_tc_dgrad(gphi, ws + P.gmax, acts, gvd, n, D, hidden_layers, params, ord, ga, gv, image, gmaxes, st);
-    if (rc == 0) tc_chain = true;
-    else if (rc != MFB_E_UNSUPPORTED) return rc;
+    if (rc) return rc;
+    tc_chain = true;
     // 1c. every weight and bias gradient of the layer in one tensor-core kernel
-    if (tc_chain && (n & 3) == 0) {
-      rc = nsf_tc_wgrad(gphi, ga, acts, v, n, D, hidden_layers, ord, gmaxes, partial, gparams, accumulate, st);
-      if (rc == 0) return launch_status();
-      if (rc != MFB_E_UNSUPPORTED) return rc;
-    }
+    rc = nsf_tc_wgrad(gphi, ga, acts, v, n, D, hidden_layers, ord, gmaxes, partial, gparams, accumulate, st);
+    return rc ? rc : launch_status();
   }
   // packed (forward) layout offsets
   const int64_t off_w1 = 0, off_b1 = (int64_t)D * kH, off_hid = off_b1 + kH;

@@ -40,12 +40,15 @@ struct Meta {
   int perm[kH];               // original hidden unit at sorted position c (backward: global rows of the activations)
 };
 
-// pointers of the backward variant (recompute + spline backward): workspace rows are feature-major [row][n]
+// pointers of the backward variant (recompute + spline backward).  Workspace matrices are tile-major:
+// element (row r, particle p) of a matrix with R rows sits at ((p / 128) * R + r) * 128 + p % 128, so
+// the rows of one 128-particle tile are contiguous (512 B each) and every row is a ready K-major
+// operand row for the weight-gradient GEMMs.
 struct BwdIO {
   const float* gy;      // [n][D] dL/dy
   const float* glogq;   // [n] dL/dlogq_out or null
-  float* acts;          // [3][64][n] post-ReLU activations (original unit order)
-  float* gphi;          // [D*64][n] dL/d(raw conditioner output)
+  float* acts;          // 192 rows (3 x 64): post-ReLU activations (original unit order)
+  float* gphi;          // D*64 rows: dL/d(raw conditioner output)
   float* gvd;           // [n][D] direct dL/dv through the spline (+ base density term)
   float* gmax;          // [n] max |gphi| of the particle
   int* gmaxes;          // [0]: batch maximum of |gphi| (float bits, atomicMax)
@@ -810,9 +813,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       // post-ReLU activations of the tile being started (= next tile), feature-major, original unit order;
       // after the hand-off so that the stores overlap the GEMM
       if (next_valid) {
-        float* al = bio.acts + (size_t)l * kH * n + next_p;
+        float* al = bio.acts + ((size_t)(next_p >> 7) * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) al[(size_t)meta.perm[c] * n] = fmaxf(acc[c], 0.f);
+        for (int c = 0; c < 64; ++c) al[meta.perm[c] * 128] = fmaxf(acc[c], 0.f);
       }
     }
     TRACE(4 + l);
@@ -880,14 +883,14 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       if (first_layer) gvf -= glq * vf;   // d/dv of log N(v; 0, I)
       sc[f] = gvf;
       if (valid) {
-        float* gp = bio.gphi + (size_t)f * kPP * n + p;
+        float* gp = bio.gphi + ((size_t)tile * (D * kPP) + f * kPP) * 128 + t;
 #pragma unroll
         for (int j = 0; j < 3 * NB - 1; ++j) {
-          gp[(size_t)j * n] = acc[j];
+          gp[j * 128] = acc[j];
           amax = fmaxf(amax, fabsf(acc[j]));
         }
 #pragma unroll
-        for (int j = 3 * NB - 1; j < kPP; ++j) gp[(size_t)j * n] = 0.f;
+        for (int j = 3 * NB - 1; j < kPP; ++j) gp[j * 128] = 0.f;
       }
     };
     if constexpr (kBwd) {

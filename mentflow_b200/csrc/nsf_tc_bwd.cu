@@ -107,10 +107,11 @@ __device__ __forceinline__ void store_row_split(const float (&x)[64], float scal
 
 template <int D, int L>
 __global__ void __launch_bounds__(kThreads, 1)
-nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float* __restrict__ gmax /* [n] */,
-                    const float* __restrict__ acts /* [L][64][n] */, const float* __restrict__ gvd /* [n][D] */,
+nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (BwdIO in nsf_tc.cu) */,
+                    const float* __restrict__ gmax /* [n] */,
+                    const float* __restrict__ acts /* L*64 rows, tile-major */, const float* __restrict__ gvd /* [n][D] */,
                     int64_t n, const unsigned char* __restrict__ image, const __grid_constant__ DgradMeta meta,
-                    float* __restrict__ gz /* [L][64][n]: dL/d(pre-activation) of hidden layer l */,
+                    float* __restrict__ gz /* L*64 rows, tile-major: dL/d(pre-activation) of hidden layer l */,
                     float* __restrict__ gv /* [n][D] */,
                     int* __restrict__ gmaxes /* [1 + L] float bits: batch maxima of |gphi|, |gz[l]| (atomicMax) */) {
   static_assert(L == 3, "compiled for three hidden layers");
@@ -231,25 +232,25 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
       const float sc0 = pow2_scale(valid ? gmax[p] : 0.f, inv0);
       float g[64];
       {
-        const float* gp = gphi + (size_t)meta.slot_feature[S - 1] * kPP * n + p;
+        const float* gp = gphi + ((size_t)tile * (D * kPP) + meta.slot_feature[S - 1] * kPP) * 128 + t;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[(size_t)j * n] : 0.f;
+        for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[j * 128] : 0.f;
       }
       // global loads are always issued BEFORE waiting for the tensor core and global stores AFTER the
       // hand-off to the issuer, so HBM latency and the release-fence of the arrive overlap the MMAs
       auto load_mask = [&](int l, float (&hv)[64]) {
-        const float* hl = acts + (size_t)l * kH * n + p;
+        const float* hl = acts + ((size_t)tile * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) hv[c] = valid ? hl[(size_t)meta.perm[c] * n] : 0.f;
+        for (int c = 0; c < 64; ++c) hv[c] = valid ? hl[meta.perm[c] * 128] : 0.f;
       };
 #pragma unroll 1
       for (int s = S - 1; s >= 0; --s) {
         store_row_split(g, sc0, a_hi, a_lo, t);
         publish();
         if (s > 0) {   // next slot's gradient rows travel while the tensor core works
-          const float* gp = gphi + (size_t)meta.slot_feature[s - 1] * kPP * n + p;
+          const float* gp = gphi + ((size_t)tile * (D * kPP) + meta.slot_feature[s - 1] * kPP) * 128 + t;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[(size_t)j * n] : 0.f;
+          for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[j * 128] : 0.f;
         } else {
           load_mask(L - 1, g);   // g now holds h3 (sorted unit order): the ReLU mask of the first chain step
         }
@@ -279,9 +280,9 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
           if ((t & 31) == 0) atomicMax(gmaxes + 1 + l, __float_as_int(wm));
         }
         if (valid) {
-          float* gl = gz + (size_t)l * kH * n + p;
+          float* gl = gz + ((size_t)tile * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) gl[(size_t)meta.perm[c] * n] = acc[c];
+          for (int c = 0; c < 64; ++c) gl[meta.perm[c] * 128] = acc[c];
         }
         if (l > 0) load_mask(l - 1, g);
         wait_done();
@@ -337,8 +338,8 @@ static int launch_dgrad(const float* gphi, const float* gmax, const float* acts,
 // =============================================================================================
 // weight + bias gradients of one layer: dW[i][j] = sum_p H[i][p] G[j][p] for the eight (G, H) pairs
 //   (dL/dphi_f, h3) x S,  (g3, h2),  (g2, h1),  (g1, v^T)
-// as tcgen05 GEMMs whose K dimension is the particle axis.  The workspace rows are feature-major
-// ([row][n]), so 128 consecutive particles of a row are contiguous: exactly a K-major operand row.
+// as tcgen05 GEMMs whose K dimension is the particle axis.  The workspace matrices are tile-major (see
+// BwdIO in nsf_tc.cu): the 128 particles of a row of a tile are contiguous, exactly a K-major operand row.
 // Loader warps turn such rows into (hi, lo) fp16 SWIZZLE_128B tiles (64 rows x 128 K, two 64-wide
 // halves), the issuer warp multiplies them into accumulators that stay in TMEM for the whole
 // launch (464 columns: 5 x 64 + 64 + 64 + 16), bias gradients are row sums taken on the way.  G is
@@ -359,8 +360,8 @@ __host__ __device__ constexpr int wgrad_rows(int D) { return kWgCols + D + 3; } 
 
 template <int D>
 __global__ void __launch_bounds__(512, 1)
-nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float* __restrict__ gz /* [3][64][n] */,
-                    const float* __restrict__ acts /* [3][64][n] */, const float* __restrict__ v /* [n][D] */,
+nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float* __restrict__ gz /* 192 rows */,
+                    const float* __restrict__ acts /* 192 rows, all tile-major */, const float* __restrict__ v /* [n][D] */,
                     int64_t n, const int* __restrict__ gmaxes, const __grid_constant__ WgradMeta meta,
                     float* __restrict__ partial /* [grid][wgrad_rows][64] */) {
   constexpr int S = D - 1;
@@ -416,7 +417,7 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
         x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
         if (r < nrows) {
           if (!strided_v) {
-            const float* src = rows + (size_t)r * n + p0 + 4 * lane;
+            const float* src = rows + (size_t)r * 128 + 4 * lane;   // rows = first row of this tile
             if (p0 + 4 * lane + 3 < n) {
               const float4 q = *reinterpret_cast<const float4*>(src);
               x[i][0] = q.x; x[i][1] = q.y; x[i][2] = q.z; x[i][3] = q.w;
@@ -472,16 +473,19 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* [D*64][n] */, const float*
     };
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t p0 = tile * 128;
-      fill_h(acts + (size_t)2 * kH * n, 64, p0, false);                                   // h3
+      const float* at = acts + (size_t)tile * (3 * kH) * 128;       // rows of this tile
+      const float* zt = gz + (size_t)tile * (3 * kH) * 128;
+      const float* pt = gphi + (size_t)tile * (D * kPP) * 128;
+      fill_h(at + 2 * kH * 128, 64, p0, false);                                           // h3
       for (int s = 0; s < S; ++s)
-        fill_g(gphi + (size_t)meta.slot_feature[s] * kPP * n, p0, gsc[0], bias + meta.slot_feature[s] * 64);
-      fill(nullptr, gphi + (size_t)meta.const_feature * kPP * n, 64, p0, 1.0f, bias + meta.const_feature * 64, false);
-      fill_h(acts + (size_t)1 * kH * n, 64, p0, false);                                   // h2
-      fill_g(gz + (size_t)2 * kH * n, p0, gsc[3], bias + (D + 0) * 64);                   // g3
-      fill_h(acts, 64, p0, false);                                                        // h1
-      fill_g(gz + (size_t)1 * kH * n, p0, gsc[2], bias + (D + 1) * 64);                   // g2
+        fill_g(pt + meta.slot_feature[s] * kPP * 128, p0, gsc[0], bias + meta.slot_feature[s] * 64);
+      fill(nullptr, pt + meta.const_feature * kPP * 128, 64, p0, 1.0f, bias + meta.const_feature * 64, false);
+      fill_h(at + 1 * kH * 128, 64, p0, false);                                           // h2
+      fill_g(zt + 2 * kH * 128, p0, gsc[3], bias + (D + 0) * 64);                         // g3
+      fill_h(at, 64, p0, false);                                                          // h1
+      fill_g(zt + 1 * kH * 128, p0, gsc[2], bias + (D + 1) * 64);                         // g2
       fill_h(v, D, p0, true);                                                             // v^T
-      fill_g(gz, p0, gsc[1], bias + (D + 2) * 64);                                        // g1
+      fill_g(zt, p0, gsc[1], bias + (D + 2) * 64);                                        // g1
     }
   } else if (warp == kWgLoaders) {
     // ===== issuer =====
@@ -664,7 +668,7 @@ int64_t nsf_tc_wgrad_partial_floats(int d) {
 int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
                  int hidden_layers, const int32_t* order, const int* gmaxes, float* partial, float* gparams,
                  int accumulate, cudaStream_t st) {
-  if (hidden_layers != 3 || d < 2 || d > 6 || (n & 3)) return MFB_E_UNSUPPORTED;
+  if (hidden_layers != 3 || d < 2 || d > 6) return MFB_E_UNSUPPORTED;
   switch (d) {
     case 2: return tc::launch_wgrad<2>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
     case 3: return tc::launch_wgrad<3>(gphi, gz, acts, v, n, order, gmaxes, partial, gparams, accumulate, st);
