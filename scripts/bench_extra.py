@@ -103,6 +103,19 @@ def train():
 
 
 out("C3 training step: forward + backward to all flow parameters", N, timed(train, reps=3, warm=1))
+from mentflow_b200.graphs import GraphedTrainStep
+for nb in (25_000, 100_000, 1_000_000):
+    opt = torch.optim.AdamW(m3.parameters(), lr=1e-5, weight_decay=0.0, capturable=True)
+    gts = GraphedTrainStep(m3, opt, nb)
+    out("C3 optimisation step (zero_grad + loss + backward + AdamW) as one CUDA-graph replay", nb, timed(gts, reps=7))
+
+    def eager_step():
+        opt.zero_grad(set_to_none=True)
+        L, H, D = m3.loss(nb)
+        L.backward()
+        opt.step()
+
+    out("C3 optimisation step, eager launches", nb, timed(eager_step, reps=7))
 # ---- C4
 m4 = flow_model(workloads.corner_2d(6, 85, 3.5), 6, "2d", n_truth=100_000)
 with torch.no_grad():
