@@ -68,6 +68,21 @@ int mfb_kde1d_normalize(const float* sums, double n_total, const float* geom, in
 /* backward of the normalisation: gsums = dL/dS given gprof = dL/dp    */
 int mfb_kde1d_normalize_bwd(const float* sums, double n_total, const float* geom, int k, int b,
                             const float* gprof, float* gsums, void* stream);
+/* Fused forward tail for the training loss (core.py:89-117 with loss.py:15-17): deposit, merge,
+ * normalise and -- when meas[K][B] is given -- kl[k] = sum_b (xlogy(t,t) - t log(p + pad)) / B in
+ * two launches.  sums[K][B] (unnormalised, kept for the backward), profiles[K][B], kl[K] (NULL iff
+ * meas is NULL).  Workspace as for mfb_project_kde1d_fwd.                                  */
+int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
+                               int k, int b, float max_sigma_over_delta, double n_total,
+                               const float* meas, float pad, float* sums, float* profiles, float* kl,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+/* The same tail from already merged (e.g. all-reduced across ranks) sums.                   */
+int mfb_kde1d_finish(const float* sums, double n_total, const float* geom, int k, int b,
+                     const float* meas, float pad, float* profiles, float* kl, void* stream);
+/* gsums = d/dS of <gprof, profiles> + <gkl, kl>; gprof or gkl may be NULL (not both).       */
+int mfb_kde1d_finish_bwd(const float* sums, double n_total, const float* geom, int k, int b,
+                         const float* meas, float pad, const float* gprof, const float* gkl,
+                         float* gsums, void* stream);
 /* dL/dx[n][d] (+)= sum_k proj_k * sum_b gsums[k][b] K_nb (-(u-c_b)/sigma^2); accumulate!=0
  * adds into gx instead of overwriting it.                                               */
 int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom,

@@ -21,6 +21,10 @@ SIGNATURES = {
     "mfb_project_kde1d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int64, P]),
     "mfb_kde1d_normalize": (c_int, [P, c_double, P, c_int, c_int, P, P]),
     "mfb_kde1d_normalize_bwd": (c_int, [P, c_double, P, c_int, c_int, P, P, P]),
+    "mfb_project_kde1d_loss_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, c_double, P, c_float, P, P, P,
+                                           P, c_int64, P]),
+    "mfb_kde1d_finish": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P]),
+    "mfb_kde1d_finish_bwd": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P, P]),
     "mfb_project_kde1d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int, P]),
     "mfb_project_hist1d": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P]),
     "mfb_kde2d_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),

@@ -67,7 +67,7 @@ class MENTFlow(nn.Module):
                  _loss.mean_absolute_error: lambda p, t: (p - t).abs().reshape(p.shape[0], -1).mean(dim=1),
                  _loss.mean_square_error: lambda p, t: (p - t).square().reshape(p.shape[0], -1).mean(dim=1)}
         fn = table.get(self.discrepancy_function)
-        if fn is None or not stacked or sum(len(s) for s, _ in stacked) != n_slots:
+        if fn is None or not stacked or sum(len(e[0]) for e in stacked) != n_slots:
             return None
         key = tuple(id(m) for row in self.measurements for m in row)
         if self._BATCHED is None or self._BATCHED[0] != key:
@@ -76,14 +76,15 @@ class MENTFlow(nn.Module):
                 offsets.append(base)
                 base += len(row)
             groups = []
-            for slots, prof in stacked:
+            for slots, prof, *_ in stacked:
                 meas = torch.stack([self.measurements[i][j] for i, j in slots]).to(prof.device)
                 index = torch.tensor([offsets[i] + j for i, j in slots], device=prof.device)
                 groups.append((meas, index))
             self._BATCHED = (key, groups)
         out = None
-        for (slots, prof), (meas, index) in zip(stacked, self._BATCHED[1]):
-            d = fn(prof, meas)
+        for (slots, prof, *fused), (meas, index) in zip(stacked, self._BATCHED[1]):
+            # one-dimensional KDE screens arrive with their KL already evaluated by the kernel
+            d = fused[0] if fused and fused[0] is not None else fn(prof, meas)
             if len(stacked) == 1 and index.numel() == n_slots:
                 return d                      # single group in natural order (the usual case)
             if out is None:
@@ -95,7 +96,10 @@ class MENTFlow(nn.Module):
         """The part of ``loss`` after sampling (used by parity tests that fix the particles)."""
         H = self.entropy_estimator(x, log_prob)
         stacked = []
-        predictions = simulate_forward(x, self.transforms, self.diagnostics, reducer=self.reducer, stacked=stacked)
+        from . import loss as _loss
+        targets = self.measurements if self.discrepancy_function is _loss.kl_divergence else None
+        predictions = simulate_forward(x, self.transforms, self.diagnostics, reducer=self.reducer, stacked=stacked,
+                                       kl_targets=targets)
         n_slots = sum(len(row) for row in predictions)
         dvec = self._batched_discrepancy(stacked, n_slots)
         if dvec is not None:

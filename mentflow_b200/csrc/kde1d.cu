@@ -324,6 +324,116 @@ kde1d_normalize_bwd_kernel(const float* __restrict__ sums, float inv_n, const fl
     gsums[(size_t)k * B + b] = (gprof[(size_t)k * B + b] / z - delta * g / z) * inv_n;
 }
 
+// ---- fused tail of the forward pass: merge per-CTA partials, normalise, KL against the measurement ----
+// One CTA per projection.  Replaces reduce_partials + normalize + the ~8 elementwise/reduce kernels of
+// loss.py:15-17 evaluated on (K, B) tensors.  Sum order is fixed (partials c = g, g+G, ... per group g,
+// groups combined in order), so the result is run-to-run deterministic.
+constexpr int kFinishThreads = 256;
+
+__device__ __forceinline__ void merge_partials_to_smem(const float* __restrict__ partial, int nparts, int64_t len,
+                                                       int k, int B, float* __restrict__ part /*[G][B]*/,
+                                                       float* __restrict__ s /*[B]*/) {
+  const int tid = threadIdx.x;
+  const int lanes = B < kFinishThreads ? B : kFinishThreads;
+  const int G = kFinishThreads / lanes;
+  const int g = tid / lanes, l = tid % lanes;
+  if (g < G) {
+    for (int b = l; b < B; b += lanes) {
+      const float* src = partial + (size_t)k * B + b;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int c = g;
+      for (; c + 3 * G < nparts; c += 4 * G) {
+        a0 += src[(size_t)c * len];
+        a1 += src[(size_t)(c + G) * len];
+        a2 += src[(size_t)(c + 2 * G) * len];
+        a3 += src[(size_t)(c + 3 * G) * len];
+      }
+      for (; c < nparts; c += G) a0 += src[(size_t)c * len];
+      part[(size_t)g * B + b] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < B; b += kFinishThreads) {
+    float t = 0.f;
+    for (int gg = 0; gg < G; ++gg) t += part[(size_t)gg * B + b];
+    s[b] = t;
+  }
+  __syncthreads();
+}
+
+// xlogy(t, t) - t log(p + pad): the summand of F.kl_div(log(p + pad), t) with 0 log 0 = 0
+__device__ __forceinline__ float kl_term(float t, float p, float pad) {
+  const float tl = t == 0.f ? 0.f : t * logf(t);
+  return tl - t * logf(p + pad);
+}
+
+__global__ void __launch_bounds__(kFinishThreads)
+kde1d_finish_kernel(const float* __restrict__ partial, int nparts, int64_t len, float inv_n,
+                    const float* __restrict__ geom, int B, const float* __restrict__ meas, float pad,
+                    float* __restrict__ sums_out, float* __restrict__ prof, float* __restrict__ kl) {
+  extern __shared__ float fsm[];
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  float* s = fsm;
+  float* part = fsm + B;
+  merge_partials_to_smem(partial, nparts, len, k, B, part, s);
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 3];  // the reference's c[1]-c[0]
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float v = s[b];
+    if (sums_out) sums_out[(size_t)k * B + b] = v;
+    acc += v * inv_n * delta;
+  }
+  const float z = block_sum_256(acc, red) + 1.0e-10f;
+  if (prof == nullptr) return;   // merge only (the all-reduce across ranks comes next)
+  float term = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float p = s[b] * inv_n / z;
+    prof[(size_t)k * B + b] = p;
+    if (meas) term += kl_term(meas[(size_t)k * B + b], p, pad);
+  }
+  if (kl) {
+    const float tot = block_sum_256(term, red);
+    if (threadIdx.x == 0) kl[k] = tot / (float)B;
+  }
+}
+
+// gradient of (profiles, KL) w.r.t. the unnormalised sums:  gp_b = gprof_b - gkl * t_b / (p_b + pad) / B,
+// then the normalisation backward of kde1d_normalize_bwd_kernel
+__global__ void __launch_bounds__(kFinishThreads)
+kde1d_finish_bwd_kernel(const float* __restrict__ sums, float inv_n, const float* __restrict__ geom, int B,
+                        const float* __restrict__ meas, float pad, const float* __restrict__ gprof,
+                        const float* __restrict__ gkl, float* __restrict__ gsums) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 3];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) acc += sums[(size_t)k * B + b] * inv_n * delta;
+  const float z = block_sum_256(acc, red) + 1.0e-10f;
+  const float gk = gkl ? gkl[k] / (float)B : 0.f;
+  float dot = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const size_t i = (size_t)k * B + b;
+    const float p = sums[i] * inv_n / z;
+    float gp = gprof ? gprof[i] : 0.f;
+    if (gkl) gp -= gk * meas[i] / (p + pad);
+    dot += gp * p;
+  }
+  const float g = block_sum_256(dot, red);
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const size_t i = (size_t)k * B + b;
+    const float p = sums[i] * inv_n / z;
+    float gp = gprof ? gprof[i] : 0.f;
+    if (gkl) gp -= gk * meas[i] / (p + pad);
+    gsums[i] = (gp / z - delta * g / z) * inv_n;
+  }
+}
+
+static inline size_t finish_smem(int b) {
+  const int lanes = b < kFinishThreads ? b : kFinishThreads;
+  return ((size_t)b + (size_t)(kFinishThreads / lanes) * b) * 4;
+}
+
 // ---- backward w.r.t. the particles: thread per particle ---------------------------------------
 template <int D, int R>
 __global__ void __launch_bounds__(256)
@@ -549,8 +659,62 @@ int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, c
   }
   if (rc) return rc;
   const int64_t len = (int64_t)k * b;
-  int rgrid = (int)((len + 255) / 256);
-  reduce_partials_kernel<<<rgrid, 256, 0, st>>>(partial, L.grid_x, len, sums);
+  if (finish_smem(b) > 48 * 1024) {   // very wide screens: the plain merge
+    int rgrid = (int)((len + 255) / 256);
+    reduce_partials_kernel<<<rgrid, 256, 0, st>>>(partial, L.grid_x, len, sums);
+    return launch_status();
+  }
+  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, len, 1.f, geom, b, nullptr, 0.f,
+                                                                 sums, nullptr, nullptr);
+  return launch_status();
+}
+
+int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                               float max_sigma_over_delta, double n_total, const float* meas, float pad,
+                               float* sums, float* profiles, float* kl, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && sums && profiles && workspace);
+  MFB_CHECK_ARG((meas != nullptr) == (kl != nullptr));
+  MFB_CHECK_ARG(n >= 1 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2 && n_total > 0);
+  if (finish_smem(b) > 48 * 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = radius_from_hint(max_sigma_over_delta);
+  const int rr = r <= 4 ? 4 : (r <= 9 ? 9 : 13);
+  KdePlan L = plan_kde(n, d, k, b, rr);
+  if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
+  if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
+  float* partial = (float*)workspace;
+  int rc;
+  switch (d) {
+    case 2: rc = launch_kde1d_deposit<2>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    case 4: rc = launch_kde1d_deposit<4>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    case 6: rc = launch_kde1d_deposit<6>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+    default: rc = launch_kde1d_deposit<0>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
+  }
+  if (rc) return rc;
+  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, (int64_t)k * b,
+                                                                 (float)(1.0 / n_total), geom, b, meas, pad, sums,
+                                                                 profiles, kl);
+  return launch_status();
+}
+
+int mfb_kde1d_finish(const float* sums, double n_total, const float* geom, int k, int b, const float* meas,
+                     float pad, float* profiles, float* kl, void* stream) {
+  MFB_CHECK_ARG(sums && geom && profiles && k >= 1 && b >= 2 && n_total > 0);
+  MFB_CHECK_ARG((meas != nullptr) == (kl != nullptr));
+  if (finish_smem(b) > 48 * 1024) return MFB_E_UNSUPPORTED;
+  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), (cudaStream_t)stream>>>(
+      sums, 1, (int64_t)k * b, (float)(1.0 / n_total), geom, b, meas, pad, nullptr, profiles, kl);
+  return launch_status();
+}
+
+int mfb_kde1d_finish_bwd(const float* sums, double n_total, const float* geom, int k, int b, const float* meas,
+                         float pad, const float* gprof, const float* gkl, float* gsums, void* stream) {
+  MFB_CHECK_ARG(sums && geom && gsums && k >= 1 && b >= 2 && n_total > 0);
+  MFB_CHECK_ARG(gprof || gkl);
+  MFB_CHECK_ARG(!gkl || meas);
+  kde1d_finish_bwd_kernel<<<k, kFinishThreads, 0, (cudaStream_t)stream>>>(sums, (float)(1.0 / n_total), geom, b, meas,
+                                                                          pad, gprof, gkl, gsums);
   return launch_status();
 }
 

@@ -21,7 +21,7 @@ import torch
 
 
 class GraphedLoss:
-    def __init__(self, model, batch_size: int, warmup: int = 2, host_chunks: int = 2) -> None:
+    def __init__(self, model, batch_size: int, warmup: int = 2, host_chunks: int = 3) -> None:
         self.model = model
         self.batch_size = int(batch_size)
         self.warmup = max(1, int(warmup))
@@ -36,6 +36,10 @@ class GraphedLoss:
         if dev.type != "cuda":
             raise RuntimeError("GraphedLoss needs a CUDA model; mentflow_b200 has no CPU fallback")
         self.device = dev
+        from . import _lib
+        # particles one launch of the flow kernel processes per pass over the SMs (one 128-row tile
+        # per compute warpgroup, three per SM): pieces of whole waves leave no ragged tail per piece
+        self._wave = max(1, _lib.load().mfb_sm_count()) * 3 * 128
         self.z = torch.empty((self.batch_size, gen.features), dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._key = None
@@ -71,16 +75,21 @@ class GraphedLoss:
 
     # ---- pinned host input: chunked copies overlapped with the flow -------------------------------
     def _chunk_bounds(self):
-        """Pieces of growing size (1 : 3 : 4 : 4 ...): only the first copy is exposed, so it is the
-        small one; tile-aligned boundaries keep every slice 16-byte aligned."""
+        """Pieces of growing size (1 : 3 : 5 : 5 ...): only the first copy is exposed, so it is the
+        small one (PCIe moves a piece about twice as fast as the flow consumes it).  Boundaries fall
+        on whole waves of the flow kernel when the batch is large enough, else on 128-row tiles;
+        either keeps every slice 16-byte aligned."""
         n, c = self.batch_size, self.host_chunks
         if c == 1 or n < 8 * 128:
             return [(0, n)]
-        weights = ([1, 3] + [4] * (c - 2))[:c]
+        unit = getattr(self, "_wave", 128)
+        if n < 4 * c * unit:
+            unit = 128
+        weights = ([1, 3] + [5] * (c - 2))[:c]
         total = sum(weights)
         bounds, a = [], 0
         for i, w in enumerate(weights):
-            b = n if i == len(weights) - 1 else min(n, (a + n * w // total + 127) // 128 * 128)
+            b = n if i == len(weights) - 1 else min(n, (a + n * w // total + unit - 1) // unit * unit)
             if b > a:
                 bounds.append((a, b))
             a = b

@@ -91,35 +91,108 @@ def kde1d_grad_x(x, proj, geom, ratio, gsums, out: Optional[torch.Tensor] = None
     return gx
 
 
+KL_PAD = 1.0e-12   # loss.py:15-17
+
+
+def kde1d_loss_forward(x, proj, geom, ratio, nbins, n_total, meas):
+    """Deposit + merge + normalise (+ KL against ``meas``) in two launches: (sums, profiles, kl)."""
+    lib = _lib.load()
+    x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
+    n, d = x.shape
+    k = proj.shape[0]
+    sums = torch.empty((k, nbins), dtype=torch.float32, device=x.device)
+    prof = torch.empty_like(sums)
+    kl = torch.empty(k, dtype=torch.float32, device=x.device) if meas is not None else None
+    with torch.cuda.device(x.device):
+        wbytes = lib.mfb_kde1d_workspace_bytes(n, d, k, nbins)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.mfb_project_kde1d_loss_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, nbins, float(ratio),
+                                                  float(n_total), _ptr(meas), KL_PAD, _ptr(sums), _ptr(prof),
+                                                  _ptr(kl), _ptr(work), wbytes, _stream()), "project_kde1d_loss_fwd")
+    return sums, prof, kl
+
+
+def kde1d_finish(sums, n_total, geom, meas):
+    """Normalise merged sums (+ KL against ``meas``): (profiles, kl)."""
+    lib = _lib.load()
+    k, b = sums.shape
+    prof = torch.empty_like(sums)
+    kl = torch.empty(k, dtype=torch.float32, device=sums.device) if meas is not None else None
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_kde1d_finish(_ptr(sums), float(n_total), _ptr(geom), k, b, _ptr(meas), KL_PAD,
+                                        _ptr(prof), _ptr(kl), _stream()), "kde1d_finish")
+    return prof, kl
+
+
+def kde1d_finish_bwd(sums, n_total, geom, meas, gprof, gkl):
+    lib = _lib.load()
+    k, b = sums.shape
+    gprof = _check_f32("gprof", gprof) if gprof is not None else None
+    gkl = _check_f32("gkl", gkl) if gkl is not None else None
+    gsums = torch.empty_like(sums)
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_kde1d_finish_bwd(_ptr(sums), float(n_total), _ptr(geom), k, b, _ptr(meas), KL_PAD,
+                                            _ptr(gprof), _ptr(gkl), _ptr(gsums), _stream()), "kde1d_finish_bwd")
+    return gsums
+
+
+_FINISH_MAX_BINS = 6000   # shared-memory bound of the fused tail kernel
+
+
 class ProjectKDE1D(torch.autograd.Function):
     """profiles[k, b] of K one-dimensional screens, differentiable w.r.t. the particles.
 
     ``reducer`` (optional) all-reduces the unnormalised sums across ranks *before* the
     non-linear normalisation and returns the global particle count.
+    ``meas`` (optional, (K, B)): also return kl[k] = KL(meas_k || profile_k) of loss.py:15-17,
+    evaluated by the same kernel that normalises.
     """
 
     @staticmethod
-    def forward(ctx, x, proj, geom, ratio, nbins, reducer):
+    def forward(ctx, x, proj, geom, ratio, nbins, reducer, meas):
+        ctx.set_materialize_grads(False)
         x = _check_f32("x", x)
-        sums = kde1d_sums(x, proj, geom, ratio, nbins)
         n_total = float(x.shape[0])
-        if reducer is not None:
-            n_total = reducer(sums, n_total)
-        prof = kde1d_normalize(sums, n_total, geom)
-        ctx.save_for_backward(x, proj, geom, sums)
+        if meas is not None:
+            meas = _check_f32("meas", meas)
+        if reducer is None and x.shape[0] > 0 and nbins <= _FINISH_MAX_BINS:
+            sums, prof, kl = kde1d_loss_forward(x, proj, geom, ratio, nbins, n_total, meas)
+        else:
+            sums = kde1d_sums(x, proj, geom, ratio, nbins)
+            if reducer is not None:
+                n_total = reducer(sums, n_total)
+            if nbins <= _FINISH_MAX_BINS:
+                prof, kl = kde1d_finish(sums, n_total, geom, meas)
+            else:
+                prof = kde1d_normalize(sums, n_total, geom)
+                kl = None
+                if meas is not None:
+                    kl = (torch.xlogy(meas, meas) - meas * torch.log(prof + KL_PAD)).sum(dim=1) / nbins
+        ctx.save_for_backward(x, proj, geom, sums, meas, prof if nbins > _FINISH_MAX_BINS else None)
         ctx.ratio, ctx.n_total = ratio, n_total
-        return prof
+        if meas is None:
+            return prof
+        return prof, kl
 
     @staticmethod
-    def backward(ctx, gprof):
-        x, proj, geom, sums = ctx.saved_tensors
-        gsums = kde1d_normalize_bwd(sums, ctx.n_total, geom, gprof)
+    def backward(ctx, gprof, gkl=None):
+        x, proj, geom, sums, meas, prof = ctx.saved_tensors
+        if gprof is None and gkl is None:
+            return None, None, None, None, None, None, None
+        if prof is not None:       # wide screens: torch expression for the KL part
+            if gkl is not None:
+                extra = -(gkl / sums.shape[1])[:, None] * meas / (prof + KL_PAD)
+                gprof = extra if gprof is None else gprof + extra
+            gsums = kde1d_normalize_bwd(sums, ctx.n_total, geom, gprof)
+        else:
+            gsums = kde1d_finish_bwd(sums, ctx.n_total, geom, meas, gprof, gkl if meas is not None else None)
         gx = kde1d_grad_x(x, proj, geom, ctx.ratio, gsums)
-        return gx, None, None, None, None, None
+        return gx, None, None, None, None, None, None
 
 
-def project_kde1d(x, proj, geom, ratio, nbins, reducer=None):
-    return ProjectKDE1D.apply(x, proj, geom, ratio, nbins, reducer)
+def project_kde1d(x, proj, geom, ratio, nbins, reducer=None, meas=None):
+    """(K, B) profiles; with ``meas`` a pair (profiles, kl[K])."""
+    return ProjectKDE1D.apply(x, proj, geom, ratio, nbins, reducer, meas)
 
 
 # --------------------------------------------------------------------------------------
@@ -297,14 +370,14 @@ def _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_l
 # moments
 # --------------------------------------------------------------------------------------
 def moments(x: torch.Tensor, logq: Optional[torch.Tensor], with_cov: bool = False) -> torch.Tensor:
-    """float64 vector: [sum logq, sum |x|^2, (sum x_i), (sum x_i x_j)]."""
+    """float64 vector: [sum logq, sum |x|^2] (+ [sum x_i, sum x_i x_j] with ``with_cov``)."""
     lib = _lib.load()
     x = _check_f32("x", x)
     if logq is not None:
         logq = _check_f32("logq", logq)
     n, d = x.shape
-    m = 2 + d + d * d
-    out = torch.zeros(m, dtype=torch.float64, device=x.device)
+    m = 2 + d + d * d if with_cov else 2      # every entry is written by the kernel
+    out = torch.empty(m, dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         wbytes = lib.mfb_moments_workspace_bytes(n, d)
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)

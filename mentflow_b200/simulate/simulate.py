@@ -45,10 +45,12 @@ def _density_from_counts(counts: torch.Tensor, widths: torch.Tensor) -> torch.Te
 
 
 def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D], kde: bool = True,
-                reducer: Optional[Callable] = None, cache: Optional[dict] = None) -> torch.Tensor:
+                reducer: Optional[Callable] = None, cache: Optional[dict] = None,
+                kl_targets: Optional[torch.Tensor] = None):
     """(K, B) profiles of K one-dimensional screens sharing the same number of bins.
     proj is (K, D): x_proj_k = x . proj_k.  ``cache`` keeps the device-side geometry between
-    calls (filled on first use)."""
+    calls (filled on first use).  With ``kl_targets`` (K, B) and KDE screens the result is a pair
+    (profiles, kl[K]): the KL of loss.py:15-17 comes out of the normalisation kernel."""
     reducer = reducer if reducer is not None else _default_reducer
     cache = {} if cache is None else cache
     nb = diags[0].nbins
@@ -57,7 +59,7 @@ def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D
             rows = [d.geometry() for d in diags]
             cache["geom"] = _geom_tensor(rows, x.device)
             cache["ratio"] = max(s / sp for _, sp, s, _ in rows)
-        return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer)
+        return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer, kl_targets)
     if "edges" not in cache:
         cache["edges"] = torch.stack([d.edges.to(x.device) for d in diags]).contiguous()
         cache["widths"] = torch.diff(cache["edges"], dim=1)
@@ -162,14 +164,34 @@ def _build_plan(x, transforms, diagnostics) -> _Plan:
     return plan
 
 
+def _stacked_targets(grp: "_Group", targets, device) -> Optional[torch.Tensor]:
+    """(K, B) stack of the measurements of a group's slots, cached on the identity of the tensors."""
+    try:
+        rows = [targets[i][j] for i, j in grp.slots]
+    except (IndexError, TypeError):
+        return None
+    if not all(torch.is_tensor(m) and m.ndim == 1 and m.shape[0] == grp.diags[0].nbins for m in rows):
+        return None
+    key = tuple((id(m), m._version) for m in rows)
+    hit = grp.cache.get("targets")
+    if hit is None or hit[0] != key or hit[1].device != device:
+        hit = grp.cache["targets"] = (key, torch.stack([m.detach().to(device=device, dtype=torch.float32)
+                                                        for m in rows]).contiguous())
+    return hit[1]
+
+
 def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List[nn.Module]],
-            reducer: Optional[Callable] = None, stacked: Optional[list] = None) -> List[List[torch.Tensor]]:
+            reducer: Optional[Callable] = None, stacked: Optional[list] = None,
+            kl_targets=None) -> List[List[torch.Tensor]]:
     """Predicted profiles for every transform / diagnostic pair (simulate/simulate.py:8-33).
 
     ``stacked`` (optional list) receives one ``(slots, profiles)`` pair per fused group, where
     ``profiles`` is the (K, ...) tensor the returned rows are views of and ``slots`` the (i, j)
     positions they fill -- callers that reduce all profiles at once (MENTFlow.loss) use it to
-    avoid K small kernels.  It is left empty if any pair needed the object-by-object path."""
+    avoid K small kernels.  It is left empty if any pair needed the object-by-object path.
+    ``kl_targets`` (optional, nested like the result): measured profiles; one-dimensional KDE
+    groups then also evaluate KL(target || profile) inside the normalisation kernel and the
+    ``stacked`` entries become ``(slots, profiles, kl)`` (kl is None for the other groups)."""
     key = (_plan_key(transforms, diagnostics), x.shape[1], str(x.device))
     plan = _plan_cache.get(key)
     if plan is None:
@@ -181,11 +203,20 @@ def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List
         _plan_cache.move_to_end(key)
     out: List[List[Optional[torch.Tensor]]] = [[None] * n for n in plan.shape]
     for grp in plan.groups.values():
-        fn = profiles_1d if grp.kind == "1d" else profiles_2d
-        prof = fn(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache)
         noisy = any(d.noise and d.noise_scale > 0.0 for d in grp.diags)
+        kl = None
+        if grp.kind == "1d":
+            targ = None
+            if kl_targets is not None and stacked is not None and grp.kde and not noisy and not plan.fallback:
+                targ = _stacked_targets(grp, kl_targets, x.device)
+            prof = profiles_1d(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache,
+                               kl_targets=targ)
+            if targ is not None:
+                prof, kl = prof
+        else:
+            prof = profiles_2d(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache)
         if stacked is not None and not noisy and not plan.fallback:
-            stacked.append((grp.slots, prof))
+            stacked.append((grp.slots, prof, kl) if kl_targets is not None else (grp.slots, prof))
         for row, (i, j), d in zip(prof.unbind(0), grp.slots, grp.diags):
             out[i][j] = d.apply_noise(row) if noisy else row
     if plan.fallback:

@@ -144,3 +144,68 @@ def test_full_size_properties():
     assert (counts.sum(dim=1) - n_in).abs().max() <= 2
     prof = ops.kde1d_normalize(full.float(), n, geom)
     assert torch.allclose(prof.sum(dim=1) * delta, torch.ones(k, device="cuda"), atol=1e-5)
+
+
+@pytest.mark.parametrize("n,d,k,nb", [(1, 6, 3, 64), (4097, 4, 11, 37), (70001, 6, 100, 64), (3000, 2, 5, 300),
+                                      (2000, 3, 2, 1000)])
+def test_fused_loss_tail_matches_separate_kernels_and_torch_kl(n, d, k, nb):
+    """deposit + merge + normalise + KL in two launches (mfb_project_kde1d_loss_fwd / _finish / _finish_bwd)
+    vs the separate normalise kernel and the torch expression of loss.py:15-17, values and gradients."""
+    gen = torch.Generator().manual_seed(7 * n + k)
+    x = torch.randn(n, d, generator=gen).cuda()
+    w = torch.randn(k, d, generator=gen)
+    w = (w / w.norm(dim=1, keepdim=True)).cuda()
+    edges = torch.linspace(-3.5, 3.5, nb + 1)
+    geom = geom_rows(edges, 0.5, k)[0].cuda()
+    meas = torch.rand(k, nb, generator=gen)
+    meas[:, : nb // 4] = 0.0                      # empty bins: 0 log 0 = 0
+    meas = (meas / meas.sum(dim=1, keepdim=True) * nb / 7.0).cuda()
+
+    xa = x.clone().requires_grad_(True)
+    prof_a, kl_a = ops.project_kde1d(xa, w, geom, 0.5, nb, None, meas)
+    xb = x.clone().requires_grad_(True)
+    prof_b = ops.project_kde1d(xb, w, geom, 0.5, nb)
+    kl_b = mf.loss.kl_divergence_batched(prof_b, meas)
+    assert float((prof_a - prof_b).abs().max()) <= 2e-6 * float(prof_b.abs().max())
+    assert torch.allclose(kl_a, kl_b, rtol=2e-5, atol=1e-6)
+    # the merged sums agree with the stand-alone merge bit for bit (same kernel, same order)
+    sums = ops.kde1d_sums(x, w, geom, 0.5, nb)
+    prof_c, kl_c = ops.kde1d_finish(sums, float(n), geom, meas)
+    assert torch.equal(prof_c, prof_a) and torch.equal(kl_c, kl_a)
+
+    coef = torch.linspace(0.5, 1.5, k).cuda()
+    side = torch.randn(k, nb, generator=gen).cuda()
+    ((kl_a * coef).sum() + (prof_a * side).sum()).backward()
+    ((kl_b * coef).sum() + (prof_b * side).sum()).backward()
+    scale = float(xb.grad.abs().max())
+    assert float((xa.grad - xb.grad).abs().max()) <= 1e-4 * scale
+    # KL only (no gradient through the profiles): the materialised-zero path is skipped
+    xc = x.clone().requires_grad_(True)
+    _, kl_only = ops.project_kde1d(xc, w, geom, 0.5, nb, None, meas)
+    kl_only.sum().backward()
+    xd = x.clone().requires_grad_(True)
+    mf.loss.kl_divergence_batched(ops.project_kde1d(xd, w, geom, 0.5, nb), meas).sum().backward()
+    assert float((xc.grad - xd.grad).abs().max()) <= 1e-4 * float(xd.grad.abs().max())
+
+
+def test_fused_loss_tail_with_reducer_path():
+    """With a reducer (sharded particles) the tail runs from the all-reduced sums: two half batches whose
+    sums are added by the 'reducer' give the profiles and KL of the whole batch."""
+    gen = torch.Generator().manual_seed(5)
+    n, d, k, nb = 20000, 6, 9, 64
+    x = torch.randn(n, d, generator=gen).cuda()
+    w = torch.randn(k, d, generator=gen)
+    w = (w / w.norm(dim=1, keepdim=True)).cuda()
+    geom = geom_rows(torch.linspace(-3.5, 3.5, nb + 1), 0.5, k)[0].cuda()
+    meas = torch.rand(k, nb, generator=gen).cuda()
+    other = ops.kde1d_sums(x[n // 2:].contiguous(), w, geom, 0.5, nb)
+
+    def reducer(sums, n_local):
+        if sums.dtype == torch.float32 and sums.shape == other.shape:
+            sums += other
+        return float(n)
+
+    prof_r, kl_r = ops.project_kde1d(x[: n // 2].contiguous(), w, geom, 0.5, nb, reducer, meas)
+    prof_f, kl_f = ops.project_kde1d(x, w, geom, 0.5, nb, None, meas)
+    assert float((prof_r - prof_f).abs().max()) <= 1e-5 * float(prof_f.abs().max())
+    assert torch.allclose(kl_r, kl_f, rtol=1e-4, atol=1e-6)
