@@ -443,7 +443,7 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(16) float sm[];
   float* s_g = sm;                          // [K][B]
-  float* s_w = s_g + (size_t)K * B;         // [K][d]
+  float* s_w = s_g + (((size_t)K * B + 3) & ~(size_t)3);   // [K][d]; 16-byte aligned so that s_q is
   float4* s_q = reinterpret_cast<float4*>(s_w + (((size_t)K * d + 3) & ~(size_t)3));  // [K] c0, inv_delta, alpha, beta
   for (int i = threadIdx.x; i < K * B; i += blockDim.x) s_g[i] = gsums[i];
   for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_w[i] = proj[i];
