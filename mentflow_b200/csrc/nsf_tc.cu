@@ -432,10 +432,18 @@ __device__ __forceinline__ float rq_spline_regs_bwd(float (&a)[64], float v, flo
   int gsel = 0;
   float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
   float h0s = h[0], h1s = h[1], h2s = h[2], h3s = h[3], yg = 0.f;
+  // raw derivative parameters of the knots around the group's four bins (u[-1..3], raw 0 at the outer
+  // knots), selected with the same predicates: nothing is indexed dynamically, so a[] stays in registers
+  float um = 0.f, u0 = a[2 * NB], u1 = a[2 * NB + 1], u2 = a[2 * NB + 2], u3 = a[2 * NB + 3];
 #pragma unroll
   for (int g = 1; g < G; ++g) {
     const bool pgm = pre[g] < target;
     gsel += pgm ? 1 : 0;
+    um = pgm ? a[2 * NB + 4 * g - 1] : um;
+    u0 = pgm ? a[2 * NB + 4 * g] : u0;
+    u1 = pgm ? a[2 * NB + 4 * g + 1] : u1;
+    u2 = pgm ? a[2 * NB + 4 * g + 2] : u2;
+    u3 = pgm ? ((4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f) : u3;
     q0 = pgm ? e[4 * g] : q0;
     q1 = pgm ? e[4 * g + 1] : q1;
     q2 = pgm ? e[4 * g + 2] : q2;
@@ -456,12 +464,8 @@ __device__ __forceinline__ float rq_spline_regs_bwd(float (&a)[64], float v, flo
   const float y0c = r2 ? p2 : (r1 ? p1 : (r0 ? p0 : yg));
   const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
   // derivative parameters at the two knots of bin k (raw 0 at the outer knots)
-  float tl = 0.f, tr = 0.f;
-#pragma unroll
-  for (int j = 0; j < NB - 1; ++j) {
-    tl = (j == k - 1) ? a[2 * NB + j] : tl;
-    tr = (j == k) ? a[2 * NB + j] : tr;
-  }
+  const float tl = r2 ? u2 : (r1 ? u1 : (r0 ? u0 : um));
+  const float tr = r2 ? u3 : (r1 ? u2 : (r0 ? u1 : u0));
   const float dd0 = fmaf(fabsf(tl), cD, 1.0f), dd1 = fmaf(fabsf(tr), cD, 1.0f);
   const float rdd = fast_rcp(dd0 * dd1);
   const float ri0 = rdd * dd1, ri1 = rdd * dd0;
