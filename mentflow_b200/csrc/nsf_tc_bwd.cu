@@ -340,13 +340,17 @@ static int launch_dgrad(const float* gphi, const float* gmax, const float* acts,
 //   (dL/dphi_f, h3) x S,  (g3, h2),  (g2, h1),  (g1, v^T)
 // as tcgen05 GEMMs whose K dimension is the particle axis.  The workspace matrices are tile-major (see
 // BwdIO in nsf_tc.cu): the 128 particles of a row of a tile are contiguous, exactly a K-major operand row.
-// Loader warps turn such rows into (hi, lo) fp16 SWIZZLE_128B tiles (64 rows x 128 K, two 64-wide
+// A producer thread streams the 64-row blocks (32 KB, contiguous) into a shared-memory staging ring
+// with cp.async.bulk, two blocks ahead of their use, so HBM latency is never on the critical path;
+// loader warps turn the staged rows into (hi, lo) fp16 SWIZZLE_128B tiles (64 rows x 128 K, two 64-wide
 // halves), the issuer warp multiplies them into accumulators that stay in TMEM for the whole
 // launch (464 columns: 5 x 64 + 64 + 64 + 16), bias gradients are row sums taken on the way.  G is
 // scaled by a power of two from the batch maximum (fp16 has no range for 1/N-sized gradients).
 // =============================================================================================
 constexpr int kWgTile = 32768;                 // one operand tile: hi (2 halves x 8 KB) | lo (2 x 8 KB)
-constexpr int kWgG = 3, kWgH = 2;              // ring depths
+constexpr int kWgG = 2, kWgH = 2;              // ring depths of the fp16 operand tiles
+constexpr int kWgS = 2;                        // ring depth of the fp32 staging blocks (64 rows x 512 B, filled by TMA)
+constexpr int kWgStage = 32768;
 constexpr int kWgLoaders = 12;                 // loader warps
 constexpr int kWgCols = 464;                   // accumulator columns
 
@@ -369,13 +373,16 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* g_ring = smem;
   unsigned char* h_ring = smem + kWgG * kWgTile;
-  // 8 KB of slack after the rings: an M = 128 MMA reads 64 rows past a 64-row tile half
-  float* bias = reinterpret_cast<float*>(smem + (kWgG + kWgH) * kWgTile + 8192);   // [D + 3][64]
+  // an M = 128 MMA reads 64 rows past a 64-row tile half: the staging ring that follows is the slack
+  float* stage_ring = reinterpret_cast<float*>(smem + (kWgG + kWgH) * kWgTile);
+  float* bias = reinterpret_cast<float*>(smem + (kWgG + kWgH) * kWgTile + kWgS * kWgStage);   // [D + 3][64]
   uint64_t* g_full = reinterpret_cast<uint64_t*>(bias + (D + 3) * 64);
   uint64_t* g_empty = g_full + kWgG;
   uint64_t* h_full = g_empty + kWgG;
   uint64_t* h_empty = h_full + kWgH;
-  uint64_t* all_done = h_empty + kWgH;
+  uint64_t* s_full = h_empty + kWgH;
+  uint64_t* s_empty = s_full + kWgS;
+  uint64_t* all_done = s_empty + kWgS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -388,6 +395,10 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
     for (int i = 0; i < kWgH; ++i) {
       mbar_init(&h_full[i], kWgLoaders);
       mbar_init(&h_empty[i], 1);
+    }
+    for (int i = 0; i < kWgS; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], kWgLoaders);
     }
     mbar_init(all_done, 1);
     fence_mbar_init();
@@ -406,31 +417,35 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
 
   if (warp < kWgLoaders) {
     // ===== loaders: rows w, w + 12, ... of every tile =====
-    uint32_t gi = 0, hi_ = 0;   // running use counters of the rings
-    auto fill = [&](unsigned char* tile, const float* rows, int nrows, int64_t p0, float scale, float* bsum, bool strided_v) {
-      // all rows of this warp are loaded before any is converted: 6 x 512 B in flight per warp
-      constexpr int kRows = (64 + kWgLoaders - 1) / kWgLoaders;
-      float x[kRows][4];
+    uint32_t gi = 0, hi_ = 0, sc_ = 0;   // running use counters of the rings
+    constexpr int kRows = (64 + kWgLoaders - 1) / kWgLoaders;
+    // rows w, w + 12, ... of the next staged block -> registers (masked beyond particle n), then the
+    // staging slot is handed back to the producer
+    auto take = [&](float (&x)[kRows][4], int nrows, int64_t p0, bool strided_v) {
+      const uint32_t slot = sc_ % kWgS, par = (sc_ / kWgS) & 1;
+      mbar_wait_bounded(&s_full[slot], par);
+      const float* st = stage_ring + (size_t)slot * (kWgStage / 4);
 #pragma unroll
       for (int i = 0; i < kRows; ++i) {
         const int r = warp + i * kWgLoaders;
         x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
         if (r < nrows) {
           if (!strided_v) {
-            const float* src = rows + (size_t)r * 128 + 4 * lane;   // rows = first row of this tile
-            if (p0 + 4 * lane + 3 < n) {
-              const float4 q = *reinterpret_cast<const float4*>(src);
-              x[i][0] = q.x; x[i][1] = q.y; x[i][2] = q.z; x[i][3] = q.w;
-            } else {
+            const float4 q = *reinterpret_cast<const float4*>(st + (size_t)r * 128 + 4 * lane);
+            x[i][0] = q.x; x[i][1] = q.y; x[i][2] = q.z; x[i][3] = q.w;
+          } else {   // the block is v[p0 .. p0+127][D], particle-major: row r of v^T is feature r
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[i][e] = (p0 + 4 * lane + e < n) ? src[e] : 0.f;
-            }
-          } else {   // v is particle-major: row r of v^T is feature r
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[i][e] = (p0 + 4 * lane + e < n) ? rows[(p0 + 4 * lane + e) * D + r] : 0.f;
+            for (int e = 0; e < 4; ++e) x[i][e] = st[(4 * lane + e) * D + r];
           }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[i][e] = (p0 + 4 * lane + e < n) ? x[i][e] : 0.f;
         }
       }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[slot])) : "memory");
+      ++sc_;
+    };
+    auto convert = [&](unsigned char* tile, const float (&x)[kRows][4], int nrows, float scale, float* bsum) {
 #pragma unroll
       for (int i = 0; i < kRows; ++i) {
         const int r = warp + i * kWgLoaders;
@@ -453,39 +468,75 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
         }
       }
     };
-    auto fill_g = [&](const float* rows, int64_t p0, float scale, float* bsum) {
+    auto fill_g = [&](int64_t p0, float scale, float* bsum) {
+      float x[kRows][4];
+      take(x, 64, p0, false);
       const uint32_t slot = gi % kWgG, par = (gi / kWgG) & 1;
       mbar_wait_bounded(&g_empty[slot], par ^ 1);
-      fill(g_ring + slot * kWgTile, rows, 64, p0, scale, bsum, false);
+      convert(g_ring + slot * kWgTile, x, 64, scale, bsum);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&g_full[slot])) : "memory");
       ++gi;
     };
-    auto fill_h = [&](const float* rows, int nrows, int64_t p0, bool strided_v) {
+    auto fill_h = [&](int nrows, int64_t p0, bool strided_v) {
+      float x[kRows][4];
+      take(x, nrows, p0, strided_v);
       const uint32_t slot = hi_ % kWgH, par = (hi_ / kWgH) & 1;
       mbar_wait_bounded(&h_empty[slot], par ^ 1);
-      fill(h_ring + slot * kWgTile, rows, nrows, p0, 1.0f, nullptr, strided_v);
+      convert(h_ring + slot * kWgTile, x, nrows, 1.0f, nullptr);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_full[slot])) : "memory");
       ++hi_;
     };
+    // the block order below is the producer's (next branch) and the issuer's
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t p0 = tile * 128;
-      const float* at = acts + (size_t)tile * (3 * kH) * 128;       // rows of this tile
-      const float* zt = gz + (size_t)tile * (3 * kH) * 128;
-      const float* pt = gphi + (size_t)tile * (D * kPP) * 128;
-      fill_h(at + 2 * kH * 128, 64, p0, false);                                           // h3
-      for (int s = 0; s < S; ++s)
-        fill_g(pt + meta.slot_feature[s] * kPP * 128, p0, gsc[0], bias + meta.slot_feature[s] * 64);
-      fill(nullptr, pt + meta.const_feature * kPP * 128, 64, p0, 1.0f, bias + meta.const_feature * 64, false);
-      fill_h(at + 1 * kH * 128, 64, p0, false);                                           // h2
-      fill_g(zt + 2 * kH * 128, p0, gsc[3], bias + (D + 0) * 64);                         // g3
-      fill_h(at, 64, p0, false);                                                          // h1
-      fill_g(zt + 1 * kH * 128, p0, gsc[2], bias + (D + 1) * 64);                         // g2
-      fill_h(v, D, p0, true);                                                             // v^T
-      fill_g(zt, p0, gsc[1], bias + (D + 2) * 64);                                        // g1
+      fill_h(64, p0, false);                                                              // h3
+      for (int s = 0; s < S; ++s) fill_g(p0, gsc[0], bias + meta.slot_feature[s] * 64);   // dL/dphi of the slots
+      {                                                                                   // bias-only feature: row sums
+        float x[kRows][4];
+        take(x, 64, p0, false);
+        convert(nullptr, x, 64, 1.0f, bias + meta.const_feature * 64);
+      }
+      fill_h(64, p0, false);                                                              // h2
+      fill_g(p0, gsc[3], bias + (D + 0) * 64);                                            // g3
+      fill_h(64, p0, false);                                                              // h1
+      fill_g(p0, gsc[2], bias + (D + 1) * 64);                                            // g2
+      fill_h(D, p0, true);                                                                // v^T
+      fill_g(p0, gsc[1], bias + (D + 2) * 64);                                            // g1
+    }
+  } else if (warp == kWgLoaders + 1) {
+    // ===== producer: one thread streams the blocks into the staging ring =====
+    if (lane == 0) {
+      uint32_t sc_ = 0;
+      auto push = [&](const float* src, uint32_t bytes) {
+        const uint32_t slot = sc_ % kWgS, par = (sc_ / kWgS) & 1;
+        mbar_wait_bounded(&s_empty[slot], par ^ 1);
+        float* dst = stage_ring + (size_t)slot * (kWgStage / 4);
+        const uint32_t bulk = bytes & ~15u;
+        for (uint32_t i = bulk / 4; i < bytes / 4; ++i) dst[i] = src[i];   // ragged tail (< 16 B) of the last v block
+        mbar_expect_tx(&s_full[slot], bulk);
+        if (bulk) tma_load_1d(dst, src, bulk, &s_full[slot]);
+        ++sc_;
+      };
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * 128;
+        const float* at = acts + (size_t)tile * (3 * kH) * 128;       // rows of this tile
+        const float* zt = gz + (size_t)tile * (3 * kH) * 128;
+        const float* pt = gphi + (size_t)tile * (D * kPP) * 128;
+        push(at + 2 * kH * 128, kWgStage);                                                  // h3
+        for (int s = 0; s < S; ++s) push(pt + meta.slot_feature[s] * kPP * 128, kWgStage);
+        push(pt + meta.const_feature * kPP * 128, kWgStage);
+        push(at + 1 * kH * 128, kWgStage);                                                  // h2
+        push(zt + 2 * kH * 128, kWgStage);                                                  // g3
+        push(at, kWgStage);                                                                 // h1
+        push(zt + 1 * kH * 128, kWgStage);                                                  // g2
+        const int64_t rows = (n - p0 < 128) ? (n - p0) : 128;
+        push(v + p0 * D, (uint32_t)(rows * D * 4));                                         // v rows of the tile
+        push(zt, kWgStage);                                                                 // g1
+      }
     }
   } else if (warp == kWgLoaders) {
     // ===== issuer =====
@@ -619,7 +670,7 @@ static int launch_wgrad(const float* gphi, const float* gz, const float* acts, c
   meta.nslots = D - 1;
   meta.const_feature = feat_of_order[0];
   for (int s = 0; s < D - 1; ++s) meta.slot_feature[s] = feat_of_order[s + 1];
-  const size_t smem = (size_t)(kWgG + kWgH) * kWgTile + 8192 + (size_t)(D + 3) * 64 * 4 + 256 + 1024;
+  const size_t smem = (size_t)(kWgG + kWgH) * kWgTile + (size_t)kWgS * kWgStage + (size_t)(D + 3) * 64 * 4 + 256 + 1024;
   auto kern = nsf_tc_wgrad_kernel<D>;
   MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (n + 127) / 128;
