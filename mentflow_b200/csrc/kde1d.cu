@@ -110,7 +110,7 @@ __device__ __forceinline__ float project_row(const float* __restrict__ xr, const
 
 // ---- forward: KDE deposit --------------------------------------------------------------------
 // Launch plan of the deposit kernel: up to 512 threads (= projections x particle slices) per CTA,
-// one private column of B + 2G bins per thread (G = 2R+1 guard rows on either side, so that no tap
+// one private column of B + 2G bins per thread (G = 2R+2 guard rows on either side, so that no tap
 // needs a bounds check: particles beyond the screen are clamped to a position whose whole window
 // lies in the guard rows).
 constexpr int kDepThreads = 512;
@@ -120,8 +120,8 @@ struct KdePlan {
 };
 static KdePlan plan_kde(int64_t n, int d, int k, int b, int r) {
   KdePlan P;
-  P.guard = 2 * r + 1;
-  P.rows = b + 2 * P.guard;
+  P.guard = 2 * r + 2;                    // even, so that rows pair up as (2i, 2i+1) from row 0
+  P.rows = (b + 2 * P.guard + 1) & ~1;
   P.kchunks = (k + kDepThreads - 1) / kDepThreads;
   P.kc = (k + P.kchunks - 1) / P.kchunks;
   int sms = sm_count();
@@ -180,7 +180,7 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
   float* bins = reinterpret_cast<float*>(tp.bar + 8);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int rows_total = B + 2 * guard;
+  const int rows_total = (B + 2 * guard + 1) & ~1;
   const int kbase = blockIdx.y * kc;
   const int kloc = tid % kc;
   const int slice = tid / kc;
@@ -215,9 +215,14 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
 
   const int64_t ntiles = (n + tile - 1) / tile;
   if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
-  // window origin of a particle at bin b0 is row b0 + guard - R of this thread's column
-  float* mybins = bins + tid + (size_t)(guard - R) * ld;
+  // The column of a thread is stored as pairs of rows: float2 (row 2i, row 2i+1) at pair index i, pairs
+  // of the CTA's threads side by side (a warp touches 256 contiguous bytes: conflict free).  A window of
+  // 2R+1 taps starting at row r0 = b0 + guard - R covers the R+1 pairs from r0 >> 1; when r0 is odd the
+  // taps shift by one slot.  8-byte accesses halve the shared-memory INSTRUCTION count, which is what
+  // bounds this kernel (the LSU pipe issues one instruction per two cycles).
+  float2* mypairs = reinterpret_cast<float2*>(bins) + tid;
   const float lo = -(float)(R + 1), hi = (float)(B + R);
+  constexpr int kPairs = R + 1;
 
   int it = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -234,7 +239,8 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
       constexpr int kPer = 4;
       for (int p = slice; p < rows; p += kPer * slices) {
         float taps[kPer][2 * R + 1];
-        float* dstp[kPer];
+        float2* dstp[kPer];
+        bool odd[kPer];
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
           const int pq = p + q * slices;
@@ -244,12 +250,22 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
           a = have ? fminf(fmaxf(a, lo), hi) : lo;   // a missing particle goes to the guard rows
           const float fb = rintf(a);
           gauss_taps<R>(a - fb, alpha, rj, taps[q]);
-          dstp[q] = mybins + (int)fb * ld;
+          const int r0 = (int)fb + guard - R;         // first row of the window (>= 1)
+          odd[q] = r0 & 1;
+          dstp[q] = mypairs + (size_t)(r0 >> 1) * ld;
         }
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
 #pragma unroll
-          for (int j = 0; j <= 2 * R; ++j) dstp[q][j * ld] += taps[q][j];
+          for (int j = 0; j < kPairs; ++j) {
+            // slots 2j, 2j+1 of the pair window hold taps 2j - odd, 2j + 1 - odd (0 outside 0..2R)
+            const float e_lo = taps[q][2 * j], e_hi = 2 * j + 1 <= 2 * R ? taps[q][2 * j + 1] : 0.f;
+            const float o_lo = j > 0 ? taps[q][2 * j - 1] : 0.f, o_hi = taps[q][2 * j];
+            float2 v = dstp[q][(size_t)j * ld];
+            v.x += odd[q] ? o_lo : e_lo;
+            v.y += odd[q] ? o_hi : e_hi;
+            dstp[q][(size_t)j * ld] = v;
+          }
         }
       }
     }
@@ -262,7 +278,8 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     const int kk = idx % kc, b = idx / kc;
     if (kbase + kk < K) {
       float s = 0.f;
-      for (int sl = 0; sl < slices; ++sl) s += bins[(size_t)(b + guard) * ld + sl * kc + kk];
+      const int row = b + guard;
+      for (int sl = 0; sl < slices; ++sl) s += bins[((size_t)(row >> 1) * ld + sl * kc + kk) * 2 + (row & 1)];
       out[(size_t)(kbase + kk) * B + b] = s;
     }
   }
