@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmentflow_b200.so")
+# MENTFLOW_B200_LIB overrides the library path (A/B runs of differently built kernels)
+LIB_PATH = os.environ.get("MENTFLOW_B200_LIB") or os.path.join(PKG_DIR, "libmentflow_b200.so")
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
 

@@ -25,7 +25,10 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 // issuer side: poll without occupying the issue port of the compute warps on the same scheduler
 __device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
-  while (!mbar_test_wait(bar, parity)) __nanosleep(40);
+#ifndef MFB_POLL_NS
+#define MFB_POLL_NS 40
+#endif
+  while (!mbar_test_wait(bar, parity)) __nanosleep(MFB_POLL_NS);
 }
 
 // Warpgroup -> issuer hand-off: every compute warp arrives (lane 0, after __syncwarp) on a request
