@@ -897,23 +897,23 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         for (int j = 3 * NB - 1; j < kPP; ++j) gp[j * 128] = 0.f;
       }
     };
-    if constexpr (kBwd) {
-      if (cur) {   // bias-only feature: its raw parameters are the same for every particle
-        float acc[64];
-        const float4* cb = reinterpret_cast<const float4*>(ctab + 6 * kCT);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 q4 = cb[i];
-          acc[4 * i] = q4.x; acc[4 * i + 1] = q4.y; acc[4 * i + 2] = q4.z; acc[4 * i + 3] = q4.w;
-        }
-        feature_bwd(acc, meta.const_feature);
-      }
-    }
+    // backward variant: the bias-only feature is iteration s = -1 of the same loop (its raw parameters
+    // come from the constant table instead of TMEM), so the spline code exists once -- the kernel is
+    // large enough for instruction-cache misses to show up as a stall reason
 #pragma unroll 1
-    for (int s = 0; s < S; ++s) {
+    for (int s = kBwd ? -1 : 0; s < S; ++s) {
       const int b = s & 1;
       float acc[64];
-      if (cur) {
+      if (kBwd && s < 0) {
+        if (cur) {
+          const float4* cb = reinterpret_cast<const float4*>(ctab + 6 * kCT);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 q4 = cb[i];
+            acc[4 * i] = q4.x; acc[4 * i + 1] = q4.y; acc[4 * i + 2] = q4.z; acc[4 * i + 3] = q4.w;
+          }
+        }
+      } else if (cur) {
         if (!(S >= 2 && s == S - 1)) wait_buf(b);   // the last slot was already waited for at kFork
         tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
         umma::fence_before_sync();
@@ -935,7 +935,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         }
       }
       if (cur) {
-        const int f = meta.slot_feature[s];
+        const int f = (kBwd && s < 0) ? meta.const_feature : meta.slot_feature[s < 0 ? 0 : s];
         if constexpr (kBwd) {
           feature_bwd(acc, f);
         } else {

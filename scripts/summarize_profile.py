@@ -1,6 +1,6 @@
 """Turn ncu outputs in gpurun_out/ into the small tracked summaries under profiles/.
 
-    python scripts/summarize_profile.py <tag> <launches.csv> [<report.ncu-rep>]
+    python scripts/summarize_profile.py <tag> <launches.csv[.gz]> [<report.ncu-rep | raw-page.csv> ...]
 """
 import collections
 import csv
@@ -25,7 +25,8 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def launches(tag, path):
-    with open(path) as f:
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt") as f:
         lines = [l for l in f if l.startswith('"')]
     r = csv.reader(io.StringIO("".join(lines)))
     hdr = next(r)
@@ -47,29 +48,51 @@ def launches(tag, path):
         f.write(f"{'ms':>10s} {'share':>7s} {'count':>6s}  kernel\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{v[1]:10.3f} {100 * v[1] / tot:6.1f}% {v[0]:6d}  {k[:150]}\n")
-    with open(path, "rb") as src, gzip.open(os.path.join(ROOT, "profiles", f"{tag}_launches.csv.gz"), "wb") as dst:
-        shutil.copyfileobj(src, dst)
+    dst_path = os.path.join(ROOT, "profiles", f"{tag}_launches.csv.gz")
+    if path.endswith(".gz"):
+        shutil.copyfile(path, dst_path)
+    else:
+        with open(path, "rb") as src, gzip.open(dst_path, "wb") as dst:
+            shutil.copyfileobj(src, dst)
     print("wrote", out)
 
 
-def full(tag, rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
+def full(tag, reps):
     out = os.path.join(ROOT, "profiles", f"{tag}_full_metrics.txt")
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on (one block per captured launch)\n")
+        for rep in reps:
+            full_one(f, rep)
+    print("wrote", out)
+
+
+STALLS = 6   # top warp-stall reasons listed per launch
+
+
+def full_one(f, rep):
+    if rep.endswith(".csv"):
+        raw = open(rep).read()      # `ncu -i report --page raw --csv`, exported on the GPU box
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    if True:
         for r in rows[2:]:
             f.write(f"\n== {r[idx['Kernel Name']][:120]}\n")
             for m in KEEP:
                 if m in idx:
                     f.write(f"  {m:72s} {r[idx[m]]} {units[idx[m]]}\n")
-    print("wrote", out)
+            stalls = []
+            for h, i in idx.items():
+                if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and r[i] not in ("", "n/a"):
+                    stalls.append((float(r[i].replace(",", "")), h.split("issue_stalled_")[1].split("_per_issue")[0]))
+            f.write("  top stalls (warps per issue-active cycle): "
+                    + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:STALLS]) + "\n")
 
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launches(sys.argv[1], sys.argv[2])
     if len(sys.argv) > 3:
-        full(sys.argv[1], sys.argv[3])
+        full(sys.argv[1], sys.argv[3:])
