@@ -89,6 +89,22 @@ int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, c
                           int k, int b, float max_sigma_over_delta, const float* gsums, float* gx,
                           int accumulate, void* stream);
 
+/* ---- the same three kernels behind a thin multipole kick -------------------------------
+ * Replaces CompositeTransform(linear.., MultipoleTransform, linear..) followed by Histogram1D
+ * (simulate/transform.py:35-55,78-146; experiments/rec_2d/nonlinear/setup.py:24-44):
+ *   u = proj_k . x + a_k Re(z^m) + b_k Im(z^m),  z = wa_k . x + i wb_k . x,  m = order - 1.
+ * mp[K][2 d + 4] = [wa (d) | wb (d) | a | b | order | 0]; everything else as in the functions
+ * without _mp.  The host side folds the matrices, the kick strength / (order-1)! and the
+ * reference's U[:,3] = X[:,1] + .. quirk into proj, a and b (simulate.multipole_terms).     */
+int mfb_project_kde1d_mp_fwd(const float* x, int64_t n, int d, const float* proj, const float* mp,
+                             const float* geom, int k, int b, float max_sigma_over_delta, float* sums,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+int mfb_project_kde1d_mp_bwd(const float* x, int64_t n, int d, const float* proj, const float* mp,
+                             const float* geom, int k, int b, float max_sigma_over_delta,
+                             const float* gsums, float* gx, int accumulate, void* stream);
+int mfb_project_hist1d_mp(const float* x, int64_t n, int d, const float* proj, const float* mp,
+                          const float* edges, int k, int b, int64_t* counts, void* stream);
+
 /* ---- fused projection + exact histogram, 1-D screens -----------------------------------
  * Replaces diagnostics/diagnostics.py:128-131 (torch.histogram(x_proj, edges)): bin i holds
  * edges[i] <= u < edges[i+1], last bin closed, everything else dropped.  edges[K][B+1];

@@ -27,6 +27,9 @@ SIGNATURES = {
     "mfb_kde1d_finish": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P]),
     "mfb_kde1d_finish_bwd": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P, P]),
     "mfb_project_kde1d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int, P]),
+    "mfb_project_kde1d_mp_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, P, P, c_int64, P]),
+    "mfb_project_kde1d_mp_bwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, P, P, c_int, P]),
+    "mfb_project_hist1d_mp": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P]),
     "mfb_project_hist1d": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P]),
     "mfb_kde2d_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "mfb_project_kde2d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int64, P]),

@@ -108,6 +108,52 @@ __device__ __forceinline__ float project_row(const float* __restrict__ xr, const
   return u;
 }
 
+// ---- thin multipole kick folded into the projection ---------------------------------------------
+// For a transfer map  linear -> MultipoleTransform -> linear  (mentflow/simulate/transform.py:78-146,
+// experiments/rec_2d/nonlinear/setup.py:24-44) the measured coordinate is
+//   u = w . x + a Re(z^m) + b Im(z^m),   z = (wa . x) + i (wb . x),   m = order - 1,
+// with w, wa, wb, a, b built on the host from the matrices and the kick strength (the reference's
+// U[:,3] = X[:,1] + ... quirk is linear and lives in w).  mp row = [wa (d) | wb (d) | a | b | order | 0].
+#define MFB_MP_STRIDE(d) (2 * (d) + 4)
+struct MpTerms {
+  float wa[kMaxDim], wb[kMaxDim];
+  float a, b;
+  int m;   // power of z
+};
+__device__ __forceinline__ void load_mp(MpTerms& t, const float* __restrict__ row, int d) {
+#pragma unroll
+  for (int i = 0; i < kMaxDim; ++i) {
+    t.wa[i] = i < d ? row[i] : 0.f;
+    t.wb[i] = i < d ? row[d + i] : 0.f;
+  }
+  t.a = row[2 * d];
+  t.b = row[2 * d + 1];
+  t.m = (int)row[2 * d + 2] - 1;
+}
+// z^m and z^(m-1) (m >= 1) by repeated complex multiplication
+__device__ __forceinline__ void zpow(float xm, float ym, int m, float& zr, float& zi, float& pr, float& pi) {
+  zr = 1.f; zi = 0.f; pr = 1.f; pi = 0.f;
+  for (int t = 0; t < m; ++t) {
+    pr = zr; pi = zi;
+    const float nr = zr * xm - zi * ym, ni = zr * ym + zi * xm;
+    zr = nr; zi = ni;
+  }
+}
+__device__ __forceinline__ float project_row_mp(const float* __restrict__ xr, const float (&w)[kMaxDim], const MpTerms& t,
+                                                int d) {
+  float u = 0.f, xm = 0.f, ym = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxDim; ++i)
+    if (i < d) {
+      u = fmaf(w[i], xr[i], u);
+      xm = fmaf(t.wa[i], xr[i], xm);
+      ym = fmaf(t.wb[i], xr[i], ym);
+    }
+  float zr, zi, pr, pi;
+  zpow(xm, ym, t.m, zr, zi, pr, pi);
+  return fmaf(t.b, zi, fmaf(t.a, zr, u));
+}
+
 // ---- forward: KDE deposit --------------------------------------------------------------------
 // Launch plan of the deposit kernel: up to 512 threads (= projections x particle slices) per CTA,
 // one private column of B + 2G bins per thread (G = 2R+2 guard rows on either side, so that no tap
@@ -166,11 +212,11 @@ __device__ __forceinline__ void gauss_taps(float f, float alpha, const float (&r
   }
 }
 
-template <int D, int R>
+template <int D, int R, bool kMP = false>
 __global__ void __launch_bounds__(kDepThreads)
 kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
                      const float* __restrict__ geom, int K, int B, int kc, int tile, int guard, int ld,
-                     float* __restrict__ partial /* [gridDim.x][K][B] */) {
+                     float* __restrict__ partial /* [gridDim.x][K][B] */, const float* __restrict__ mp = nullptr) {
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TilePipe tp;
@@ -212,6 +258,10 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
 #pragma unroll
     for (int j = 0; j < R; ++j) rj[j] = exp2f(alpha * (float)(2 * j + 1));
   }
+  MpTerms mpt;
+  if constexpr (kMP) {
+    if (active) load_mp(mpt, mp + (size_t)k * MFB_MP_STRIDE(d), d);
+  }
 
   const int64_t ntiles = (n + tile - 1) / tile;
   if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
@@ -245,7 +295,10 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
         for (int q = 0; q < kPer; ++q) {
           const int pq = p + q * slices;
           const bool have = pq < rows;
-          const float u = project_row<D>(xs + (size_t)(have ? pq : p) * d, w, d);
+          const float* xr = xs + (size_t)(have ? pq : p) * d;
+          float u;
+          if constexpr (kMP) u = project_row_mp(xr, w, mpt, d);
+          else u = project_row<D>(xr, w, d);
           float a = fmaf(u, inv_delta, -c0s);
           a = have ? fminf(fmaxf(a, lo), hi) : lo;   // a missing particle goes to the guard rows
           const float fb = rintf(a);
@@ -452,18 +505,22 @@ static inline size_t finish_smem(int b) {
 }
 
 // ---- backward w.r.t. the particles: thread per particle ---------------------------------------
-template <int D, int R>
+template <int D, int R, bool kMP = false>
 __global__ void __launch_bounds__(256)
 kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
                  const float* __restrict__ geom, int K, int B, const float* __restrict__ gsums,
-                 float* __restrict__ gx, int accumulate) {
+                 float* __restrict__ gx, int accumulate, const float* __restrict__ mp = nullptr) {
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(16) float sm[];
   float* s_g = sm;                          // [K][B]
   float* s_w = s_g + (((size_t)K * B + 3) & ~(size_t)3);   // [K][d]; 16-byte aligned so that s_q is
   float4* s_q = reinterpret_cast<float4*>(s_w + (((size_t)K * d + 3) & ~(size_t)3));  // [K] c0, inv_delta, alpha, beta
+  float* s_mp = reinterpret_cast<float*>(s_q + K);   // [K][2d + 4] (multipole variant only)
   for (int i = threadIdx.x; i < K * B; i += blockDim.x) s_g[i] = gsums[i];
   for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_w[i] = proj[i];
+  if constexpr (kMP) {
+    for (int i = threadIdx.x; i < K * MFB_MP_STRIDE(d); i += blockDim.x) s_mp[i] = mp[i];
+  }
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float* g = geom + (size_t)k * MFB_GEOM_STRIDE;
     const float r = g[1] / g[2];
@@ -484,6 +541,25 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
 #pragma unroll
       for (int i = 0; i < kMaxDim; ++i)
         if (i < d) u = fmaf(wk[i], xr[i], u);
+      float cx = 0.f, cy = 0.f;   // du/d(xm), du/d(ym) of the multipole terms
+      if constexpr (kMP) {
+        const float* mk = s_mp + (size_t)k * MFB_MP_STRIDE(d);
+        float xm = 0.f, ym = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxDim; ++i)
+          if (i < d) {
+            xm = fmaf(mk[i], xr[i], xm);
+            ym = fmaf(mk[d + i], xr[i], ym);
+          }
+        const float a = mk[2 * d], bq = mk[2 * d + 1];
+        const int m = (int)mk[2 * d + 2] - 1;
+        float zr, zi, pr, pi;
+        zpow(xm, ym, m, zr, zi, pr, pi);
+        u = fmaf(bq, zi, fmaf(a, zr, u));
+        // d z^m / d xm = m z^(m-1),  d z^m / d ym = i m z^(m-1)
+        cx = (float)m * (a * pr + bq * pi);
+        cy = (float)m * (bq * pr - a * pi);
+      }
       const float4 q = s_q[k];
       float a = (u - q.x) * q.y;
       a = fminf(fmaxf(a, lo), hi);
@@ -502,7 +578,14 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
       const float gu = q.w * acc;
 #pragma unroll
       for (int i = 0; i < kMaxDim; ++i)
-        if (i < d) g[i] = fmaf(wk[i], gu, g[i]);
+        if (i < d) {
+          float wi = wk[i];
+          if constexpr (kMP) {
+            const float* mk = s_mp + (size_t)k * MFB_MP_STRIDE(d);
+            wi = fmaf(cx, mk[i], fmaf(cy, mk[d + i], wi));
+          }
+          g[i] = fmaf(wi, gu, g[i]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < kMaxDim; ++i)
@@ -514,11 +597,11 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
 }
 
 // ---- exact histogram deposit ----------------------------------------------------------------------
-template <int D>
+template <int D, bool kMP = false>
 __global__ void __launch_bounds__(kBinThreads)
 hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
                       const float* __restrict__ edges, int K, int B, int kc, int tile,
-                      unsigned long long* __restrict__ counts /* [K][B] */) {
+                      unsigned long long* __restrict__ counts /* [K][B] */, const float* __restrict__ mp = nullptr) {
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TilePipe tp;
@@ -559,6 +642,10 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
     eB = E[B];
     inv_w = (float)B / (eB - e0);
   }
+  MpTerms mpt;
+  if constexpr (kMP) {
+    if (active) load_mp(mpt, mp + (size_t)k * MFB_MP_STRIDE(d), d);
+  }
 
   const int64_t ntiles = (n + tile - 1) / tile;
   if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
@@ -575,7 +662,9 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
     const float* xs = tp.buf[stage];
     if (active) {
       for (int p = slice; p < rows; p += slices) {
-        const float u = project_row<D>(xs + (size_t)p * d, w, d);
+        float u;
+        if constexpr (kMP) u = project_row_mp(xs + (size_t)p * d, w, mpt, d);
+        else u = project_row<D>(xs + (size_t)p * d, w, d);
         if (u >= e0 && u <= eB) {  // NaN fails both
           int b = (int)((u - e0) * inv_w);
           b = min(max(b, 0), B - 1);
@@ -599,15 +688,16 @@ hist1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const fl
 }
 
 // ---- host-side dispatch -----------------------------------------------------------------------------
-template <int D>
+template <int D, bool kMP = false>
 static int launch_kde1d_deposit(int r, const KdePlan& L, const float* x, int64_t n, int d, const float* proj,
-                                const float* geom, int k, int b, float* partial, cudaStream_t st) {
+                                const float* geom, int k, int b, float* partial, cudaStream_t st,
+                                const float* mp = nullptr) {
   dim3 grid(L.grid_x, L.kchunks), block(L.threads);
 #define MFB_LAUNCH_R(RR)                                                                                   \
   {                                                                                                        \
-    MFB_CUDA(cudaFuncSetAttribute(kde1d_deposit_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    MFB_CUDA(cudaFuncSetAttribute(kde1d_deposit_kernel<D, RR, kMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)L.smem));                                                           \
-    kde1d_deposit_kernel<D, RR><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, L.guard, L.ld, partial); \
+    kde1d_deposit_kernel<D, RR, kMP><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, L.guard, L.ld, partial, mp); \
   }
   if (r <= 4) MFB_LAUNCH_R(4)
   else if (r <= 9) MFB_LAUNCH_R(9)
@@ -617,15 +707,28 @@ static int launch_kde1d_deposit(int r, const KdePlan& L, const float* x, int64_t
   return launch_status();
 }
 
-template <int D>
+// deposit of all projections into the per-CTA partials; mp != nullptr selects the multipole variant
+// (runtime dimension: the non-linear configurations are low-dimensional)
+static int deposit_dispatch(int r, const KdePlan& L, const float* x, int64_t n, int d, const float* proj,
+                            const float* geom, int k, int b, float* partial, cudaStream_t st, const float* mp) {
+  if (mp) return launch_kde1d_deposit<0, true>(r, L, x, n, d, proj, geom, k, b, partial, st, mp);
+  switch (d) {
+    case 2: return launch_kde1d_deposit<2>(r, L, x, n, d, proj, geom, k, b, partial, st);
+    case 4: return launch_kde1d_deposit<4>(r, L, x, n, d, proj, geom, k, b, partial, st);
+    case 6: return launch_kde1d_deposit<6>(r, L, x, n, d, proj, geom, k, b, partial, st);
+    default: return launch_kde1d_deposit<0>(r, L, x, n, d, proj, geom, k, b, partial, st);
+  }
+}
+
+template <int D, bool kMP = false>
 static int launch_kde1d_bwd(int r, int grid, size_t smem, const float* x, int64_t n, int d, const float* proj,
                             const float* geom, int k, int b, const float* gsums, float* gx, int acc,
-                            cudaStream_t st) {
+                            cudaStream_t st, const float* mp = nullptr) {
 #define MFB_LAUNCH_R(RR)                                                                                \
   {                                                                                                     \
-    MFB_CUDA(cudaFuncSetAttribute(kde1d_bwd_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+    MFB_CUDA(cudaFuncSetAttribute(kde1d_bwd_kernel<D, RR, kMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                   (int)smem));                                                          \
-    kde1d_bwd_kernel<D, RR><<<grid, 256, smem, st>>>(x, n, d, proj, geom, k, b, gsums, gx, acc);         \
+    kde1d_bwd_kernel<D, RR, kMP><<<grid, 256, smem, st>>>(x, n, d, proj, geom, k, b, gsums, gx, acc, mp);    \
   }
   if (r <= 4) MFB_LAUNCH_R(4)
   else if (r <= 9) MFB_LAUNCH_R(9)
@@ -654,9 +757,9 @@ int64_t mfb_kde1d_workspace_bytes(int64_t n, int d, int k, int b) {
   return gx * k * b * 4;
 }
 
-int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
-                            float max_sigma_over_delta, float* sums, void* workspace, int64_t workspace_bytes,
-                            void* stream) {
+static int kde1d_fwd_impl(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* geom,
+                         int k, int b, float max_sigma_over_delta, float* sums, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
   MFB_CHECK_ARG(x && proj && geom && sums && workspace);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2);
   cudaStream_t st = (cudaStream_t)stream;
@@ -667,13 +770,7 @@ int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, c
   if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
   if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
   float* partial = (float*)workspace;
-  int rc;
-  switch (d) {
-    case 2: rc = launch_kde1d_deposit<2>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    case 4: rc = launch_kde1d_deposit<4>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    case 6: rc = launch_kde1d_deposit<6>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    default: rc = launch_kde1d_deposit<0>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-  }
+  int rc = deposit_dispatch(r, L, x, n, d, proj, geom, k, b, partial, st, mp);
   if (rc) return rc;
   const int64_t len = (int64_t)k * b;
   if (finish_smem(b) > 48 * 1024) {   // very wide screens: the plain merge
@@ -684,6 +781,21 @@ int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, c
   kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, len, 1.f, geom, b, nullptr, 0.f,
                                                                  sums, nullptr, nullptr);
   return launch_status();
+}
+
+int mfb_project_kde1d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                          float max_sigma_over_delta, float* sums, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
+  return kde1d_fwd_impl(x, n, d, proj, nullptr, geom, k, b, max_sigma_over_delta, sums, workspace, workspace_bytes,
+                        stream);
+}
+
+int mfb_project_kde1d_mp_fwd(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* geom,
+                             int k, int b, float max_sigma_over_delta, float* sums, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  MFB_CHECK_ARG(mp);
+  return kde1d_fwd_impl(x, n, d, proj, mp, geom, k, b, max_sigma_over_delta, sums, workspace, workspace_bytes,
+                        stream);
 }
 
 int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
@@ -701,13 +813,7 @@ int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* pr
   if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
   if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
   float* partial = (float*)workspace;
-  int rc;
-  switch (d) {
-    case 2: rc = launch_kde1d_deposit<2>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    case 4: rc = launch_kde1d_deposit<4>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    case 6: rc = launch_kde1d_deposit<6>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-    default: rc = launch_kde1d_deposit<0>(r, L, x, n, d, proj, geom, k, b, partial, st); break;
-  }
+  int rc = deposit_dispatch(r, L, x, n, d, proj, geom, k, b, partial, st, nullptr);
   if (rc) return rc;
   kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, (int64_t)k * b,
                                                                  (float)(1.0 / n_total), geom, b, meas, pad, sums,
@@ -750,16 +856,16 @@ int mfb_kde1d_normalize_bwd(const float* sums, double n_total, const float* geom
   return launch_status();
 }
 
-int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
-                            float max_sigma_over_delta, const float* gsums, float* gx, int accumulate,
-                            void* stream) {
+static int kde1d_bwd_impl(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* geom,
+                         int k, int b, float max_sigma_over_delta, const float* gsums, float* gx, int accumulate,
+                         void* stream) {
   MFB_CHECK_ARG(x && proj && geom && gsums && gx);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2);
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int r = radius_from_hint(max_sigma_over_delta);
   // projections are processed in chunks whose gradient table fits in shared memory
-  const size_t per_k = (size_t)b * 4 + (size_t)d * 4 + 16;
+  const size_t per_k = (size_t)b * 4 + (size_t)d * 4 + 16 + (mp ? (size_t)MFB_MP_STRIDE(d) * 4 : 0);
   int kchunk = (int)((160 * 1024) / per_k);
   if (kchunk < 1) return MFB_E_UNSUPPORTED;
   if (kchunk > k) kchunk = k;
@@ -767,7 +873,8 @@ int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, c
   int64_t blocks = (n + 255) / 256;
   for (int k0 = 0; k0 < k; k0 += kchunk) {
     const int kk = (k - k0 < kchunk) ? (k - k0) : kchunk;
-    const size_t smem = (size_t)kk * b * 4 + (((size_t)kk * d + 3) & ~(size_t)3) * 4 + (size_t)kk * 16 + 16;
+    const size_t smem = (size_t)kk * b * 4 + (((size_t)kk * d + 3) & ~(size_t)3) * 4 + (size_t)kk * 16 + 16 +
+                        (mp ? (size_t)kk * MFB_MP_STRIDE(d) * 4 : 0);
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
@@ -778,6 +885,12 @@ int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, c
     const float* pj = proj + (size_t)k0 * d;
     const float* gm = geom + (size_t)k0 * MFB_GEOM_STRIDE;
     const float* gs = gsums + (size_t)k0 * b;
+    if (mp) {
+      rc = launch_kde1d_bwd<0, true>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st,
+                                     mp + (size_t)k0 * MFB_MP_STRIDE(d));
+      if (rc) return rc;
+      continue;
+    }
     switch (d) {
       case 2: rc = launch_kde1d_bwd<2>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
       case 4: rc = launch_kde1d_bwd<4>(r, (int)grid, smem, x, n, d, pj, gm, kk, b, gs, gx, acc, st); break;
@@ -789,8 +902,20 @@ int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, c
   return 0;
 }
 
-int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, const float* edges, int k, int b,
-                       int64_t* counts, void* stream) {
+int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                          float max_sigma_over_delta, const float* gsums, float* gx, int accumulate, void* stream) {
+  return kde1d_bwd_impl(x, n, d, proj, nullptr, geom, k, b, max_sigma_over_delta, gsums, gx, accumulate, stream);
+}
+
+int mfb_project_kde1d_mp_bwd(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* geom,
+                             int k, int b, float max_sigma_over_delta, const float* gsums, float* gx, int accumulate,
+                             void* stream) {
+  MFB_CHECK_ARG(mp);
+  return kde1d_bwd_impl(x, n, d, proj, mp, geom, k, b, max_sigma_over_delta, gsums, gx, accumulate, stream);
+}
+
+static int hist1d_impl(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* edges, int k,
+                       int b, int64_t* counts, void* stream) {
   MFB_CHECK_ARG(x && proj && edges && counts);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 1);
   if (n == 0) return 0;
@@ -807,6 +932,12 @@ int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, cons
                                   (int)L.smem));                                                          \
     hist1d_deposit_kernel<DD><<<grid, block, L.smem, st>>>(x, n, d, proj, edges, k, b, L.kc, L.tile, c);   \
   }
+  if (mp) {
+    MFB_CUDA(cudaFuncSetAttribute(hist1d_deposit_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)L.smem));
+    hist1d_deposit_kernel<0, true><<<grid, block, L.smem, st>>>(x, n, d, proj, edges, k, b, L.kc, L.tile, c, mp);
+    return launch_status();
+  }
   switch (d) {
     case 2: MFB_LAUNCH_D(2) break;
     case 4: MFB_LAUNCH_D(4) break;
@@ -815,6 +946,17 @@ int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, cons
   }
 #undef MFB_LAUNCH_D
   return launch_status();
+}
+
+int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, const float* edges, int k, int b,
+                       int64_t* counts, void* stream) {
+  return hist1d_impl(x, n, d, proj, nullptr, edges, k, b, counts, stream);
+}
+
+int mfb_project_hist1d_mp(const float* x, int64_t n, int d, const float* proj, const float* mp, const float* edges,
+                          int k, int b, int64_t* counts, void* stream) {
+  MFB_CHECK_ARG(mp);
+  return hist1d_impl(x, n, d, proj, mp, edges, k, b, counts, stream);
 }
 
 }  // extern "C"

@@ -43,8 +43,17 @@ def _check_f32(name: str, t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # projection + KDE, 1-D screens
 # --------------------------------------------------------------------------------------
-def kde1d_sums(x: torch.Tensor, proj: torch.Tensor, geom: torch.Tensor, ratio: float, nbins: int) -> torch.Tensor:
-    """S[k, b] = sum_n exp(-0.5 ((proj_k . x_n - c_b) / sigma_k)^2)  (unnormalised)."""
+def _check_mp(mp: torch.Tensor, k: int, d: int) -> torch.Tensor:
+    mp = _check_f32("mp", mp)
+    if mp.shape != (k, 2 * d + 4):
+        raise ValueError(f"multipole terms must have shape ({k}, {2 * d + 4}), got {tuple(mp.shape)}")
+    return mp
+
+
+def kde1d_sums(x: torch.Tensor, proj: torch.Tensor, geom: torch.Tensor, ratio: float, nbins: int,
+               mp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """S[k, b] = sum_n exp(-0.5 ((u_kn - c_b) / sigma_k)^2)  (unnormalised), u_kn = proj_k . x_n, plus the
+    multipole terms of ``mp`` (K, 2D+4) when given (see ``simulate.multipole_terms``)."""
     lib = _lib.load()
     x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
     n, d = x.shape
@@ -53,8 +62,14 @@ def kde1d_sums(x: torch.Tensor, proj: torch.Tensor, geom: torch.Tensor, ratio: f
     with torch.cuda.device(x.device):
         wbytes = lib.mfb_kde1d_workspace_bytes(n, d, k, nbins)
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
-        _lib.check(lib.mfb_project_kde1d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, nbins, float(ratio),
-                                             _ptr(sums), _ptr(work), wbytes, _stream()), "project_kde1d_fwd")
+        if mp is None:
+            _lib.check(lib.mfb_project_kde1d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, nbins, float(ratio),
+                                                 _ptr(sums), _ptr(work), wbytes, _stream()), "project_kde1d_fwd")
+        else:
+            mp = _check_mp(mp, k, d)
+            _lib.check(lib.mfb_project_kde1d_mp_fwd(_ptr(x), n, d, _ptr(proj), _ptr(mp), _ptr(geom), k, nbins,
+                                                    float(ratio), _ptr(sums), _ptr(work), wbytes, _stream()),
+                       "project_kde1d_mp_fwd")
     return sums
 
 
@@ -79,15 +94,20 @@ def kde1d_normalize_bwd(sums, n_total, geom, gprof):
     return gsums
 
 
-def kde1d_grad_x(x, proj, geom, ratio, gsums, out: Optional[torch.Tensor] = None):
+def kde1d_grad_x(x, proj, geom, ratio, gsums, out: Optional[torch.Tensor] = None, mp: Optional[torch.Tensor] = None):
     lib = _lib.load()
     n, d = x.shape
     k, b = gsums.shape
     acc = 1 if out is not None else 0
     gx = out if out is not None else torch.empty_like(x)
     with torch.cuda.device(x.device):
-        _lib.check(lib.mfb_project_kde1d_bwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, b, float(ratio),
-                                             _ptr(gsums), _ptr(gx), acc, _stream()), "project_kde1d_bwd")
+        if mp is None:
+            _lib.check(lib.mfb_project_kde1d_bwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, b, float(ratio),
+                                                 _ptr(gsums), _ptr(gx), acc, _stream()), "project_kde1d_bwd")
+        else:
+            mp = _check_mp(mp, k, d)
+            _lib.check(lib.mfb_project_kde1d_mp_bwd(_ptr(x), n, d, _ptr(proj), _ptr(mp), _ptr(geom), k, b, float(ratio),
+                                                    _ptr(gsums), _ptr(gx), acc, _stream()), "project_kde1d_mp_bwd")
     return gx
 
 
@@ -149,16 +169,16 @@ class ProjectKDE1D(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, proj, geom, ratio, nbins, reducer, meas):
+    def forward(ctx, x, proj, geom, ratio, nbins, reducer, meas, mp=None):
         ctx.set_materialize_grads(False)
         x = _check_f32("x", x)
         n_total = float(x.shape[0])
         if meas is not None:
             meas = _check_f32("meas", meas)
-        if reducer is None and x.shape[0] > 0 and nbins <= _FINISH_MAX_BINS:
+        if reducer is None and mp is None and x.shape[0] > 0 and nbins <= _FINISH_MAX_BINS:
             sums, prof, kl = kde1d_loss_forward(x, proj, geom, ratio, nbins, n_total, meas)
         else:
-            sums = kde1d_sums(x, proj, geom, ratio, nbins)
+            sums = kde1d_sums(x, proj, geom, ratio, nbins, mp)
             if reducer is not None:
                 n_total = reducer(sums, n_total)
             if nbins <= _FINISH_MAX_BINS:
@@ -168,7 +188,7 @@ class ProjectKDE1D(torch.autograd.Function):
                 kl = None
                 if meas is not None:
                     kl = (torch.xlogy(meas, meas) - meas * torch.log(prof + KL_PAD)).sum(dim=1) / nbins
-        ctx.save_for_backward(x, proj, geom, sums, meas, prof if nbins > _FINISH_MAX_BINS else None)
+        ctx.save_for_backward(x, proj, geom, sums, meas, prof if nbins > _FINISH_MAX_BINS else None, mp)
         ctx.ratio, ctx.n_total = ratio, n_total
         if meas is None:
             return prof
@@ -176,9 +196,9 @@ class ProjectKDE1D(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gprof, gkl=None):
-        x, proj, geom, sums, meas, prof = ctx.saved_tensors
+        x, proj, geom, sums, meas, prof, mp = ctx.saved_tensors
         if gprof is None and gkl is None:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         if prof is not None:       # wide screens: torch expression for the KL part
             if gkl is not None:
                 extra = -(gkl / sums.shape[1])[:, None] * meas / (prof + KL_PAD)
@@ -186,21 +206,22 @@ class ProjectKDE1D(torch.autograd.Function):
             gsums = kde1d_normalize_bwd(sums, ctx.n_total, geom, gprof)
         else:
             gsums = kde1d_finish_bwd(sums, ctx.n_total, geom, meas, gprof, gkl if meas is not None else None)
-        gx = kde1d_grad_x(x, proj, geom, ctx.ratio, gsums)
-        return gx, None, None, None, None, None, None
+        gx = kde1d_grad_x(x, proj, geom, ctx.ratio, gsums, mp=mp)
+        return gx, None, None, None, None, None, None, None
 
 
-def project_kde1d(x, proj, geom, ratio, nbins, reducer=None, meas=None):
-    """(K, B) profiles; with ``meas`` a pair (profiles, kl[K])."""
-    return ProjectKDE1D.apply(x, proj, geom, ratio, nbins, reducer, meas)
+def project_kde1d(x, proj, geom, ratio, nbins, reducer=None, meas=None, mp=None):
+    """(K, B) profiles; with ``meas`` a pair (profiles, kl[K]); ``mp``: multipole terms (K, 2D+4)."""
+    return ProjectKDE1D.apply(x, proj, geom, ratio, nbins, reducer, meas, mp)
 
 
 # --------------------------------------------------------------------------------------
 # projection + exact histogram, 1-D screens
 # --------------------------------------------------------------------------------------
 def project_hist1d(x: torch.Tensor, proj: torch.Tensor, edges: torch.Tensor,
-                   counts: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """int64 counts[k, b]; edges is (K, B+1).  Adds into ``counts`` when given."""
+                   counts: Optional[torch.Tensor] = None, mp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64 counts[k, b]; edges is (K, B+1).  Adds into ``counts`` when given.  ``mp``: multipole
+    terms (K, 2D+4) of the transfer maps, see ``simulate.multipole_terms``."""
     lib = _lib.load()
     x, proj, edges = _check_f32("x", x), _check_f32("proj", proj), _check_f32("edges", edges)
     n, d = x.shape
@@ -208,8 +229,13 @@ def project_hist1d(x: torch.Tensor, proj: torch.Tensor, edges: torch.Tensor,
     if counts is None:
         counts = torch.zeros((k, b), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.mfb_project_hist1d(_ptr(x), n, d, _ptr(proj), _ptr(edges), k, b, _ptr(counts), _stream()),
-                   "project_hist1d")
+        if mp is None:
+            _lib.check(lib.mfb_project_hist1d(_ptr(x), n, d, _ptr(proj), _ptr(edges), k, b, _ptr(counts), _stream()),
+                       "project_hist1d")
+        else:
+            mp = _check_mp(mp, k, d)
+            _lib.check(lib.mfb_project_hist1d_mp(_ptr(x), n, d, _ptr(proj), _ptr(mp), _ptr(edges), k, b, _ptr(counts),
+                                                 _stream()), "project_hist1d_mp")
     return counts
 
 

@@ -1,2 +1,3 @@
 from .simulate import Simulator, forward
-from .transform import CompositeTransform, LinearTransform, Transform, rotation_matrix
+from .transform import (CompositeTransform, LinearTransform, MultipoleTransform, ProjectionTransform, Transform,
+                        reverse_momentum, rotation_matrix)

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..diagnostics.diagnostics import Histogram1D, Histogram2D
-from .transform import CompositeTransform, LinearTransform
+from .transform import CompositeTransform, LinearTransform, MultipoleTransform
 
 # set by mentflow_b200.distributed when particles are sharded across ranks: a callable
 # reducer(sums_tensor, n_local) -> n_global that all-reduces in place
@@ -46,11 +46,12 @@ def _density_from_counts(counts: torch.Tensor, widths: torch.Tensor) -> torch.Te
 
 def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D], kde: bool = True,
                 reducer: Optional[Callable] = None, cache: Optional[dict] = None,
-                kl_targets: Optional[torch.Tensor] = None):
+                kl_targets: Optional[torch.Tensor] = None, mp: Optional[torch.Tensor] = None):
     """(K, B) profiles of K one-dimensional screens sharing the same number of bins.
     proj is (K, D): x_proj_k = x . proj_k.  ``cache`` keeps the device-side geometry between
     calls (filled on first use).  With ``kl_targets`` (K, B) and KDE screens the result is a pair
-    (profiles, kl[K]): the KL of loss.py:15-17 comes out of the normalisation kernel."""
+    (profiles, kl[K]): the KL of loss.py:15-17 comes out of the normalisation kernel.  ``mp`` (K, 2D+4):
+    multipole terms of the transfer maps (``multipole_terms``)."""
     reducer = reducer if reducer is not None else _default_reducer
     cache = {} if cache is None else cache
     nb = diags[0].nbins
@@ -59,11 +60,11 @@ def profiles_1d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram1D
             rows = [d.geometry() for d in diags]
             cache["geom"] = _geom_tensor(rows, x.device)
             cache["ratio"] = max(s / sp for _, sp, s, _ in rows)
-        return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer, kl_targets)
+        return ops.project_kde1d(x, proj, cache["geom"], cache["ratio"], nb, reducer, kl_targets, mp)
     if "edges" not in cache:
         cache["edges"] = torch.stack([d.edges.to(x.device) for d in diags]).contiguous()
         cache["widths"] = torch.diff(cache["edges"], dim=1)
-    counts = ops.project_hist1d(x.detach(), proj, cache["edges"])
+    counts = ops.project_hist1d(x.detach(), proj, cache["edges"], mp=mp)
     if reducer is not None:
         reducer(counts, 0.0)
     return _density_from_counts(counts, cache["widths"])
@@ -98,12 +99,13 @@ def profiles_2d(x: torch.Tensor, proj: torch.Tensor, diags: Sequence[Histogram2D
 # plan: which (transform, screen) pairs fuse, grouped by screen shape
 # --------------------------------------------------------------------------------------
 class _Group:
-    __slots__ = ("kind", "kde", "slots", "diags", "proj", "cache")
+    __slots__ = ("kind", "kde", "slots", "diags", "proj", "cache", "mp")
 
     def __init__(self, kind, kde):
         self.kind, self.kde = kind, kde
         self.slots, self.diags, self.proj = [], [], []
         self.cache = {}
+        self.mp = None      # list of multipole rows (1-D groups behind a MultipoleTransform), else None
 
 
 class _Plan:
@@ -117,10 +119,63 @@ def _linear_matrix(transform) -> Optional[torch.Tensor]:
     if isinstance(transform, LinearTransform):
         return transform.matrix
     if isinstance(transform, CompositeTransform):
-        return transform.as_matrix()
+        m = transform.as_matrix()
+        return NotImplemented if m is None and len(transform.transforms) > 0 else m
     if transform is None or isinstance(transform, nn.Identity):
         return None
     return NotImplemented
+
+
+def _multipole_chain(transform):
+    """(pre, multipole, post) if ``transform`` is linear* -> MultipoleTransform -> linear* (pre / post are
+    product matrices or None for the identity), else None."""
+    stages = [transform] if isinstance(transform, MultipoleTransform) else (
+        list(transform.transforms) if isinstance(transform, CompositeTransform) else None)
+    if stages is None:
+        return None
+    pre = post = kick = None
+    for t in stages:
+        if isinstance(t, MultipoleTransform):
+            if kick is not None:
+                return None
+            kick = t
+        elif isinstance(t, LinearTransform):
+            m = t.matrix.detach().to("cpu", torch.float64)
+            if kick is None:
+                pre = m if pre is None else m @ pre
+            else:
+                post = m if post is None else m @ post
+        else:
+            return None
+    if kick is None or kick.order not in (3, 4, 5):
+        return None
+    return pre, kick, post
+
+
+def multipole_terms(row: torch.Tensor, pre: Optional[torch.Tensor], kick: MultipoleTransform, ndim: int):
+    """(w, mp): the measured coordinate of ``post-row . kick(pre x)`` as
+    ``w . x + a Re(z^m) + b Im(z^m)``, z = wa . x + i wb . x, m = order - 1, mp = [wa | wb | a | b | order | 0].
+
+    ``row`` (D,) is the measured row of the linear part after the kick.  Follows
+    MultipoleTransform.forward (simulate/transform.py:107-143): normal kick U1 = X1 - k Re, U3 = X1 + k Im
+    (the reference reads column 1 there: a linear term, folded into w); skew kick U1 = X1 + k Im,
+    U3 = X3 + k Re; columns 2.. exist only for D > 2.  Evaluated in float64 on the host."""
+    row = row.detach().to("cpu", torch.float64)
+    pre = torch.eye(ndim, dtype=torch.float64) if pre is None else pre
+    k = kick.coefficient()
+    w = row @ pre
+    wa = pre[0].clone()
+    wb = pre[2].clone() if ndim > 2 else torch.zeros(ndim, dtype=torch.float64)
+    r1 = float(row[1])
+    r3 = float(row[3]) if ndim > 2 else 0.0
+    if kick.skew:
+        a, b = k * r3, k * r1
+    else:
+        a, b = -k * r1, k * r3
+        if ndim > 2:
+            w = w + r3 * (pre[1] - pre[3])
+    mp = torch.cat([wa, wb, torch.tensor([a, b, float(kick.order), 0.0], dtype=torch.float64)])
+    return w.to(torch.float32), mp.to(torch.float32)
 
 
 def _plan_key(transforms, diagnostics):
@@ -128,6 +183,10 @@ def _plan_key(transforms, diagnostics):
     for t, row in zip(transforms, diagnostics):
         m = getattr(t, "matrix", None)
         key.append((id(t), id(m), getattr(m, "_version", 0)))
+        for st in (getattr(t, "transforms", None) or [t]):      # stages of a composite map
+            sm = getattr(st, "matrix", None)
+            key.append((id(st), id(sm), getattr(sm, "_version", 0), getattr(st, "order", None),
+                        getattr(st, "strength", None), getattr(st, "skew", None)))
         for d in row:
             key.append((id(d), getattr(d, "kde", None), getattr(d, "axis", None), id(getattr(d, "direction", None))))
     return tuple(key)
@@ -143,7 +202,23 @@ def _build_plan(x, transforms, diagnostics) -> _Plan:
     for i, (t, row) in enumerate(zip(transforms, diagnostics)):
         plan.shape.append(len(row))
         matrix = _linear_matrix(t)
+        chain = _multipole_chain(t) if matrix is NotImplemented else None
         for j, d in enumerate(row):
+            if chain is not None and type(d) is Histogram1D and ndim <= 8:
+                # thin multipole between linear sections: folded into the projection kernel
+                pre, kick, post = chain
+                row_post = d.projection_vector(post.to(torch.float32) if post is not None else None, ndim, "cpu")
+                vec, mp_row = multipole_terms(row_post, pre, kick, ndim)
+                gkey = ("1d-mp", bool(d.kde), d.nbins)
+                grp = plan.groups.get(gkey)
+                if grp is None:
+                    grp = plan.groups[gkey] = _Group("1d", bool(d.kde))
+                    grp.mp = []
+                grp.slots.append((i, j))
+                grp.diags.append(d)
+                grp.proj.append(vec.to(device))
+                grp.mp.append(mp_row.to(device))
+                continue
             if matrix is NotImplemented or type(d) not in (Histogram1D, Histogram2D):
                 plan.fallback.append((i, j))
                 continue
@@ -161,6 +236,8 @@ def _build_plan(x, transforms, diagnostics) -> _Plan:
             grp.proj.append(vec)
     for grp in plan.groups.values():
         grp.proj = torch.stack(grp.proj).contiguous()
+        if grp.mp is not None:
+            grp.mp = torch.stack(grp.mp).contiguous()
     return plan
 
 
@@ -210,7 +287,7 @@ def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List
             if kl_targets is not None and stacked is not None and grp.kde and not noisy and not plan.fallback:
                 targ = _stacked_targets(grp, kl_targets, x.device)
             prof = profiles_1d(x, grp.proj, grp.diags, kde=grp.kde, reducer=reducer, cache=grp.cache,
-                               kl_targets=targ)
+                               kl_targets=targ, mp=grp.mp)
             if targ is not None:
                 prof, kl = prof
         else:

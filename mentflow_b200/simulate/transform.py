@@ -1,7 +1,7 @@
 """Transfer maps between the reconstruction point and the screens.
 
 API of ``mentflow/simulate/transform.py`` (``Transform``, ``LinearTransform``,
-``CompositeTransform``, ``rotation_matrix``).  On the hot path a ``LinearTransform`` is never
+``CompositeTransform``, ``MultipoleTransform``, ``ProjectionTransform``, ``rotation_matrix``).  On the hot path a ``LinearTransform`` is never
 *applied*: ``simulate.forward`` reads ``.matrix`` and folds the measured row into the fused
 projection kernel.  ``forward``/``inverse`` exist for callers that want the full (N, D)
 image (classical MENT's integration mode, notebooks) and are plain matmuls.
@@ -81,3 +81,71 @@ class CompositeTransform(Transform):
                 return None
             m = t.matrix if m is None else t.matrix @ m
         return m
+
+
+class MultipoleTransform(Transform):
+    """Thin multipole kick (simulate/transform.py:78-146).
+
+    ``simulate.forward`` folds a chain ``linear* -> multipole -> linear*`` into the fused projection
+    kernel (``multipole_terms``); ``forward`` is the stand-alone (N, D) image with the reference's
+    semantics, quirks included: only orders 3, 4, 5 are accepted (the reference's ``if`` ladder falls
+    into its ``else: raise`` for orders 1 and 2, :118-134), and the normal kick sets
+    ``U[:, 3] = X[:, 1] + k Im(z^(n-1))`` -- from column 1, not column 3 (:144).
+    """
+
+    def __init__(self, order: int, strength: float, skew: bool = False) -> None:
+        super().__init__()
+        self.order = order
+        self.strength = strength
+        self.skew = skew
+
+    def coefficient(self) -> float:
+        return float(self.strength) / math.factorial(int(self.order) - 1)
+
+    def _zn(self, x, y):
+        if self.order == 3:
+            return x ** 2 - y ** 2, 2.0 * x * y
+        if self.order == 4:
+            return x ** 3 - 3.0 * y ** 2 * x, -(y ** 3) + 3.0 * x ** 2 * y
+        if self.order == 5:
+            return x ** 4 - 6.0 * x ** 2 * y ** 2 + y ** 4, 4.0 * x ** 3 * y - 4.0 * x * y ** 3
+        raise ValueError("MPS-compatible MultipoleTransform requires order <= 5.")
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        U = X.clone()
+        x = X[:, 0]
+        y = X[:, 2] if X.shape[1] > 2 else 0.0 * X[:, 0]
+        zn_real, zn_imag = self._zn(x, y)
+        k = self.coefficient()
+        if self.skew:
+            U[:, 1] = X[:, 1] + k * zn_imag
+            if X.shape[1] > 2:
+                U[:, 3] = X[:, 3] + k * zn_real
+        else:
+            U[:, 1] = X[:, 1] - k * zn_real
+            if X.shape[1] > 2:
+                U[:, 3] = X[:, 1] + k * zn_imag
+        return U
+
+    def inverse(self, u: torch.Tensor) -> torch.Tensor:
+        """Momentum reversal, kick, momentum reversal (:148-149).  Unlike the reference, which flips
+        the momenta of its argument in place, the input is left untouched."""
+        return reverse_momentum(self.forward(reverse_momentum(u.clone())))
+
+
+def reverse_momentum(x: torch.Tensor) -> torch.Tensor:
+    """In place, like simulate/transform.py:18-21."""
+    for i in range(0, x.shape[1], 2):
+        x[:, i + 1] *= -1.0
+    return x
+
+
+class ProjectionTransform(Transform):
+    """(N, 1) projection on a direction, normalised at construction (simulate/transform.py:152-159)."""
+
+    def __init__(self, direction: torch.Tensor) -> None:
+        super().__init__()
+        self.direction = direction / torch.norm(direction)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.sum(x * self.direction.to(x.device), dim=1)[:, None]

@@ -66,6 +66,40 @@ def linear_map(x: torch.Tensor, matrix: torch.Tensor) -> torch.Tensor:
     return torch.matmul(x, matrix.T)
 
 
+def multipole_kick(x: torch.Tensor, order: int, strength: float, skew: bool = False) -> torch.Tensor:
+    """simulate/transform.py:78-146 (MultipoleTransform.forward), quirks included: the `if / if /
+    if-elif-else` ladder (:118-134) raises for every order outside 3..5 (orders 1 and 2 fall into
+    the final `else`), and the normal (non-skew) kick writes U[:, 3] = X[:, 1] + k Im(z^(n-1)),
+    i.e. from column 1, not column 3 (:144).  k = strength / (order - 1)!."""
+    if order not in (3, 4, 5):
+        raise ValueError("MPS-compatible MultipoleTransform requires order <= 5.")
+    u = x.clone()
+    xx = x[:, 0]
+    yy = x[:, 2] if x.shape[1] > 2 else 0.0 * x[:, 0]
+    if order == 3:
+        zr, zi = xx ** 2 - yy ** 2, 2.0 * xx * yy
+    elif order == 4:
+        zr, zi = xx ** 3 - 3.0 * yy ** 2 * xx, -(yy ** 3) + 3.0 * xx ** 2 * yy
+    else:
+        zr, zi = xx ** 4 - 6.0 * xx ** 2 * yy ** 2 + yy ** 4, 4.0 * xx ** 3 * yy - 4.0 * xx * yy ** 3
+    k = strength / math.factorial(order - 1)
+    if skew:
+        u[:, 1] = x[:, 1] + k * zi
+        if x.shape[1] > 2:
+            u[:, 3] = x[:, 3] + k * zr
+    else:
+        u[:, 1] = x[:, 1] - k * zr
+        if x.shape[1] > 2:
+            u[:, 3] = x[:, 1] + k * zi
+    return u
+
+
+def projection_transform(x: torch.Tensor, direction: torch.Tensor) -> torch.Tensor:
+    """simulate/transform.py:149-156: (N, 1) projection on the normalised direction."""
+    d = direction / torch.norm(direction)
+    return torch.sum(x * d, dim=1)[:, None]
+
+
 def project_1d(u: torch.Tensor, axis: int = 0, direction: Optional[torch.Tensor] = None):
     """diagnostics/diagnostics.py:116-122 (direction is normalised at construction, :104-106)."""
     if direction is None:

@@ -263,5 +263,61 @@ def main():
         print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KB")
 
 
+def make_multipole():
+    """Non-linear transfer maps: MultipoleTransform (simulate/transform.py:78-146) alone for D = 2, 4, 6,
+    and the rec_2d/nonlinear composition multipole -> rotation (experiments/rec_2d/nonlinear/setup.py:24-44)
+    through the reference's simulate.forward with KDE screens, with the gradient of the mean KL."""
+    mf = ref_import.load()
+    out = {}
+    torch.manual_seed(21)
+    cases = []
+    for d in (2, 4, 6):
+        x = (torch.randn(500, d) * 0.8).float()
+        for order in (3, 4, 5):
+            for skew in (False, True):
+                strength = 0.7 if order < 5 else -0.4
+                u = mf.simulate.MultipoleTransform(order=order, strength=strength, skew=skew)(x)
+                key = f"d{d}_o{order}_{'s' if skew else 'n'}"
+                out[f"kick_x_{key}"] = npy(x)
+                out[f"kick_u_{key}"] = npy(u)
+                cases.append((d, order, strength, skew))
+    out["kick_cases"] = np.array([(d, o, s, int(k)) for d, o, s, k in cases], dtype=np.float64)
+    # rec_2d/nonlinear: order 3, strengths linspace(-s, s, num), constant rotation
+    num, order, smax, angle = 6, 3, 1.0, math.radians(45.0)
+    n, nb = 4000, 85
+    x = (torch.randn(n, 2) * torch.tensor([1.0, 0.7])).float()
+    edges = torch.linspace(-3.5, 3.5, nb + 1)
+    strengths = np.linspace(-smax, smax, num)
+    c, s_ = np.cos(angle), np.sin(angle)
+    matrix = torch.tensor([[c, s_], [-s_, c]]).type(torch.float32)
+    tfs = [mf.simulate.CompositeTransform(mf.simulate.MultipoleTransform(order=order, strength=float(st)),
+                                          mf.simulate.LinearTransform(matrix)) for st in strengths]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5)
+    diags = [[diag] for _ in tfs]
+    kde = torch.stack([p[0] for p in mf.simulate.forward(x, tfs, diags)])
+    diag.kde = False
+    hard = torch.stack([p[0] for p in mf.simulate.forward(x, tfs, diags)])
+    xm = (torch.randn(20000, 2) * torch.tensor([0.8, 1.1])).float()
+    meas = torch.stack([p[0] for p in mf.simulate.forward(xm, tfs, diags)])
+    diag.kde = True
+    meas = meas / meas.sum(dim=1, keepdim=True) / (edges[1] - edges[0])
+    xg = x.clone().requires_grad_(True)
+    pg = mf.simulate.forward(xg, tfs, diags)
+    loss = sum(mf.loss.kl_divergence(p[0], m) for p, m in zip(pg, meas)) / num
+    loss.backward()
+    out.update(nl_x=npy(x), nl_edges=npy(edges), nl_strengths=strengths, nl_order=order, nl_matrix=npy(matrix),
+               nl_kde=npy(kde), nl_hard=npy(hard), nl_meas=npy(meas), nl_mean_kl=npy(loss), nl_grad_x=npy(xg.grad))
+    # ProjectionTransform (simulate/transform.py:149-156)
+    direction = torch.tensor([0.3, -1.2, 0.5, 2.0])
+    x4 = torch.randn(100, 4).float()
+    out.update(pt_x=npy(x4), pt_direction=npy(direction), pt_u=npy(mf.simulate.ProjectionTransform(direction)(x4)))
+    np.savez_compressed(os.path.join(OUT, "multipole.npz"), **out)
+    print("wrote multipole.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-multipole" in sys.argv:
+        make_multipole()
+    else:
+        main()
+        make_multipole()

@@ -209,3 +209,78 @@ def test_fused_loss_tail_with_reducer_path():
     prof_f, kl_f = ops.project_kde1d(x, w, geom, 0.5, nb, None, meas)
     assert float((prof_r - prof_f).abs().max()) <= 1e-5 * float(prof_f.abs().max())
     assert torch.allclose(kl_r, kl_f, rtol=1e-4, atol=1e-6)
+
+
+def _nonlinear_setup(g):
+    matrix = t32(g["nl_matrix"]).cuda()
+    tfs = [mf.simulate.CompositeTransform(mf.simulate.MultipoleTransform(order=int(g["nl_order"]), strength=float(st)),
+                                          mf.simulate.LinearTransform(matrix)) for st in g["nl_strengths"]]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=t32(g["nl_edges"]), bandwidth=0.5).to("cuda")
+    return tfs, [[diag] for _ in tfs], diag
+
+
+def test_multipole_chain_runs_in_the_fused_kernel_and_matches_reference(golden):
+    """rec_2d/nonlinear (experiments/rec_2d/nonlinear/setup.py:24-44): multipole kick -> rotation -> screen.
+    KDE profiles, exact histograms and the gradient of the mean KL against the reference's own outputs."""
+    from mentflow_b200.simulate import simulate as sim
+    g = golden("multipole")
+    tfs, diags, diag = _nonlinear_setup(g)
+    x = cuda(g["nl_x"]).requires_grad_(True)
+    sim._plan_cache.clear()
+    out = mf.simulate.forward(x, tfs, diags)
+    plan = next(iter(sim._plan_cache.values()))
+    assert not plan.fallback and [k[0] for k in plan.groups] == ["1d-mp"]     # no object-by-object path
+    kde = torch.stack([o[0] for o in out])
+    ref = t32(g["nl_kde"])
+    assert profile_err(kde.detach().cpu(), ref) < TOL
+    meas = cuda(g["nl_meas"])
+    loss = torch.stack([mf.loss.kl_divergence(o[0], m) for o, m in zip(out, meas)]).sum() / len(tfs)
+    loss.backward()
+    assert abs(float(loss) - float(g["nl_mean_kl"])) <= TOL * abs(float(g["nl_mean_kl"]))
+    gref = t32(g["nl_grad_x"])
+    assert (x.grad.cpu() - gref).abs().max() <= TOL * gref.abs().max()
+    # exact histograms: identical up to particles whose fp32 coordinate rounds across an edge
+    diag.kde = False
+    hard = torch.stack([o[0] for o in mf.simulate.forward(x.detach(), tfs, diags)]).cpu()
+    diag.kde = True
+    n, width = x.shape[0], float(g["nl_edges"][1] - g["nl_edges"][0])
+    moved = ((hard - t32(g["nl_hard"])).abs() * n * width).sum(dim=1)          # in particles, per screen
+    assert float(moved.max()) <= 4.5
+
+
+@pytest.mark.parametrize("d,order,skew", [(2, 4, False), (4, 3, False), (4, 5, True), (6, 3, True), (6, 4, False)])
+def test_multipole_chain_general_matrices_vs_oracle(d, order, skew):
+    """linear -> kick -> linear with random matrices in 2, 4 and 6 dimensions: fused kernel vs the dense CPU
+    oracle applied to the coordinates the transform classes produce (reference semantics), and the
+    particle gradient vs torch autograd through the same classes."""
+    gen = torch.Generator().manual_seed(100 * d + order)
+    n, k, nb = 5000, 5, 64
+    x = (torch.randn(n, d, generator=gen) * 0.7).float()
+    edges = torch.linspace(-3.5, 3.5, nb + 1)
+    chains, cpu_chains = [], []
+    for i in range(k):
+        pre = torch.eye(d) + 0.3 * torch.randn(d, d, generator=gen)
+        post = torch.eye(d) + 0.3 * torch.randn(d, d, generator=gen)
+        st = 0.5 - 0.2 * i
+        cpu_chains.append(mf.simulate.CompositeTransform(mf.simulate.LinearTransform(pre.double()),
+                                                         mf.simulate.MultipoleTransform(order, st, skew),
+                                                         mf.simulate.LinearTransform(post.double())))
+        chains.append(mf.simulate.CompositeTransform(mf.simulate.LinearTransform(pre.cuda()),
+                                                     mf.simulate.MultipoleTransform(order, st, skew),
+                                                     mf.simulate.LinearTransform(post.cuda())))
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5).to("cuda")
+    xg = x.cuda().requires_grad_(True)
+    out = mf.simulate.forward(xg, chains, [[diag] for _ in chains])
+    side = torch.randn(k, nb, generator=gen).cuda()
+    (torch.stack([o[0] for o in out]) * side).sum().backward()
+    sigma = 0.5 * float(edges[1] - edges[0])
+    xr = x.double().requires_grad_(True)
+    ref = []
+    for c in cpu_chains:
+        u = c(xr)[:, 0]
+        ref.append(hp.kde_profile_1d(u, edges.double(), sigma))
+    ref = torch.stack(ref)
+    (ref * side.cpu().double()).sum().backward()
+    got = torch.stack([o[0] for o in out]).detach().cpu().double()
+    assert float((got - ref.detach()).abs().max()) <= TOL * float(ref.abs().max())
+    assert float((xg.grad.cpu().double() - xr.grad).abs().max()) <= TOL * float(xr.grad.abs().max())

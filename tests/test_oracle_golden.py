@@ -1,6 +1,7 @@
 """Pins oracle/hotpath.py to outputs of the REAL reference code (tests/golden/*.npz made by
 oracle/make_goldens.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import hotpath as hp
@@ -160,3 +161,61 @@ def test_ment_integrate_mode(golden):
             tables[i][0] = hp.gauss_seidel_table(tables[i][0], meas[i], integrate(i, tables), 1.0, 1e-10)
     got = torch.stack([t[0] for t in tables])
     assert torch.allclose(got, t32(g["tables_after_2"]), rtol=1e-4, atol=1e-7)
+
+
+def test_multipole_kick_and_projection_transform_match_reference(golden):
+    """oracle.hotpath.multipole_kick / projection_transform and the package's transform classes against
+    the reference's MultipoleTransform / ProjectionTransform outputs (simulate/transform.py:78-156)."""
+    import mentflow_b200 as mf
+    g = golden("multipole")
+    for d, order, strength, skew in g["kick_cases"]:
+        key = f"d{int(d)}_o{int(order)}_{'s' if skew else 'n'}"
+        x, u = t32(g["kick_x_" + key]), t32(g["kick_u_" + key])
+        assert torch.equal(hp.multipole_kick(x, int(order), float(strength), bool(skew)), u)
+        assert torch.equal(mf.simulate.MultipoleTransform(int(order), float(strength), bool(skew))(x), u)
+    for bad in (1, 2, 6):
+        with pytest.raises(ValueError):
+            hp.multipole_kick(t32(g["kick_x_d2_o3_n"]), bad, 1.0)
+        with pytest.raises(ValueError):
+            mf.simulate.MultipoleTransform(bad, 1.0)(t32(g["kick_x_d2_o3_n"]))
+    x4, direction = t32(g["pt_x"]), t32(g["pt_direction"])
+    assert torch.equal(hp.projection_transform(x4, direction), t32(g["pt_u"]))
+    assert torch.equal(mf.simulate.ProjectionTransform(direction)(x4), t32(g["pt_u"]))
+    # inverse of the kick: momentum reversal, kick, momentum reversal; the argument is not modified
+    kick = mf.simulate.MultipoleTransform(3, 0.7)
+    x = t32(g["kick_x_d4_o3_n"])
+    keep = x.clone()
+    back = kick.inverse(kick(x))
+    assert torch.equal(x, keep)
+    assert torch.allclose(back[:, [0, 2]], x[:, [0, 2]])
+
+
+def test_multipole_terms_reproduce_the_composite_map(golden):
+    """Host-side folding of linear -> kick -> linear into (w, wa, wb, a, b): the measured coordinate of the
+    closed form equals row . CompositeTransform(x) of the reference semantics, all orders, skew or not."""
+    import mentflow_b200 as mf
+    from mentflow_b200.simulate.simulate import _multipole_chain, multipole_terms
+    gen = torch.Generator().manual_seed(4)
+    for d in (2, 4, 6):
+        x = torch.randn(300, d, generator=gen, dtype=torch.float64) * 0.7
+        for order in (3, 4, 5):
+            for skew in (False, True):
+                pre = torch.randn(d, d, generator=gen, dtype=torch.float64)
+                post = torch.randn(d, d, generator=gen, dtype=torch.float64)
+                chain = mf.simulate.CompositeTransform(mf.simulate.LinearTransform(pre),
+                                                       mf.simulate.MultipoleTransform(order, 0.6, skew),
+                                                       mf.simulate.LinearTransform(post))
+                got = _multipole_chain(chain)
+                assert got is not None
+                for axis in range(d):
+                    w, mp = multipole_terms(post[axis], got[0], got[1], d)
+                    w, mp = w.double(), mp.double()
+                    wa, wb, a, b, m = mp[:d], mp[d:2 * d], mp[2 * d], mp[2 * d + 1], int(mp[2 * d + 2]) - 1
+                    z = torch.complex(x @ wa, x @ wb) ** m
+                    u = x @ w + a * z.real + b * z.imag
+                    ref = chain(x)[:, axis]
+                    assert float((u - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    # a chain with two kicks, or an unsupported order, is not folded
+    two = mf.simulate.CompositeTransform(mf.simulate.MultipoleTransform(3, 0.1), mf.simulate.MultipoleTransform(3, 0.1))
+    assert _multipole_chain(two) is None
+    assert _multipole_chain(mf.simulate.MultipoleTransform(2, 0.1)) is None
