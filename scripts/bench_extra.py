@@ -49,7 +49,7 @@ def trained_like(m, f=3.0):
 def flow_model(wl, d, kind, n_truth=200_000):
     torch.manual_seed(0)
     gen = trained_like(mf.generate.NSFGenerator(d)).to(dev)
-    tfs = [mf.simulate.LinearTransform(m.to(dev)) for m in wl["matrices"]]
+    tfs = wl.get("transforms") or [mf.simulate.LinearTransform(m.to(dev)) for m in wl["matrices"]]
     if kind == "1d":
         diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(dev)
     else:
@@ -74,6 +74,20 @@ N = 1_000_000
 m1 = flow_model(workloads.rotations_2d(7, 85, 3.5), 2, "1d")
 with torch.no_grad():
     out("C1 rec_2d/linear: 2-D NSF + 7 x KDE-1D(85) + KL, forward", N, timed(lambda: m1.loss(N)))
+# ---- C1n: rec_2d/nonlinear (experiments/rec_2d/nonlinear/setup.py:24-44, config rec_2d_nonlinear_flow.yaml):
+#      sextupole kicks of strength linspace(-1.5, 1.5, num) followed by a 90 degree rotation
+import math
+import numpy as np
+rot = mf.simulate.rotation_matrix(math.radians(90.0)).float().to(dev)
+for num in (4, 7):
+    wl_n = {"edges": torch.linspace(-3.5, 3.5, 86), "transforms": [
+        mf.simulate.CompositeTransform(mf.simulate.MultipoleTransform(order=3, strength=float(st)),
+                                       mf.simulate.LinearTransform(rot)) for st in np.linspace(-1.5, 1.5, num)]}
+    m1n = flow_model(wl_n, 2, "1d")
+    with torch.no_grad():
+        out(f"C1n rec_2d/nonlinear: 2-D NSF + {num} x (sextupole kick -> rotation -> KDE-1D(85)) + KL, forward", N,
+            timed(lambda: m1n.loss(N)))
+    del m1n
 # ---- C3 pieces
 m3 = flow_model(workloads.isotropic_1d(6, 100, 64, 3.5), 6, "1d")
 g3 = m3.generator
