@@ -47,7 +47,7 @@ struct Meta {
 struct BwdIO {
   const float* gy;      // [n][D] dL/dy
   const float* glogq;   // [n] dL/dlogq_out or null
-  float* acts;          // 192 rows (3 x 64): post-ReLU activations (original unit order)
+  float* acts;          // 192 rows (3 x 64): post-ReLU activations (sorted unit order: row c = unit perm[c])
   float* gphi;          // D*64 rows: dL/d(raw conditioner output)
   float* gvd;           // [n][D] direct dL/dv through the spline (+ base density term)
   float* gmax;          // [n] max |gphi| of the particle
@@ -814,12 +814,14 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     umma::fence_before_sync();
     request_arrive(req_chain);
     if constexpr (kBwd) {
-      // post-ReLU activations of the tile being started (= next tile), feature-major, original unit order;
-      // after the hand-off so that the stores overlap the GEMM
+      // post-ReLU activations of the tile being started (= next tile), feature-major, in the SORTED unit
+      // order of the operand images (row c = unit meta.perm[c]; the weight-gradient reduce maps back):
+      // constant row offsets, no address arithmetic per element.  After the hand-off so that the stores
+      // overlap the GEMM
       if (next_valid) {
         float* al = bio.acts + ((size_t)(next_p >> 7) * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) al[meta.perm[c] * 128] = fmaxf(acc[c], 0.f);
+        for (int c = 0; c < 64; ++c) al[c * 128] = fmaxf(acc[c], 0.f);
       }
     }
     TRACE(4 + l);

@@ -241,7 +241,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
       auto load_mask = [&](int l, float (&hv)[64]) {
         const float* hl = acts + ((size_t)tile * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) hv[c] = valid ? hl[meta.perm[c] * 128] : 0.f;
+        for (int c = 0; c < 64; ++c) hv[c] = valid ? hl[c * 128] : 0.f;   // rows are in sorted unit order
       };
 #pragma unroll 1
       for (int s = S - 1; s >= 0; --s) {
@@ -282,7 +282,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
         if (valid) {
           float* gl = gz + ((size_t)tile * (L * kH) + l * kH) * 128 + t;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) gl[meta.perm[c] * 128] = acc[c];
+          for (int c = 0; c < 64; ++c) gl[c * 128] = acc[c];   // sorted unit order, like acts
         }
         if (l > 0) load_mask(l - 1, g);
         wait_done();
@@ -355,6 +355,7 @@ constexpr int kWgLoaders = 12;                 // loader warps
 constexpr int kWgCols = 464;                   // accumulator columns
 
 struct WgradMeta {
+  int perm[kH];               // acts / gz rows are in sorted unit order: row c = hidden unit perm[c]
   int slot_feature[kMaxDim];
   int const_feature;
   int nslots;
@@ -634,21 +635,23 @@ __global__ void nsf_tc_wgrad_reduce_kernel(const float* __restrict__ partial, in
   const int64_t off_wout = off_hid + (int64_t)(L - 1) * (kH * kH + kH);
   const int64_t off_bout = off_wout + (int64_t)D * kH * kPP;
   int64_t dst = -1;
-  if (c < 320) {                                  // dWout_t[f][i][q]: column block s, i = c % 64, q = j
+  // hidden-unit indices arrive in the sorted order of the workspace rows: unit = perm[sorted index]
+  const int uj = meta.perm[j];
+  if (c < 320) {                                  // dWout_t[f][i][q]: column block s, i = perm[c % 64], q = j
     const int sl = c / 64;
-    if (sl < meta.nslots) dst = off_wout + ((int64_t)meta.slot_feature[sl] * kH + (c % 64)) * kPP + j;
+    if (sl < meta.nslots) dst = off_wout + ((int64_t)meta.slot_feature[sl] * kH + meta.perm[c % 64]) * kPP + j;
   } else if (c < 384) {                           // W3: hidden block l = 1, Wt[in i][out j]
-    dst = off_hid + 1 * (kH * kH + kH) + (int64_t)(c - 320) * kH + j;
+    dst = off_hid + 1 * (kH * kH + kH) + (int64_t)meta.perm[c - 320] * kH + uj;
   } else if (c < 448) {                           // W2: hidden block l = 0
-    dst = off_hid + (int64_t)(c - 384) * kH + j;
-  } else if (c < kWgCols) {                       // W1t[i][j]
-    if (c - 448 < D) dst = off_w1 + (int64_t)(c - 448) * kH + j;
+    dst = off_hid + (int64_t)meta.perm[c - 384] * kH + uj;
+  } else if (c < kWgCols) {                       // W1t[i][j]: i = input feature
+    if (c - 448 < D) dst = off_w1 + (int64_t)(c - 448) * kH + uj;
   } else {
     const int kind = c - kWgCols;                 // bias rows: features 0..D-1, then g3, g2, g1
     if (kind < D) dst = off_bout + (int64_t)kind * kPP + j;
-    else if (kind == D) dst = off_hid + 1 * (kH * kH + kH) + kH * kH + j;
-    else if (kind == D + 1) dst = off_hid + kH * kH + j;
-    else dst = off_b1 + j;
+    else if (kind == D) dst = off_hid + 1 * (kH * kH + kH) + kH * kH + uj;
+    else if (kind == D + 1) dst = off_hid + kH * kH + uj;
+    else dst = off_b1 + uj;
   }
   if (dst >= 0) gparams[dst] = accumulate ? gparams[dst] + sacc : sacc;
 }
@@ -665,6 +668,8 @@ static int launch_wgrad(const float* gphi, const float* gz, const float* acts, c
                         cudaStream_t st) {
   constexpr int L = 3;
   WgradMeta meta = {};
+  int cls[kH];
+  hidden_classes(D, cls, meta.perm);
   int feat_of_order[kMaxDim];
   for (int i = 0; i < D; ++i) feat_of_order[order[i]] = i;
   meta.nslots = D - 1;
