@@ -100,7 +100,11 @@ __device__ __forceinline__ void store_ktile_row(unsigned char* tile, int row, co
   *reinterpret_cast<uint4*>(tile + umma::sw32_offset(row, 1)) = reinterpret_cast<const uint4*>(v)[1];
 }
 
-// one block per layer; params = packed fp32 block of nsf_common.cuh (pre-masked, [in][out])
+// grid (layers, kPrepSlices): the rows of a layer's image are dealt out over kPrepSlices blocks (a single
+// block took 28 us per layer, which a training step pays per layer and per step).  The image must have
+// been zeroed before the launch (padding rows / columns are exact zeros): the launchers do that with a
+// memset node.  params = packed fp32 block of nsf_common.cuh (pre-masked, [in][out])
+constexpr int kPrepSlices = 8;
 __global__ void __launch_bounds__(256)
 nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride, int D, int L, int nb,
                       const __grid_constant__ PrepArgs args, int layer0, unsigned char* __restrict__ images,
@@ -119,17 +123,12 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
   float* f32 = reinterpret_cast<float*>(img + off_f32(D, L));
   const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.0f);
 
-  // zero everything first (padding rows / columns must be exact zeros)
-  for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-
   // tasks: 128 ones rows | 64 first-layer rows | (L-1) x 64 x 8 hidden chunks | (L-1+S) x 64 bias rows |
   //        sum_s nk(s) x 64 slot rows
   const int n_ones = 128, n_b1 = kH, n_hid = (L - 1) * kH * 8, n_bias = (L - 1 + S) * kH;
   const int n_slot = slot_koff(D, S) * kH;
   const int ntask = n_ones + n_b1 + n_hid + n_bias + n_slot;
-  for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+  for (int task = blockIdx.y * blockDim.x + threadIdx.x; task < ntask; task += blockDim.x * gridDim.y) {
     int t2 = task;
     if (t2 < n_ones) {
       __align__(16) __half v[16];
@@ -197,7 +196,7 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
     }
   }
   // constant feature: knots of its bias-only spline (same formulas as the epilogue)
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.y == gridDim.y - 1) {
     float* ct = f32;
     const float* bf = bout + pm.const_feature * kPP;
     float ew[32], eh[32];
@@ -1088,8 +1087,9 @@ int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64
   tc::Meta meta;
   tc::make_meta(d, order, &meta, &args.layer[0]);
   unsigned char* img = reinterpret_cast<unsigned char*>(image);
-  tc::nsf_tc_prepare_kernel<<<1, 256, 0, st>>>(params, 0, d, hidden_layers, bins, args, 0, img,
-                                               tc::image_bytes(d, hidden_layers));
+  MFB_CUDA(cudaMemsetAsync(img, 0, (size_t)tc::image_bytes(d, hidden_layers), st));
+  tc::nsf_tc_prepare_kernel<<<dim3(1, tc::kPrepSlices), 256, 0, st>>>(params, 0, d, hidden_layers, bins, args, 0, img,
+                                                                      tc::image_bytes(d, hidden_layers));
   int rc = launch_status();
   if (rc) return rc;
   const tc::BwdIO bio = {gy, glogq, acts, gphi, gvd, gmax, gmaxes};
@@ -1144,8 +1144,11 @@ int mfb_nsf_tc_prepare(const float* params, int64_t layer_stride_floats, int n_l
       if (!tc::valid_order(d, orders_host + (size_t)(l0 + l) * d)) return MFB_E_BADARG;
       tc::make_meta(d, orders_host + (size_t)(l0 + l) * d, nullptr, &args.layer[l]);
     }
-    tc::nsf_tc_prepare_kernel<<<nl, 256, 0, st>>>(params, layer_stride_floats, d, hidden_layers, bins, args, l0,
-                                                  reinterpret_cast<unsigned char*>(images), img_bytes);
+    MFB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(images) + (size_t)l0 * img_bytes, 0,
+                             (size_t)nl * img_bytes, st));
+    tc::nsf_tc_prepare_kernel<<<dim3(nl, tc::kPrepSlices), 256, 0, st>>>(
+        params, layer_stride_floats, d, hidden_layers, bins, args, l0, reinterpret_cast<unsigned char*>(images),
+        img_bytes);
     const int rc = launch_status();
     if (rc) return rc;
   }

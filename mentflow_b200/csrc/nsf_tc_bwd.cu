@@ -46,10 +46,9 @@ nsf_tc_dgrad_prepare_kernel(const float* __restrict__ params, int D, int L, cons
   const float* W1t = params;
   const float* hid = W1t + D * kH + kH;
   const float* Wout = hid + (size_t)(L - 1) * (kH * kH + kH);
-  for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
+  // the image was zeroed by a memset node before the launch; the rows are dealt out over gridDim.x blocks
   const int n_slot = S * kH * 8, n_hid = (L - 1) * kH * 8, n_first = 16 * 8;
-  for (int task = threadIdx.x; task < n_slot + n_hid + n_first; task += blockDim.x) {
+  for (int task = blockIdx.x * blockDim.x + threadIdx.x; task < n_slot + n_hid + n_first; task += blockDim.x * gridDim.x) {
     int t2 = task;
     float x[8];
     if (t2 < n_slot) {
@@ -322,7 +321,8 @@ static int launch_dgrad(const float* gphi, const float* gmax, const float* acts,
     meta.slot_nk[s] = (cnt + 15) / 16;
   }
   const int img_bytes = dgrad_image_bytes(D, L);
-  nsf_tc_dgrad_prepare_kernel<<<1, 256, 0, st>>>(params, D, L, meta, image, img_bytes);
+  MFB_CUDA(cudaMemsetAsync(image, 0, (size_t)img_bytes, st));
+  nsf_tc_dgrad_prepare_kernel<<<8, 256, 0, st>>>(params, D, L, meta, image, img_bytes);
   int rc = launch_status();
   if (rc) return rc;
   const size_t smem = (size_t)img_bytes + kWG * kABytes + 128 + 1024;
@@ -626,11 +626,18 @@ __global__ void nsf_tc_wgrad_reduce_kernel(const float* __restrict__ partial, in
                                            const __grid_constant__ WgradMeta meta, float* __restrict__ gparams,
                                            int accumulate) {
   const int rows = wgrad_rows(D);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over rows * 64 partial entries
-  if (idx >= rows * 64) return;
-  const int c = idx / 64, j = idx % 64;
+  // eight lanes per entry: lane q adds partials q, q + 8, ...; fixed shuffle tree => deterministic
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gid >> 3, q = gid & 7;
+  const bool live = idx < rows * 64;
   float sacc = 0.f;
-  for (int k = 0; k < nparts; ++k) sacc += partial[(size_t)k * rows * 64 + idx];
+  if (live)
+    for (int k = q; k < nparts; k += 8) sacc += partial[(size_t)k * rows * 64 + idx];
+  sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+  sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+  sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+  if (!live || q != 0) return;
+  const int c = idx / 64, j = idx % 64;
   const int64_t off_w1 = 0, off_b1 = (int64_t)D * kH, off_hid = off_b1 + kH;
   const int64_t off_wout = off_hid + (int64_t)(L - 1) * (kH * kH + kH);
   const int64_t off_bout = off_wout + (int64_t)D * kH * kPP;
@@ -685,7 +692,7 @@ static int launch_wgrad(const float* gphi, const float* gz, const float* acts, c
   int rc = launch_status();
   if (rc) return rc;
   const int entries = wgrad_rows(D) * 64;
-  nsf_tc_wgrad_reduce_kernel<<<(entries + 255) / 256, 256, 0, st>>>(partial, grid, D, L, meta, gparams, accumulate);
+  nsf_tc_wgrad_reduce_kernel<<<(entries * 8 + 255) / 256, 256, 0, st>>>(partial, grid, D, L, meta, gparams, accumulate);
   if (!accumulate) {
     const int64_t off_wout = (int64_t)D * kH + kH + (int64_t)(L - 1) * (kH * kH + kH);
     nsf_tc_wgrad_zero_const_kernel<<<(kH * kPP + 255) / 256, 256, 0, st>>>(
