@@ -195,6 +195,15 @@ int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64
                       float* gparams, int accumulate, void* workspace, int64_t workspace_bytes,
                       void* stream);
 
+/* The same with the layer's tcgen05 operand image that mfb_nsf_tc_prepare built for the forward pass of
+ * this step (tc_image, mfb_nsf_tc_image_bytes bytes, 16-byte aligned; NULL = build it here): a
+ * training step then builds each image once instead of twice.                              */
+int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, int64_t n, int d,
+                          int hidden_units, int hidden_layers, int bins, const float* params,
+                          const float* params_om, const int32_t* order_host, int first_layer,
+                          const void* tc_image, float* gv, float* gparams, int accumulate,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Monte-Carlo entropy pieces (entropy.py:58-62, prior.py:25-26) ----------------------
  * out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j
  * (double precision, deterministic two-stage reduction; the x_i / x_i x_j block only when

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mfb_nsf_layer_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "mfb_nsf_layer_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P,
                                   c_int64, P]),
+    "mfb_nsf_layer_bwd_img": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P, c_int, P,
+                                      c_int64, P]),
     "mfb_ment_prob": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_prob_grid": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_integrate": (c_int, [c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float,

@@ -479,10 +479,12 @@ int64_t nsf_tc_dgrad_image_bytes(int d);
 int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
                  int* gmaxes, cudaStream_t st);
-// tcgen05 recompute + spline forward/backward (nsf_tc.cu); image: mfb_nsf_tc_image_bytes scratch
+// tcgen05 recompute + spline forward/backward (nsf_tc.cu); image: mfb_nsf_tc_image_bytes scratch the operand
+// image is built in, unless ready_image (the image mfb_nsf_tc_prepare built for the forward pass) is given
 int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
                       int bins, const float* params, const int32_t* order, int first_layer, float* acts,
-                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, cudaStream_t st);
+                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
+                      cudaStream_t st);
 // tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu)
 int64_t nsf_tc_wgrad_partial_floats(int d);
 int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const float* v, int64_t n, int d,
@@ -534,7 +536,8 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
 template <int D>
 static int run_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int hidden_layers, int nb,
                          const float* params, const float* params_om, const FeatureOrder& order, int first,
-                         float* gv, float* gparams, int accumulate, float* ws, cudaStream_t st) {
+                         float* gv, float* gparams, int accumulate, float* ws, cudaStream_t st,
+                         const void* ready_image = nullptr) {
   const BwdPlan P = plan_bwd(n, D, hidden_layers);
   const int64_t np = nsf_param_floats(D, hidden_layers);
   float* acts = ws + P.acts;
@@ -553,7 +556,7 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
     int rc = nsf_tc_spline_bwd(v, gy, glogq, n, D, hidden_layers, nb, params, ord, first, acts, gphi, gvd, ws + P.gmax,
-                               gmaxes, image, st);
+                               gmaxes, image, ready_image, st);
     if (rc == 0) tc_spline = true;
     else if (rc != MFB_E_UNSUPPORTED) return rc;
   }
@@ -661,10 +664,10 @@ int64_t mfb_nsf_layer_param_om_floats(int d, int hidden_units, int hidden_layers
   return (int64_t)kH * d + (int64_t)(hidden_layers - 1) * kH * kH + (int64_t)d * kPP * kH;
 }
 
-int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
-                      int hidden_layers, int bins, const float* params, const float* params_om,
-                      const int32_t* order_host, int first_layer, float* gv, float* gparams, int accumulate,
-                      void* workspace, int64_t workspace_bytes, void* stream) {
+static int layer_bwd_impl(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
+                          int hidden_layers, int bins, const float* params, const float* params_om,
+                          const int32_t* order_host, int first_layer, const void* tc_image, float* gv, float* gparams,
+                          int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
   MFB_CHECK_ARG(v && gy && params && params_om && gv && gparams && workspace && n >= 1);
   if (hidden_units != kH || hidden_layers < 1 || bins < 2 || 3 * bins - 1 > kPP || d < 2 || d > 6)
     return MFB_E_UNSUPPORTED;
@@ -675,7 +678,7 @@ int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64
   float* ws = (float*)workspace;
 #define MFB_BWD(DD)                                                                                              \
   return run_layer_bwd<DD>(v, gy, glogq, n, hidden_layers, bins, params, params_om, ord, first_layer, gv, gparams, \
-                           accumulate, ws, st)
+                           accumulate, ws, st, tc_image)
   switch (d) {
     case 2: MFB_BWD(2);
     case 3: MFB_BWD(3);
@@ -685,6 +688,22 @@ int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64
     default: return MFB_E_UNSUPPORTED;
   }
 #undef MFB_BWD
+}
+
+int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
+                      int hidden_layers, int bins, const float* params, const float* params_om,
+                      const int32_t* order_host, int first_layer, float* gv, float* gparams, int accumulate,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  return layer_bwd_impl(v, gy, glogq, n, d, hidden_units, hidden_layers, bins, params, params_om, order_host,
+                        first_layer, nullptr, gv, gparams, accumulate, workspace, workspace_bytes, stream);
+}
+
+int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
+                          int hidden_layers, int bins, const float* params, const float* params_om,
+                          const int32_t* order_host, int first_layer, const void* tc_image, float* gv,
+                          float* gparams, int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  return layer_bwd_impl(v, gy, glogq, n, d, hidden_units, hidden_layers, bins, params, params_om, order_host,
+                        first_layer, tc_image, gv, gparams, accumulate, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -1078,7 +1078,8 @@ static int launch_layer_bwd(const float* v, int64_t n, const unsigned char* imag
 // forward/backward.  MFB_E_UNSUPPORTED for shapes the tcgen05 kernels are not compiled for.
 int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
                       int bins, const float* params, const int32_t* order, int first_layer, float* acts,
-                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, cudaStream_t st) {
+                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
+                      cudaStream_t st) {
   if (!(d >= 2 && d <= 6 && hidden_layers == 3 && bins == 20)) return MFB_E_UNSUPPORTED;
   if (!tc::valid_order(d, order)) return MFB_E_BADARG;
   tc::PrepArgs args = {};
@@ -1086,12 +1087,18 @@ int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64
   tc::hidden_classes(d, cls, args.perm);
   tc::Meta meta;
   tc::make_meta(d, order, &meta, &args.layer[0]);
-  unsigned char* img = reinterpret_cast<unsigned char*>(image);
-  MFB_CUDA(cudaMemsetAsync(img, 0, (size_t)tc::image_bytes(d, hidden_layers), st));
-  tc::nsf_tc_prepare_kernel<<<dim3(1, tc::kPrepSlices), 256, 0, st>>>(params, 0, d, hidden_layers, bins, args, 0, img,
-                                                                      tc::image_bytes(d, hidden_layers));
-  int rc = launch_status();
-  if (rc) return rc;
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(ready_image);
+  if (img == nullptr) {   // no image from the forward pass: build it in the scratch buffer
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(image);
+    MFB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)tc::image_bytes(d, hidden_layers), st));
+    tc::nsf_tc_prepare_kernel<<<dim3(1, tc::kPrepSlices), 256, 0, st>>>(params, 0, d, hidden_layers, bins, args, 0,
+                                                                        scratch, tc::image_bytes(d, hidden_layers));
+    int rc = launch_status();
+    if (rc) return rc;
+    img = scratch;
+  } else if ((reinterpret_cast<uintptr_t>(img) & 15u) != 0) {
+    return MFB_E_BADARG;    // the image is loaded with a bulk copy: 16-byte aligned
+  }
   const tc::BwdIO bio = {gy, glogq, acts, gphi, gvd, gmax, gmaxes};
   switch (d) {
     case 2: return tc::launch_layer_bwd<2>(v, n, img, meta, first_layer, bio, st);

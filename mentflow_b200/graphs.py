@@ -157,7 +157,8 @@ class GraphedTrainStep:
     """``zero_grad(); loss, H, D = model.loss(n); loss.backward(); optimizer.step()`` -- the body of
     the reference's training loop (train/train.py:164-169) -- as ONE CUDA-graph replay.
 
-    The optimiser must be capturable (``torch.optim.AdamW(..., capturable=True)``): its step counter
+    The optimiser must be capturable (``torch.optim.AdamW(..., capturable=True)``; add ``fused=True`` for
+    one launch instead of sixteen): its step counter
     and the learning rate then live on the device, so LR schedulers keep working between replays.
     One difference from the reference loop: a non-finite loss cannot skip the update from inside a
     graph; ``step.finite`` (a device flag refreshed by every replay) lets the caller notice.

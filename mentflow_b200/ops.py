@@ -425,8 +425,11 @@ class NSFForward(torch.autograd.Function):
         orders, hidden_units, hidden_layers, bins, want_logq, images = meta
         z = _check_f32("z", z)
         packed = _check_f32("packed", packed)
+        if images is None and NSF_USE_TENSOR_CORES and nsf_tc_supported(z.shape[1], hidden_units, hidden_layers, bins):
+            images = nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins)
         steps, logq = _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq, images)
         ctx.meta = meta
+        ctx.images = images        # the backward kernels read the same operand images (~1 MB, not rebuilt)
         ctx.save_for_backward(packed, packed_om, *steps[:-1])
         if logq is None:
             logq = z.new_empty(0)
@@ -435,19 +438,22 @@ class NSFForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gx, glogq):
         orders, hidden_units, hidden_layers, bins, want_logq, _ = ctx.meta
+        images = ctx.images
         packed, packed_om, *inputs = ctx.saved_tensors
         n, d = inputs[0].shape
         gx = _check_f32("gx", gx) if gx is not None else torch.zeros_like(inputs[0])
         gl = _check_f32("glogq", glogq) if (want_logq and glogq is not None and glogq.numel() == n) else None
-        gz, gpacked = nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, gl)
+        gz, gpacked = nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, gl,
+                                   images=images)
         return gz, gpacked, None, None
 
 
 NSF_BWD_CHUNK = 1 << 20   # particles per backward pass: bounds the recompute workspace (~2.9 KB/particle)
 
 
-def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, glogq):
-    """(dL/dz, dL/dpacked) given the per-layer inputs saved by the forward pass."""
+def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers, bins, gx, glogq, images=None):
+    """(dL/dz, dL/dpacked) given the per-layer inputs saved by the forward pass.  ``images``: the tcgen05
+    operand images of the same packed weights (``nsf_tc_images``), reused instead of being rebuilt."""
     lib = _lib.load()
     n, d = inputs[0].shape
     dev = inputs[0].device
@@ -464,11 +470,12 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
             for t in range(len(orders) - 1, -1, -1):
                 order_arr = (ctypes.c_int32 * d)(*[int(o) for o in orders[t]])
                 out = gz[start:start + m] if t == 0 else torch.empty((m, d), dtype=torch.float32, device=dev)
-                _lib.check(lib.mfb_nsf_layer_bwd(_ptr(inputs[t][start:start + m]), _ptr(g), _ptr(gl), m, d, hidden_units,
-                                                 hidden_layers, bins, _ptr(packed[t]), _ptr(packed_om[t]),
-                                                 ctypes.cast(order_arr, ctypes.c_void_p), 1 if t == 0 else 0,
-                                                 _ptr(out), _ptr(gpacked[t]), 1 if start > 0 else 0, _ptr(work),
-                                                 wbytes, _stream()), "nsf_layer_bwd")
+                _lib.check(lib.mfb_nsf_layer_bwd_img(_ptr(inputs[t][start:start + m]), _ptr(g), _ptr(gl), m, d,
+                                                     hidden_units, hidden_layers, bins, _ptr(packed[t]),
+                                                     _ptr(packed_om[t]), ctypes.cast(order_arr, ctypes.c_void_p),
+                                                     1 if t == 0 else 0, _ptr(images[t]) if images is not None else None,
+                                                     _ptr(out), _ptr(gpacked[t]), 1 if start > 0 else 0, _ptr(work),
+                                                     wbytes, _stream()), "nsf_layer_bwd")
                 g = out
     return gz, gpacked
 

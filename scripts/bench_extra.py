@@ -119,7 +119,7 @@ def train():
 out("C3 training step: forward + backward to all flow parameters", N, timed(train, reps=3, warm=1))
 from mentflow_b200.graphs import GraphedTrainStep
 for nb in (25_000, 100_000, 1_000_000):
-    opt = torch.optim.AdamW(m3.parameters(), lr=1e-5, weight_decay=0.0, capturable=True)
+    opt = torch.optim.AdamW(m3.parameters(), lr=1e-5, weight_decay=0.0, capturable=True, fused=True)
     gts = GraphedTrainStep(m3, opt, nb)
     out("C3 optimisation step (zero_grad + loss + backward + AdamW) as one CUDA-graph replay", nb, timed(gts, reps=7))
 
