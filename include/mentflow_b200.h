@@ -121,6 +121,11 @@ int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, cons
  * of 2^-44; this is what ranks all-reduce exactly).                                      */
 #define MFB_KDE2D_FRAC_BITS 44
 int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by);
+/* Screens of up to 128 x 96 bins and batches of at least 4096 particles run as tcgen05 GEMMs over the
+ * particle axis (the reference's own formulation, diagnostics/histogram.py:47-74: P = Kx^T Ky), dense
+ * kernel rows in split bf16; otherwise windowed fixed-point deposits.  enable: 1 / 0 switches the
+ * tensor-core path, < 0 only queries; returns the previous setting (process-wide; for A/B tests).   */
+int mfb_kde2d_use_tensor_cores(int enable);
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
                           int k, int bx, int by, float max_sigma_over_delta, float* sums,
                           void* workspace, int64_t workspace_bytes, void* stream);

@@ -336,13 +336,29 @@ static int radius2d(float hint) {
   return ri < 1 ? 1 : ri;
 }
 
+// tensor-core path (kde2d_tc.cu): dense kernel rows as tcgen05 operands, screens up to 128 x 96 bins
+namespace mfb {
+bool kde2d_tc_supported(int64_t n, int d, int bx, int by);
+int64_t kde2d_tc_partial_bytes(int k, int bx, int by);
+int kde2d_tc_forward(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx, int by,
+                     float* sums, unsigned long long* acc, float* partial, cudaStream_t st);
+}  // namespace mfb
+static int g_use_tc_kde2d = 1;
+
 extern "C" {
+
+int mfb_kde2d_use_tensor_cores(int enable) {
+  const int prev = g_use_tc_kde2d;
+  if (enable >= 0) g_use_tc_kde2d = enable ? 1 : 0;
+  return prev;
+}
 
 int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by) {
   (void)n;
   (void)d;
   if (k < 1 || bx < 1 || by < 1) return 0;
-  return (int64_t)k * bx * by * 16;  // two int64 planes: units 2^-22 and 2^-44
+  // two int64 planes (units 2^-22 and 2^-44) + the per-CTA partial screens of the tensor-core path
+  return (int64_t)k * bx * by * 16 + kde2d_tc_partial_bytes(k, bx, by);
 }
 
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx,
@@ -356,6 +372,11 @@ int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, c
   if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* acc = (unsigned long long*)workspace;
+  if (g_use_tc_kde2d && kde2d_tc_supported(n, d, bx, by) &&
+      workspace_bytes >= len * 16 + kde2d_tc_partial_bytes(k, bx, by)) {
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + len * 16);
+    return kde2d_tc_forward(x, n, d, proj, geom, k, bx, by, sums, acc, partial, st);
+  }
   MFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)len * 16, st));
   if (n > 0) {
     int gx;

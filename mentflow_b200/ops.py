@@ -250,11 +250,14 @@ def kde2d_sums(x, proj, geom, ratio, bx, by):
     n, d = x.shape
     k = proj.shape[0]
     sums = torch.empty((k, bx, by), dtype=torch.float32, device=x.device)
-    acc = torch.empty((2, k, bx, by), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
+        # workspace = the two int64 planes, then the per-CTA partial screens of the tensor-core path
+        wbytes = int(lib.mfb_kde2d_workspace_bytes(n, d, k, bx, by))
+        work = torch.empty((wbytes + 7) // 8, dtype=torch.int64, device=x.device)
         _lib.check(lib.mfb_project_kde2d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, bx, by, float(ratio),
-                                             _ptr(sums), _ptr(acc), acc.numel() * 8, _stream()),
+                                             _ptr(sums), _ptr(work), wbytes, _stream()),
                    "project_kde2d_fwd")
+    acc = work[: 2 * k * bx * by].view(2, k, bx, by)
     return sums, acc
 
 

@@ -76,3 +76,45 @@ def test_kde2d_vs_oracle_shapes(n, d, k, bx, by):
     ref = torch.stack([hp.kde_profile_2d(x @ w[i, 0], x @ w[i, 1], ex, ey, sx, sy, chunk=20000)
                        for i in range(k)])
     assert profile_err(prof, ref) < TOL
+
+
+def test_kde2d_tensor_core_and_fixed_point_paths_agree():
+    """The tcgen05 GEMM over the particle axis (dense kernel rows in split bf16, kde2d_tc.cu) and the windowed
+    44-bit fixed-point deposits against a float64 evaluation of the reference's dense form
+    (diagnostics/histogram.py:47-74), bin by bin and by magnitude decade, far tails included; the
+    tensor-core path is run-to-run bit-reproducible and its fixed-point planes reproduce its sums."""
+    from mentflow_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(9)
+    n, d, k, bx, by = 60_000, 6, 7, 85, 85          # 7 screens: two groups of TMEM-resident accumulators
+    x = (torch.randn(n, d, generator=gen) * 0.8).cuda()
+    w = torch.randn(k, 2, d, generator=gen)
+    w = (w / w.norm(dim=2, keepdim=True)).cuda()
+    ex, ey = torch.linspace(-3.5, 3.5, bx + 1), torch.linspace(-3.5, 3.5, by + 1)
+    (gx, sx), (gy, sy) = geom_rows(ex, 0.5, k), geom_rows(ey, 0.5, k)
+    geom = torch.stack([gx, gy], dim=1).cuda()
+    prev = lib.mfb_kde2d_use_tensor_cores(1)
+    try:
+        tc, acc = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
+        tc2, _ = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
+        lib.mfb_kde2d_use_tensor_cores(0)
+        fx, _ = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
+    finally:
+        lib.mfb_kde2d_use_tensor_cores(prev)
+    assert torch.equal(tc, tc2)
+    assert not torch.equal(tc, fx)                   # the two paths really are different kernels
+    cx, cy = (0.5 * (ex[1:] + ex[:-1])).double().cuda(), (0.5 * (ey[1:] + ey[:-1])).double().cuda()
+    xd = x.double()
+    ref = torch.stack([
+        torch.exp(-0.5 * (((xd @ w[i, 0].double())[:, None] - cx[None]) / float(sx)) ** 2).T
+        @ torch.exp(-0.5 * (((xd @ w[i, 1].double())[:, None] - cy[None]) / float(sy)) ** 2) for i in range(k)])
+    peak = float(ref.max())
+    tc, fx = tc.double(), fx.double()
+    for lo, bound in [(1e-3, 1e-4), (1e-9, 3e-4), (1e-12, 1e-3)]:
+        m = ref > lo * peak
+        err_tc = float(((tc - ref).abs() / ref)[m].max())
+        err_fx = float(((fx - ref).abs() / ref)[m].max())
+        assert err_tc < bound and err_fx < bound, (lo, err_tc, err_fx)
+    planes = acc.double()
+    rebuilt = (planes[0] + planes[1] / 2 ** 22) / 2 ** 22
+    assert float((rebuilt - tc).abs().max()) <= 1e-6 * float(tc.max())
