@@ -30,7 +30,7 @@ using tc::mbar_wait_bounded;
 using tc::mbar_wait_polite;
 
 constexpr int kThreads = 512;
-constexpr int kLoaderWarps = 15;                 // warps 0..14 build operands, warp 15 issues the MMAs
+constexpr int kLoaderWarps = 12;                 // warps 0..11 build operands, warp 12 issues the MMAs
 constexpr int kLoaders = kLoaderWarps * 32;
 constexpr int kKT = 64;                          // particles per operand tile (one 128-byte K row)
 constexpr int kGroup = 5;                        // screens resident in TMEM
@@ -46,10 +46,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 struct ScreenAxis {
-  float c0, inv_delta, scale;   // scale = sqrt(0.5 log2 e) * delta / sigma: kernel value = 2^-((a - r) scale)^2
+  float c0, inv_delta, alpha;
 };
-// |a - r| * scale beyond this gives 2^-x^2 = 0 in fp32 (ex2.approx.ftz flushes below 2^-126): exact zeros
-constexpr float kZeroDist = 11.3f;
 
 __global__ void __launch_bounds__(kThreads, 1)
 kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj /* [K][2][d] */,
@@ -107,7 +105,7 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
       const float r = gp[1] / gp[2];
       s_ax[i].c0 = gp[0];
       s_ax[i].inv_delta = 1.0f / gp[1];
-      s_ax[i].scale = sqrtf(0.5f * kLog2e) * r;
+      s_ax[i].alpha = -0.5f * r * r * kLog2e;
     }
     __syncthreads();
 
@@ -129,14 +127,14 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
             a = (u - s_ax[sa].c0) * s_ax[sa].inv_delta;
             a = fminf(fmaxf(a, -1.0e4f), 1.0e4f);
           }
-          cbuf[i] = a * s_ax[sa].scale;
+          cbuf[i] = a;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
         for (int s = 0; s < ns; ++s, ++it) {
           const uint32_t slot = it % kStages, par = (it / kStages) & 1;
           mbar_wait_bounded(&empty[slot], par ^ 1);
           unsigned char* st = stages + slot * kStageBytes;
-          const float ax_scale = s_ax[2 * s].scale, ay_scale = s_ax[2 * s + 1].scale;
+          const float ax_alpha = s_ax[2 * s].alpha, ay_alpha = s_ax[2 * s + 1].alpha;
           const float* cx = cbuf + (2 * s) * kKT;
           const float* cy = cx + kKT;
           // task = (operand row, 8 consecutive particles): dense kernel values, bf16 (hi, mid), 16 B each
@@ -144,33 +142,23 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
             const int row = q >> 3, chunk = q & 7;
             const bool isa = row < BX;
             const int r = isa ? row : row - BX;
-            const float rs = (float)r * (isa ? ax_scale : ay_scale);
+            const float alpha = isa ? ax_alpha : ay_alpha;
             const float4 c0v = *reinterpret_cast<const float4*>((isa ? cx : cy) + chunk * 8);
             const float4 c1v = *reinterpret_cast<const float4*>((isa ? cx : cy) + chunk * 8 + 4);
-            const float tt[8] = {c0v.x - rs, c0v.y - rs, c0v.z - rs, c0v.w - rs, c1v.x - rs, c1v.y - rs, c1v.z - rs, c1v.w - rs};
-            float nearest = fabsf(tt[0]);
-#pragma unroll
-            for (int e = 1; e < 8; ++e) nearest = fminf(nearest, fabsf(tt[e]));
-            unsigned char* base = st + (isa ? 0 : 2 * kABytes);
-            const uint32_t off = umma::sw128_offset(r, chunk);
-            uint4* dst_hi = reinterpret_cast<uint4*>(base + off);
-            uint4* dst_mid = reinterpret_cast<uint4*>(base + (isa ? kABytes : kBBytes) + off);
-            if (nearest > kZeroDist) {   // every value of the chunk is an exact fp32 zero: no exponentials
-              *dst_hi = make_uint4(0u, 0u, 0u, 0u);
-              *dst_mid = make_uint4(0u, 0u, 0u, 0u);
-              continue;
-            }
+            const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
             __align__(16) __nv_bfloat162 hi[4], mid[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float ta = tt[2 * e], tb = tt[2 * e + 1];
-              const float va = fast_exp2(-(ta * ta)), vb = fast_exp2(-(tb * tb));
+              const float ta = cc[2 * e] - (float)r, tb = cc[2 * e + 1] - (float)r;
+              const float va = fast_exp2(alpha * ta * ta), vb = fast_exp2(alpha * tb * tb);
               hi[e] = __floats2bfloat162_rn(va, vb);
               const float2 hf = __bfloat1622float2(hi[e]);
               mid[e] = __floats2bfloat162_rn(va - hf.x, vb - hf.y);
             }
-            *dst_hi = *reinterpret_cast<const uint4*>(hi);
-            *dst_mid = *reinterpret_cast<const uint4*>(mid);
+            unsigned char* base = st + (isa ? 0 : 2 * kABytes);
+            const uint32_t off = umma::sw128_offset(r, chunk);
+            *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(base + (isa ? kABytes : kBBytes) + off) = *reinterpret_cast<const uint4*>(mid);
           }
           fence_proxy_async();
           __syncwarp();
