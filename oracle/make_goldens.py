@@ -315,9 +315,36 @@ def make_multipole():
     print("wrote multipole.npz")
 
 
+def make_noise():
+    """Measurement noise of Histogram.forward (diagnostics/diagnostics.py:50-68): a generator re-seeded on
+    every call, multiplicative gaussian / uniform noise, clamped at zero; 1-D and 2-D screens."""
+    mf = ref_import.load()
+    torch.manual_seed(31)
+    x = torch.randn(2000, 4).float()
+    edges = torch.linspace(-3.5, 3.5, 33)
+    out = {"x": npy(x), "edges": npy(edges)}
+    for kind in ("gaussian", "uniform"):
+        for seed in (3, 11):
+            d1 = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5, noise=True, noise_scale=0.4,
+                                            noise_type=kind, seed=seed)
+            d2 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=(edges, edges), bandwidth=(0.5, 0.5), noise=True,
+                                            noise_scale=0.4, noise_type=kind, seed=seed)
+            out[f"h1_{kind}_{seed}"] = npy(d1(x))
+            out[f"h2_{kind}_{seed}"] = npy(d2(x))
+    d1 = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5)
+    d2 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=(edges, edges), bandwidth=(0.5, 0.5))
+    out["h1_clean"] = npy(d1(x))
+    out["h2_clean"] = npy(d2(x))
+    np.savez_compressed(os.path.join(OUT, "noise.npz"), **out)
+    print("wrote noise.npz")
+
+
 if __name__ == "__main__":
     if "--only-multipole" in sys.argv:
         make_multipole()
+    elif "--only-noise" in sys.argv:
+        make_noise()
     else:
         main()
         make_multipole()
+        make_noise()

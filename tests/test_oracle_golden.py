@@ -219,3 +219,29 @@ def test_multipole_terms_reproduce_the_composite_map(golden):
     two = mf.simulate.CompositeTransform(mf.simulate.MultipoleTransform(3, 0.1), mf.simulate.MultipoleTransform(3, 0.1))
     assert _multipole_chain(two) is None
     assert _multipole_chain(mf.simulate.MultipoleTransform(2, 0.1)) is None
+
+
+def test_measurement_noise_matches_reference(golden):
+    """Histogram.forward's noise (diagnostics/diagnostics.py:50-68): the oracle's apply_noise and the package's
+    Histogram.apply_noise applied to the reference's clean profile reproduce the reference's noisy one --
+    same generator stream (re-seeded per call), gaussian and uniform, 1-D and 2-D screens, clamp at zero."""
+    import mentflow_b200 as mf
+    g = golden("noise")
+    edges = t32(g["edges"])
+    for kind in ("gaussian", "uniform"):
+        for seed in (3, 11):
+            for tag, clean in (("h1", t32(g["h1_clean"])), ("h2", t32(g["h2_clean"]))):
+                ref = t32(g[f"{tag}_{kind}_{seed}"])
+                assert float(ref.min()) >= 0.0 and not torch.equal(ref, clean)
+                got = hp.apply_noise(clean, 0.4, kind, seed)
+                assert torch.allclose(got, ref, rtol=1e-6, atol=1e-9)
+                if tag == "h1":
+                    diag = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5, noise=True, noise_scale=0.4,
+                                                      noise_type=kind, seed=seed)
+                else:
+                    diag = mf.diagnostics.Histogram2D(axis=(0, 2), edges=(edges, edges), bandwidth=(0.5, 0.5),
+                                                      noise=True, noise_scale=0.4, noise_type=kind, seed=seed)
+                assert torch.allclose(diag.apply_noise(clean), ref, rtol=1e-6, atol=1e-9)
+                assert torch.equal(diag.apply_noise(clean), diag.apply_noise(clean))     # re-seeded on every call
+                diag.set_noise(False)
+                assert torch.equal(diag.apply_noise(clean), clean)
