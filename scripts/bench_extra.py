@@ -137,6 +137,21 @@ with torch.no_grad():
     x4 = m4.generator.forward(z)
     out("C4 screens only: 15 x KDE-2D(85x85)", N,
         timed(lambda: mf.simulate.forward(x4, m4.transforms, m4.diagnostics), reps=3, warm=1))
+from mentflow_b200.graphs import GraphedLoss as _GL
+for nb in (30_000, 1_000_000):      # 30,000: the reference's rec_nd_2d batch size
+    g4 = _GL(m4, nb)
+    out("C4 rec_nd_2d forward as one CUDA-graph replay", nb, timed(lambda: g4(None), reps=5))
+    del g4
+
+
+def train4():
+    for p in m4.parameters():
+        p.grad = None
+    L, H, D = m4.loss(N)
+    L.backward()
+
+
+out("C4 training step: forward + backward to all flow parameters", N, timed(train4, reps=3, warm=1))
 # ---- C5
 d, K, res, xmax = 6, 25, 16, 3.5
 wl5 = workloads.isotropic_1d(d, K, 64, xmax)
