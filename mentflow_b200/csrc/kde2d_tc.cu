@@ -33,7 +33,11 @@ constexpr int kThreads = 512;
 constexpr int kLoaderWarps = 12;                 // warps 0..11 build operands, warp 12 issues the MMAs
 constexpr int kLoaders = kLoaderWarps * 32;
 constexpr int kKT = 64;                          // particles per operand tile (one 128-byte K row)
+constexpr int kCRow = kKT + 4;                   // coordinate row: the second half shifted by 16 B, so that the eight
+                                                 // 32-byte chunks a quarter warp reads fall into distinct banks
+__host__ __device__ constexpr int crow_index(int p) { return p + ((p >> 5) << 2); }
 constexpr int kGroup = 5;                        // screens resident in TMEM
+constexpr int kCoordPer = (kGroup * 2 * kKT + kLoaders - 1) / kLoaders;   // coordinates per loader thread and tile
 constexpr int kCols = 96;                        // accumulator columns per screen (By <= 96)
 constexpr int kABytes = 128 * 128;               // 128 rows x 128 B (Bx <= 128; M = 128 reads all of them)
 constexpr int kBBytes = 96 * 128;
@@ -56,8 +60,8 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
-  float* coord = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [2 buffers][kGroup][2][kKT]
-  float* s_w = coord + 2 * kGroup * 2 * kKT;                               // [kGroup][2][kMaxDim]
+  float* coord = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [2 buffers][kGroup][2][kCRow]
+  float* s_w = coord + 2 * kGroup * 2 * kCRow;                               // [kGroup][2][kMaxDim]
   ScreenAxis* s_ax = reinterpret_cast<ScreenAxis*>(s_w + kGroup * 2 * kMaxDim);   // [kGroup][2]
   uint64_t* full = reinterpret_cast<uint64_t*>(s_ax + kGroup * 2);
   uint64_t* empty = full + kStages;
@@ -112,39 +116,59 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
     if (warp < kLoaderWarps) {
       // ===== loaders =====
       int cb = 0;   // coordinate buffer of this K tile
-      for (int64_t t = t0; t < t1; ++t, cb ^= 1) {
-        const int64_t p0 = t * kKT;
-        float* cbuf = coord + cb * (kGroup * 2 * kKT);
-        // bin coordinates a = (u - c0) / delta of the tile's particles on both axes of every screen
-        for (int i = tid; i < ns * 2 * kKT; i += kLoaders) {
+      // Scaled bin coordinates a = (u - c0) / delta of a tile's particles on both axes of every screen.
+      // The particle rows of tile t+1 are loaded into registers before the operands of tile t are generated
+      // and turned into coordinates afterwards, so their L2 / HBM latency is never waited for.
+      float xr[kCoordPer][kMaxDim];
+      auto load_rows = [&](int64_t t) {
+#pragma unroll
+        for (int j = 0; j < kCoordPer; ++j) {
+          const int i = tid + j * kLoaders;
+          const int64_t p = t * kKT + (i % kKT);
+          const bool live = i < ns * 2 * kKT && t < t1 && p < n;
+#pragma unroll
+          for (int c = 0; c < kMaxDim; ++c) xr[j][c] = (live && c < d) ? x[p * d + c] : 0.f;
+        }
+      };
+      auto store_coords = [&](int64_t t, float* cbuf) {
+#pragma unroll
+        for (int j = 0; j < kCoordPer; ++j) {
+          const int i = tid + j * kLoaders;
+          if (i >= ns * 2 * kKT) continue;
           const int sa = i / kKT, p = i % kKT;       // sa = screen * 2 + axis
           float a = -1.0e4f;                         // no particle: every kernel value is 0
-          if (p0 + p < n) {
-            const float* xr = x + (p0 + p) * d;
+          if (t * kKT + p < n) {
             const float* w = s_w + sa * kMaxDim;
             float u = 0.f;
-            for (int c = 0; c < d; ++c) u = fmaf(w[c], xr[c], u);
+#pragma unroll
+            for (int c = 0; c < kMaxDim; ++c) u = fmaf(w[c], xr[j][c], u);   // w is zero beyond d
             a = (u - s_ax[sa].c0) * s_ax[sa].inv_delta;
             a = fminf(fmaxf(a, -1.0e4f), 1.0e4f);
           }
-          cbuf[i] = a;
+          cbuf[sa * kCRow + crow_index(p)] = a;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
+      };
+      load_rows(t0);
+      store_coords(t0, coord);
+      asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
+      for (int64_t t = t0; t < t1; ++t, cb ^= 1) {
+        float* cbuf = coord + cb * (kGroup * 2 * kCRow);
+        load_rows(t + 1);
         for (int s = 0; s < ns; ++s, ++it) {
           const uint32_t slot = it % kStages, par = (it / kStages) & 1;
           mbar_wait_bounded(&empty[slot], par ^ 1);
           unsigned char* st = stages + slot * kStageBytes;
           const float ax_alpha = s_ax[2 * s].alpha, ay_alpha = s_ax[2 * s + 1].alpha;
-          const float* cx = cbuf + (2 * s) * kKT;
-          const float* cy = cx + kKT;
+          const float* cx = cbuf + (2 * s) * kCRow;
+          const float* cy = cx + kCRow;
           // task = (operand row, 8 consecutive particles): dense kernel values, bf16 (hi, mid), 16 B each
           for (int q = tid; q < rows_ab * 8; q += kLoaders) {
             const int row = q >> 3, chunk = q & 7;
             const bool isa = row < BX;
             const int r = isa ? row : row - BX;
             const float alpha = isa ? ax_alpha : ay_alpha;
-            const float4 c0v = *reinterpret_cast<const float4*>((isa ? cx : cy) + chunk * 8);
-            const float4 c1v = *reinterpret_cast<const float4*>((isa ? cx : cy) + chunk * 8 + 4);
+            const float4 c0v = *reinterpret_cast<const float4*>((isa ? cx : cy) + crow_index(chunk * 8));
+            const float4 c1v = *reinterpret_cast<const float4*>((isa ? cx : cy) + crow_index(chunk * 8) + 4);
             const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
             __align__(16) __nv_bfloat162 hi[4], mid[4];
 #pragma unroll
@@ -165,6 +189,9 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
           if (lane == 0)
             asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
         }
+        // coordinates of the next tile into the other buffer (its last readers passed the previous barrier)
+        if (t + 1 < t1) store_coords(t + 1, coord + (cb ^ 1) * (kGroup * 2 * kCRow));
+        asm volatile("bar.sync 1, %0;" ::"n"(kLoaders) : "memory");
       }
       // ===== epilogue of the group (warps 0..3: TMEM lanes 32 w .. 32 w + 31 = screen rows bx) =====
       if (warp < 4) {
@@ -260,7 +287,7 @@ int kde2d_tc_forward(const float* x, int64_t n, int d, const float* proj, const 
   if (grid > ntiles) grid = ntiles;
   const int64_t per = (ntiles + grid - 1) / grid;
   grid = (ntiles + per - 1) / per;     // every CTA has at least one tile
-  const size_t smem = (size_t)kStages * kStageBytes + (size_t)2 * kGroup * 2 * kKT * 4 + (size_t)kGroup * 2 * kMaxDim * 4 +
+  const size_t smem = (size_t)kStages * kStageBytes + (size_t)2 * kGroup * 2 * kCRow * 4 + (size_t)kGroup * 2 * kMaxDim * 4 +
                       (size_t)kGroup * 2 * sizeof(ScreenAxis) + 256 + 1024;
   MFB_CUDA(cudaFuncSetAttribute(kde2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kde2d_tc_kernel<<<(int)grid, kThreads, smem, st>>>(x, n, d, proj, geom, k, bx, by, per, partial);
