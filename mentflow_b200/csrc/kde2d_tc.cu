@@ -161,19 +161,28 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
           const float ax_alpha = s_ax[2 * s].alpha, ay_alpha = s_ax[2 * s + 1].alpha;
           const float* cx = cbuf + (2 * s) * kCRow;
           const float* cy = cx + kCRow;
-          // task = (operand row, 8 consecutive particles): dense kernel values, bf16 (hi, mid), 16 B each
-          for (int q = tid; q < rows_ab * 8; q += kLoaders) {
-            const int row = q >> 3, chunk = q & 7;
+          // A thread owns one 8-particle chunk of the tile and every (kLoaders / 8)-th operand row: the chunk's
+          // coordinates on both axes are read once per stage and stay in registers (re-reading them per row
+          // cost as much shared-memory bandwidth as writing the operands).  Per (row, chunk): dense kernel
+          // values, bf16 (hi, mid), 16 B each.
+          const int chunk = tid & 7;
+          float ccx[8], ccy[8];
+          {
+            const float4 a0 = *reinterpret_cast<const float4*>(cx + crow_index(chunk * 8));
+            const float4 a1 = *reinterpret_cast<const float4*>(cx + crow_index(chunk * 8) + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(cy + crow_index(chunk * 8));
+            const float4 b1 = *reinterpret_cast<const float4*>(cy + crow_index(chunk * 8) + 4);
+            ccx[0] = a0.x; ccx[1] = a0.y; ccx[2] = a0.z; ccx[3] = a0.w; ccx[4] = a1.x; ccx[5] = a1.y; ccx[6] = a1.z; ccx[7] = a1.w;
+            ccy[0] = b0.x; ccy[1] = b0.y; ccy[2] = b0.z; ccy[3] = b0.w; ccy[4] = b1.x; ccy[5] = b1.y; ccy[6] = b1.z; ccy[7] = b1.w;
+          }
+          for (int row = tid >> 3; row < rows_ab; row += kLoaders / 8) {
             const bool isa = row < BX;
             const int r = isa ? row : row - BX;
             const float alpha = isa ? ax_alpha : ay_alpha;
-            const float4 c0v = *reinterpret_cast<const float4*>((isa ? cx : cy) + crow_index(chunk * 8));
-            const float4 c1v = *reinterpret_cast<const float4*>((isa ? cx : cy) + crow_index(chunk * 8) + 4);
-            const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
             __align__(16) __nv_bfloat162 hi[4], mid[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float ta = cc[2 * e] - (float)r, tb = cc[2 * e + 1] - (float)r;
+              const float ta = (isa ? ccx[2 * e] : ccy[2 * e]) - (float)r, tb = (isa ? ccx[2 * e + 1] : ccy[2 * e + 1]) - (float)r;
               const float va = fast_exp2(alpha * ta * ta), vb = fast_exp2(alpha * tb * tb);
               hi[e] = __floats2bfloat162_rn(va, vb);
               const float2 hf = __bfloat1622float2(hi[e]);
