@@ -83,65 +83,67 @@ class CompositeTransform(Transform):
         return m
 
 
+# Re(z^(n-1)), Im(z^(n-1)) of z = x + i y for the multipole orders the reference accepts, in the
+# reference's own expanded form (simulate/transform.py:118-134) so that results agree to the last bit
+_KICK_POLYNOMIALS = {
+    3: lambda x, y: (x ** 2 - y ** 2, 2.0 * x * y),
+    4: lambda x, y: (x ** 3 - 3.0 * y ** 2 * x, -(y ** 3) + 3.0 * x ** 2 * y),
+    5: lambda x, y: (x ** 4 - 6.0 * x ** 2 * y ** 2 + y ** 4, 4.0 * x ** 3 * y - 4.0 * x * y ** 3),
+}
+
+
 class MultipoleTransform(Transform):
     """Thin multipole kick (simulate/transform.py:78-146).
 
     ``simulate.forward`` folds a chain ``linear* -> multipole -> linear*`` into the fused projection
     kernel (``multipole_terms``); ``forward`` is the stand-alone (N, D) image with the reference's
     semantics, quirks included: only orders 3, 4, 5 are accepted (the reference's ``if`` ladder falls
-    into its ``else: raise`` for orders 1 and 2, :118-134), and the normal kick sets
-    ``U[:, 3] = X[:, 1] + k Im(z^(n-1))`` -- from column 1, not column 3 (:144).
+    into its ``else: raise`` for orders 1 and 2, :118-134), and the normal kick sets column 3 to
+    ``column 1 + k Im(z^(n-1))`` -- from column 1, not column 3 (:144).
     """
 
     def __init__(self, order: int, strength: float, skew: bool = False) -> None:
         super().__init__()
-        self.order = order
-        self.strength = strength
-        self.skew = skew
+        self.order, self.strength, self.skew = order, strength, skew
 
     def coefficient(self) -> float:
+        """Integrated strength / (order - 1)!"""
         return float(self.strength) / math.factorial(int(self.order) - 1)
 
-    def _zn(self, x, y):
-        if self.order == 3:
-            return x ** 2 - y ** 2, 2.0 * x * y
-        if self.order == 4:
-            return x ** 3 - 3.0 * y ** 2 * x, -(y ** 3) + 3.0 * x ** 2 * y
-        if self.order == 5:
-            return x ** 4 - 6.0 * x ** 2 * y ** 2 + y ** 4, 4.0 * x ** 3 * y - 4.0 * x * y ** 3
-        raise ValueError("MPS-compatible MultipoleTransform requires order <= 5.")
-
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
-        U = X.clone()
-        x = X[:, 0]
-        y = X[:, 2] if X.shape[1] > 2 else 0.0 * X[:, 0]
-        zn_real, zn_imag = self._zn(x, y)
+    def forward(self, particles: torch.Tensor) -> torch.Tensor:
+        poly = _KICK_POLYNOMIALS.get(self.order)
+        if poly is None:
+            raise ValueError("MPS-compatible MultipoleTransform requires order <= 5.")
+        four_d = particles.shape[1] > 2
+        pos_x, mom_x = particles[:, 0], particles[:, 1]
+        pos_y = particles[:, 2] if four_d else 0.0 * pos_x
+        re, im = poly(pos_x, pos_y)
         k = self.coefficient()
+        out = particles.clone()
         if self.skew:
-            U[:, 1] = X[:, 1] + k * zn_imag
-            if X.shape[1] > 2:
-                U[:, 3] = X[:, 3] + k * zn_real
+            out[:, 1] = mom_x + k * im
+            if four_d:
+                out[:, 3] = particles[:, 3] + k * re
         else:
-            U[:, 1] = X[:, 1] - k * zn_real
-            if X.shape[1] > 2:
-                U[:, 3] = X[:, 1] + k * zn_imag
-        return U
+            out[:, 1] = mom_x - k * re
+            if four_d:
+                out[:, 3] = mom_x + k * im        # sic: the reference adds to column 1 here
+        return out
 
     def inverse(self, u: torch.Tensor) -> torch.Tensor:
-        """Momentum reversal, kick, momentum reversal (:148-149).  Unlike the reference, which flips
+        """Momentum reversal, kick, momentum reversal (:145-146).  Unlike the reference, which flips
         the momenta of its argument in place, the input is left untouched."""
         return reverse_momentum(self.forward(reverse_momentum(u.clone())))
 
 
 def reverse_momentum(x: torch.Tensor) -> torch.Tensor:
-    """In place, like simulate/transform.py:18-21."""
-    for i in range(0, x.shape[1], 2):
-        x[:, i + 1] *= -1.0
+    """Flip the sign of every momentum column (1, 3, ...), in place like simulate/transform.py:18-21."""
+    x[:, 1::2].neg_()
     return x
 
 
 class ProjectionTransform(Transform):
-    """(N, 1) projection on a direction, normalised at construction (simulate/transform.py:152-159)."""
+    """(N, 1) projection on a direction, normalised at construction (simulate/transform.py:149-156)."""
 
     def __init__(self, direction: torch.Tensor) -> None:
         super().__init__()
