@@ -178,3 +178,45 @@ def test_graphed_loss_chunk_plan():
         assert all(a % 128 == 0 for a, _ in b) and len(b) <= c
         if len(b) > 1:
             assert b[0][1] - b[0][0] <= b[1][1] - b[1][0]
+
+
+def test_plan_groups_multipole_chains_and_tracks_their_parameters():
+    """simulate.forward's plan (host logic only, no kernel runs): linear maps and linear -> kick -> linear
+    chains in front of 1-D screens go to fused groups, everything else to the object-by-object path; the
+    plan key follows the kick's mutable attributes."""
+    import mentflow_b200 as mf
+    from mentflow_b200.simulate import simulate as sim
+    x = torch.zeros(4, 4)
+    edges = torch.linspace(-1.0, 1.0, 9)
+    h1 = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5)
+    h2 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=(edges, edges), bandwidth=(0.5, 0.5))
+    lin = mf.simulate.LinearTransform(torch.eye(4))
+    kick = mf.simulate.MultipoleTransform(order=3, strength=0.5)
+    chain = mf.simulate.CompositeTransform(lin, kick, mf.simulate.LinearTransform(2.0 * torch.eye(4)))
+    two_kicks = mf.simulate.CompositeTransform(kick, mf.simulate.MultipoleTransform(order=4, strength=0.1))
+
+    class Custom(mf.simulate.Transform):
+        def forward(self, x):
+            return x
+
+    transforms = [lin, chain, kick, two_kicks, Custom(), mf.simulate.CompositeTransform(lin, lin)]
+    diagnostics = [[h1, h2], [h1, h2], [h1], [h1], [h1], [h1]]
+    plan = sim._build_plan(x, transforms, diagnostics)
+    kinds = {key[0]: grp for key, grp in plan.groups.items()}
+    assert set(kinds) == {"1d", "2d", "1d-mp"}
+    assert kinds["1d"].slots == [(0, 0), (5, 0)] and kinds["2d"].slots == [(0, 1)]
+    assert kinds["1d-mp"].slots == [(1, 0), (2, 0)]
+    assert kinds["1d-mp"].proj.shape == (2, 4) and kinds["1d-mp"].mp.shape == (2, 12)
+    # a 2-D screen behind a kick, a chain with two kicks and a user-defined map are not fused
+    assert plan.fallback == [(1, 1), (3, 0), (4, 0)]
+    # measured row of the chain: post = 2 I, pre = I, normal kick: w = 2 e0, a = b = 0 (row has no momentum part)
+    w, mp = kinds["1d-mp"].proj[0], kinds["1d-mp"].mp[0]
+    assert torch.allclose(w, torch.tensor([2.0, 0.0, 0.0, 0.0])) and float(mp[8]) == 0.0 and float(mp[9]) == 0.0
+    assert int(mp[10]) == 3
+    key = sim._plan_key(transforms, diagnostics)
+    kick.strength = 0.7
+    assert sim._plan_key(transforms, diagnostics) != key
+    kick.strength = 0.5
+    assert sim._plan_key(transforms, diagnostics) == key
+    kick.order = 2                      # not an order the reference accepts: no folding
+    assert sim._multipole_chain(chain) is None
