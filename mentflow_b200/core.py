@@ -119,35 +119,34 @@ class MENTFlow(nn.Module):
     def parameters(self, recurse: bool = True) -> Iterator[nn.Parameter]:
         return self.generator.parameters()
 
+    # checkpoint layout of the reference (core.py:122-143): one dict with the generator's state_dict and the
+    # pickled measurement setup under these keys
+    _CHECKPOINT_OBJECTS = ("entropy_estimator", "transforms", "diagnostics", "measurements")
+
     def save(self, path) -> None:
-        state = {
-            "generator": self.generator.state_dict(),
-            "entropy_estimator": self.entropy_estimator,
-            "transforms": self.transforms,
-            "diagnostics": self.diagnostics,
-            "measurements": self.measurements,
-        }
+        state = {name: getattr(self, name) for name in self._CHECKPOINT_OBJECTS}
+        state["generator"] = self.generator.state_dict()
         torch.save(state, path)
 
     def load(self, path, device=None):
         state = torch.load(path, map_location=device, weights_only=False)
         try:
             self.generator.load_state_dict(state["generator"])
-        except RuntimeError:
-            raise RuntimeError("Error loading generative model. Architecture mismatch?")
-        self.entropy_estimator = state["entropy_estimator"]
-        self.transforms = state["transforms"]
-        self.diagnostics = state["diagnostics"]
-        self.measurements = state["measurements"]
+        except RuntimeError as err:
+            raise RuntimeError("Error loading generative model. Architecture mismatch?") from err
+        for name in self._CHECKPOINT_OBJECTS:
+            setattr(self, name, state[name])
         self.to(device)
 
     def to(self, device):
+        """Move transforms, screens, measurements and the generator (core.py:145-159)."""
+        def moved(rows):
+            return None if rows is None else [[item.to(device) for item in row] for row in rows]
+
         if self.transforms is not None:
             self.transforms = [t.to(device) for t in self.transforms]
-        if self.diagnostics is not None:
-            self.diagnostics = [[d.to(device) for d in row] for row in self.diagnostics]
-        if self.measurements is not None:
-            self.measurements = [[m.to(device) for m in row] for row in self.measurements]
+        self.diagnostics = moved(self.diagnostics)
+        self.measurements = moved(self.measurements)
         if self.generator is not None:
             self.generator = self.generator.to(device)
         return self

@@ -220,3 +220,38 @@ def test_plan_groups_multipole_chains_and_tracks_their_parameters():
     assert sim._plan_key(transforms, diagnostics) == key
     kick.order = 2                      # not an order the reference accepts: no folding
     assert sim._multipole_chain(chain) is None
+
+
+def test_mentflow_checkpoint_round_trip(tmp_path):
+    """MENTFlow.save / load (core.py:122-143): generator weights under zuko-style names plus the pickled
+    measurement setup; loading into a freshly initialised model reproduces weights and setup."""
+    import mentflow_b200 as mf
+    torch.manual_seed(0)
+    edges = torch.linspace(-2.0, 2.0, 17)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        gen = mf.generate.build_generator("nsf", input_features=2, output_features=2, hidden_layers=3,
+                                          hidden_units=64, transforms=2, bins=20)
+        tfs = [mf.simulate.LinearTransform(mf.simulate.rotation_matrix(a).float()) for a in (0.0, 0.7)]
+        diags = [[mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5)] for _ in tfs]
+        meas = [[torch.rand(16)] for _ in tfs]
+        prior = mf.prior.Gaussian(ndim=2, scale=2.0)
+        return mf.MENTFlow(transforms=tfs, diagnostics=diags, measurements=meas, generator=gen, prior=prior,
+                           entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                           discrepancy_function="kld", penalty_parameter=5.0)
+
+    a, b = make(1), make(2)
+    assert a.discrepancy_function is mf.loss.kl_divergence          # the reference's string default is resolved
+    assert not torch.equal(next(a.parameters()), next(b.parameters()))
+    path = tmp_path / "model.pt"
+    a.save(path)
+    b.load(path, device="cpu")
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa, pb)
+    assert torch.equal(b.measurements[1][0], a.measurements[1][0])
+    assert torch.equal(b.transforms[1].matrix, a.transforms[1].matrix)
+    assert isinstance(b.entropy_estimator, mf.entropy.MonteCarloEntropyEstimator)
+    state = torch.load(path, weights_only=False)
+    assert set(state) == {"generator", "entropy_estimator", "transforms", "diagnostics", "measurements"}
+    assert any(k.startswith("_flow.transform.transforms.0.hyper.0.") for k in state["generator"])
