@@ -253,6 +253,18 @@ int mfb_cdf_sample(const double* cdf, int64_t g, const void* workspace, int d,
 int mfb_gs_update(float* table, const float* meas, const float* pred, int n, float lr, float thresh,
                   void* stream);
 
+/* ---- base noise of the flow ---------------------------------------------------------------
+ * generate/flows/zuko.py:15-16,24-26 (`flow.base.rsample`: zuko DiagNormal -> torch.randn).
+ * out[numel] ~ N(0,1) from Philox4x32-10 with torch's CUDA element assignment: for the (seed,
+ * offset) of torch's CUDA generator the result is bitwise the tensor torch.randn(numel,
+ * device="cuda") returns, and mfb_randn_offset_increment(numel) is what torch adds to the offset.
+ * _state form: state[0] = seed, state[1] = offset live in DEVICE memory; with advance != 0 the
+ * offset is moved on after the draw (stream-ordered), so a captured graph draws fresh noise at
+ * every replay.                                                                              */
+int64_t mfb_randn_offset_increment(int64_t numel);
+int mfb_randn_philox(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream);
+int mfb_randn_philox_state(float* out, int64_t numel, uint64_t* state, int advance, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------
  * Self-test of the tcgen05/TMEM building blocks: d[128][n] = a[128][64] * b[n][64]^T through
  * fp16 (hi,lo)-split kind::f16 MMAs with TMEM accumulators (n = 64, 128 or 256).  *err != 0

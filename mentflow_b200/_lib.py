@@ -57,6 +57,9 @@ SIGNATURES = {
     "mfb_ment_prob_grid": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_integrate": (c_int, [c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float,
                                    c_float, P, P]),
+    "mfb_randn_offset_increment": (c_int64, [c_int64]),
+    "mfb_randn_philox": (c_int, [P, c_int64, c_uint64, c_uint64, P]),
+    "mfb_randn_philox_state": (c_int, [P, c_int64, P, c_int, P]),
     "mfb_cdf_workspace_bytes": (c_int64, [c_int64]),
     "mfb_cdf_build": (c_int, [P, c_int64, c_double, P, P, c_int64, P]),
     "mfb_cdf_sample": (c_int, [P, c_int64, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int64, P, P]),

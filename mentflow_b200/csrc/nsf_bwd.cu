@@ -43,32 +43,37 @@ __device__ __forceinline__ float rq_spline_backward(float* col, int stride, int 
     col[(nb + j) * stride] = q;
     mh = fmaxf(mh, q);
   }
-  float sw = 0.f, sh = 0.f;
-  for (int j = 0; j < nb; ++j) {
-    sw += expf(col[j * stride] - mw);
-    sh += expf(col[(nb + j) * stride] - mh);
-  }
-  // bin search on the horizontal knots
-  float cum = 0.f, xl = -kBound, x0 = 0.f, wk = 0.f;
-  int kbin = -1;
-  for (int j = 0; j < nb; ++j) {
-    const float wj = expf(col[j * stride] - mw) / sw;
-    cum += wj;
-    const float xr = fmaf(2.0f * kBound, cum, -kBound);
-    if (kbin < 0 && xl < v && v <= xr) {
-      kbin = j;
-      x0 = xl;
-      wk = wj;
-    }
-    xl = xr;
-  }
-  if (kbin < 0) {  // identity outside the spline box: no parameter gradient
+  // knot sums in double (see knot_search in nsf_common.cuh); the exponentials are recomputed where
+  // they are needed instead of being stored (col holds the clipped parameters for the clip derivative)
+  const bool inside = v > -kBound && v <= kBound;
+  if (!inside) {  // identity outside the spline box: no parameter gradient
     for (int j = 0; j < ptotal; ++j) col[j * stride] = 0.f;
     return gy;
   }
-  float cumh = 0.f;
-  for (int j = 0; j < kbin; ++j) cumh += expf(col[(nb + j) * stride] - mh) / sh;
-  const float hk = expf(col[(nb + kbin) * stride] - mh) / sh;
+  double swd = 0.0, shd = 0.0;
+  for (int j = 0; j < nb; ++j) {
+    swd += (double)expf(col[j * stride] - mw);
+    shd += (double)expf(col[(nb + j) * stride] - mh);
+  }
+  const float sw = (float)swd, sh = (float)shd;
+  const double target = ((double)v + (double)kBound) * (0.5 / (double)kBound) * swd;
+  double cumd = 0.0;
+  int kbin = nb - 1;
+  for (int j = 0; j < nb - 1; ++j) {
+    const double nxt = cumd + (double)expf(col[j * stride] - mw);
+    if (target <= nxt) {
+      kbin = j;
+      break;
+    }
+    cumd = nxt;
+  }
+  const float ekw = expf(col[kbin * stride] - mw);
+  const float wk = (float)((double)ekw / swd);
+  const float x0 = (float)(2.0 * (double)kBound * (cumd / swd) - (double)kBound);
+  double cumhd = 0.0;
+  for (int j = 0; j < kbin; ++j) cumhd += (double)expf(col[(nb + j) * stride] - mh);
+  const float cumh = (float)(cumhd / shd);
+  const float hk = (float)((double)expf(col[(nb + kbin) * stride] - mh) / shd);
   float* cold = col + 2 * nb * stride;
   float d0 = 1.0f, d1 = 1.0f, c0 = 0.f, c1 = 0.f;
   if (kbin > 0) {
@@ -83,7 +88,7 @@ __device__ __forceinline__ float rq_spline_backward(float* col, int stride, int 
   }
   const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hk;
   const float s = hk / wk;
-  float t = (v - x0) / dx;
+  float t = (float)((target - cumd) / (double)ekw);
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   const float omt = 1.0f - t, q = t * omt;
   const float A = d0 + d1 - 2.0f * s;

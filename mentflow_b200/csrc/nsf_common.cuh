@@ -62,37 +62,63 @@ __device__ __forceinline__ float softmax_inplace(float* col, int stride, int nb)
   return sum;
 }
 
+// Position of v in the horizontal knot array, from the un-normalised softmax terms e_j (col[j*stride],
+// as left by softmax_inplace).  The running sums are carried in double: in fp32 they are the largest
+// rounding error of the whole spline (scripts/emul_spline.py; every fp32 add at the magnitude of the
+// sum moves the knot by an ulp of the BOX, not of the bin).  These CUDA-core kernels are the fallback /
+// cross-check path, so the few double adds per feature are not a cost that matters.
+// Returns the bin k, the un-normalised bin width e_k, its left knot sum and the total, all exact to
+// double rounding; v must be inside (-B, B].
+struct KnotPos {
+  int k;
+  double cum, sum, target;
+};
+__device__ __forceinline__ KnotPos knot_search(const float* col, int stride, int nb, float v) {
+  KnotPos kp;
+  double sum = 0.0;
+  for (int j = 0; j < nb; ++j) sum += (double)col[j * stride];
+  kp.sum = sum;
+  kp.target = ((double)v + (double)kBound) * (0.5 / (double)kBound) * sum;
+  double cum = 0.0;
+  int k = nb - 1;
+  for (int j = 0; j < nb - 1; ++j) {   // knot_k < v <= knot_{k+1}
+    const double nxt = cum + (double)col[j * stride];
+    if (kp.target <= nxt) {
+      k = j;
+      break;
+    }
+    cum = nxt;
+  }
+  kp.k = k;
+  kp.cum = cum;
+  return kp;
+}
+
 // One univariate spline: parameters (3*nb-1 raw conditioner outputs) in col[j*stride].
 // Returns y and adds log dy/dv to ladj.
 //
 // Conditioning: zuko differences the cumulative knot arrays (x1 - x0, y1 - y0), which cancels
 // catastrophically in narrow bins (widths go down to 1e-3 of the mean).  Here the bin width and
 // height are taken directly from the softmax values (dx = 2B W_k, dy = 2B H_k), which is the same
-// number in exact arithmetic but accurate to an ulp; only the bin origin comes from the
-// cumulative sum.  This puts the kernel closer to the float64 truth than a plain fp32 evaluation.
+// number in exact arithmetic but accurate to an ulp, and the position inside the bin comes from
+// knot sums carried in double (knot_search).
 __device__ __forceinline__ float rq_spline_forward(float* col, int stride, int nb, float v, float& ladj) {
-  // horizontal knots + bin search: k = #(knots < v) - 1
-  const float sum_w = softmax_inplace(col, stride, nb);
-  float cum = 0.f, xl = -kBound, x0 = 0.f, wk = 0.f;
-  int kbin = -1;
-  for (int j = 0; j < nb; ++j) {
-    const float wj = col[j * stride] / sum_w;
-    cum += wj;
-    const float xr = fmaf(2.0f * kBound, cum, -kBound);
-    if (kbin < 0 && xl < v && v <= xr) {
-      kbin = j;
-      x0 = xl;
-      wk = wj;
-    }
-    xl = xr;
-  }
-  if (kbin < 0) return v;  // outside [-bound, bound]: identity, ladj += 0
+  if (!(v > -kBound && v <= kBound)) return v;  // outside (-bound, bound]: identity, ladj += 0
+  softmax_inplace(col, stride, nb);
+  const KnotPos kp = knot_search(col, stride, nb, v);
+  const int kbin = kp.k;
+  const float ek = col[kbin * stride];
+  const float wk = (float)((double)ek / kp.sum);
   float* colh = col + nb * stride;
-  const float sum_h = softmax_inplace(colh, stride, nb);
-  cum = 0.f;
-  for (int j = 0; j < kbin; ++j) cum += colh[j * stride] / sum_h;
-  const float y0 = fmaf(2.0f * kBound, cum, -kBound);
-  const float hk = colh[kbin * stride] / sum_h;
+  softmax_inplace(colh, stride, nb);
+  double sum_h = 0.0, cumh = 0.0;
+  for (int j = 0; j < nb; ++j) {
+    const double e = (double)colh[j * stride];
+    if (j < kbin) cumh += e;
+    sum_h += e;
+  }
+  const float y0 = (float)(2.0 * (double)kBound * (cumh / sum_h) - (double)kBound);
+  const float hk = (float)((double)colh[kbin * stride] / sum_h);
   const float* cold = col + 2 * nb * stride;
   float d0 = 1.0f, d1 = 1.0f;
   if (kbin > 0) {
@@ -103,9 +129,9 @@ __device__ __forceinline__ float rq_spline_forward(float* col, int stride, int n
     const float r = cold[kbin * stride];
     d1 = expf(r / (1.0f + kClipD * fabsf(r)));
   }
-  const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hk;
+  const float dy = 2.0f * kBound * hk;
   const float s = hk / wk;
-  float t = (v - x0) / dx;
+  float t = (float)((kp.target - kp.cum) / (double)ek);
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   const float omt = 1.0f - t;
   const float tomt = t * omt;

@@ -16,27 +16,23 @@ namespace mfb {
 // RQS(v) = y and, if want_ladj, adds log dy/dv (forward direction) at v to ladj.
 __device__ __forceinline__ float rq_spline_inverse(float* col, int stride, int nb, float y, bool want_ladj,
                                                    float& ladj) {
+  if (!(y > -kBound && y <= kBound)) return y;  // identity outside the box
+  // knot sums in double, as in the forward direction (knot_search): the bin in y, then the same bin in x
   float* colh = col + nb * stride;
-  const float sum_h = softmax_inplace(colh, stride, nb);
-  float cum = 0.f, yl = -kBound, y0 = 0.f, hk = 0.f;
-  int kbin = -1;
+  softmax_inplace(colh, stride, nb);
+  const KnotPos kp = knot_search(colh, stride, nb, y);
+  const int kbin = kp.k;
+  const float hk = (float)((double)colh[kbin * stride] / kp.sum);
+  const float yy = (float)((kp.target - kp.cum) * (2.0 * (double)kBound) / kp.sum);   // y - y0
+  softmax_inplace(col, stride, nb);
+  double sum_w = 0.0, cumw = 0.0;
   for (int j = 0; j < nb; ++j) {
-    const float hj = colh[j * stride] / sum_h;
-    cum += hj;
-    const float yr = fmaf(2.0f * kBound, cum, -kBound);
-    if (kbin < 0 && yl < y && y <= yr) {
-      kbin = j;
-      y0 = yl;
-      hk = hj;
-    }
-    yl = yr;
+    const double e = (double)col[j * stride];
+    if (j < kbin) cumw += e;
+    sum_w += e;
   }
-  if (kbin < 0) return y;  // identity outside the box
-  const float sum_w = softmax_inplace(col, stride, nb);
-  cum = 0.f;
-  for (int j = 0; j < kbin; ++j) cum += col[j * stride] / sum_w;
-  const float x0 = fmaf(2.0f * kBound, cum, -kBound);
-  const float wk = col[kbin * stride] / sum_w;
+  const double x0 = 2.0 * (double)kBound * (cumw / sum_w) - (double)kBound;
+  const float wk = (float)((double)col[kbin * stride] / sum_w);
   const float* cold = col + 2 * nb * stride;
   float d0 = 1.0f, d1 = 1.0f;
   if (kbin > 0) {
@@ -49,7 +45,6 @@ __device__ __forceinline__ float rq_spline_inverse(float* col, int stride, int n
   }
   const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hk;
   const float s = hk / wk;
-  const float yy = y - y0;
   const float A = d0 + d1 - 2.0f * s;
   const float a = dy * (s - d0) + yy * A;
   const float b = dy * d0 - yy * A;
@@ -62,7 +57,7 @@ __device__ __forceinline__ float rq_spline_inverse(float* col, int stride, int n
     const float jac = s * s * (2.0f * s * q + d0 * omt * omt + d1 * t * t) / (den * den);
     ladj += logf(jac);
   }
-  return fmaf(t, dx, x0);
+  return (float)(x0 + (double)t * (double)dx);
 }
 
 template <int D>

@@ -23,13 +23,12 @@
 // triangular; K steps whose weights are all zero for a block of outputs are not issued (14 of 20
 // output-layer K steps at D = 6).  The feature that is first in the layer's order has a bias-only
 // spline: its knots are precomputed into a table in the image.
+#include "nsf_spline_regs.cuh"
 #include "nsf_tc_common.cuh"
 
 namespace mfb {
 namespace tc {
 
-constexpr int kCT = 24;              // stride of the constant-feature tables (floats)
-constexpr int kConstFloats = 6 * kCT + kPP;   // knot tables + the raw parameters (x log2 e) of the bias-only feature
 
 struct Meta {
   int slot_feature[kMaxDim];  // feature handled by output slot s (order > 0, ascending order)
@@ -195,41 +194,45 @@ nsf_tc_prepare_kernel(const float* __restrict__ params_all, int64_t layer_stride
       store_ktile_row(img + off_slot(D, L, sl, ks, 1), q, lo);
     }
   }
-  // constant feature: knots of its bias-only spline (same formulas as the epilogue)
+  // constant feature: knots of its bias-only spline, evaluated in double (once per layer and image) and
+  // rounded to fp32 at the end; the left knot in x is stored as (hi, lo)
   if (threadIdx.x == 0 && blockIdx.y == gridDim.y - 1) {
     float* ct = f32;
     const float* bf = bout + pm.const_feature * kPP;
-    float ew[32], eh[32];
-    float sw = 0.f, sh = 0.f;
+    double ew[32], eh[32];
+    double sw = 0.0, sh = 0.0;
     for (int j = 0; j < nb; ++j) {
-      const float w = bf[j], h = bf[nb + j];
-      ew[j] = expf(w / (1.0f + kClipW * fabsf(w)));
-      eh[j] = expf(h / (1.0f + kClipW * fabsf(h)));
+      const double w = bf[j], h = bf[nb + j];
+      ew[j] = exp(w / (1.0 + (double)kClipW * fabs(w)));
+      eh[j] = exp(h / (1.0 + (double)kClipW * fabs(h)));
       sw += ew[j];
       sh += eh[j];
     }
-    float cw = 0.f, ch = 0.f;
+    double cw = 0.0, ch = 0.0;
     for (int j = 0; j < nb; ++j) {
-      const float wj = ew[j] / sw, hj = eh[j] / sh;
-      float dl = 1.f, dr = 1.f;
+      const double wj = ew[j] / sw, hj = eh[j] / sh;
+      double dl = 1.0, dr = 1.0;
       if (j > 0) {
-        const float r = bf[2 * nb + j - 1];
-        dl = expf(r / (1.0f + kClipD * fabsf(r)));
+        const double r = bf[2 * nb + j - 1];
+        dl = exp(r / (1.0 + (double)kClipD * fabs(r)));
       }
       if (j < nb - 1) {
-        const float r = bf[2 * nb + j];
-        dr = expf(r / (1.0f + kClipD * fabsf(r)));
+        const double r = bf[2 * nb + j];
+        dr = exp(r / (1.0 + (double)kClipD * fabs(r)));
       }
-      ct[0 * kCT + j] = fmaf(2.0f * kBound, cw, -kBound);  // left knot x
-      ct[1 * kCT + j] = 2.0f * kBound * wj;                // bin width
-      ct[2 * kCT + j] = fmaf(2.0f * kBound, ch, -kBound);  // left knot y
-      ct[3 * kCT + j] = 2.0f * kBound * hj;                // bin height
-      ct[4 * kCT + j] = dl;
-      ct[5 * kCT + j] = dr;
+      const double x0 = 2.0 * kBound * cw - kBound;
+      const float x0f = (float)x0;
+      ct[0 * kCT + j] = x0f;                                         // left knot x
+      ct[1 * kCT + j] = (float)(2.0 * kBound * wj);                  // bin width
+      ct[2 * kCT + j] = (float)(2.0 * kBound * ch - kBound);         // left knot y
+      ct[3 * kCT + j] = (float)(2.0 * kBound * hj);                  // bin height
+      ct[4 * kCT + j] = (float)dl;
+      ct[5 * kCT + j] = (float)dr;
+      ct[6 * kCT + j] = (float)(x0 - (double)x0f);
       cw += wj;
       ch += hj;
     }
-    for (int j = 0; j < kPP; ++j) ct[6 * kCT + j] = (j < 3 * nb - 1) ? bf[j] * kLog2e : 0.f;   // backward only
+    for (int j = 0; j < kPP; ++j) ct[kConstRows * kCT + j] = (j < 3 * nb - 1) ? bf[j] * kLog2e : 0.f;   // backward only
   }
 }
 
@@ -252,298 +255,6 @@ __device__ __forceinline__ float fast_lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// MUFU reciprocal + one Newton step (the raw approximation's 1 ulp is amplified by the
-// ill-conditioned knot sums; with the step the spline is as accurate as a divide)
-__device__ __forceinline__ float rcp_nr(float x) {
-  const float r = fast_rcp(x);
-  return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-
-// soft clip + exp of two raw (log2e-scaled) parameters with one reciprocal:
-//   e = 2^(t / (1 + c |t|))
-__device__ __forceinline__ void clip_exp2_pair(float t0, float t1, float c, float& e0, float& e1) {
-  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
-#ifdef MFB_TC_EXACT
-  e0 = exp2f(t0 / d0);
-  e1 = exp2f(t1 / d1);
-#else
-  const float r = fast_rcp(d0 * d1);
-  e0 = fast_exp2(t0 * (r * d1));
-  e1 = fast_exp2(t1 * (r * d0));
-#endif
-}
-
-// the same for four parameters with ONE reciprocal (the spline phases are bound by the MUFU pipe:
-// 8 issue slots per MUFU instruction, so three extra multiplies per quad are the cheaper side)
-__device__ __forceinline__ void clip_exp2_quad(float t0, float t1, float t2, float t3, float c, float& e0, float& e1,
-                                               float& e2, float& e3) {
-  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
-  const float d2 = fmaf(fabsf(t2), c, 1.0f), d3 = fmaf(fabsf(t3), c, 1.0f);
-  const float p01 = d0 * d1, p23 = d2 * d3;
-  const float r = fast_rcp(p01 * p23);
-  const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
-  e0 = fast_exp2(t0 * (r01 * d1));
-  e1 = fast_exp2(t1 * (r01 * d0));
-  e2 = fast_exp2(t2 * (r23 * d3));
-  e3 = fast_exp2(t3 * (r23 * d2));
-}
-
-// Rational-quadratic spline of one feature from the raw conditioner outputs a[0..3NB-2] (already
-// multiplied by log2 e through the weights, bias included by the bias MMA).  Works in
-// un-normalised softmax units: the bin is searched on the running sum of e_j against
-// (v + B) / 2B * sum, and bin width / height come from e_k directly (no differencing of knots).
-// The search is two-level -- which group of four bins, then which bin of the group -- with
-// predicated selects, so that nothing is indexed dynamically and everything stays in registers.
-// Multiplies jac by dy/dv (1 outside [-B, B]) and returns y.
-template <int NB>
-__device__ __forceinline__ float rq_spline_regs(const float (&a)[64], float v, float& jac) {
-  static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
-  constexpr int G = NB / 4;
-  constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
-  // ---- widths: e_j, sums of the groups of four and their prefixes P_g (short dependency chains;
-  //      P_G is the total, so bin origin + bin width + remainder add up consistently)
-  float e[NB], pre[G + 1];
-#pragma unroll
-  for (int j = 0; j < NB; j += 4) {
-    clip_exp2_quad(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
-  }
-  pre[0] = 0.f;
-#pragma unroll
-  for (int g = 0; g < G; ++g) pre[g + 1] = pre[g] + ((e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]));
-  const float sum = pre[G];
-  const float target = (v + kBound) * (0.5f / kBound) * sum;
-  // level 1: pg[g] <=> the bin of v lies beyond group g (monotone in g)
-  bool pg[G - 1];
-#pragma unroll
-  for (int g = 0; g < G - 1; ++g) pg[g] = pre[g + 1] < target;
-  float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
-#pragma unroll
-  for (int g = 1; g < G; ++g) {
-    q0 = pg[g - 1] ? e[4 * g] : q0;
-    q1 = pg[g - 1] ? e[4 * g + 1] : q1;
-    q2 = pg[g - 1] ? e[4 * g + 2] : q2;
-    q3 = pg[g - 1] ? e[4 * g + 3] : q3;
-    xg = pg[g - 1] ? pre[g] : xg;
-  }
-  // level 2: running sums inside the group, then the bin of the group
-  const float c0 = xg + q0, c1 = c0 + q1, c2 = c1 + q2;
-  const bool r0 = c0 < target, r1 = c1 < target, r2 = c2 < target;
-  const float x0c = r2 ? c2 : (r1 ? c1 : (r0 ? c0 : xg));
-  const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
-  // ---- heights, one group at a time
-  float run = 0.f, yg = 0.f, h0s = 0.f, h1s = 0.f, h2s = 0.f, h3s = 0.f;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    float h0, h1, h2, h3;
-    clip_exp2_quad(a[NB + 4 * g], a[NB + 4 * g + 1], a[NB + 4 * g + 2], a[NB + 4 * g + 3], cW, h0, h1, h2, h3);
-    const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
-    h0s = take ? h0 : h0s;
-    h1s = take ? h1 : h1s;
-    h2s = take ? h2 : h2s;
-    h3s = take ? h3 : h3s;
-    yg = take ? run : yg;
-    run += (h0 + h1) + (h2 + h3);
-  }
-  const float sumh = run;
-  const float p0 = yg + h0s, p1 = p0 + h1s, p2 = p1 + h2s;
-  const float y0c = r2 ? p2 : (r1 ? p1 : (r0 ? p0 : yg));
-  const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
-  // ---- derivatives at the two knots of the bin (raw 0 -> slope 1 at the outer knots):
-  //      u[-1..3] = raw parameters of the knots around the group's four bins
-  float um = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, prev = 0.f;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const float t0 = a[2 * NB + 4 * g], t1 = a[2 * NB + 4 * g + 1], t2 = a[2 * NB + 4 * g + 2];
-    const float t3 = (4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f;
-    const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
-    um = take ? prev : um;
-    u0 = take ? t0 : u0;
-    u1 = take ? t1 : u1;
-    u2 = take ? t2 : u2;
-    u3 = take ? t3 : u3;
-    prev = t3;
-  }
-  const float tl = r2 ? u2 : (r1 ? u1 : (r0 ? u0 : um));
-  const float tr = r2 ? u3 : (r1 ? u2 : (r0 ? u1 : u0));
-  float d0, d1;
-  clip_exp2_pair(tl, tr, cD, d0, d1);
-  // ---- rational quadratic
-  const float r_e = rcp_nr(ek), r_sh = rcp_nr(sumh);
-  float t = (target - x0c) * r_e;
-  t = fminf(fmaxf(t, 0.0f), 1.0f);
-  const float hn = hk * r_sh;                 // normalised bin height / 2B
-  const float s = hn * sum * r_e;             // dy / dx
-  const float omt = 1.0f - t, tomt = t * omt;
-  const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
-  const float r_den = rcp_nr(den);
-  const float y0 = fmaf(2.0f * kBound, y0c * r_sh, -kBound);
-  const float y = fmaf(2.0f * kBound * hn * (s * t * t + d0 * tomt), r_den, y0);
-  const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
-  const bool inside = (v > -kBound) && (v <= kBound);
-  jac *= inside ? j1 : 1.0f;
-  return inside ? y : v;
-}
-
-// soft clip + exp of four parameters like clip_exp2_quad; additionally returns 1 / (1 + c |t_j|) in place
-// of t_j: the derivative of the clip is its square
-__device__ __forceinline__ void clip_exp2_quad_bwd(float& t0, float& t1, float& t2, float& t3, float c, float& e0,
-                                                   float& e1, float& e2, float& e3) {
-  const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
-  const float d2 = fmaf(fabsf(t2), c, 1.0f), d3 = fmaf(fabsf(t3), c, 1.0f);
-  const float p01 = d0 * d1, p23 = d2 * d3;
-  const float r = fast_rcp(p01 * p23);
-  const float r01 = r * p23, r23 = r * p01;
-  const float i0 = r01 * d1, i1 = r01 * d0, i2 = r23 * d3, i3 = r23 * d2;
-  e0 = fast_exp2(t0 * i0);
-  e1 = fast_exp2(t1 * i1);
-  e2 = fast_exp2(t2 * i2);
-  e3 = fast_exp2(t3 * i3);
-  t0 = i0; t1 = i1; t2 = i2; t3 = i3;
-}
-
-// Spline forward + backward of one feature in registers (backward variant of rq_spline_regs; the
-// formulas are those of rq_spline_backward in nsf_bwd.cu, prototype scripts/proto_spline_bwd.py).
-// a[]: raw parameters (x log2 e) in, dL/d(raw natural parameter) out (j < 3NB-1).  gy = dL/dy,
-// gl = dL/d(log dy/dv).  Returns the direct dL/dv.
-template <int NB>
-__device__ __forceinline__ float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl) {
-  static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
-  constexpr int G = NB / 4;
-  constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
-  float e[NB], h[NB], pre[G + 1], preh[G + 1];
-#pragma unroll
-  for (int j = 0; j < NB; j += 4) {
-    clip_exp2_quad_bwd(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
-    clip_exp2_quad_bwd(a[NB + j], a[NB + j + 1], a[NB + j + 2], a[NB + j + 3], cW, h[j], h[j + 1], h[j + 2], h[j + 3]);
-  }
-  pre[0] = 0.f;
-  preh[0] = 0.f;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    pre[g + 1] = pre[g] + ((e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]));
-    preh[g + 1] = preh[g] + ((h[4 * g] + h[4 * g + 1]) + (h[4 * g + 2] + h[4 * g + 3]));
-  }
-  const float sum = pre[G], sumh = preh[G];
-  const float target = (v + kBound) * (0.5f / kBound) * sum;
-  // two-level search as in the forward pass, plus the integer bin index for the scatter below
-  int gsel = 0;
-  float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
-  float h0s = h[0], h1s = h[1], h2s = h[2], h3s = h[3], yg = 0.f;
-  // raw derivative parameters of the knots around the group's four bins (u[-1..3], raw 0 at the outer
-  // knots), selected with the same predicates: nothing is indexed dynamically, so a[] stays in registers
-  float um = 0.f, u0 = a[2 * NB], u1 = a[2 * NB + 1], u2 = a[2 * NB + 2], u3 = a[2 * NB + 3];
-#pragma unroll
-  for (int g = 1; g < G; ++g) {
-    const bool pgm = pre[g] < target;
-    gsel += pgm ? 1 : 0;
-    um = pgm ? a[2 * NB + 4 * g - 1] : um;
-    u0 = pgm ? a[2 * NB + 4 * g] : u0;
-    u1 = pgm ? a[2 * NB + 4 * g + 1] : u1;
-    u2 = pgm ? a[2 * NB + 4 * g + 2] : u2;
-    u3 = pgm ? ((4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f) : u3;
-    q0 = pgm ? e[4 * g] : q0;
-    q1 = pgm ? e[4 * g + 1] : q1;
-    q2 = pgm ? e[4 * g + 2] : q2;
-    q3 = pgm ? e[4 * g + 3] : q3;
-    xg = pgm ? pre[g] : xg;
-    h0s = pgm ? h[4 * g] : h0s;
-    h1s = pgm ? h[4 * g + 1] : h1s;
-    h2s = pgm ? h[4 * g + 2] : h2s;
-    h3s = pgm ? h[4 * g + 3] : h3s;
-    yg = pgm ? preh[g] : yg;
-  }
-  const float c0 = xg + q0, c1 = c0 + q1, c2 = c1 + q2;
-  const bool r0 = c0 < target, r1 = c1 < target, r2 = c2 < target;
-  const int k = 4 * gsel + (r0 ? 1 : 0) + (r1 ? 1 : 0) + (r2 ? 1 : 0);
-  const float x0c = r2 ? c2 : (r1 ? c1 : (r0 ? c0 : xg));
-  const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
-  const float p0 = yg + h0s, p1 = p0 + h1s, p2 = p1 + h2s;
-  const float y0c = r2 ? p2 : (r1 ? p1 : (r0 ? p0 : yg));
-  const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
-  // derivative parameters at the two knots of bin k (raw 0 at the outer knots)
-  const float tl = r2 ? u2 : (r1 ? u1 : (r0 ? u0 : um));
-  const float tr = r2 ? u3 : (r1 ? u2 : (r0 ? u1 : u0));
-  const float dd0 = fmaf(fabsf(tl), cD, 1.0f), dd1 = fmaf(fabsf(tr), cD, 1.0f);
-  const float rdd = fast_rcp(dd0 * dd1);
-  const float ri0 = rdd * dd1, ri1 = rdd * dd0;
-  const float d0 = fast_exp2(tl * ri0), d1 = fast_exp2(tr * ri1);
-  // forward quantities in natural units
-  const float inv_s = rcp_nr(sum), inv_sh = rcp_nr(sumh);
-  const float wk = ek * inv_s, hn = hk * inv_sh;
-  const float cumw = x0c * inv_s, cumh = y0c * inv_sh;
-  const float dx = 2.0f * kBound * wk, dy = 2.0f * kBound * hn;
-  const float r_wk = rcp_nr(wk), r_dx = rcp_nr(dx);
-  const float s = hn * r_wk;
-  float t = (target - x0c) * rcp_nr(ek);
-  t = fminf(fmaxf(t, 0.0f), 1.0f);
-  const float omt = 1.0f - t, q = t * omt;
-  const float A = d0 + d1 - 2.0f * s;
-  const float den = fmaf(A, q, s);
-  const float n1 = s * t * t + d0 * q;
-  const float n2 = 2.0f * s * q + d0 * omt * omt + d1 * t * t;
-  const float dq_dt = 1.0f - 2.0f * t;
-  const float dden_dt = A * dq_dt, dden_ds = 1.0f - 2.0f * q, dden_dd = q;
-  const float inv_den = rcp_nr(den), inv_n2 = rcp_nr(n2);
-  const float r1q = n1 * inv_den;
-  const float dy_dt = dy * (2.0f * s * t + d0 * dq_dt - r1q * dden_dt) * inv_den;
-  const float dy_ds = dy * (t * t - r1q * dden_ds) * inv_den;
-  const float dy_dd0 = dy * (q - r1q * dden_dd) * inv_den;
-  const float dy_dd1 = dy * (-r1q * dden_dd) * inv_den;
-  const float dl_dt = (2.0f * s * dq_dt - 2.0f * d0 * omt + 2.0f * d1 * t) * inv_n2 - 2.0f * dden_dt * inv_den;
-  const float dl_ds = 2.0f * rcp_nr(s) + 2.0f * q * inv_n2 - 2.0f * dden_ds * inv_den;
-  const float dl_dd0 = omt * omt * inv_n2 - 2.0f * dden_dd * inv_den;
-  const float dl_dd1 = t * t * inv_n2 - 2.0f * dden_dd * inv_den;
-  const float g_t = gy * dy_dt + gl * dl_dt;
-  const float g_s = gy * dy_ds + gl * dl_ds;
-  const float g_d0 = gy * dy_dd0 + gl * dl_dd0;
-  const float g_d1 = gy * dy_dd1 + gl * dl_dd1;
-  const float g_dy = gy * r1q;
-  const float gv = g_t * r_dx;
-  const float g_dx = -g_t * t * r_dx;
-  const float gW_lo = -2.0f * kBound * gv;
-  const float gW_k = 2.0f * kBound * g_dx - g_s * s * r_wk;
-  const float gH_lo = 2.0f * kBound * gy;
-  const float gH_k = 2.0f * kBound * g_dy + g_s * r_wk;
-  const float dotW = gW_lo * cumw + gW_k * wk;
-  const float dotH = gH_lo * cumh + gH_k * hn;
-  const bool inside = (v > -kBound) && (v <= kBound);
-  const float live = inside ? 1.0f : 0.0f;   // identity outside the spline box: no parameter gradient
-  const float ws = inv_s * live, hs = inv_sh * live;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const float gw = (j < k ? gW_lo : (j == k ? gW_k : 0.f)) - dotW;
-    const float gh = (j < k ? gH_lo : (j == k ? gH_k : 0.f)) - dotH;
-    a[j] = (e[j] * ws) * gw * (a[j] * a[j]);                  // softmax Jacobian, then the clip derivative
-    a[NB + j] = (h[j] * hs) * gh * (a[NB + j] * a[NB + j]);
-  }
-  const float gd0 = g_d0 * d0 * ri0 * ri0 * live, gd1 = g_d1 * d1 * ri1 * ri1 * live;
-#pragma unroll
-  for (int j = 0; j < NB - 1; ++j) a[2 * NB + j] = (j == k - 1) ? gd0 : ((j == k) ? gd1 : 0.f);
-  return inside ? gv : gy;
-}
-
-// bias-only spline from the precomputed knot tables (shared memory, broadcast reads)
-template <int NB>
-__device__ __forceinline__ float rq_spline_const(const float* __restrict__ ct, float v, float& jac) {
-  int k = 0;
-#pragma unroll
-  for (int j = 1; j < NB; ++j) k += (ct[j] < v) ? 1 : 0;
-  const float x0 = ct[k], dx = ct[kCT + k], y0 = ct[2 * kCT + k], dy = ct[3 * kCT + k];
-  const float d0 = ct[4 * kCT + k], d1 = ct[5 * kCT + k];
-  const float r_dx = rcp_nr(dx);
-  const float s = dy * r_dx;
-  float t = (v - x0) * r_dx;
-  t = fminf(fmaxf(t, 0.0f), 1.0f);
-  const float omt = 1.0f - t, tomt = t * omt;
-  const float den = fmaf(d0 + d1 - 2.0f * s, tomt, s);
-  const float r_den = rcp_nr(den);
-  const float y = fmaf(dy * (s * t * t + d0 * tomt), r_den, y0);
-  const float j1 = s * s * (2.0f * s * tomt + d0 * omt * omt + d1 * t * t) * r_den * r_den;
-  const bool inside = (v > -kBound) && (v <= kBound);
-  jac *= inside ? j1 : 1.0f;
-  return inside ? y : v;
 }
 
 // relu + (hi, lo) fp16 split of two activations with the ReLU folded into the conversions:
@@ -907,7 +618,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       float acc[64];
       if (kBwd && s < 0) {
         if (cur) {
-          const float4* cb = reinterpret_cast<const float4*>(ctab + 6 * kCT);
+          const float4* cb = reinterpret_cast<const float4*>(ctab + kConstRows * kCT);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 q4 = cb[i];

@@ -95,6 +95,7 @@ class NSFGenerator(GenerativeModel):
         self.register_buffer("m_out", torch.stack(m_out).float(), persistent=False)
         self._orders = [layer_order(D, t) for t in range(T)]
         self._pack_key, self._pack_cache = None, None
+        self._rng = None
         if device is not None:
             self.to(device)
 
@@ -169,8 +170,22 @@ class NSFGenerator(GenerativeModel):
         return torch.nn.modules.module._IncompatibleKeys(missing, [])
 
     # ------------------------------------------------------------------ sampling direction
-    def sample_base(self, n: int) -> torch.Tensor:
-        return torch.randn((int(n), self.features), dtype=torch.float32, device=self.w_in.device)
+    def sample_base(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """z ~ N(0, I) (generate/flows/zuko.py:15-16).  On a CUDA device the draw is the library's
+        Philox kernel on torch's own generator state: bitwise the tensor ``torch.randn((n, D),
+        device=...)`` returns for the same seed, and torch's generator is moved on identically."""
+        dev = self.w_in.device
+        if dev.type != "cuda":
+            return torch.randn((int(n), self.features), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty((int(n), self.features), dtype=torch.float32, device=dev)
+        return self.rng(dev).normal_(out)
+
+    def rng(self, device=None) -> "ops.PhiloxStream":
+        dev = torch.device(device) if device is not None else self.w_in.device
+        if self._rng is None or self._rng.device != dev:
+            self._rng = ops.PhiloxStream(dev)
+        return self._rng
 
     def _packed_cached(self):
         """(packed parameters, tensor-core operand images) for the current weights, rebuilt only when a

@@ -45,6 +45,12 @@ class GraphedLoss:
         self._key = None
         self._held = None
         self.out = None
+        # second capture with the base-noise draw inside (``__call__()`` without z): the library's Philox
+        # kernel reads torch's generator state from a device tensor and advances it itself
+        self._rng_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._rng_key = None
+        self._rng_out = None
+        self._rng = None
 
     def _step(self):
         gen = self.model.generator
@@ -72,6 +78,29 @@ class GraphedLoss:
             with torch.cuda.graph(self.graph):
                 self.out = self._step()
         self._key = self._weights_key()
+
+    def _step_draw(self):
+        self.model.generator.sample_base(self.batch_size, out=self.z)
+        return self._step()
+
+    def _capture_draw(self) -> None:
+        gen = self.model.generator
+        self._rng = gen.rng(self.device)
+        with torch.cuda.device(self.device), torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self._step_draw()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._held_rng = getattr(gen, "_pack_cache", None)
+            self._rng.begin_capture()
+            self._rng_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._rng_graph):
+                self._rng_out = self._step_draw()
+            self._rng_increment = self._rng.captured_increment
+        self._rng_key = self._weights_key()
 
     # ---- pinned host input: chunked copies overlapped with the flow -------------------------------
     def _chunk_bounds(self):
@@ -143,12 +172,18 @@ class GraphedLoss:
                 self._capture_host(z)
             self._host_graph.replay()
             return self._host_out
+        if z is None:
+            # sample on the device inside the graph: the call the reference makes, model.loss(batch_size)
+            if self._rng_graph is None or self._rng_key != self._weights_key():
+                self._capture_draw()
+            self._rng.captured_increment = self._rng_increment
+            self._rng.sync()
+            self._rng_graph.replay()
+            self._rng.consumed()
+            return self._rng_out
         if self.graph is None or self._key != self._weights_key():
             self._capture()
-        if z is None:
-            self.z.normal_()
-        else:
-            self.z.copy_(z, non_blocking=True)
+        self.z.copy_(z, non_blocking=True)
         self.graph.replay()
         return self.out
 
@@ -158,8 +193,15 @@ class GraphedTrainStep:
     the reference's training loop (train/train.py:164-169) -- as ONE CUDA-graph replay.
 
     The optimiser must be capturable (``torch.optim.AdamW(..., capturable=True)``; add ``fused=True`` for
-    one launch instead of sixteen): its step counter
-    and the learning rate then live on the device, so LR schedulers keep working between replays.
+    one launch instead of sixteen): its step counter then lives on the device.  The learning rate is read
+    by the captured kernels from wherever the optimiser keeps it: a *tensor* ``lr`` (``AdamW(lr=torch.tensor(
+    1e-3, device=...))``) is followed live, so LR schedulers keep working between replays; a Python float
+    is a constant of the graph, so the step is RE-CAPTURED whenever a param group's float ``lr`` (or the
+    model's penalty parameter) changes -- ``lr_scheduler.step(loss)`` of the reference trainer
+    (train/train.py:205-207) is therefore honoured either way.
+    The warm-up passes a capture needs run real optimiser steps; parameters and optimiser state are
+    snapshotted before and restored after them, so a (re-)capture leaves the training state exactly
+    where the caller had it and every counted step is one replay.
     One difference from the reference loop: a non-finite loss cannot skip the update from inside a
     graph; ``step.finite`` (a device flag refreshed by every replay) lets the caller notice.
     """
@@ -175,10 +217,44 @@ class GraphedTrainStep:
                 raise ValueError("GraphedTrainStep needs an optimizer constructed with capturable=True")
         self.device = dev
         self._penalty = None
+        self._lrs = None
+        self._rng = None
+        self._rng_increment = 0
         self.graph = None
         self.out = None
         self.finite = None
         self.warmup = max(3, int(warmup))
+
+    def _float_lrs(self):
+        """the Python-float learning rates a captured graph would bake in (tensor lrs are read live)"""
+        return tuple(float(g["lr"]) for g in self.optimizer.param_groups if not torch.is_tensor(g["lr"]))
+
+    def _snapshot(self):
+        params = [p.detach().clone() for g in self.optimizer.param_groups for p in g["params"]]
+        state = {}
+        for p, st in self.optimizer.state.items():
+            state[p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return params, state
+
+    def _restore(self, snap) -> None:
+        params, state = snap
+        with torch.no_grad():
+            i = 0
+            for g in self.optimizer.param_groups:
+                for p in g["params"]:
+                    p.copy_(params[i])
+                    i += 1
+            for p, st in list(self.optimizer.state.items()):
+                if p not in state:            # state created by the warm-up: back to "never stepped"
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.zero_()
+                    continue
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.copy_(state[p][k])
+                    else:
+                        st[k] = state[p][k]
 
     def _body(self):
         L, H, D = self.model.loss(self.batch_size)
@@ -187,7 +263,10 @@ class GraphedTrainStep:
         return L.detach(), H.detach() if torch.is_tensor(H) else H, [d.detach() for d in D]
 
     def _capture(self) -> None:
+        gen = self.model.generator
+        self._rng = gen.rng(self.device) if hasattr(gen, "rng") else None
         with torch.cuda.device(self.device):
+            snap = self._snapshot()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -196,17 +275,28 @@ class GraphedTrainStep:
                     self._body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            self._restore(snap)
+            if self._rng is not None:
+                self._rng.begin_capture()
             self.graph = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(self.graph):
                 self.out = self._body()
                 self.finite = torch.isfinite(self.out[0])
+            self._rng_increment = self._rng.captured_increment if self._rng is not None else 0
         self._penalty = float(self.model.penalty_parameter)
+        self._lrs = self._float_lrs()
 
     def __call__(self):
         """One optimisation step; returns (L, H, [D_k]) of the batch it was taken on (static tensors,
         overwritten by the next call)."""
-        if self.graph is None or self._penalty != float(self.model.penalty_parameter):
-            self._capture()     # the penalty parameter is a host scalar baked into the graph
+        if (self.graph is None or self._penalty != float(self.model.penalty_parameter)
+                or self._lrs != self._float_lrs()):
+            self._capture()     # penalty parameter and float learning rates are constants of the graph
+        if self._rng is not None:
+            self._rng.captured_increment = self._rng_increment
+            self._rng.sync()
         self.graph.replay()
+        if self._rng is not None:
+            self._rng.consumed()
         return self.out

@@ -617,3 +617,84 @@ def gs_update(table: torch.Tensor, meas: torch.Tensor, pred: torch.Tensor, lr: f
     with torch.cuda.device(table.device):
         _lib.check(lib.mfb_gs_update(_ptr(table), _ptr(meas), _ptr(pred), n, float(lr), float(thresh), _stream()),
                    "gs_update")
+
+
+# --------------------------------------------------------------------------------------
+# base noise on the device (generate/flows/zuko.py:15-16 -> torch.randn)
+# --------------------------------------------------------------------------------------
+class PhiloxStream:
+    """torch's CUDA generator, mirrored for the library's randn kernel.
+
+    ``normal_(out)`` fills ``out`` with exactly the values ``torch.randn(out.shape, device=...)`` would
+    produce for the generator's current (seed, offset) and moves the generator on by the same amount, so
+    library draws and torch draws interleave as if all of them were torch's.  While a CUDA graph is being
+    captured the (seed, offset) pair is read from a device tensor instead, and the kernel advances it
+    itself; ``sync()`` before a replay re-primes that tensor if the generator was re-seeded or used by
+    somebody else in the meantime, ``consumed()`` after it books the replay's draws on the generator.
+    """
+
+    def __init__(self, device) -> None:
+        self.device = torch.device(device)
+        self.state: Optional[torch.Tensor] = None   # int64[2] on the device: seed, offset
+        self._mirror = None                          # (seed, offset) the device tensor holds
+        self._pinned = None
+        self.captured_increment = 0                  # offset consumed by one replay of the captured draws
+
+    def _generator(self):
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return torch.cuda.default_generators[idx]
+
+    @staticmethod
+    def _as_i64(v: int) -> int:
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def normal_(self, out: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        if not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("PhiloxStream.normal_: contiguous float32 CUDA tensor expected; there is no CPU fallback")
+        numel = out.numel()
+        if numel == 0:
+            return out
+        with torch.cuda.device(out.device):
+            inc = int(lib.mfb_randn_offset_increment(numel))
+            if torch.cuda.is_current_stream_capturing():
+                if self.state is None:
+                    raise RuntimeError("PhiloxStream: call begin_capture() before capturing a draw")
+                _lib.check(lib.mfb_randn_philox_state(_ptr(out), numel, _ptr(self.state), 1, _stream()), "randn_philox_state")
+                self.captured_increment += inc
+            else:
+                g = self._generator()
+                seed, off = int(g.initial_seed()), int(g.get_offset())
+                _lib.check(lib.mfb_randn_philox(_ptr(out), numel, ctypes.c_uint64(seed & ((1 << 64) - 1)),
+                                                ctypes.c_uint64(off), _stream()), "randn_philox")
+                g.set_offset(off + inc)
+        return out
+
+    # ---- graph replay support ---------------------------------------------------------------
+    def begin_capture(self) -> None:
+        """Allocate / prime the device state; call right before the graph capture starts."""
+        if self.state is None:
+            self.state = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._pinned = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.captured_increment = 0
+        self._mirror = None
+        self.sync()
+
+    def sync(self) -> None:
+        """Make the device state equal to torch's generator (no-op in steady state)."""
+        g = self._generator()
+        cur = (int(g.initial_seed()), int(g.get_offset()))
+        if self._mirror != cur:
+            self._pinned[0] = self._as_i64(cur[0])
+            self._pinned[1] = self._as_i64(cur[1])
+            self.state.copy_(self._pinned, non_blocking=True)
+            self._mirror = cur
+
+    def consumed(self) -> None:
+        """Book one replay of the captured draws on torch's generator."""
+        if self.captured_increment:
+            g = self._generator()
+            off = int(g.get_offset()) + self.captured_increment
+            g.set_offset(off)
+            self._mirror = (self._mirror[0], off)

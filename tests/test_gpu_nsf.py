@@ -3,13 +3,14 @@
 Metric: e = |a-b| / max(1, |b|) for samples and log q, tolerance 1e-4.
 A 5-layer spline flow is ill-conditioned on a small fraction of particles (near-degenerate
 spline bins): the reference's own fp32 evaluation (torch CPU, same weights) deviates from the
-float64 truth by up to 4e-4 in x and 6e-3 in log q there.  So the bar is: median two orders below
-the tolerance, the count of entries beyond 1e-4 no more than twice torch-fp32's plus 0.5 % of the
-sample (the golden files hold 512 particles: a fixed slack of 2 flips with the summation order),
-and the worst entry no worse than 10x what torch-fp32 itself achieves on the same input (the maximum
-over a few hundred particles is the error of the single worst-conditioned one; measured on 1e5
-particles with the golden weights, scripts/tc_stats.py: p99.9 of log q = 1.0e-4 torch-fp32, 1.7e-4
-both CUDA kernels).  With default-initialised weights EVERY entry is within 1e-4
+float64 truth by up to 4e-4 in x and 6e-3 in log q there, so "every entry within 1e-4" is not
+attainable in fp32 by anybody.  The bar is therefore the reference's own fp32 accuracy: median two
+orders below the tolerance, the COUNT of entries beyond 1e-4 at most 1.25x torch-fp32's on the same
+input (+2: the golden files hold 512 particles), and the worst entry at most 2.5x torch-fp32's worst
+(the maximum over a sample is the error of its single worst-conditioned particle and scatters by
+about 2x between two equally accurate evaluations: tests/test_spline_host.py, scripts/emul_spline.py).
+Round 1 needed 2x / 10x here; the knot arithmetic of the spline epilogue was re-derived since (centred
+differences, nsf_spline_regs.cuh).  With default-initialised weights EVERY entry is within 1e-4
 (test_default_init_all_within_tolerance).
 Both conditioner kernels are checked: the tcgen05 one (default) and the fp32 CUDA-core one."""
 import pytest
@@ -23,14 +24,14 @@ TOL = 1.0e-4
 
 
 def assert_parity(got, truth64, torch32):
-    """bulk: median error two orders below the tolerance; tail: no more entries beyond the
-    tolerance, and no worse a maximum, than ~2-3x what torch-fp32 shows on the same input."""
+    """bulk: median error two orders below the tolerance; tail: the reference's own fp32 accuracy
+    (count beyond the tolerance <= 1.25x torch-fp32's, worst entry <= 2.5x its worst)."""
     e = ((got.double().cpu() - truth64.double()).abs() / truth64.double().abs().clamp_min(1.0)).flatten()
     e32 = ((torch32.double() - truth64.double()).abs() / truth64.double().abs().clamp_min(1.0)).flatten()
     assert float(e.median()) < 1.0e-5, f"median error {float(e.median()):.2e}"
     bad, bad32 = int((e > TOL).sum()), int((e32 > TOL).sum())
-    assert bad <= 2 * bad32 + 2 + (e.numel() + 199) // 200, f"{bad} entries beyond {TOL} (torch-fp32: {bad32}) of {e.numel()}"
-    assert float(e.max()) < max(TOL, 10.0 * float(e32.max())), f"max {float(e.max()):.2e} vs torch-fp32 {float(e32.max()):.2e}"
+    assert bad <= 1.25 * bad32 + 2, f"{bad} entries beyond {TOL} (torch-fp32: {bad32}) of {e.numel()}"
+    assert float(e.max()) < max(TOL, 2.5 * float(e32.max())), f"max {float(e.max()):.2e} vs torch-fp32 {float(e32.max()):.2e}"
 
 
 @pytest.fixture(params=["tcgen05", "cuda_core"])
@@ -74,6 +75,27 @@ def test_forward_vs_oracle_shapes_and_scales(d, n, scale, conditioner):
     gen = gen.to("cuda")
     z = torch.randn(n, d)
     z[: max(1, n // 100)] *= 4.0     # exercise the identity tails beyond +-5
+    with torch.no_grad():
+        x, logq = gen.forward_and_log_prob(z.cuda())
+        xr, lr = ref.forward_and_log_prob(z.double())
+        x32, l32 = ref32.forward_and_log_prob(z)
+    assert_parity(x, xr, x32)
+    assert_parity(logq, lr, l32)
+
+
+@pytest.mark.parametrize("d", [2, 4, 6])
+def test_benchmark_weights_tail_matches_reference_fp32(d, conditioner):
+    """The weights bench.py measures on (default init x3, seed 0), 1e5 particles: the tail beyond 1e-4
+    is no heavier than the reference's own fp32 evaluation."""
+    torch.manual_seed(0)
+    gen = mf.generate.NSFGenerator(d)
+    with torch.no_grad():
+        for p in gen.parameters():
+            p.mul_(3.0)
+    ref, ref32 = oracle_from_generator(gen), oracle_from_generator(gen, torch.float32)
+    gen = gen.to("cuda")
+    torch.manual_seed(5)
+    z = torch.randn(100_000, d)
     with torch.no_grad():
         x, logq = gen.forward_and_log_prob(z.cuda())
         xr, lr = ref.forward_and_log_prob(z.double())
