@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-chunks", type=int, default=3, help="pieces the pinned-host input is copied in (e2e leg)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations (C1, C3/25, C4, training steps)")
     return ap.parse_args()
 
 
@@ -179,6 +180,166 @@ def time_cpu(step, n, reps, warmup=1, budget_s=12.0):
     return n / min(ts), ts
 
 
+# ncu --set full capture of ONE nsf_tc_layer_kernel<6,3,20> launch of this workload (profiles/, this round)
+NCU_PROFILE = {}
+
+
+def shard_parity_check(model, reducer, gen, n, d, rank, world, device):
+    """N > 1: the sharded step against ONE GPU doing the union batch on the same particles, outside every timed
+    region.  Each rank pushes its own base noise through the flow; rank 0 gathers the particles of all ranks and
+    evaluates profiles and loss unsharded.  {max_rel_profile, rel_loss}; the run fails beyond 1e-5."""
+    import torch.distributed as dist
+
+    import mentflow_b200 as mf
+    with torch.no_grad():
+        z = gen.sample_base(n)
+        x, logq = gen.forward_and_log_prob(z)
+        preds = mf.simulate.forward(x, model.transforms, model.diagnostics, reducer=reducer)
+        prof = torch.stack([p[0] for p in preds])
+        L = model.loss_from_particles(x, logq)[0]
+        xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+        ls = [torch.empty_like(logq) for _ in range(world)] if rank == 0 else None
+        dist.gather(x, xs, dst=0)
+        dist.gather(logq, ls, dst=0)
+        out = None
+        if rank == 0:
+            x_all, l_all = torch.cat(xs), torch.cat(ls)
+            saved, saved_e = model.reducer, model.entropy_estimator.reducer
+            model.reducer = model.entropy_estimator.reducer = None
+            try:
+                preds_u = mf.simulate.forward(x_all, model.transforms, model.diagnostics)
+                prof_u = torch.stack([p[0] for p in preds_u])
+                L_u = model.loss_from_particles(x_all, l_all)[0]
+            finally:
+                model.reducer, model.entropy_estimator.reducer = saved, saved_e
+            rel_p = float(((prof - prof_u).abs().amax(dim=1) / prof_u.abs().amax(dim=1)).max())
+            rel_l = float((L - L_u).abs() / L_u.abs())
+            out = {"max_rel_profile": rel_p, "rel_loss": rel_l, "particles": int(x_all.shape[0]),
+                   "ok": bool(rel_p <= 1e-5 and rel_l <= 1e-5),
+                   "what": "sharded step (NCCL all-reduce of the unnormalised sums) vs the union batch on one GPU, same particles"}
+        dist.barrier()
+        torch.cuda.synchronize()
+    return out
+
+
+def _timed(fn, reps=5, warm=2, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def extras(args, device, pk):
+    """The other BASELINE configurations on one GPU, after (and outside) the headline measurement: each entry
+    is one forward step (or training step) through the public API, median of CUDA-event timings after warm-up,
+    256 MB L2 flush between repeats, with the roofline that bounds its dominant kernel."""
+    import math
+
+    import mentflow_b200 as mf
+    from mentflow_b200 import workloads
+    from mentflow_b200.graphs import GraphedLoss, GraphedTrainStep
+    N = args.particles
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+    out = []
+
+    def model_for(wl, d, kind, n_truth=200_000):
+        torch.manual_seed(0)
+        gen = mf.generate.NSFGenerator(d)
+        trained_like_(gen)
+        gen = gen.to(device)
+        tfs = [mf.simulate.LinearTransform(m.to(device)) for m in wl["matrices"]]
+        if kind == "1d":
+            diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(device)
+        else:
+            diag = mf.diagnostics.Histogram2D(axis=wl["axis"], edges=wl["edges"], bandwidth=(0.5, 0.5)).to(device)
+        diags = [[diag] for _ in tfs]
+        truth = workloads.gaussian_mixture(n_truth, ndim=d, seed=1, device=device)
+        with torch.no_grad():
+            meas = [[m[0].detach()] for m in mf.simulate.forward(truth, tfs, diags)]
+        prior = mf.prior.Gaussian(ndim=d, scale=3.0)
+        return mf.MENTFlow(transforms=tfs, diagnostics=diags, measurements=meas, generator=gen, prior=prior,
+                           entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                           discrepancy_function=mf.loss.kl_divergence, penalty_parameter=25.0)
+
+    def tensor_roof(flop_per_particle, n, ms, kernel):
+        a = flop_per_particle * n / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": kernel, "achieved": a, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": a / pk["bf16_tflops_sustained"], "traffic": None,
+                "note": "whole step time as divisor (kernel inside a step: sustained peak); mask-aware algorithmic FLOP"}
+
+    def entry(case, n, ms, roof, **kw):
+        out.append({"case": case, "particles_per_step": n, "ms_per_step": ms, "value": n / ms * 1e3, "unit": "particles/s",
+                    "roofline": roof, **kw})
+
+    # C1 rec_2d/linear: 2-D flow, 7 rotations, 85 bins
+    m1 = model_for(workloads.rotations_2d(7, 85, 3.5), 2, "1d")
+    g1 = GraphedLoss(m1, N)
+    ms = _timed(lambda: g1(None), flush=flush)
+    hbm_bytes = 5 * (2 * 2 * 4 + 8) + 2 * 4 + 2 * 2 * 4      # flow layers (v in, y out, log q) + draw + one read by entropy and KDE each
+    roof = tensor_roof(FLOP_MASK_AWARE[2], N, ms, "nsf_tc_layer_kernel<2,3,20> x5")
+    roof["hbm"] = {"bound": "hbm", "achieved": hbm_bytes * N / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": hbm_bytes * N / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_particle": hbm_bytes}
+    entry("C1 rec_2d/linear: 2-D NSF + 7 x KDE-1D(85) + KL, forward (graph replay, draw inside)", N, ms, roof)
+    del g1, m1
+    # C3 with 25 projections
+    m25 = model_for(workloads.isotropic_1d(6, 25, 64, 3.5), 6, "1d")
+    g25 = GraphedLoss(m25, N)
+    ms = _timed(lambda: g25(None), flush=flush)
+    entry("C3 rec_nd_1d, 25 projections: 6-D NSF + 25 x KDE-1D(64) + KL, forward (graph replay)", N, ms,
+          tensor_roof(FLOP_MASK_AWARE[6], N, ms, "nsf_tc_layer_kernel<6,3,20> x5"))
+    del g25, m25
+    # C3 at the reference's batch sizes (100 projections)
+    m3 = model_for(workloads.isotropic_1d(6, args.num_proj, args.bins, 3.5), 6, "1d")
+    for nb in (25_000, 100_000):
+        g3 = GraphedLoss(m3, nb)
+        ms = _timed(lambda: g3(None), reps=9, flush=flush)
+        entry(f"C3 rec_nd_1d, {args.num_proj} projections at the reference batch size, forward (graph replay)", nb, ms,
+              tensor_roof(FLOP_MASK_AWARE[6], nb, ms, "nsf_tc_layer_kernel<6,3,20> x5"))
+        del g3
+    # optimisation steps: zero_grad + loss + backward + AdamW as one graph replay
+    for nb in (25_000, N):
+        opt = torch.optim.AdamW(m3.parameters(), lr=1e-5, weight_decay=0.0, capturable=True, fused=True)
+        gts = GraphedTrainStep(m3, opt, nb)
+        ms = _timed(gts, reps=5, flush=flush)
+        entry("C3 optimisation step (zero_grad + loss + backward + fused AdamW) as one CUDA-graph replay", nb, ms,
+              tensor_roof(3 * FLOP_MASK_AWARE[6], nb, ms, "nsf_tc_layer_kernel<6,3,20,bwd> + dgrad + wgrad x5"))
+        del gts, opt
+    del m3
+    # C4 rec_nd_2d: 15 two-dimensional screens 85 x 85
+    m4 = model_for(workloads.corner_2d(6, 85, 3.5), 6, "2d", n_truth=100_000)
+    g4 = GraphedLoss(m4, N)
+    ms = _timed(lambda: g4(None), reps=3, warm=1, flush=flush)
+    with torch.no_grad():
+        x4 = m4.generator.forward(torch.randn(N, 6, device=device))
+        ms_scr = _timed(lambda: mf.simulate.forward(x4, m4.transforms, m4.diagnostics), reps=3, warm=1, flush=flush)
+    flop_scr = 15 * 2 * 85 * 85      # the screens as a GEMM: K_x^T K_y per screen, 2 * Bx * By per particle
+    entry("C4 rec_nd_2d: 6-D NSF + 15 x KDE-2D(85x85) + KL, forward (graph replay)", N, ms,
+          tensor_roof(FLOP_MASK_AWARE[6] + flop_scr, N, ms, "kde2d_tc_kernel + nsf_tc_layer_kernel<6,3,20> x5"),
+          screens_only_ms=ms_scr,
+          screens_roofline=tensor_roof(flop_scr, N, ms_scr, "kde2d_tc_kernel (tcgen05 split-bf16, accumulators in TMEM)"))
+    del g4
+
+    def train4():
+        for p_ in m4.parameters():
+            p_.grad = None
+        m4.loss(N)[0].backward()
+
+    ms = _timed(train4, reps=3, warm=1, flush=flush)
+    entry("C4 training step: forward + backward to all flow parameters (eager)", N, ms,
+          tensor_roof(3 * FLOP_MASK_AWARE[6] + 2 * flop_scr, N, ms, "nsf backward kernels + kde2d_bwd_kernel"))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 def run_reference(args, rank):
     if rank != 0:
@@ -245,7 +406,8 @@ def main():
     gen = model.generator
     n, d = args.particles, args.ndim
 
-    # inputs resident in HBM: a distinct base-noise block per rank
+    torch.cuda.manual_seed(1234 + rank)      # a distinct Philox stream per rank for the draws inside the step
+    # base noise resident in HBM / pinned host memory for the legs that are handed z (a distinct block per rank)
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     z_dev = torch.randn(n, d, generator=g, device=device)
     z_host = torch.empty(n, d, dtype=torch.float32).pin_memory()
@@ -341,9 +503,33 @@ def main():
         losses.append(L.clone())
     barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in marks)
-    # ---- end to end: z from pinned host memory, loss read back ----------------------------
+    # ---- end to end through the public API: model.loss(batch_size) as GraphedLoss(model, n)() -------
+    # The step's only host-side inputs are the batch size (a constant of the captured graph) and the state
+    # of torch's random generator.  Every step re-seeds the generator the way a reproducible training loop
+    # does (torch.cuda.manual_seed(step)), so the 16-byte (seed, offset) pair crosses from pinned host
+    # memory inside the timed region; the loss is read back to the host (4 bytes) every step.
+    def e2e_step(it):
+        torch.cuda.manual_seed(10_000 + 1_000_003 * rank + it)
+        if graphed is not None:
+            L = graphed(None)[0]
+        else:
+            L = step(gen.sample_base(n))
+        return float(L.item())
+
     e2e_s = 0.0
     for it in range(-2, args.steps):       # two untimed passes of this very loop first
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lval = e2e_step(it)
+        if it < 0:
+            continue
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    # ---- the same with the base noise handed over in pinned HOST memory (round-1 e2e leg): 24 B per
+    #      particle cross PCIe every step, copied in pieces that overlap the flow layers
+    host_s = 0.0
+    for it in range(-2, args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -355,9 +541,7 @@ def main():
         lval = float(L.item())
         if it < 0:
             continue
-        e2e_s += time.perf_counter() - t0
-        if os.environ.get("MFB_BENCH_DEBUG"):
-            print(f"e2e iter {time.perf_counter() - t0:.6f} s", file=sys.stderr)
+        host_s += time.perf_counter() - t0
     barrier()
     # ---- training step (forward + backward), reported beside the headline ----------------------
     tsteps = max(2, args.steps // 4)
@@ -375,10 +559,12 @@ def main():
     barrier()
     clocks = sampler.finish()
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=device)
+    shard_parity = shard_parity_check(model, reducer, gen, n, d, rank, world, device) if world > 1 else None
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms, host_s * 1e3], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_ms, train_ms, host_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     value = n * world * args.steps / (total_ms * 1e-3)
     e2e_value = n * world * args.steps / (e2e_ms * 1e-3)
 
@@ -394,7 +580,11 @@ def main():
                       f"nsf_layer_fwd_kernel<{d}> x{layers} (fp32 CUDA-core kernel)")
         # the operand images are cached while the weights do not change: no prepare kernel in a forward-only step
         nsf_launches = {"nsf_tc_layer_kernel": layers} if tc else {"nsf_layer_fwd_kernel": layers}
+        rest = {"randn_philox + advance": 2, "moments": 2, "kde1d deposit + merge/normalise/KL": 2}
+        if world > 1:
+            rest["f64 split/join (packed all-reduce)"] = 2
         pieces = len(graphed._chunk_bounds()) if graphed is not None else 1
+        prof = NCU_PROFILE if (tc and d == 6 and n == 1_000_000) else {}
         line = {
             "metric": "particles/sec/GPU for flow sample+log_prob+project+KDE (6D, 100 proj)",
             "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -402,50 +592,68 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"rec_nd_1d C3: D={d}, K={args.num_proj} random 1-D projections, B={args.bins}, "
                                    f"NSF 5 layers x MaskedMLP[{d},64,64,64,{59 * d}] 20-bin RQ spline, forward "
-                                   f"(sample+log_prob+entropy+project+KDE+KL loss)",
+                                   f"(base-noise draw + sample + log_prob + entropy + project + KDE + KL loss)",
                        "particles_per_gpu_per_step": n, "parallelism": f"particles sharded x{world}",
                        "l2": "256 MB flush write between timed iterations",
-                       "launch": ("CUDA graph replay of the forward step (mentflow_b200.graphs.GraphedLoss)"
-                                  if use_graph else "eager launches"),
+                       "launch": ("CUDA graph replay of the forward step, base-noise draw (Philox) inside the graph "
+                                  "(mentflow_b200.graphs.GraphedLoss)" if use_graph else "eager launches"),
                        "weights": "default init x3 (trained-like), seed 0", "value_per_gpu": value / world},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": n * d * 4,
+            "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": 16,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": ("GraphedLoss(model, n)(z_pinned_host): H2D copy + graph replay of generator.forward_and_log_prob "
-                            "+ MENTFlow.loss_from_particles; loss.item()" if use_graph else
-                            "generator.forward_and_log_prob(z_from_pinned_host) + entropy + simulate.forward + KL; loss.item()")},
+                    "api": ("torch.cuda.manual_seed(step); GraphedLoss(model, n)() [= model.loss(n): the base noise is drawn "
+                            "on the device from torch's generator state, 16 B (seed, offset) from pinned host memory]; "
+                            "loss.item()" if use_graph else
+                            "torch.cuda.manual_seed(step); model.loss(n) eager; loss.item()")},
+            # round-1 definition of the e2e leg, kept for comparison: z handed over in pinned host memory
+            "e2e_host_z": {"value": n * world * args.steps / (host_ms * 1e-3), "unit": "particles/s",
+                           "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": 4, "ms_per_step": host_ms / args.steps,
+                           "api": "GraphedLoss(model, n)(z_pinned_host): chunked H2D copies overlapped with the flow; loss.item()"},
             # this library's kernels inside the timed region of `value` (one graph replay per step holds them all)
-            "gpu_launches": args.steps * (sum(nsf_launches.values()) + 2 + 2),
-            "gpu_launches_per_step": {**nsf_launches, "moments": 2, "kde1d deposit + merge/normalise/KL": 2},
-            # the e2e step runs the flow once per piece of the pinned-host input (copy / compute overlap)
-            "gpu_launches_per_e2e_step": {**{k: v * pieces for k, v in nsf_launches.items()}, "moments": 2,
-                                          "kde1d deposit + merge/normalise/KL": 2},
+            "gpu_launches": args.steps * (sum(nsf_launches.values()) + sum(rest.values())),
+            "gpu_launches_per_step": {**nsf_launches, **rest},
+            "gpu_launches_per_e2e_host_z_step": {**{k: v * pieces for k, v in nsf_launches.items()}, "moments": 2,
+                                                 "kde1d deposit + merge/normalise/KL": 2},
             "roofline": {"bound": "tensor", "kernel": nsf_kernel,
-                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_tflops_sustained"],
-                         # ncu --set full of one layer launch at this workload (profiles/r1c_full_metrics.txt):
-                         # dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic 56 B/particle is read z +
-                         # log q in, write y + log q out (the writes are still in L2 when the launch ends)
-                         "traffic": 28.3e6 if (tc and d == 6 and n == 1_000_000) else None,
+                         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_tflops"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one layer launch at this workload, from
+                         # the ncu --set full capture named in `profile`
+                         "traffic": prof.get("dram_bytes_per_launch"),
                          "traffic_unit": "bytes per layer launch (ncu)",
-                         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
+                         "peak_source": pk["source"] + " bf16 burst (the five layer launches are timed by CUDA events "
+                                                       "around eager launches, i.e. alone)",
+                         "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                          "algorithmic_flop_per_particle": FLOP_MASK_AWARE.get(d), "dense_equivalent_flop": FLOP_DENSE.get(d),
                          "kernel_ms_per_step": nsf_step_ms, "share_of_step": nsf_step_ms / (total_ms / args.steps),
                          "entropy_project_kde_loss_ms_per_step": statistics.mean(kde_ms),
-                         "hbm_gbs_nsf": (n * (2 * d * 4 + 8) * layers) / (nsf_step_ms * 1e-3) / 1e9},
+                         "hbm_gbs_nsf": (n * (2 * d * 4 + 8) * layers) / (nsf_step_ms * 1e-3) / 1e9,
+                         # the kernel is bound by instruction issue and the MUFU pipe, not by the tensor pipe: the
+                         # pipe fractions ncu reports for the same launch (profile named below)
+                         "pipe_fractions_ncu": prof.get("pipes"), "profile": prof.get("file")},
             "loss": float(losses[-1]),
             "train_step": {"value": n * world * tsteps / (train_ms * 1e-3), "unit": "particles/s",
                            "ms_per_step": train_ms / tsteps, "steps": tsteps,
                            "what": "loss forward + hand-written backward to all flow parameters"
                                    + (" + gradient all-reduce" if world > 1 else "")},
         }
+        if shard_parity is not None:
+            line["shard_parity"] = shard_parity
         if world == 1 and not args.no_cpu_baseline:
             stepf, ncpu = cpu_step_factory(args)
             v, ts = time_cpu(stepf, ncpu, reps=5)
             line["cpu_baseline"] = {"value": v, "unit": "particles/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{ncpu} particles per step, best of {len(ts)} after 1 warm-up "
+                                    "sample": f"{ncpu} particles per step (the reference's batch size; NOT the GPU arm's "
+                                              f"{n}: the dense (N, B) temporaries of the reference formulation need tens of "
+                                              f"GB there), best of {len(ts)} after 1 warm-up "
                                               f"({sum(ts):.1f} s of CPU work); flow = oracle restatement of zuko NSF"}
+        if world == 1 and not args.no_extra:
+            del graphed
+            line["extra"] = extras(args, device, pk)
         print(json.dumps(line), flush=True)
+        if shard_parity is not None and not shard_parity["ok"]:
+            print("shard parity violated: " + json.dumps(shard_parity), file=sys.stderr, flush=True)
+            os._exit(3)
     if world > 1:
         # captured graphs hold NCCL work: drop them before the communicator goes away, and leave without
         # the (blocking) communicator teardown -- every rank is past its last collective here

@@ -216,6 +216,11 @@ int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, i
 int64_t mfb_moments_workspace_bytes(int64_t n, int d);
 int mfb_moments(const float* x, const float* logq, int64_t n, int d, int with_cov, double* out,
                 void* workspace, int64_t workspace_bytes, void* stream);
+/* Multi-GPU plumbing of the entropy sums (ONE packed all-reduce per forward step): n doubles
+ * <-> 2n floats (hi[0..n), lo[0..n)), hi + lo = value to 2^-48, so that they can ride at the tail of the
+ * float32 all-reduce of the profile sums; the two halves are summed over ranks separately.            */
+int mfb_f64_split(const double* in, int n, float* out_hi_lo, void* stream);
+int mfb_f64_join(const float* in_hi_lo, int n, double* out, void* stream);
 
 /* ---- classical MENT (ment.py, sample.py) --------------------------------------------------
  * rho(x) = exp(log prior(x)) * prod_k clamp(h_k(proj_k . x), 0, 1e10); h_k = linear interpolation
@@ -240,6 +245,28 @@ int mfb_ment_integrate(int d, const float* meas_coords, int nb_meas, int meas_ax
                        const float* int_step_host, const float* minv, const float* proj,
                        const float* coords, const float* tables, int k, int b,
                        float prior_neg_half_inv_s2, float prior_log_norm, float* pred, void* stream);
+/* The same three entry points with two-dimensional screens as well (ment.py:36-49: LagrangeFunction over an N-D
+ * RegularGridInterpolator; experiments/config/rec_nd_2d_ment.yaml): k2 tables tables2[k2][bx][by] on the bin-centre
+ * grids cx2[k2][bx] x cy2[k2][by], bilinear, zero outside the box of the centres, evaluated in double like scipy;
+ * proj2[k2][2][d] are the two measured rows of each transfer matrix.  rho = prior * prod(1-D tables) * prod(2-D
+ * tables); either family may be empty (k = 0 / k2 = 0).  _integrate_nd: meas_axis2 >= 0 selects a 2-D screen
+ * (pred[nb_meas][nb_meas2], integration over the other d-2 axes), meas_axis2 = -1 a 1-D one.              */
+int mfb_ment_prob_nd(const float* x, int64_t g, int d, const float* proj, const float* coords, const float* tables,
+                     int k, int b, const float* proj2, const float* cx2, const float* cy2, const float* tables2,
+                     int k2, int bx, int by, float prior_neg_half_inv_s2, float prior_log_norm, float* out,
+                     void* stream);
+int mfb_ment_prob_grid_nd(int d, const int32_t* shape_host, const float* first_centre_host, const float* step_host,
+                          const float* proj, const float* coords, const float* tables, int k, int b,
+                          const float* proj2, const float* cx2, const float* cy2, const float* tables2, int k2,
+                          int bx, int by, float prior_neg_half_inv_s2, float prior_log_norm, float* out,
+                          void* stream);
+int mfb_ment_integrate_nd(int d, const float* meas_coords, int nb_meas, int meas_axis, const float* meas_coords2,
+                          int nb_meas2, int meas_axis2, int n_int_axes, const int32_t* int_shape_host,
+                          const float* int_first_host, const float* int_step_host, const float* minv,
+                          const float* proj, const float* coords, const float* tables, int k, int b,
+                          const float* proj2, const float* cx2, const float* cy2, const float* tables2, int k2,
+                          int bx, int by, float prior_neg_half_inv_s2, float prior_log_norm, float* pred,
+                          void* stream);
 /* sample.py:27-57: cdf of (rho + pad) over the cells in double, then `size` draws: cell by
  * inverse-CDF search with a Philox4x32-10 stream (seed, offset), uniform position inside the
  * cell (+ 0.5*U(-delta,delta) when jitter != 0).  workspace[0] (device double) = total mass. */

@@ -57,6 +57,12 @@ SIGNATURES = {
     "mfb_ment_prob_grid": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_integrate": (c_int, [c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float,
                                    c_float, P, P]),
+    "mfb_ment_prob_nd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, c_float,
+                                 c_float, P, P]),
+    "mfb_ment_prob_grid_nd": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, c_float,
+                                      c_float, P, P]),
+    "mfb_ment_integrate_nd": (c_int, [c_int, P, c_int, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int,
+                                      P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P]),
     "mfb_randn_offset_increment": (c_int64, [c_int64]),
     "mfb_randn_philox": (c_int, [P, c_int64, c_uint64, c_uint64, P]),
     "mfb_randn_philox_state": (c_int, [P, c_int64, P, c_int, P]),
@@ -68,6 +74,8 @@ SIGNATURES = {
     "mfb_selftest_umma_sw32": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "mfb_moments_workspace_bytes": (c_int64, [c_int64, c_int]),
     "mfb_moments": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
+    "mfb_f64_split": (c_int, [P, c_int, P, P]),
+    "mfb_f64_join": (c_int, [P, c_int, P, P]),
 }
 
 _lib = None

@@ -69,7 +69,8 @@ class MENTFlow(nn.Module):
         fn = table.get(self.discrepancy_function)
         if fn is None or not stacked or sum(len(e[0]) for e in stacked) != n_slots:
             return None
-        key = tuple(id(m) for row in self.measurements for m in row)
+        held = [m for row in self.measurements for m in row]
+        key = tuple((id(m), getattr(m, "_version", 0)) for m in held)
         if self._BATCHED is None or self._BATCHED[0] != key:
             offsets, base = [], 0
             for row in self.measurements:
@@ -80,7 +81,7 @@ class MENTFlow(nn.Module):
                 meas = torch.stack([self.measurements[i][j] for i, j in slots]).to(prof.device)
                 index = torch.tensor([offsets[i] + j for i, j in slots], device=prof.device)
                 groups.append((meas, index))
-            self._BATCHED = (key, groups)
+            self._BATCHED = (key, groups, held)   # `held` keeps the ids in the key owned by these tensors
         out = None
         for (slots, prof, *fused), (meas, index) in zip(stacked, self._BATCHED[1]):
             # one-dimensional KDE screens arrive with their KL already evaluated by the kernel
@@ -94,12 +95,19 @@ class MENTFlow(nn.Module):
 
     def loss_from_particles(self, x: torch.Tensor, log_prob: torch.Tensor):
         """The part of ``loss`` after sampling (used by parity tests that fix the particles)."""
-        H = self.entropy_estimator(x, log_prob)
+        est = self.entropy_estimator
+        # sharded particles: the entropy's two moment sums are stashed on the reducer and travel at the tail
+        # of the all-reduce of the profile sums -- one collective on the critical path instead of two
+        pending = est.begin(x, log_prob) if (self.reducer is not None and hasattr(est, "begin")) else None
+        if pending is None:
+            H = est(x, log_prob)
         stacked = []
         from . import loss as _loss
         targets = self.measurements if self.discrepancy_function is _loss.kl_divergence else None
         predictions = simulate_forward(x, self.transforms, self.diagnostics, reducer=self.reducer, stacked=stacked,
                                        kl_targets=targets)
+        if pending is not None:
+            H = est.finish(pending)
         n_slots = sum(len(row) for row in predictions)
         dvec = self._batched_discrepancy(stacked, n_slots)
         if dvec is not None:

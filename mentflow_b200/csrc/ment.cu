@@ -42,6 +42,58 @@ __device__ __forceinline__ float lagrange_eval(const float* __restrict__ c, cons
   return (float)((double)h[i] * (1.0 - w) + (double)h[i + 1] * w);
 }
 
+// Lagrange functions of two-dimensional screens (ment.py:36-49: N-D RegularGridInterpolator): K2 tables of
+// Bx x By values on the bin-centre grid of each screen, bilinear in between, zero outside the box of the
+// centres.  They stay in global memory (85 x 85 floats per screen: L1 / L2 resident), four reads per point.
+struct Tables2D {
+  int k, bx, by;
+  const float* proj;    // [k][2][D]  rows of the transfer matrix that land on the screen's two axes
+  const float* cx;      // [k][bx]    bin centres, first axis
+  const float* cy;      // [k][by]
+  const float* tab;     // [k][bx][by]
+};
+
+// interval index and normalised distance on one axis (scipy find_indices: searchsorted - 1, clipped)
+__device__ __forceinline__ bool axis_locate(const float* __restrict__ c, int B, float u, int& i, double& w) {
+  if (!(u >= c[0] && u <= c[B - 1])) return false;
+  const float inv = (float)(B - 1) / (c[B - 1] - c[0]);
+  i = (int)((u - c[0]) * inv);
+  i = min(max(i, 0), B - 2);
+  while (i > 0 && u < c[i]) --i;
+  while (i < B - 2 && u > c[i + 1]) ++i;
+  const double x0 = (double)c[i], x1 = (double)c[i + 1];
+  w = ((double)u - x0) / (x1 - x0);
+  return true;
+}
+
+template <int D>
+__device__ __forceinline__ float tables2d_product(const float (&x)[D], const Tables2D& t2) {
+  float prob = 1.0f;
+  for (int k = 0; k < t2.k; ++k) {
+    const float* pr = t2.proj + (size_t)k * 2 * D;
+    float ux = 0.f, uy = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      ux = fmaf(__ldg(pr + i), x[i], ux);
+      uy = fmaf(__ldg(pr + D + i), x[i], uy);
+    }
+    int ix, iy;
+    double wx, wy;
+    float h = 0.f;
+    if (axis_locate(t2.cx + (size_t)k * t2.bx, t2.bx, ux, ix, wx) &&
+        axis_locate(t2.cy + (size_t)k * t2.by, t2.by, uy, iy, wy)) {
+      const float* tb = t2.tab + ((size_t)k * t2.bx + ix) * t2.by + iy;
+      const double v00 = (double)__ldg(tb), v01 = (double)__ldg(tb + 1);
+      const double v10 = (double)__ldg(tb + t2.by), v11 = (double)__ldg(tb + t2.by + 1);
+      h = (float)(v00 * (1.0 - wx) * (1.0 - wy) + v01 * (1.0 - wx) * wy + v10 * wx * (1.0 - wy) + v11 * wx * wy);
+    }
+    h = fminf(fmaxf(h, 0.0f), 1.0e10f);   // ment.py:246
+    prob *= h;
+    if (prob == 0.f) break;               // every remaining factor is finite (clamped): the product stays 0
+  }
+  return prob;
+}
+
 template <int D>
 __device__ __forceinline__ float ment_density(const float (&x)[D], const float* __restrict__ s_proj,
                                               const float* __restrict__ s_c, const float* __restrict__ s_h,
@@ -78,7 +130,7 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(kMentThreads)
 ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const float* __restrict__ proj,
                  const float* __restrict__ coords, const float* __restrict__ tables, int K, int B,
-                 MentPrior prior, float* __restrict__ out) {
+                 MentPrior prior, const Tables2D t2, float* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
   float* s_proj = sm;
   float* s_c = s_proj + (((size_t)K * D + 3) & ~(size_t)3);
@@ -100,7 +152,9 @@ ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const fl
         xr[i] = fmaf((float)idx, grid.step[i], grid.lo[i]);
       }
     }
-    out[g] = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    if (t2.k > 0) rho *= tables2d_product<D>(xr, t2);
+    out[g] = rho;
   }
 }
 
@@ -108,10 +162,11 @@ ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const fl
 // one CTA per measured pixel, deterministic block reduction
 template <int D>
 __global__ void __launch_bounds__(kMentThreads)
-ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int meas_axis, MentGrid igrid,
+ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int meas_axis,
+                      const float* __restrict__ meas_coords2, int nb_meas2, int meas_axis2, MentGrid igrid,
                       const float* __restrict__ minv /* [D][D] */, const float* __restrict__ proj,
                       const float* __restrict__ coords, const float* __restrict__ tables, int K, int B,
-                      MentPrior prior, float* __restrict__ pred) {
+                      MentPrior prior, const Tables2D t2, float* __restrict__ pred) {
   extern __shared__ __align__(16) float sm[];
   float* s_proj = sm;
   float* s_c = s_proj + (((size_t)K * D + 3) & ~(size_t)3);
@@ -124,8 +179,10 @@ ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int me
   __syncthreads();
   int64_t Q = 1;
   for (int i = 0; i < igrid.ndim; ++i) Q *= igrid.shape[i];
+  // pixel of the screen: b (1-D) or (b / nb_meas2, b % nb_meas2) (2-D, meas_axis2 >= 0)
   const int b = blockIdx.x;
-  const float cm = meas_coords[b];
+  const float cm = meas_coords[meas_axis2 >= 0 ? b / nb_meas2 : b];
+  const float cm2 = meas_axis2 >= 0 ? meas_coords2[b % nb_meas2] : 0.f;
   float acc = 0.f;  // the reference sums fp32 densities with torch.sum
   double dacc = 0.0;
   for (int64_t q = threadIdx.x; q < Q; q += kMentThreads) {
@@ -136,6 +193,8 @@ ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int me
     for (int i = D - 1; i >= 0; --i) {
       if (i == meas_axis) {
         u[i] = cm;
+      } else if (i == meas_axis2) {
+        u[i] = cm2;
       } else {
         const int idx = (int)(rem % igrid.shape[ia]);
         rem /= igrid.shape[ia];
@@ -151,7 +210,9 @@ ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int me
       for (int j = 0; j < D; ++j) s = fmaf(u[j], s_minv[i * D + j], s);
       xr[i] = s;
     }
-    dacc += (double)ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    if (t2.k > 0) rho *= tables2d_product<D>(xr, t2);
+    dacc += (double)rho;
   }
   (void)acc;
   dacc = warp_sum(dacc);
@@ -315,7 +376,7 @@ static MentGrid make_grid(int ndim, const int32_t* shape, const float* lo, const
 template <int D>
 static int launch_prob(int mode, const float* x, int64_t G, const MentGrid& grid, const float* proj,
                        const float* coords, const float* tables, int K, int B, MentPrior prior, float* out,
-                       cudaStream_t st) {
+                       cudaStream_t st, const Tables2D& t2 = Tables2D{0, 0, 0, nullptr, nullptr, nullptr, nullptr}) {
   const size_t smem = ment_smem(K, B, D);
   if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
   int64_t blocks = (G + kMentThreads - 1) / kMentThreads;
@@ -323,11 +384,30 @@ static int launch_prob(int mode, const float* x, int64_t G, const MentGrid& grid
   const int gridx = (int)(blocks < cap ? blocks : cap);
   if (mode == 0) {
     MFB_CUDA(cudaFuncSetAttribute(ment_prob_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ment_prob_kernel<D, 0><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, out);
+    ment_prob_kernel<D, 0><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, t2, out);
   } else {
     MFB_CUDA(cudaFuncSetAttribute(ment_prob_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ment_prob_kernel<D, 1><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, out);
+    ment_prob_kernel<D, 1><<<gridx, kMentThreads, smem, st>>>(x, G, grid, proj, coords, tables, K, B, prior, t2, out);
   }
+  return launch_status();
+}
+
+static int check_tables2d(const Tables2D& t2) {
+  if (t2.k < 0) return MFB_E_BADARG;
+  if (t2.k > 0 && !(t2.proj && t2.cx && t2.cy && t2.tab && t2.bx >= 2 && t2.by >= 2)) return MFB_E_BADARG;
+  return 0;
+}
+
+template <int D>
+static int launch_integrate(const float* mc, int nb, int ax, const float* mc2, int nb2, int ax2, const MentGrid& grid,
+                            const float* minv, const float* proj, const float* coords, const float* tables, int k, int b,
+                            MentPrior pr, const Tables2D& t2, float* pred, cudaStream_t st) {
+  const size_t smem = ment_smem(k, b, D);
+  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
+  MFB_CUDA(cudaFuncSetAttribute(ment_integrate_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int pixels = ax2 >= 0 ? nb * nb2 : nb;
+  ment_integrate_kernel<D><<<pixels, kMentThreads, smem, st>>>(mc, nb, ax, mc2, nb2, ax2, grid, minv, proj, coords, tables,
+                                                              k, b, pr, t2, pred);
   return launch_status();
 }
 
@@ -337,30 +417,52 @@ using namespace mfb;
 
 extern "C" {
 
-int mfb_ment_prob(const float* x, int64_t g, int d, const float* proj, const float* coords, const float* tables,
-                  int k, int b, float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
-  MFB_CHECK_ARG(x && proj && coords && tables && out && g >= 0 && k >= 0 && b >= 2 && d >= 1 && d <= kMaxDim);
+#define MFB_DISPATCH_D(d, CALL)          \
+  switch (d) {                           \
+    case 1: return CALL(1);              \
+    case 2: return CALL(2);              \
+    case 3: return CALL(3);              \
+    case 4: return CALL(4);              \
+    case 5: return CALL(5);              \
+    case 6: return CALL(6);              \
+    case 7: return CALL(7);              \
+    default: return CALL(8);             \
+  }
+
+int mfb_ment_prob_nd(const float* x, int64_t g, int d, const float* proj, const float* coords, const float* tables,
+                     int k, int b, const float* proj2, const float* cx2, const float* cy2, const float* tables2, int k2,
+                     int bx, int by, float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(x && out && g >= 0 && k >= 0 && d >= 1 && d <= kMaxDim);
+  MFB_CHECK_ARG(k == 0 || (proj && coords && tables && b >= 2));
+  const Tables2D t2{k2, bx, by, proj2, cx2, cy2, tables2};
+  if (check_tables2d(t2)) return MFB_E_BADARG;
   if (g == 0) return 0;
+  if (k == 0) b = 2;
   MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
   MentGrid grid = make_grid(0, nullptr, nullptr, nullptr);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (d) {
-    case 1: return launch_prob<1>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 2: return launch_prob<2>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 3: return launch_prob<3>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 4: return launch_prob<4>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 5: return launch_prob<5>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 6: return launch_prob<6>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 7: return launch_prob<7>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-    default: return launch_prob<8>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st);
-  }
+#define MFB_CALL(DD) launch_prob<DD>(0, x, g, grid, proj, coords, tables, k, b, pr, out, st, t2)
+  MFB_DISPATCH_D(d, MFB_CALL)
+#undef MFB_CALL
 }
 
-int mfb_ment_prob_grid(int d, const int32_t* shape_host, const float* first_centre_host, const float* step_host,
-                       const float* proj, const float* coords, const float* tables, int k, int b,
-                       float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
-  MFB_CHECK_ARG(shape_host && first_centre_host && step_host && proj && coords && tables && out);
-  MFB_CHECK_ARG(k >= 0 && b >= 2 && d >= 1 && d <= kMaxDim);
+int mfb_ment_prob(const float* x, int64_t g, int d, const float* proj, const float* coords, const float* tables,
+                  int k, int b, float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(proj && coords && tables && b >= 2);
+  return mfb_ment_prob_nd(x, g, d, proj, coords, tables, k, b, nullptr, nullptr, nullptr, nullptr, 0, 0, 0,
+                          prior_neg_half_inv_s2, prior_log_norm, out, stream);
+}
+
+int mfb_ment_prob_grid_nd(int d, const int32_t* shape_host, const float* first_centre_host, const float* step_host,
+                          const float* proj, const float* coords, const float* tables, int k, int b,
+                          const float* proj2, const float* cx2, const float* cy2, const float* tables2, int k2, int bx,
+                          int by, float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(shape_host && first_centre_host && step_host && out);
+  MFB_CHECK_ARG(k >= 0 && d >= 1 && d <= kMaxDim);
+  MFB_CHECK_ARG(k == 0 || (proj && coords && tables && b >= 2));
+  const Tables2D t2{k2, bx, by, proj2, cx2, cy2, tables2};
+  if (check_tables2d(t2)) return MFB_E_BADARG;
+  if (k == 0) b = 2;
   int64_t g = 1;
   for (int i = 0; i < d; ++i) {
     MFB_CHECK_ARG(shape_host[i] >= 1);
@@ -369,47 +471,60 @@ int mfb_ment_prob_grid(int d, const int32_t* shape_host, const float* first_cent
   MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
   MentGrid grid = make_grid(d, shape_host, first_centre_host, step_host);
   cudaStream_t st = (cudaStream_t)stream;
+#define MFB_CALL(DD) launch_prob<DD>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st, t2)
+  MFB_DISPATCH_D(d, MFB_CALL)
+#undef MFB_CALL
+}
+
+int mfb_ment_prob_grid(int d, const int32_t* shape_host, const float* first_centre_host, const float* step_host,
+                       const float* proj, const float* coords, const float* tables, int k, int b,
+                       float prior_neg_half_inv_s2, float prior_log_norm, float* out, void* stream) {
+  MFB_CHECK_ARG(proj && coords && tables && b >= 2);
+  return mfb_ment_prob_grid_nd(d, shape_host, first_centre_host, step_host, proj, coords, tables, k, b, nullptr, nullptr,
+                               nullptr, nullptr, 0, 0, 0, prior_neg_half_inv_s2, prior_log_norm, out, stream);
+}
+
+int mfb_ment_integrate_nd(int d, const float* meas_coords, int nb_meas, int meas_axis, const float* meas_coords2,
+                          int nb_meas2, int meas_axis2, int n_int_axes, const int32_t* int_shape_host,
+                          const float* int_first_host, const float* int_step_host, const float* minv, const float* proj,
+                          const float* coords, const float* tables, int k, int b, const float* proj2, const float* cx2,
+                          const float* cy2, const float* tables2, int k2, int bx, int by, float prior_neg_half_inv_s2,
+                          float prior_log_norm, float* pred, void* stream) {
+  MFB_CHECK_ARG(meas_coords && minv && pred && int_shape_host && int_first_host && int_step_host);
+  MFB_CHECK_ARG(k >= 0 && (k == 0 || (proj && coords && tables && b >= 2)));
+  const int n_meas = meas_axis2 >= 0 ? 2 : 1;
+  MFB_CHECK_ARG(d >= 2 && d <= kMaxDim && n_int_axes == d - n_meas && n_int_axes >= 1);
+  MFB_CHECK_ARG(meas_axis >= 0 && meas_axis < d && nb_meas >= 1 && meas_axis2 < d && meas_axis2 != meas_axis);
+  MFB_CHECK_ARG(meas_axis2 < 0 || (meas_coords2 && nb_meas2 >= 1));
+  const Tables2D t2{k2, bx, by, proj2, cx2, cy2, tables2};
+  if (check_tables2d(t2)) return MFB_E_BADARG;
+  if (k == 0) b = 2;
+  MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
+  MentGrid grid = make_grid(n_int_axes, int_shape_host, int_first_host, int_step_host);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MFB_CALL(DD)                                                                                                    \
+  launch_integrate<DD>(meas_coords, nb_meas, meas_axis, meas_coords2, nb_meas2, meas_axis2, grid, minv, proj, coords, \
+                       tables, k, b, pr, t2, pred, st)
   switch (d) {
-    case 1: return launch_prob<1>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 2: return launch_prob<2>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 3: return launch_prob<3>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 4: return launch_prob<4>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 5: return launch_prob<5>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 6: return launch_prob<6>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    case 7: return launch_prob<7>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
-    default: return launch_prob<8>(1, nullptr, g, grid, proj, coords, tables, k, b, pr, out, st);
+    case 2: return MFB_CALL(2);
+    case 3: return MFB_CALL(3);
+    case 4: return MFB_CALL(4);
+    case 5: return MFB_CALL(5);
+    case 6: return MFB_CALL(6);
+    case 7: return MFB_CALL(7);
+    default: return MFB_CALL(8);
   }
+#undef MFB_CALL
 }
 
 int mfb_ment_integrate(int d, const float* meas_coords, int nb_meas, int meas_axis, int n_int_axes,
                        const int32_t* int_shape_host, const float* int_first_host, const float* int_step_host,
                        const float* minv, const float* proj, const float* coords, const float* tables, int k,
                        int b, float prior_neg_half_inv_s2, float prior_log_norm, float* pred, void* stream) {
-  MFB_CHECK_ARG(meas_coords && minv && proj && coords && tables && pred && int_shape_host && int_first_host &&
-                int_step_host);
-  MFB_CHECK_ARG(d >= 2 && d <= kMaxDim && n_int_axes == d - 1 && meas_axis >= 0 && meas_axis < d && nb_meas >= 1);
-  MentPrior pr{prior_neg_half_inv_s2, prior_log_norm};
-  MentGrid grid = make_grid(n_int_axes, int_shape_host, int_first_host, int_step_host);
-  const size_t smem = ment_smem(k, b, d);
-  if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
-#define MFB_INT(DD)                                                                                                \
-  {                                                                                                                \
-    MFB_CUDA(cudaFuncSetAttribute(ment_integrate_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ment_integrate_kernel<DD><<<nb_meas, kMentThreads, smem, st>>>(meas_coords, nb_meas, meas_axis, grid, minv, proj, \
-                                                                  coords, tables, k, b, pr, pred);                 \
-  }
-  switch (d) {
-    case 2: MFB_INT(2) break;
-    case 3: MFB_INT(3) break;
-    case 4: MFB_INT(4) break;
-    case 5: MFB_INT(5) break;
-    case 6: MFB_INT(6) break;
-    case 7: MFB_INT(7) break;
-    default: MFB_INT(8) break;
-  }
-#undef MFB_INT
-  return launch_status();
+  MFB_CHECK_ARG(proj && coords && tables && b >= 2);
+  return mfb_ment_integrate_nd(d, meas_coords, nb_meas, meas_axis, nullptr, 0, -1, n_int_axes, int_shape_host,
+                               int_first_host, int_step_host, minv, proj, coords, tables, k, b, nullptr, nullptr,
+                               nullptr, nullptr, 0, 0, 0, prior_neg_half_inv_s2, prior_log_norm, pred, stream);
 }
 
 int64_t mfb_cdf_workspace_bytes(int64_t g) {

@@ -81,11 +81,38 @@ static int launch_moments(const float* x, const float* logq, int64_t n, int cov,
   return launch_status();
 }
 
+// double <-> (hi, lo) float pairs: lets a few double partial sums ride at the tail of a float32 all-reduce
+// (out[i] = hi, out[n + i] = lo; hi + lo = in to 2^-48, and sums of hi and of lo over ranks are formed separately)
+__global__ void f64_split_kernel(const double* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float hi = (float)in[i];
+    out[i] = hi;
+    out[n + i] = (float)(in[i] - (double)hi);
+  }
+}
+__global__ void f64_join_kernel(const float* __restrict__ in, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i] + (double)in[n + i];
+}
+
 }  // namespace mfb
 
 using namespace mfb;
 
 extern "C" {
+
+int mfb_f64_split(const double* in, int n, float* out_hi_lo, void* stream) {
+  MFB_CHECK_ARG(in && out_hi_lo && n >= 1);
+  f64_split_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, n, out_hi_lo);
+  return launch_status();
+}
+
+int mfb_f64_join(const float* in_hi_lo, int n, double* out, void* stream) {
+  MFB_CHECK_ARG(in_hi_lo && out && n >= 1);
+  f64_join_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in_hi_lo, n, out);
+  return launch_status();
+}
 
 int64_t mfb_moments_workspace_bytes(int64_t n, int d) {
   if (d < 1 || d > kMaxDim) return 0;

@@ -105,10 +105,11 @@ class Histogram1D(Histogram):
 
     def geometry(self) -> Tuple[float, float, float, float]:
         """(c0, spacing, sigma, delta): one geometry record of the C ABI."""
-        if self._geom is None:
+        key = (self.edges.data_ptr(), self.edges._version, self.bandwidth.data_ptr(), self.bandwidth._version)
+        if self._geom is None or self._geom[0] != key:     # recomputed when the public buffers change
             c0, spacing, delta = _uniform_geometry(self.edges, "Histogram1D")
-            self._geom = (c0, spacing, float(self.bandwidth.detach().cpu()), delta)
-        return self._geom
+            self._geom = (key, (c0, spacing, float(self.bandwidth.detach().cpu()), delta))
+        return self._geom[1]
 
     def projection_vector(self, matrix: Optional[torch.Tensor], ndim: int, device) -> torch.Tensor:
         """Row vector w with x_proj = x . w for particles x *before* the linear map M:
@@ -172,12 +173,13 @@ class Histogram2D(Histogram):
         return (self.edges_x.shape[0] - 1, self.edges_y.shape[0] - 1)
 
     def geometry(self):
-        if self._geom is None:
+        key = tuple((t.data_ptr(), t._version) for t in (self.edges_x, self.edges_y, self.bandwidth_x, self.bandwidth_y))
+        if self._geom is None or self._geom[0] != key:     # recomputed when the public buffers change
             cx, sx, dx = _uniform_geometry(self.edges_x, "Histogram2D (x)")
             cy, sy, dy = _uniform_geometry(self.edges_y, "Histogram2D (y)")
-            self._geom = ((cx, sx, float(self.bandwidth_x.detach().cpu()), dx),
-                          (cy, sy, float(self.bandwidth_y.detach().cpu()), dy))
-        return self._geom
+            self._geom = (key, ((cx, sx, float(self.bandwidth_x.detach().cpu()), dx),
+                                (cy, sy, float(self.bandwidth_y.detach().cpu()), dy)))
+        return self._geom[1]
 
     def projection_vectors(self, matrix: Optional[torch.Tensor], ndim: int, device) -> torch.Tensor:
         if matrix is None:

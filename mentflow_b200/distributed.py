@@ -39,15 +39,46 @@ class ShardReducer:
         self.equal_shards = equal_shards
         self.calls = 0
         self.bytes = 0
+        self._stash = None          # float64 partial sums waiting for a float32 all-reduce to ride on
+        self._stash_result = None
 
     @property
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def __call__(self, tensor: torch.Tensor, n_local: float) -> float:
+    # ---- one packed all-reduce per forward step --------------------------------------
+    def stash(self, values: torch.Tensor) -> None:
+        """Leave a small float64 vector of partial sums to be reduced together with the next float32
+        tensor that offers room for it (``tail_floats``); ``pop_result`` returns the reduced vector."""
+        self._stash, self._stash_result = values, None
+
+    def tail_floats(self) -> int:
+        return 0 if self._stash is None or self.world_size == 1 else 2 * self._stash.numel()
+
+    def pop_result(self) -> Optional[torch.Tensor]:
+        res, self._stash_result = self._stash_result, None
+        return res
+
+    def global_count(self, n_local: float) -> Optional[float]:
+        """particles over all ranks if that is known without communication (equal shards)"""
         if self.world_size == 1:
             return float(n_local)
-        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+        return float(n_local) * self.world_size if self.equal_shards else None
+
+    def __call__(self, tensor: torch.Tensor, n_local: float, flat: Optional[torch.Tensor] = None) -> float:
+        """``flat``: a flat float32 buffer whose head is ``tensor`` and whose last ``tail_floats()`` entries
+        are free for the stashed partial sums."""
+        if self.world_size == 1:
+            return float(n_local)
+        if flat is not None and self._stash is not None:
+            from . import ops
+            tail = flat[flat.numel() - 2 * self._stash.numel():]
+            ops.f64_split(self._stash, tail)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._stash_result, self._stash = ops.f64_join(tail), None
+            tensor = flat
+        else:
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         self.calls += 1
         self.bytes += tensor.numel() * tensor.element_size()
         if self.equal_shards or n_local == 0.0:
@@ -59,11 +90,18 @@ class ShardReducer:
 
 def shard_model(model, group: Optional[dist.ProcessGroup] = None, equal_shards: bool = True) -> ShardReducer:
     """Attach a reducer to a ``MENTFlow`` model (and its entropy estimator) so that
-    ``model.loss(n_local)`` returns the loss of the *global* batch on every rank."""
+    ``model.loss(n_local)`` returns the loss of the *global* batch on every rank, or to a classical
+    ``MENT`` model so that ``gauss_seidel_update`` draws ``n_samples`` particles over all ranks."""
     reducer = ShardReducer(group, equal_shards)
     model.reducer = reducer
     if getattr(model, "entropy_estimator", None) is not None and hasattr(model.entropy_estimator, "reducer"):
         model.entropy_estimator.reducer = reducer
+    if hasattr(model, "shard") and hasattr(model, "gauss_seidel_update"):
+        # classical MENT: every rank draws its slice of the n_samples particles (ment.py:319-326)
+        world = reducer.world_size
+        model.shard = (dist.get_rank(group) if world > 1 else 0, world)
+        if world > 1:
+            reducer.equal_shards = False if model.n_samples % world else reducer.equal_shards
     return reducer
 
 

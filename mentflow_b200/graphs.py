@@ -87,6 +87,7 @@ class GraphedLoss:
         gen = self.model.generator
         self._rng = gen.rng(self.device)
         with torch.cuda.device(self.device), torch.no_grad():
+            rng_mark = self._rng.mark()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -94,6 +95,7 @@ class GraphedLoss:
                     self._step_draw()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            self._rng.rewind(rng_mark)     # the warm-up passes leave torch's random stream where it was
             self._held_rng = getattr(gen, "_pack_cache", None)
             self._rng.begin_capture()
             self._rng_graph = torch.cuda.CUDAGraph()
@@ -267,6 +269,7 @@ class GraphedTrainStep:
         self._rng = gen.rng(self.device) if hasattr(gen, "rng") else None
         with torch.cuda.device(self.device):
             snap = self._snapshot()
+            rng_mark = self._rng.mark() if self._rng is not None else None
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -277,6 +280,7 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             self._restore(snap)
             if self._rng is not None:
+                self._rng.rewind(rng_mark)
                 self._rng.begin_capture()
             self.graph = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)

@@ -5,7 +5,15 @@ Interface of the reference's ``MENT`` / ``LagrangeFunction``; the arithmetic run
 library: ``prob`` is one fused kernel over all measurements (the reference does a device->numpy
 ->scipy->device round trip per measurement), sampling is a scan + inverse-CDF kernel, the
 predicted profile of the sampled particles is the fused projection+KDE kernel, and the table
-update is one elementwise kernel.  1-D screens (Histogram1D) are supported.
+update is one elementwise kernel.  One- and two-dimensional screens (Histogram1D / Histogram2D:
+experiments/config/rec_nd_1d_ment.yaml, rec_nd_2d_ment.yaml) may be mixed; within each family the
+screens must have the same number of bins.
+
+Sharded over GPUs (``mentflow_b200.distributed.shard_model``; BASELINE config 5): every rank evaluates
+the same density, draws ITS slice of the ``n_samples`` particles from the same Philox stream (particle s
+always uses counter s, whichever rank draws it), and the unnormalised profile sums are all-reduced before
+the normalisation -- so every rank applies the identical table update and the union of the particles is
+the set one GPU would have drawn.
 """
 import math
 from typing import Any, Callable, List, Optional, Tuple
@@ -13,7 +21,7 @@ from typing import Any, Callable, List, Optional, Tuple
 import torch
 
 from . import ops
-from .diagnostics import Histogram1D
+from .diagnostics import Histogram1D, Histogram2D
 from .loss import kl_divergence
 from .prior import Gaussian, Uniform
 from .simulate import forward as simulate_forward
@@ -22,8 +30,9 @@ from .utils import coords_from_edges, get_grid_points, unravel
 
 
 class LagrangeFunction:
-    """One h_k: values on the bin centres, linear interpolation in between, zero outside
-    (ment.py:20-52; scipy RegularGridInterpolator(method="linear", fill_value=0))."""
+    """One h_k: values on the bin centres (1-D) or on the grid of bin centres (2-D), multilinear
+    interpolation in between, zero outside (ment.py:20-52; scipy RegularGridInterpolator(method="linear",
+    bounds_error=False, fill_value=0), evaluated in double)."""
 
     def __init__(self, coords, values: torch.Tensor, **interpolation_kws) -> None:
         method = interpolation_kws.get("method", "linear")
@@ -36,10 +45,15 @@ class LagrangeFunction:
         self.values = values
 
     def __call__(self, u: torch.Tensor) -> torch.Tensor:
-        u = u.reshape(-1, 1).to(torch.float32)
-        one = torch.ones((1, 1), dtype=torch.float32, device=u.device)
-        return ops.ment_prob(u, one, self.coords.reshape(1, -1).to(u.device), self.values.reshape(1, -1).to(u.device),
-                             0.0, 0.0)
+        if self.values.ndim == 1:
+            u = u.reshape(-1, 1).to(torch.float32)
+            one = torch.ones((1, 1), dtype=torch.float32, device=u.device)
+            return ops.ment_prob(u, one, self.coords.reshape(1, -1).to(u.device),
+                                 self.values.reshape(1, -1).to(u.device), 0.0, 0.0)
+        u = u.reshape(-1, 2).to(torch.float32)
+        eye = torch.eye(2, dtype=torch.float32, device=u.device).reshape(1, 2, 2)
+        cx, cy = (c.reshape(1, -1).to(u.device) for c in self.coords)
+        return ops.ment_prob_nd(u, None, (eye, cx, cy, self.values.to(u.device)[None]), 0.0, 0.0)
 
 
 class MENT:
@@ -66,10 +80,11 @@ class MENT:
         self.interpolation = interpolation
         self.reducer = None
         self._packed = None
+        self.shard = None     # (rank, world_size) when the particles are sharded over GPUs
         for row in self.diagnostics:
             for d in row:
-                if not isinstance(d, Histogram1D):
-                    raise NotImplementedError("MENT on the CUDA path supports 1-D screens (Histogram1D)")
+                if not isinstance(d, (Histogram1D, Histogram2D)):
+                    raise NotImplementedError("MENT on the CUDA path supports Histogram1D / Histogram2D screens")
         self.lagrange_functions = self.initialize_lagrange_functions()
 
     # ------------------------------------------------------------------ bookkeeping
@@ -91,7 +106,10 @@ class MENT:
         for index in range(len(self.measurements)):
             row = []
             for measurement, diagnostic in zip(self.measurements[index], self.diagnostics[index]):
-                coords = coords_from_edges(diagnostic.edges)
+                if measurement.ndim == 1:
+                    coords = coords_from_edges(diagnostic.edges)
+                else:
+                    coords = [coords_from_edges(e) for e in diagnostic.edges]
                 values = (measurement > 0.0).float()
                 row.append(LagrangeFunction(coords, values, method=self.interpolation))
             self.lagrange_functions.append(row)
@@ -102,29 +120,48 @@ class MENT:
         return [(i, j) for i in range(len(self.diagnostics)) for j in range(len(self.diagnostics[i]))]
 
     def _pack(self, device):
-        """Static part of the kernel arguments: projection rows and bin centres of every table."""
+        """Static part of the kernel arguments: projection rows and bin centres of every table, the 1-D and
+        the 2-D screens as two families."""
         if self._packed is not None and self._packed["device"] == device:
             return self._packed
-        proj, coords = [], []
-        nb = None
+        slots1, proj1, coords1 = [], [], []
+        slots2, proj2, cx2, cy2 = [], [], [], []
         for i, j in self._slots():
             d = self.diagnostics[i][j]
             matrix = _linear_matrix(self.transforms[i])
             if matrix is NotImplemented:
                 raise NotImplementedError("MENT on the CUDA path needs linear transforms")
-            proj.append(d.projection_vector(matrix, self.ndim, device))
-            c = coords_from_edges(d.edges.to(torch.float32)).to(device)
-            nb = c.shape[0] if nb is None else nb
-            if c.shape[0] != nb:
-                raise NotImplementedError("all screens of a MENT model must have the same number of bins")
-            coords.append(c)
-        self._packed = {"device": device, "proj": torch.stack(proj).contiguous(),
-                        "coords": torch.stack(coords).contiguous()}
+            if isinstance(d, Histogram2D):
+                slots2.append((i, j))
+                proj2.append(d.projection_vectors(matrix, self.ndim, device))
+                cx2.append(coords_from_edges(d.edges_x.to(torch.float32)).to(device))
+                cy2.append(coords_from_edges(d.edges_y.to(torch.float32)).to(device))
+            else:
+                slots1.append((i, j))
+                proj1.append(d.projection_vector(matrix, self.ndim, device))
+                coords1.append(coords_from_edges(d.edges.to(torch.float32)).to(device))
+        for family in (coords1, cx2, cy2):
+            if len({int(c.shape[0]) for c in family}) > 1:
+                raise NotImplementedError("all screens of one kind in a MENT model must have the same number of bins")
+        self._packed = {"device": device, "slots1": slots1, "slots2": slots2,
+                        "proj": torch.stack(proj1).contiguous() if proj1 else None,
+                        "coords": torch.stack(coords1).contiguous() if coords1 else None,
+                        "proj2": torch.stack(proj2).contiguous() if proj2 else None,
+                        "cx2": torch.stack(cx2).contiguous() if cx2 else None,
+                        "cy2": torch.stack(cy2).contiguous() if cy2 else None}
         return self._packed
 
-    def _tables(self, device) -> torch.Tensor:
-        return torch.stack([self.lagrange_functions[i][j].values.to(device=device, dtype=torch.float32).reshape(-1)
-                            for i, j in self._slots()]).contiguous()
+    def _groups(self, device):
+        """(g1, g2) for ``ops.ment_prob_nd``: the current tables of the two screen families."""
+        pk = self._pack(device)
+
+        def stack(slots):
+            return torch.stack([self.lagrange_functions[i][j].values.to(device=device, dtype=torch.float32)
+                                for i, j in slots]).contiguous()
+
+        g1 = (pk["proj"], pk["coords"], stack(pk["slots1"])) if pk["slots1"] else None
+        g2 = (pk["proj2"], pk["cx2"], pk["cy2"], stack(pk["slots2"])) if pk["slots2"] else None
+        return g1, g2
 
     def _prior_args(self) -> Tuple[float, float]:
         if isinstance(self.prior, Gaussian):
@@ -136,17 +173,17 @@ class MENT:
     # ------------------------------------------------------------------ density
     def prob(self, x: torch.Tensor) -> torch.Tensor:
         """rho(x) (ment.py:239-249)."""
-        pk = self._pack(x.device)
+        g1, g2 = self._groups(x.device)
         a, b = self._prior_args()
-        return ops.ment_prob(x, pk["proj"], pk["coords"], self._tables(x.device), a, b)
+        return ops.ment_prob_nd(x, g1, g2, a, b)
 
     def prob_on_grid(self, sampler) -> torch.Tensor:
         """rho on the cell centres of a GridSampler grid, straight from the grid index."""
-        device = self.device if self.device is not None else "cuda"
-        pk = self._pack(torch.device(device))
+        device = torch.device(self.device if self.device is not None else "cuda")
+        g1, g2 = self._groups(device)
         a, b = self._prior_args()
-        return ops.ment_prob_grid(list(sampler.shape), sampler.first_centres(), sampler.cell_sizes(), pk["proj"],
-                                  pk["coords"], self._tables(pk["proj"].device), a, b)
+        return ops.ment_prob_grid_nd(list(sampler.shape), sampler.first_centres(), sampler.cell_sizes(), g1, g2, a, b,
+                                     device)
 
     def log_prob(self, x: torch.Tensor, pad: float = 1.0e-12) -> torch.Tensor:
         return torch.log(self.prob(x) + pad)
@@ -156,7 +193,14 @@ class MENT:
         return self.lagrange_functions[index][diag_index](diagnostic.project(u))
 
     def sample(self, size: int) -> torch.Tensor:
-        return self.send(self.sampler(self.prob, int(size)))
+        """``size`` particles from rho.  Sharded (``self.shard``): this rank's slice of them -- the sampler draws
+        particle s with Philox counter s, so the slices of all ranks together are the particles of one draw."""
+        size = int(size)
+        if self.shard is not None and self.shard[1] > 1 and getattr(self.sampler, "supports_offset", False):
+            from .distributed import shard_slice
+            sl = shard_slice(size, self.shard[0], self.shard[1])
+            return self.send(self.sampler(self.prob, sl.stop - sl.start, offset=sl.start))
+        return self.send(self.sampler(self.prob, size))
 
     def sample_and_log_prob(self, size: int):
         x = self.sample(size)
@@ -169,11 +213,17 @@ class MENT:
     # ------------------------------------------------------------------ simulation of one profile
     def normalize_projection(self, projection: torch.Tensor, index: int, diag_index: int) -> torch.Tensor:
         diagnostic = self.diagnostics[index][diag_index]
-        bin_volume = diagnostic.edges[1] - diagnostic.edges[0]
+        if isinstance(diagnostic, Histogram2D):
+            bin_volume = math.prod(float(e[1] - e[0]) for e in diagnostic.edges)
+        else:
+            bin_volume = diagnostic.edges[1] - diagnostic.edges[0]
         return projection / projection.sum() / bin_volume
 
     def get_meas_points(self, index: int, diag_index: int) -> torch.Tensor:
-        return coords_from_edges(self.diagnostics[index][diag_index].edges)
+        diagnostic = self.diagnostics[index][diag_index]
+        if isinstance(diagnostic, Histogram2D):
+            return get_grid_points(*[coords_from_edges(e) for e in diagnostic.edges])
+        return coords_from_edges(diagnostic.edges)
 
     def get_integration_points(self, index: int, diag_index: int) -> torch.Tensor:
         limits = self.integration_limits[index][diag_index]
@@ -188,14 +238,20 @@ class MENT:
         diagnostic = self.diagnostics[index][diag_index]
         transform = self.transforms[index]
         device = torch.device(self.device if self.device is not None else "cuda")
-        pk = self._pack(device)
+        g1, g2 = self._groups(device)
         a, b = self._prior_args()
         first = [float(limits[k][0]) for k in range(len(shape))]
         step = [(float(limits[k][1]) - float(limits[k][0])) / max(shape[k] - 1, 1) for k in range(len(shape))]
-        meas_coords = coords_from_edges(diagnostic.edges.to(torch.float32)).to(device)
-        pred = ops.ment_integrate(self.ndim, meas_coords, diagnostic.axis, shape, first, step,
-                                  transform.matrix_inv.to(device=device, dtype=torch.float32).contiguous(), pk["proj"],
-                                  pk["coords"], self._tables(device), a, b)
+        minv = transform.matrix_inv.to(device=device, dtype=torch.float32).contiguous()
+        if isinstance(diagnostic, Histogram2D):
+            cx = coords_from_edges(diagnostic.edges_x.to(torch.float32)).to(device)
+            cy = coords_from_edges(diagnostic.edges_y.to(torch.float32)).to(device)
+            ax, ay = diagnostic.axis
+            pred = ops.ment_integrate_nd(self.ndim, cx, ax, cy, ay, shape, first, step, minv, g1, g2, a, b)
+        else:
+            meas_coords = coords_from_edges(diagnostic.edges.to(torch.float32)).to(device)
+            pred = ops.ment_integrate_nd(self.ndim, meas_coords, diagnostic.axis, None, -1, shape, first, step, minv,
+                                         g1, g2, a, b)
         return self.normalize_projection(pred, index, diag_index)
 
     def _simulate_sample(self, index: int, diag_index: int) -> torch.Tensor:

@@ -51,14 +51,14 @@ def _check_mp(mp: torch.Tensor, k: int, d: int) -> torch.Tensor:
 
 
 def kde1d_sums(x: torch.Tensor, proj: torch.Tensor, geom: torch.Tensor, ratio: float, nbins: int,
-               mp: Optional[torch.Tensor] = None) -> torch.Tensor:
+               mp: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """S[k, b] = sum_n exp(-0.5 ((u_kn - c_b) / sigma_k)^2)  (unnormalised), u_kn = proj_k . x_n, plus the
     multipole terms of ``mp`` (K, 2D+4) when given (see ``simulate.multipole_terms``)."""
     lib = _lib.load()
     x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
     n, d = x.shape
     k = proj.shape[0]
-    sums = torch.empty((k, nbins), dtype=torch.float32, device=x.device)
+    sums = out if out is not None else torch.empty((k, nbins), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         wbytes = lib.mfb_kde1d_workspace_bytes(n, d, k, nbins)
         work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
@@ -178,9 +178,17 @@ class ProjectKDE1D(torch.autograd.Function):
         if reducer is None and mp is None and x.shape[0] > 0 and nbins <= _FINISH_MAX_BINS:
             sums, prof, kl = kde1d_loss_forward(x, proj, geom, ratio, nbins, n_total, meas)
         else:
-            sums = kde1d_sums(x, proj, geom, ratio, nbins, mp)
-            if reducer is not None:
-                n_total = reducer(sums, n_total)
+            # sharded: the unnormalised sums are all-reduced before the non-linear tail; float64 partial sums
+            # another op stashed on the reducer (the entropy moments) ride at the end of the same buffer
+            tail = reducer.tail_floats() if hasattr(reducer, "tail_floats") else 0
+            if tail:
+                flat = torch.empty(proj.shape[0] * nbins + tail, dtype=torch.float32, device=x.device)
+                sums = kde1d_sums(x, proj, geom, ratio, nbins, mp, out=flat[: proj.shape[0] * nbins].view(-1, nbins))
+                n_total = reducer(sums, n_total, flat=flat)
+            else:
+                sums = kde1d_sums(x, proj, geom, ratio, nbins, mp)
+                if reducer is not None:
+                    n_total = reducer(sums, n_total)
             if nbins <= _FINISH_MAX_BINS:
                 prof, kl = kde1d_finish(sums, n_total, geom, meas)
             else:
@@ -415,6 +423,24 @@ def moments(x: torch.Tensor, logq: Optional[torch.Tensor], with_cov: bool = Fals
     return out
 
 
+def f64_split(values: torch.Tensor, out: torch.Tensor) -> None:
+    """float64 (n,) -> float32 (2n,) [hi | lo] written into ``out`` (a slice of an all-reduce buffer)."""
+    lib = _lib.load()
+    n = values.numel()
+    assert values.dtype == torch.float64 and out.dtype == torch.float32 and out.numel() == 2 * n and out.is_contiguous()
+    with torch.cuda.device(values.device):
+        _lib.check(lib.mfb_f64_split(_ptr(values), n, _ptr(out), _stream()), "f64_split")
+
+
+def f64_join(pairs: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    n = pairs.numel() // 2
+    out = torch.empty(n, dtype=torch.float64, device=pairs.device)
+    with torch.cuda.device(pairs.device):
+        _lib.check(lib.mfb_f64_join(_ptr(pairs), n, _ptr(out), _stream()), "f64_join")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # whole flow (all layers), differentiable
 # --------------------------------------------------------------------------------------
@@ -462,6 +488,8 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
     dev = inputs[0].device
     gpacked = torch.zeros_like(packed)
     gz = torch.empty_like(inputs[0])
+    if n == 0:
+        return gz, gpacked
     chunk = min(n, NSF_BWD_CHUNK)
     with torch.cuda.device(dev):
         wbytes = lib.mfb_nsf_layer_bwd_workspace_bytes(chunk, d, hidden_layers)
@@ -585,6 +613,80 @@ def ment_integrate(d, meas_coords, meas_axis, int_shape, int_first, int_step, mi
     return pred
 
 
+def _ment_groups(g1, g2, device):
+    """C-ABI arguments of the two table families: g1 = (proj (K,D), coords (K,B), tables (K,B)) or None,
+    g2 = (proj2 (K2,2,D), cx (K2,Bx), cy (K2,By), tables2 (K2,Bx,By)) or None."""
+    keep = []
+    if g1 is not None:
+        proj, coords, tables = (_check_f32(n, t) for n, t in zip(("proj", "coords", "tables"), g1))
+        keep += [proj, coords, tables]
+        a1 = [_ptr(proj), _ptr(coords), _ptr(tables), tables.shape[0], tables.shape[1]]
+    else:
+        a1 = [None, None, None, 0, 2]
+    if g2 is not None:
+        proj2, cx, cy, tab2 = (_check_f32(n, t) for n, t in zip(("proj2", "cx", "cy", "tables2"), g2))
+        if proj2.ndim != 3 or proj2.shape[1] != 2 or tab2.shape != (proj2.shape[0], cx.shape[1], cy.shape[1]):
+            raise ValueError("2-D Lagrange tables: proj2 (K,2,D), cx (K,Bx), cy (K,By), tables2 (K,Bx,By) expected")
+        keep += [proj2, cx, cy, tab2]
+        a2 = [_ptr(proj2), _ptr(cx), _ptr(cy), _ptr(tab2), tab2.shape[0], tab2.shape[1], tab2.shape[2]]
+    else:
+        a2 = [None, None, None, None, 0, 0, 0]
+    return a1, a2, keep
+
+
+def ment_prob_nd(x, g1, g2, neg_half_inv_s2: float, log_norm: float) -> torch.Tensor:
+    """rho at explicit points with one- and two-dimensional Lagrange tables (see ``_ment_groups``)."""
+    lib = _lib.load()
+    x = _check_f32("x", x)
+    g, d = x.shape
+    a1, a2, keep = _ment_groups(g1, g2, x.device)
+    out = torch.empty(g, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mfb_ment_prob_nd(_ptr(x), g, d, *a1, *a2, float(neg_half_inv_s2), float(log_norm), _ptr(out),
+                                        _stream()), "ment_prob_nd")
+    return out
+
+
+def ment_prob_grid_nd(shape, first_centre, step, g1, g2, neg_half_inv_s2, log_norm, device) -> torch.Tensor:
+    lib = _lib.load()
+    d = len(shape)
+    g = 1
+    for s_ in shape:
+        g *= int(s_)
+    a1, a2, keep = _ment_groups(g1, g2, device)
+    out = torch.empty(g, dtype=torch.float32, device=device)
+    h1, p1 = _host_i32(shape)
+    h2, p2 = _host_f32(first_centre)
+    h3, p3 = _host_f32(step)
+    with torch.cuda.device(device):
+        _lib.check(lib.mfb_ment_prob_grid_nd(d, p1, p2, p3, *a1, *a2, float(neg_half_inv_s2), float(log_norm), _ptr(out),
+                                             _stream()), "ment_prob_grid_nd")
+    return out
+
+
+def ment_integrate_nd(d, meas_coords, meas_axis, meas_coords2, meas_axis2, int_shape, int_first, int_step, minv, g1, g2,
+                      neg_half_inv_s2, log_norm) -> torch.Tensor:
+    """Integration-mode prediction of one screen: 1-D (meas_axis2 = -1) -> (B,), 2-D -> (Bx, By)."""
+    lib = _lib.load()
+    meas_coords, minv = _check_f32("meas_coords", meas_coords), _check_f32("minv", minv)
+    nb = meas_coords.shape[0]
+    nb2 = 0
+    if meas_axis2 >= 0:
+        meas_coords2 = _check_f32("meas_coords2", meas_coords2)
+        nb2 = meas_coords2.shape[0]
+    a1, a2, keep = _ment_groups(g1, g2, minv.device)
+    pred = torch.empty((nb, nb2) if meas_axis2 >= 0 else (nb,), dtype=torch.float32, device=minv.device)
+    h1, p1 = _host_i32(int_shape)
+    h2, p2 = _host_f32(int_first)
+    h3, p3 = _host_f32(int_step)
+    with torch.cuda.device(minv.device):
+        _lib.check(lib.mfb_ment_integrate_nd(d, _ptr(meas_coords), nb, int(meas_axis),
+                                             _ptr(meas_coords2) if meas_axis2 >= 0 else None, nb2, int(meas_axis2),
+                                             len(int_shape), p1, p2, p3, _ptr(minv), *a1, *a2, float(neg_half_inv_s2),
+                                             float(log_norm), _ptr(pred), _stream()), "ment_integrate_nd")
+    return pred
+
+
 def cdf_sample(rho: torch.Tensor, shape, first_edge, cell, size: int, seed: int, offset: int = 0,
                jitter: bool = False, pad: float = 1.0e-15) -> torch.Tensor:
     """`size` particles from the piecewise-constant density rho (flattened grid, 'ij' order)."""
@@ -670,6 +772,15 @@ class PhiloxStream:
                                                 ctypes.c_uint64(off), _stream()), "randn_philox")
                 g.set_offset(off + inc)
         return out
+
+    def mark(self) -> int:
+        """current offset of torch's generator (see ``rewind``)"""
+        return int(self._generator().get_offset())
+
+    def rewind(self, mark: int) -> None:
+        """put torch's generator back to a marked offset (warm-up passes of a capture must not consume
+        the caller's random stream)"""
+        self._generator().set_offset(int(mark))
 
     # ---- graph replay support ---------------------------------------------------------------
     def begin_capture(self) -> None:

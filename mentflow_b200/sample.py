@@ -65,7 +65,11 @@ class GridSampler:
             self.points = points
         return points
 
-    def __call__(self, prob_func: Callable, size: int, seed: Optional[int] = None) -> torch.Tensor:
+    supports_offset = True    # __call__ takes the index of the first particle to draw (sharded MENT)
+
+    def __call__(self, prob_func: Callable, size: int, seed: Optional[int] = None, offset: int = 0) -> torch.Tensor:
+        """``size`` particles; particle s of the call uses Philox counter ``offset + s``, so ranks that pass the
+        same seed (torch.manual_seed on every rank) and disjoint offsets draw disjoint slices of one stream."""
         owner = getattr(prob_func, "__self__", None)
         if owner is not None and hasattr(owner, "prob_on_grid") and getattr(prob_func, "__name__", "") == "prob":
             prob = owner.prob_on_grid(self)           # density from the grid index, nothing materialised
@@ -74,7 +78,7 @@ class GridSampler:
         self.calls += 1
         first = [float(self.limits[a][0]) for a in range(self.ndim)]
         x = ops.cdf_sample(prob, list(self.shape), first, self.cell_sizes(), int(size),
-                           _draw_seed() if seed is None else seed, jitter=bool(self.noise))
+                           _draw_seed() if seed is None else seed, offset=int(offset), jitter=bool(self.noise))
         return x
 
     def to(self, device):

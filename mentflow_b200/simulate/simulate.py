@@ -113,6 +113,7 @@ class _Plan:
         self.groups: "OrderedDict[tuple, _Group]" = OrderedDict()
         self.fallback: List[tuple] = []
         self.shape: List[int] = []
+        self.refs: list = []     # keeps the objects the cache key identifies alive (see _plan_key)
 
 
 def _linear_matrix(transform) -> Optional[torch.Tensor]:
@@ -178,18 +179,43 @@ def multipole_terms(row: torch.Tensor, pre: Optional[torch.Tensor], kick: Multip
     return w.to(torch.float32), mp.to(torch.float32)
 
 
+def _tensor_key(t):
+    """identity + in-place version of a tensor (None-safe)"""
+    return (id(t), getattr(t, "_version", 0)) if t is not None else None
+
+
 def _plan_key(transforms, diagnostics):
-    key = []
+    """(key, refs): the key is built from object identities and tensor version counters; ``refs`` lists
+    every object whose id() went into it.  The cached plan keeps ``refs`` alive, so that CPython cannot
+    hand a recycled id to a new transform / matrix / screen while the plan that was built for the old one
+    is still in the cache (a fresh ``LinearTransform`` per call would otherwise silently reuse stale
+    projection rows).  Screen geometry (edges, bandwidth) is part of the key through the buffers' version
+    counters, so editing ``diag.bandwidth`` or the edges in place rebuilds the plan."""
+    key, refs = [], []
     for t, row in zip(transforms, diagnostics):
         m = getattr(t, "matrix", None)
-        key.append((id(t), id(m), getattr(m, "_version", 0)))
+        key.append((id(t), _tensor_key(m)))
+        refs += [t, m]
         for st in (getattr(t, "transforms", None) or [t]):      # stages of a composite map
             sm = getattr(st, "matrix", None)
-            key.append((id(st), id(sm), getattr(sm, "_version", 0), getattr(st, "order", None),
+            key.append((id(st), _tensor_key(sm), getattr(st, "order", None),
                         getattr(st, "strength", None), getattr(st, "skew", None)))
+            refs += [st, sm]
         for d in row:
-            key.append((id(d), getattr(d, "kde", None), getattr(d, "axis", None), id(getattr(d, "direction", None))))
-    return tuple(key)
+            direction = getattr(d, "direction", None)
+            geom = []
+            for name in ("edges", "edges_x", "edges_y", "bandwidth", "bandwidth_x", "bandwidth_y"):
+                v = getattr(d, name, None)
+                if torch.is_tensor(v):
+                    geom.append(_tensor_key(v))
+                    refs.append(v)
+                elif isinstance(v, (int, float)):
+                    geom.append(float(v))
+                elif isinstance(v, (tuple, list)) and all(isinstance(q, (int, float)) for q in v):
+                    geom.append(tuple(float(q) for q in v))
+            key.append((id(d), getattr(d, "kde", None), getattr(d, "axis", None), _tensor_key(direction), tuple(geom)))
+            refs += [d, direction]
+    return tuple(key), refs
 
 
 _plan_cache: "OrderedDict[tuple, _Plan]" = OrderedDict()
@@ -252,8 +278,9 @@ def _stacked_targets(grp: "_Group", targets, device) -> Optional[torch.Tensor]:
     key = tuple((id(m), m._version) for m in rows)
     hit = grp.cache.get("targets")
     if hit is None or hit[0] != key or hit[1].device != device:
+        # `rows` is kept with the entry: the ids in the key stay owned by these very tensors
         hit = grp.cache["targets"] = (key, torch.stack([m.detach().to(device=device, dtype=torch.float32)
-                                                        for m in rows]).contiguous())
+                                                        for m in rows]).contiguous(), rows)
     return hit[1]
 
 
@@ -269,10 +296,12 @@ def forward(x: torch.Tensor, transforms: List[nn.Module], diagnostics: List[List
     ``kl_targets`` (optional, nested like the result): measured profiles; one-dimensional KDE
     groups then also evaluate KL(target || profile) inside the normalisation kernel and the
     ``stacked`` entries become ``(slots, profiles, kl)`` (kl is None for the other groups)."""
-    key = (_plan_key(transforms, diagnostics), x.shape[1], str(x.device))
+    pkey, refs = _plan_key(transforms, diagnostics)
+    key = (pkey, x.shape[1], str(x.device))
     plan = _plan_cache.get(key)
     if plan is None:
         plan = _build_plan(x, transforms, diagnostics)
+        plan.refs = refs
         _plan_cache[key] = plan
         while len(_plan_cache) > _PLAN_CACHE_SIZE:
             _plan_cache.popitem(last=False)

@@ -315,6 +315,83 @@ def make_multipole():
     print("wrote multipole.npz")
 
 
+def make_ment_2d_screens():
+    """Classical MENT with TWO-dimensional screens (ment.py:20-52 N-D LagrangeFunction, :184-199, :267-317;
+    experiments/config/rec_nd_2d_ment.yaml: 4-D, corner optics): the density at explicit points and on the
+    sampler grid with randomised 2-D tables, a mixed 1-D + 2-D model, and the integration-mode prediction of
+    one 2-D screen followed by a Gauss-Seidel sweep (deterministic: no sampling involved)."""
+    mf = ref_import.load()
+    torch.manual_seed(41)
+    d = 4
+    mats = corner_matrices(d)                      # 6 axis pairs onto the measured axes (0, 2)
+    ex = torch.linspace(-4.0, 4.0, 17)
+    ey = torch.linspace(-3.5, 3.5, 15)
+    diag = mf.diagnostics.Histogram2D(axis=(0, 2), edges=[ex, ey], bandwidth=(0.5, 0.5))
+    tfs = [mf.simulate.LinearTransform(m) for m in mats]
+    xt = torch.randn(60000, d).float() * torch.tensor([1.2, 0.8, 1.0, 0.9])
+    xt[:, 2] += 0.4 * xt[:, 0]
+    diag.kde = False
+    meas = [p[0] for p in mf.simulate.forward(xt, tfs, [[diag] for _ in tfs])]
+    diag.kde = True
+    cell = (ex[1] - ex[0]) * (ey[1] - ey[0])
+    meas = [m / m.sum() / cell for m in meas]
+    meas[1][:2, :3] = 0.0                          # exercise the g == 0 branch
+    res = 9
+    sampler = mf.sample.GridSampler(limits=d * [(-4.0, 4.0)], shape=tuple(d * [res]))
+    prior = mf.prior.Gaussian(ndim=d, scale=2.0)
+    ment = mf.ment.MENT(ndim=d, transforms=tfs, diagnostics=[[diag] for _ in tfs], measurements=[[m] for m in meas],
+                        prior=prior, mode="sample", sampler=sampler, n_samples=1000)
+    for i in range(len(tfs)):
+        lf = ment.lagrange_functions[i][0]
+        lf.set_values(lf.values * (0.5 + torch.rand(lf.values.shape)))
+    tables0 = torch.stack([ment.lagrange_functions[i][0].values.clone() for i in range(len(tfs))])
+    xq = torch.randn(3000, d).float() * 1.5
+    xq[:4] *= 5.0
+    prob_q = ment.prob(xq)
+    prob_grid = ment.prob(sampler.get_grid_points())
+    out = dict(matrices=npy(torch.stack(mats)), edges_x=npy(ex), edges_y=npy(ey), meas=npy(torch.stack(meas)),
+               prior_scale=2.0, grid_res=res, grid_xmax=4.0, tables0=npy(tables0), xq=npy(xq), prob_q=npy(prob_q),
+               prob_grid=npy(prob_grid))
+    # mixed model: the six 2-D screens plus three 1-D screens
+    mats1 = isotropic_matrices(3, d, seed=5)
+    e1 = torch.linspace(-4.0, 4.0, 25)
+    diag1 = mf.diagnostics.Histogram1D(axis=0, edges=e1, bandwidth=0.5)
+    tfs1 = [mf.simulate.LinearTransform(m) for m in mats1]
+    diag1.kde = False
+    meas1 = [p[0] for p in mf.simulate.forward(xt, tfs1, [[diag1] for _ in tfs1])]
+    diag1.kde = True
+    meas1 = [m / m.sum() / (e1[1] - e1[0]) for m in meas1]
+    mixed = mf.ment.MENT(ndim=d, transforms=tfs + tfs1, diagnostics=[[diag] for _ in tfs] + [[diag1] for _ in tfs1],
+                         measurements=[[m] for m in meas] + [[m] for m in meas1], prior=prior, mode="sample",
+                         sampler=sampler, n_samples=1000)
+    for i in range(len(tfs)):
+        mixed.lagrange_functions[i][0].set_values(tables0[i].clone())
+    t1 = []
+    for i in range(len(tfs1)):
+        lf = mixed.lagrange_functions[len(tfs) + i][0]
+        lf.set_values(lf.values * (0.5 + torch.rand(lf.values.shape)))
+        t1.append(lf.values.clone())
+    out.update(matrices1=npy(torch.stack(mats1)), edges1=npy(e1), meas1=npy(torch.stack(meas1)),
+               tables1d=npy(torch.stack(t1)), prob_q_mixed=npy(mixed.prob(xq)))
+    # integration mode with 2-D screens: 4-D, the two unmeasured axes on a 13 x 11 grid
+    ment_i = mf.ment.MENT(ndim=d, transforms=tfs, diagnostics=[[diag] for _ in tfs], measurements=[[m] for m in meas],
+                          prior=prior, mode="integrate",
+                          integration_limits=[[[(-4.0, 4.0), (-3.0, 3.0)]] for _ in tfs],
+                          integration_shape=[[(13, 11)] for _ in tfs])
+    for i in range(len(tfs)):
+        ment_i.lagrange_functions[i][0].set_values(tables0[i].clone())
+    # reference quirk: _simulate_integrate reshapes with `diagnostic.shape` (ment.py:309), which the reference's
+    # Histogram2D never defines -- the attribute is supplied here so that the reference's own arithmetic runs
+    diag.shape = (ex.numel() - 1, ey.numel() - 1)
+    pred = ment_i.simulate(2, 0)
+    ment_i.gauss_seidel_update(lr=0.8, thresh=1.0e-10)
+    tables_gs = torch.stack([ment_i.lagrange_functions[i][0].values.clone() for i in range(len(tfs))])
+    out.update(int_limits=np.array([[-4.0, 4.0], [-3.0, 3.0]]), int_shape=np.array([13, 11]), pred_2_0=npy(pred), lr=0.8,
+               tables_after_gs=npy(tables_gs))
+    np.savez_compressed(os.path.join(OUT, "ment_2d_screens.npz"), **out)
+    print("wrote ment_2d_screens.npz")
+
+
 def make_noise():
     """Measurement noise of Histogram.forward (diagnostics/diagnostics.py:50-68): a generator re-seeded on
     every call, multiplicative gaussian / uniform noise, clamped at zero; 1-D and 2-D screens."""
@@ -344,7 +421,10 @@ if __name__ == "__main__":
         make_multipole()
     elif "--only-noise" in sys.argv:
         make_noise()
+    elif "--only-ment2d" in sys.argv:
+        make_ment_2d_screens()
     else:
         main()
         make_multipole()
         make_noise()
+        make_ment_2d_screens()

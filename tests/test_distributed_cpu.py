@@ -50,6 +50,33 @@ def _worker(rank, world, port, equal, out):
         reducer(counts, 0.0)
         mom = torch.stack([logq[sl].double().sum(), (x[sl].double() ** 2).sum()])
         reducer(mom, float(x[sl].shape[0]))
+        # packed exchange (one all-reduce per forward step): the entropy sums ride as (hi, lo) float pairs at
+        # the tail of the float32 buffer of the profile sums.  The split / join kernels are CUDA; their
+        # arithmetic is restated here so that the host logic runs under gloo
+        from mentflow_b200 import ops as _ops
+
+        def _split(values, out):
+            hi = values.float()
+            out[: values.numel()] = hi
+            out[values.numel():] = (values - hi.double()).float()
+
+        _ops.f64_split = _split
+        _ops.f64_join = lambda pairs: pairs[: pairs.numel() // 2].double() + pairs[pairs.numel() // 2:].double()
+        packed_ok = True
+        if equal:
+            mom2 = torch.stack([logq[sl].double().sum(), (x[sl].double() ** 2).sum()])
+            reducer.stash(mom2)
+            assert reducer.tail_floats() == 4
+            flat = torch.empty(32 + 4)
+            sums2 = flat[:32].view(1, 32)
+            sums2.copy_(hp.kde_sums_1d(x[sl] @ w, edges, 0.5 * float(edges[1] - edges[0])).float()[None])
+            calls0 = reducer.calls
+            n2 = reducer(sums2, float(x[sl].shape[0]), flat=flat)
+            got = reducer.pop_result()
+            packed_ok = (reducer.calls == calls0 + 1 and n2 == n and reducer.tail_floats() == 0
+                         and torch.allclose(sums2, sums, rtol=1e-6)
+                         and torch.allclose(got, mom, rtol=1e-6) and reducer.pop_result() is None)
+            reducer.calls = calls0
         # backward exchange: flattened gradient all-reduce
         p1, p2 = torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 3))
         p1.grad = torch.full((5,), float(rank + 1))
@@ -63,7 +90,7 @@ def _worker(rank, world, port, equal, out):
                   and torch.allclose(mom, torch.stack([logq.double().sum(), (x.double() ** 2).sum()]), rtol=1e-12)
                   and torch.equal(p1.grad, torch.full((5,), 3.0))
                   and torch.equal(p2.grad, torch.arange(6.0).reshape(2, 3) * 3)
-                  and reducer.calls == 3)
+                  and reducer.calls == 3 and packed_ok)
             out.put(bool(ok))
     finally:
         dist.destroy_process_group()

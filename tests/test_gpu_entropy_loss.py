@@ -38,6 +38,24 @@ def test_entropy_gradients():
     assert torch.allclose(lq.grad, lr.grad, rtol=1e-6)
 
 
+def test_covariance_entropy_gradient_matches_reference_expression():
+    """entropy.py:27-38 is differentiable in the reference (torch.cov / torch.det); so is the kernel path."""
+    import numpy as np
+    torch.manual_seed(1)
+    a = torch.randn(6, 6, device="cuda") * 0.7
+    x = (torch.randn(20000, 6, device="cuda") @ a).requires_grad_(True)
+    est = mf.entropy.CovarianceEntropyEstimator()
+    h = est(x, None)
+    (3.0 * h).backward()
+    xr = x.detach().double().requires_grad_(True)
+    cov = torch.cov(xr.T)
+    href = -3.0 * np.log(2.0 * np.pi * np.e) - torch.log(torch.sqrt(torch.det(cov)) + est.pad)
+    (3.0 * href).backward()
+    assert abs(float(h) - float(href)) <= 1e-5 * abs(float(href))
+    scale = float(xr.grad.abs().max())
+    assert float((x.grad.double() - xr.grad).abs().max()) <= 1e-4 * scale
+
+
 def test_mentflow_loss_matches_reference(golden):
     g, k = golden("entropy_loss"), golden("kde1d_6d")
     mats, edges, meas = t32(k["matrices"]), t32(k["edges"]), cuda(k["meas"])

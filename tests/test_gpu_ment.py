@@ -145,3 +145,128 @@ def test_gs_update_kernel_matches_rule():
     t = table.clone().cuda()
     ops.gs_update(t, meas.cuda(), pred.cuda(), 0.9, 1e-10)
     assert torch.allclose(t.cpu(), want, rtol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------------
+# two-dimensional screens (ment.py:20-52 N-D tables; experiments/config/rec_nd_2d_ment.yaml)
+# --------------------------------------------------------------------------------------------------
+def _model_2d(g, mode="sample", with_1d=False, n_samples=1000):
+    mats, ex, ey, meas = t32(g["matrices"]), t32(g["edges_x"]), t32(g["edges_y"]), t32(g["meas"])
+    d = mats.shape[1]
+    tfs = [mf.simulate.LinearTransform(m.cuda()) for m in mats]
+    diag = mf.diagnostics.Histogram2D(axis=(0, 2), edges=(ex, ey), bandwidth=(0.5, 0.5)).to("cuda")
+    diags = [[diag] for _ in tfs]
+    ms = [[m.cuda()] for m in meas]
+    if with_1d:
+        mats1, e1, meas1 = t32(g["matrices1"]), t32(g["edges1"]), t32(g["meas1"])
+        diag1 = mf.diagnostics.Histogram1D(axis=0, edges=e1, bandwidth=0.5).to("cuda")
+        tfs += [mf.simulate.LinearTransform(m.cuda()) for m in mats1]
+        diags += [[diag1] for _ in mats1]
+        ms += [[m.cuda()] for m in meas1]
+    kw = {}
+    xmax, res = float(g["grid_xmax"]), int(g["grid_res"])
+    if mode == "sample":
+        kw["sampler"] = mf.sample.GridSampler(limits=d * [(-xmax, xmax)], shape=tuple(d * [res]), device="cuda")
+        kw["n_samples"] = n_samples
+    else:
+        lim = [tuple(float(v) for v in row) for row in g["int_limits"]]
+        kw["integration_limits"] = [[lim] for _ in tfs]
+        kw["integration_shape"] = [[tuple(int(v) for v in g["int_shape"])] for _ in tfs]
+    model = mf.ment.MENT(ndim=d, transforms=tfs, diagnostics=diags, measurements=ms,
+                         prior=mf.prior.Gaussian(ndim=d, scale=float(g["prior_scale"])), mode=mode, device="cuda", **kw)
+    for i, t in enumerate(t32(g["tables0"])):
+        model.lagrange_functions[i][0].set_values(t.cuda())
+    return model
+
+
+def test_prob_with_2d_screens_matches_reference(golden):
+    g = golden("ment_2d_screens")
+    model = _model_2d(g)
+    assert model.lagrange_functions[0][0].values.shape == (16, 14)
+    prob = model.prob(cuda(g["xq"])).cpu()
+    ref = t32(g["prob_q"])
+    assert torch.allclose(prob, ref, rtol=1e-4, atol=1e-9 * float(ref.max()))
+    assert int((ref > 0).sum()) > 500                     # the comparison is not vacuous
+    grid = model.prob_on_grid(model.sampler).cpu()
+    refg = t32(g["prob_grid"])
+    assert torch.allclose(grid, refg, rtol=1e-4, atol=2e-6 * float(refg.max()))
+    # one 2-D Lagrange function called like the reference's interpolator: bilinear, zero outside the centres
+    lf = model.lagrange_functions[3][0]
+    cx, cy = hp.centres(t32(g["edges_x"])), hp.centres(t32(g["edges_y"]))
+    torch.manual_seed(2)
+    u = torch.rand(5000, 2) * torch.tensor([9.0, 8.0]) - torch.tensor([4.5, 4.0])
+    got = lf(u.cuda()).cpu()
+    tab = t32(g["tables0"])[3].double()
+    ix = (torch.searchsorted(cx.double(), u[:, 0].double()) - 1).clamp(0, cx.numel() - 2)
+    iy = (torch.searchsorted(cy.double(), u[:, 1].double()) - 1).clamp(0, cy.numel() - 2)
+    wx = (u[:, 0].double() - cx.double()[ix]) / (cx.double()[ix + 1] - cx.double()[ix])
+    wy = (u[:, 1].double() - cy.double()[iy]) / (cy.double()[iy + 1] - cy.double()[iy])
+    want = (tab[ix, iy] * (1 - wx) * (1 - wy) + tab[ix, iy + 1] * (1 - wx) * wy + tab[ix + 1, iy] * wx * (1 - wy)
+            + tab[ix + 1, iy + 1] * wx * wy)
+    inside = (u[:, 0] >= cx[0]) & (u[:, 0] <= cx[-1]) & (u[:, 1] >= cy[0]) & (u[:, 1] <= cy[-1])
+    want = torch.where(inside, want, torch.zeros_like(want)).float()
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_prob_with_mixed_1d_and_2d_screens_matches_reference(golden):
+    g = golden("ment_2d_screens")
+    model = _model_2d(g, with_1d=True)
+    for i, t in enumerate(t32(g["tables1d"])):
+        model.lagrange_functions[6 + i][0].set_values(t.cuda())
+    prob = model.prob(cuda(g["xq"])).cpu()
+    ref = t32(g["prob_q_mixed"])
+    assert torch.allclose(prob, ref, rtol=1e-4, atol=1e-9 * float(ref.max()))
+
+
+def test_integrate_mode_with_2d_screens_matches_reference(golden):
+    g = golden("ment_2d_screens")
+    model = _model_2d(g, mode="integrate")
+    pred = model.simulate(2, 0).cpu()
+    ref = t32(g["pred_2_0"])
+    assert pred.shape == ref.shape == (16, 14)
+    assert torch.allclose(pred, ref, rtol=1e-4, atol=1e-7 * float(ref.max()))
+    model.gauss_seidel_update(lr=float(g["lr"]), thresh=1.0e-10)
+    got = torch.stack([model.lagrange_functions[i][0].values.cpu() for i in range(6)])
+    want = t32(g["tables_after_gs"])
+    assert torch.allclose(got, want, rtol=5e-4, atol=1e-6)
+    assert torch.equal(got == 0, want == 0)
+
+
+def test_sample_mode_sweep_with_2d_screens_runs_and_is_consistent(golden):
+    """rec_nd_2d_ment.yaml runs in sample mode: a sweep at high statistics must agree with the integration-mode
+    sweep of the same model on a fine grid (both estimate the same projections)."""
+    g = golden("ment_2d_screens")
+    torch.manual_seed(3)
+    model = _model_2d(g, n_samples=4_000_000)
+    model.sampler = mf.sample.GridSampler(limits=4 * [(-4.0, 4.0)], shape=(24, 24, 24, 24), device="cuda")
+    pred_s = model.simulate(2, 0).cpu()
+    fine = _model_2d(g, mode="integrate")
+    fine.integration_limits = [[[(-4.0, 4.0), (-4.0, 4.0)]] for _ in fine.transforms]
+    fine.integration_shape = [[(160, 160)] for _ in fine.transforms]
+    pred_i = fine.simulate(2, 0).cpu()
+    cell = float((t32(g["edges_x"])[1] - t32(g["edges_x"])[0]) * (t32(g["edges_y"])[1] - t32(g["edges_y"])[0]))
+    assert abs(float(pred_s.sum()) * cell - 1.0) < 1e-4
+    # the sampled profile is the integrated one smoothed by the KDE kernel and the grid cells: compare totals of
+    # coarse blocks rather than pixels
+    bs, bi = pred_s[:16, :12].reshape(4, 4, 3, 4).sum(dim=(1, 3)), pred_i[:16, :12].reshape(4, 4, 3, 4).sum(dim=(1, 3))
+    assert float((bs - bi).abs().max()) < 0.12 * float(bi.max())
+    model.gauss_seidel_update(lr=0.5)
+    assert model.epoch == 1 and all(torch.isfinite(model.lagrange_functions[i][0].values).all() for i in range(6))
+
+
+def test_sharded_draws_are_slices_of_one_stream(golden):
+    """What rank r of W draws (offset = first index of its slice) is the slice of the single-GPU draw."""
+    g = golden("ment_4d")
+    model = _model(g, n_samples=100_003)
+    for i, t in enumerate(t32(g["tables0"])):
+        model.lagrange_functions[i][0].set_values(t.cuda())
+    torch.manual_seed(17)
+    full = model.sample(100_003)
+    parts = []
+    for r in range(3):
+        model.shard = (r, 3)
+        torch.manual_seed(17)
+        parts.append(model.sample(100_003))
+    model.shard = None
+    assert [p.shape[0] for p in parts] == [33_335, 33_334, 33_334]
+    assert torch.equal(torch.cat(parts), full)

@@ -222,6 +222,42 @@ def test_plan_groups_multipole_chains_and_tracks_their_parameters():
     assert sim._multipole_chain(chain) is None
 
 
+def test_plan_cache_is_not_fooled_by_recycled_ids(monkeypatch):
+    """A fresh LinearTransform per call (its id may be the id of a freed one) must never reuse the projection
+    rows of an earlier transform; editing a screen's bandwidth in place rebuilds its geometry."""
+    from mentflow_b200.simulate import simulate as sim
+    seen = []
+
+    def fake_project_kde1d(x, proj, geom, ratio, nbins, reducer=None, meas=None, mp=None):
+        seen.append((proj.clone(), geom.clone()))
+        return torch.zeros(proj.shape[0], nbins)
+
+    monkeypatch.setattr(sim.ops, "project_kde1d", fake_project_kde1d)
+    sim._plan_cache.clear()
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=torch.linspace(-3, 3, 33), bandwidth=0.5)
+    x = torch.zeros(4, 2)
+    torch.manual_seed(0)
+    for it in range(300):
+        m = torch.randn(2, 2)
+        sim.forward(x, [mf.simulate.LinearTransform(m)], [[diag]])
+        proj, _ = seen[-1]
+        assert torch.equal(proj[0], m[0]), f"stale projection row at call {it}"
+    sigma0 = float(seen[-1][1][0, 2])
+    t = mf.simulate.LinearTransform(torch.eye(2))
+    sim.forward(x, [t], [[diag]])
+    diag.bandwidth.mul_(2.0)
+    sim.forward(x, [t], [[diag]])
+    assert abs(float(seen[-1][1][0, 2]) - 2.0 * sigma0) < 1e-7
+
+
+def test_philox_stream_contract_without_gpu():
+    """base noise never falls back to the host: a CPU tensor is refused"""
+    with pytest.raises(RuntimeError):
+        ops.PhiloxStream("cpu").normal_(torch.empty(4, 2))
+    lib = _lib.load()
+    assert lib.mfb_randn_offset_increment(0) == 0
+
+
 def test_mentflow_checkpoint_round_trip(tmp_path):
     """MENTFlow.save / load (core.py:122-143): generator weights under zuko-style names plus the pickled
     measurement setup; loading into a freshly initialised model reproduces weights and setup."""

@@ -136,6 +136,42 @@ def test_ment_prob_sampling_and_update(golden):
     assert torch.allclose(torch.stack(cur), t32(g["tables1"]), rtol=1e-5, atol=1e-8)
 
 
+def test_ment_prob_with_2d_screens(golden):
+    """N-D Lagrange tables (ment.py:20-52) on the reference's rec_nd_2d_ment set-up, plus a mixed 1-D / 2-D model
+    and the integration-mode prediction of a 2-D screen (ment.py:267-317)."""
+    g = golden("ment_2d_screens")
+    mats, ex, ey = t32(g["matrices"]), t32(g["edges_x"]), t32(g["edges_y"])
+    scr = [[hp.Screen2D(axis=(0, 2), edges_x=ex, edges_y=ey)] for _ in mats]
+    tables = [[t] for t in t32(g["tables0"])]
+    s = float(g["prior_scale"])
+    xq = t32(g["xq"])
+    assert torch.allclose(hp.ment_prob(xq, list(mats), scr, tables, s), t32(g["prob_q"]), rtol=1e-5, atol=1e-30)
+    res, xmax = int(g["grid_res"]), float(g["grid_xmax"])
+    pts = hp.grid_points([hp.centres(torch.linspace(-xmax, xmax, res + 1)) for _ in range(4)])
+    assert torch.allclose(hp.ment_prob(pts, list(mats), scr, tables, s), t32(g["prob_grid"]), rtol=1e-5, atol=1e-30)
+    mats1, e1 = t32(g["matrices1"]), t32(g["edges1"])
+    scr_m = scr + _screens1d(e1, len(mats1))
+    tab_m = tables + [[t] for t in t32(g["tables1d"])]
+    got = hp.ment_prob(xq, list(mats) + list(mats1), scr_m, tab_m, s)
+    assert torch.allclose(got, t32(g["prob_q_mixed"]), rtol=1e-5, atol=1e-30)
+    # integration mode, screen 2: u = [pixel on axes (0, 2); grid on axes (1, 3)], x = M^-1 u, sum of rho
+    lim, shape = g["int_limits"], [int(v) for v in g["int_shape"]]
+    c1 = torch.linspace(float(lim[0][0]), float(lim[0][1]), shape[0])
+    c3 = torch.linspace(float(lim[1][0]), float(lim[1][1]), shape[1])
+    grid = hp.grid_points([c1, c3])
+    cx, cy = hp.centres(ex), hp.centres(ey)
+    minv = torch.linalg.inv(mats[2])
+    pred = torch.zeros(cx.numel(), cy.numel())
+    for i, px in enumerate(cx):
+        for j, py in enumerate(cy):
+            u = torch.zeros(grid.shape[0], 4)
+            u[:, 0], u[:, 2], u[:, 1], u[:, 3] = px, py, grid[:, 0], grid[:, 1]
+            pred[i, j] = hp.ment_prob(hp.linear_map(u, minv), list(mats), scr, tables, s).sum()
+    pred = hp.normalize_projection(pred, (ex[1] - ex[0]) * (ey[1] - ey[0]))
+    ref = t32(g["pred_2_0"])
+    assert torch.allclose(pred, ref, rtol=1e-4, atol=1e-7 * float(ref.max()))
+
+
 def test_ment_integrate_mode(golden):
     g = golden("ment_2d_integrate")
     mats, edges, meas = t32(g["matrices"]), t32(g["edges"]), t32(g["meas"])
