@@ -337,6 +337,86 @@ def extras(args, device, pk):
     ms = _timed(train4, reps=3, warm=1, flush=flush)
     entry("C4 training step: forward + backward to all flow parameters (eager)", N, ms,
           tensor_roof(3 * FLOP_MASK_AWARE[6] + 2 * flop_scr, N, ms, "nsf backward kernels + kde2d_bwd_kernel"))
+    del m4, x4, flush
+    torch.cuda.empty_cache()
+    out.append(ment_step_measure(device, 0, 1))
+    return out
+
+
+def ment_step_measure(device, rank, world, n_per_gpu=12_500_000, num_proj=25, res=16, bins=64, reps=2, parity=True):
+    """BASELINE config 5: classical MENT, 6-D, `num_proj` 1-D screens, density on a res^6 sampler grid, one
+    gauss_seidel_step = num_proj measurement updates, each drawing n_per_gpu x world particles (sample mode,
+    ment.py:319-371).  Particles are sharded: every rank draws its slice of one Philox stream and the unnormalised
+    profile sums are all-reduced (NCCL) before the update.  Timed with CUDA events, max over ranks."""
+    import torch.distributed as dist
+
+    import mentflow_b200 as mf
+    from mentflow_b200 import distributed as mfd
+    from mentflow_b200 import workloads
+    d, xmax = 6, 3.5
+    wl = workloads.isotropic_1d(d, num_proj, bins, xmax)
+    tfs = [mf.simulate.LinearTransform(m.to(device)) for m in wl["matrices"]]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(device)
+    diags = [[diag] for _ in tfs]
+    truth = workloads.gaussian_mixture(200_000, ndim=d, seed=1, device=device)
+    with torch.no_grad():
+        meas = [[p[0]] for p in mf.simulate.forward(truth, tfs, diags)]
+
+    def make(n_total, shard):
+        sampler = mf.sample.GridSampler(limits=d * [(-xmax, xmax)], shape=tuple(d * [res]), device=device)
+        m = mf.ment.MENT(ndim=d, transforms=tfs, diagnostics=diags, measurements=meas,
+                         prior=mf.prior.Gaussian(ndim=d, scale=3.0), mode="sample", sampler=sampler, n_samples=n_total,
+                         device=device)
+        if shard and world > 1:
+            mfd.shard_model(m)
+        return m
+
+    n_total = n_per_gpu * world
+    model = make(n_total, True)
+    torch.manual_seed(77)                    # the same sampler seeds on every rank
+    model.gauss_seidel_update(lr=0.9)        # warm-up sweep
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        model.gauss_seidel_update(lr=0.9)
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = torch.tensor([min(ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t[0])
+    out = {"case": f"C5 classical MENT gauss_seidel_step: 6-D, {num_proj} x KDE-1D({bins}), sampler grid {res}^6, "
+                   f"{n_per_gpu} sampled particles per GPU and measurement update",
+           "n_gpus": world, "particles_per_step": n_total * num_proj, "ms_per_step": step_ms,
+           "value": n_total * num_proj / step_ms * 1e3, "unit": "sampled particles/s",
+           "grid_points_per_s": res ** d * num_proj / step_ms * 1e3}
+    if parity and world > 1:
+        # One measurement update, sharded, against the same update on ONE GPU from the same tables and sampler seed:
+        # the ranks' slices are the particles one GPU draws, so the predicted profile differs by fp32 summation
+        # order only.  (A whole sweep cannot be compared this way: a 1e-7 change of a table moves the inverse-CDF
+        # cell of a sizeable fraction of the next update's particles, i.e. the later updates see a different --
+        # statistically equivalent -- sample.)
+        start = [lf[0].values.clone() for lf in model.lagrange_functions]
+        torch.manual_seed(78)
+        got = model.simulate(0, 0)
+        rel = None
+        if rank == 0:
+            single = make(n_total, False)
+            for lf, v in zip(single.lagrange_functions, start):
+                lf[0].set_values(v.clone())
+            torch.manual_seed(78)
+            want = single.simulate(0, 0)
+            rel = float((got - want).abs().max() / want.abs().max())
+        dist.barrier()
+        if rank == 0:
+            out["shard_parity"] = {"max_rel_profile": rel, "ok": bool(rel <= 1e-5), "particles": n_total,
+                                   "what": "predicted profile of one sharded measurement update (slices of one Philox "
+                                           "stream + NCCL all-reduce of the sums) vs the same update on one GPU"}
     return out
 
 
@@ -560,6 +640,10 @@ def main():
     clocks = sampler.finish()
 
     shard_parity = shard_parity_check(model, reducer, gen, n, d, rank, world, device) if world > 1 else None
+    ment_line = None
+    if world > 1 and not args.no_extra:
+        # BASELINE config 5 (classical MENT, particles sharded over the ranks), after and outside the headline timing
+        ment_line = ment_step_measure(device, rank, world)
 
     t = torch.tensor([total_ms, e2e_s * 1e3, train_ms, host_s * 1e3], dtype=torch.float64, device=device)
     if world > 1:
@@ -639,6 +723,8 @@ def main():
         }
         if shard_parity is not None:
             line["shard_parity"] = shard_parity
+        if ment_line is not None:
+            line["extra"] = [ment_line]
         if world == 1 and not args.no_cpu_baseline:
             stepf, ncpu = cpu_step_factory(args)
             v, ts = time_cpu(stepf, ncpu, reps=5)

@@ -6,7 +6,6 @@
 // called from generate/flows/zuko.py:24-29.
 #pragma once
 #include <math.h>
-#include <string.h>
 
 #include "nsf_common.cuh"
 
@@ -111,28 +110,8 @@ MFB_HD void two_sum(float a, float b, float& s, float& err) {
 // 1e-4 of float64: 1.0-1.2x torch-fp32's, was 4x).  MFB_SPLINE_COMP additionally carries the group
 // prefixes as (hi, lo) pairs (0.3-0.9x torch-fp32's).
 // Multiplies jac by dy/dv (1 outside [-B, B]) and returns y.
-// raw TMEM words or floats: the accumulator columns reach the spline as 32-bit registers
-MFB_HD float as_f32(float x) { return x; }
-MFB_HD float as_f32(uint32_t x) {
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(x);
-#else
-  float f;
-  memcpy(&f, &x, 4);
-  return f;
-#endif
-}
-
-struct SplineNoSync {
-  MFB_HD void operator()() const {}
-};
-
-// `mid` is called once, after the last use of the width parameters a[0..NB-1] and before the first use of
-// anything else: the GPU kernel waits there for the second half of its TMEM load (issued before the call),
-// so that the width phase runs under the load's latency.
-template <int NB, typename Mid = SplineNoSync, typename Word = float>
-MFB_HD float rq_spline_regs(const Word (&aw)[64], float v, float& jac, Mid mid = Mid()) {
-  auto a = [&](int j) -> float { return as_f32(aw[j]); };
+template <int NB>
+MFB_HD float rq_spline_regs(const float (&a)[64], float v, float& jac) {
   static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
   constexpr int G = NB / 4;
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
@@ -140,7 +119,7 @@ MFB_HD float rq_spline_regs(const Word (&aw)[64], float v, float& jac, Mid mid =
   float e[NB], pre[G + 1], plo[G + 1];
 #pragma unroll
   for (int j = 0; j < NB; j += 4) {
-    clip_exp2_quad(a(j), a(j + 1), a(j + 2), a(j + 3), cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
+    clip_exp2_quad(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
   }
   pre[0] = 0.f;
   plo[0] = 0.f;
@@ -181,13 +160,12 @@ MFB_HD float rq_spline_regs(const Word (&aw)[64], float v, float& jac, Mid mid =
   const bool r0 = q0 < rem, r1 = i1 < rem, r2 = i2 < rem;
   const float numer = rem - (r2 ? i2 : (r1 ? i1 : (r0 ? q0 : 0.f)));
   const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
-  mid();
   // ---- heights, one group at a time
   float run = 0.f, runl = 0.f, yg = 0.f, ygl = 0.f, h0s = 0.f, h1s = 0.f, h2s = 0.f, h3s = 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     float h0, h1, h2, h3;
-    clip_exp2_quad(a(NB + 4 * g), a(NB + 4 * g + 1), a(NB + 4 * g + 2), a(NB + 4 * g + 3), cW, h0, h1, h2, h3);
+    clip_exp2_quad(a[NB + 4 * g], a[NB + 4 * g + 1], a[NB + 4 * g + 2], a[NB + 4 * g + 3], cW, h0, h1, h2, h3);
     const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
     h0s = take ? h0 : h0s;
     h1s = take ? h1 : h1s;
@@ -214,8 +192,8 @@ MFB_HD float rq_spline_regs(const Word (&aw)[64], float v, float& jac, Mid mid =
   float um = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, prev = 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const float t0 = a(2 * NB + 4 * g), t1 = a(2 * NB + 4 * g + 1), t2 = a(2 * NB + 4 * g + 2);
-    const float t3 = (4 * g + 3 < NB - 1) ? a(2 * NB + 4 * g + 3) : 0.f;
+    const float t0 = a[2 * NB + 4 * g], t1 = a[2 * NB + 4 * g + 1], t2 = a[2 * NB + 4 * g + 2];
+    const float t3 = (4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f;
     const bool take = g == 0 ? true : pg[g > 0 ? g - 1 : 0];
     um = take ? prev : um;
     u0 = take ? t0 : u0;

@@ -290,22 +290,6 @@ __device__ __forceinline__ void store_hidden(const float (&acc)[64], unsigned ch
   }
 }
 
-// one half (32 accumulator columns = chunks 4 H .. 4 H + 3) of the same, from raw TMEM words
-template <int H>
-__device__ __forceinline__ void store_hidden_half(const uint32_t (&r)[64], unsigned char* a_hi, unsigned char* a_lo,
-                                                  int row) {
-#pragma unroll
-  for (int c = 4 * H; c < 4 * H + 4; ++c) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      split_relu_pair(__uint_as_float(r[8 * c + 2 * e]), __uint_as_float(r[8 * c + 2 * e + 1]), hi[e], lo[e]);
-    const uint32_t off = umma::sw128_offset(row, c);
-    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-}
-
 // output-layer tile of one feature: nk K steps, N = 64
 __device__ __forceinline__ void mma_slot(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                          int nk, uint32_t idesc) {
@@ -533,26 +517,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   // GEMM (l < L-1) or the first two output-layer tiles (l == L-1)
   auto hidden_step = [&](int l) {
     wait_buf(kHB);
-#if (MFB_TC_SPLITLD & 1)
-    // the accumulator comes out of TMEM in two halves: the second load runs under the conversion and the
-    // shared-memory stores of the first
-    uint32_t racc[64];
-    tmem_ld_half_issue<0>(col0 + (uint32_t)(kHB * 64) + lane_sel, racc);
-    tmem_ld_wait_half<0>(racc);
-    tmem_ld_half_issue<1>(col0 + (uint32_t)(kHB * 64) + lane_sel, racc);
-    store_hidden_half<0>(racc, a_hi, a_lo, t);
-    tmem_ld_wait_half<1>(racc);
-    store_hidden_half<1>(racc, a_hi, a_lo, t);
-    float acc[kBwd ? 64 : 1];
-    if constexpr (kBwd) {
-#pragma unroll
-      for (int c = 0; c < 64; ++c) acc[c] = __uint_as_float(racc[c]);
-    }
-#else
     float acc[64];
     tmem_ld64(col0 + (uint32_t)(kHB * 64) + lane_sel, acc);
     store_hidden(acc, a_hi, a_lo, t);   // biases are already in the accumulator (bias MMA)
-#endif
     fence_proxy_async();
     umma::fence_before_sync();
     request_arrive(req_chain);
@@ -649,9 +616,6 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     for (int s = kBwd ? -1 : 0; s < S; ++s) {
       const int b = s & 1;
       float acc[64];
-#if (MFB_TC_SPLITLD & 2)
-      uint32_t racc[64];
-#endif
       if (kBwd && s < 0) {
         if (cur) {
           const float4* cb = reinterpret_cast<const float4*>(ctab + kConstRows * kCT);
@@ -663,20 +627,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         }
       } else if (cur) {
         if (!(S >= 2 && s == S - 1)) wait_buf(b);   // the last slot was already waited for at kFork
-#if (MFB_TC_SPLITLD & 2)
-        if constexpr (!kBwd) {
-          // widths first: columns 0..31 now, columns 32..63 in flight while the width phase of the spline runs;
-          // the buffer is handed back to the issuer from inside the spline, once the second half has landed
-          tmem_ld_half_issue<0>(col0 + (uint32_t)(b * 64) + lane_sel, racc);
-          tmem_ld_wait_half<0>(racc);
-          tmem_ld_half_issue<1>(col0 + (uint32_t)(b * 64) + lane_sel, racc);
-        } else
-#endif
-        {
-          tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
-          umma::fence_before_sync();
-          if (s + 2 < S) request_arrive(req_chain + 1 + b);
-        }
+        tmem_ld64(col0 + (uint32_t)(b * 64) + lane_sel, acc);
+        umma::fence_before_sync();
+        if (s + 2 < S) request_arrive(req_chain + 1 + b);
         // slot 0 is complete => every warp is past its last read of the other staging buffer
         if (s == 0 && t == 0 && has_next) prefetch(tile + tstride, nbuf);
         TRACE(10 + s);
@@ -700,15 +653,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
         } else {
           const float vf = sc[f];
           ss = fmaf(vf, vf, ss);
-#if (MFB_TC_SPLITLD & 2)
-          sc[f] = rq_spline_regs<NB>(racc, vf, jac, [&]() {
-            tmem_ld_wait_half<1>(racc);
-            umma::fence_before_sync();
-            if (s + 2 < S) request_arrive(req_chain + 1 + b);
-          });
-#else
           sc[f] = rq_spline_regs<NB>(acc, vf, jac);
-#endif
         }
         TRACE(20 + s);
       }

@@ -28,7 +28,12 @@ __device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity)
 #ifndef MFB_POLL_NS
 #define MFB_POLL_NS 40
 #endif
+#if defined(MFB_ISSUER_TRYWAIT)
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   while (!mbar_test_wait(bar, parity)) __nanosleep(MFB_POLL_NS);
+#endif
 }
 
 // Warpgroup -> issuer hand-off: every compute warp arrives (lane 0, after __syncwarp) on a request
@@ -89,40 +94,6 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// The same load in two halves that can be waited for separately: half H covers columns 32 H .. 32 H + 31
-// of the 64-column accumulator.  tmem_ld_half_issue only issues; tmem_ld_wait_half is tcgen05.wait::ld
-// with the half's 32 registers as in/out operands, which pins every use of them behind the wait (the
-// compiler sees the registers as defined by the wait, not by the load).
-template <int H>
-__device__ __forceinline__ void tmem_ld_half_issue(uint32_t taddr, uint32_t (&r)[64]) {
-  constexpr int o = 32 * H;
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]),
-        "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]),
-        "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15]), "=r"(r[o + 16]), "=r"(r[o + 17]), "=r"(r[o + 18]),
-        "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]), "=r"(r[o + 22]), "=r"(r[o + 23]), "=r"(r[o + 24]),
-        "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]), "=r"(r[o + 29]), "=r"(r[o + 30]),
-        "=r"(r[o + 31])
-      : "r"(taddr + (uint32_t)o)
-      : "memory");
-}
-template <int H>
-__device__ __forceinline__ void tmem_ld_wait_half(uint32_t (&r)[64]) {
-  constexpr int o = 32 * H;
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[o + 0]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]),
-                 "+r"(r[o + 6]), "+r"(r[o + 7]), "+r"(r[o + 8]), "+r"(r[o + 9]), "+r"(r[o + 10]), "+r"(r[o + 11]),
-                 "+r"(r[o + 12]), "+r"(r[o + 13]), "+r"(r[o + 14]), "+r"(r[o + 15]), "+r"(r[o + 16]), "+r"(r[o + 17]),
-                 "+r"(r[o + 18]), "+r"(r[o + 19]), "+r"(r[o + 20]), "+r"(r[o + 21]), "+r"(r[o + 22]), "+r"(r[o + 23]),
-                 "+r"(r[o + 24]), "+r"(r[o + 25]), "+r"(r[o + 26]), "+r"(r[o + 27]), "+r"(r[o + 28]), "+r"(r[o + 29]),
-                 "+r"(r[o + 30]), "+r"(r[o + 31])
-               :
-               : "memory");
 }
 
 // Split MMAs of one K step.  The cross terms (hi*lo + lo*hi, 2^-11 of the result) of ALL K steps

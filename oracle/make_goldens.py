@@ -392,6 +392,86 @@ def make_ment_2d_screens():
     print("wrote ment_2d_screens.npz")
 
 
+def make_baseline_sized():
+    """Reference outputs at the sizes of BASELINE.json's configs (the other fixtures are small on purpose):
+    C3  rec_nd_1d: 6-D, K = 100 random projections, 64 bins, N = 20,000 (experiments/rec_nd_1d, run_gmm.sh)
+    C4  rec_nd_2d: 6-D, 15 corner screens 85 x 85, N = 5,000
+    C5  classical MENT: 6-D, K = 25, sampler grid 8^6: density on the grid (every 5th cell) and one sample-mode
+        Gauss-Seidel sweep with 200,000 particles per update (torch CPU generator: statistical comparison only)."""
+    mf = ref_import.load()
+    # ---- C3
+    torch.manual_seed(51)
+    d, k, nb, n = 6, 100, 64, 20000
+    x = (torch.randn(n, d) * torch.tensor([1.0, 0.6, 1.4, 0.8, 1.1, 0.9])).float()
+    x[:, 1] += 0.3 * x[:, 0] ** 2 - 0.3
+    mats = isotropic_matrices(k, d, seed=0)
+    edges = torch.linspace(-3.5, 3.5, nb + 1)
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=edges, bandwidth=0.5)
+    tfs = [mf.simulate.LinearTransform(m) for m in mats]
+    kde = torch.stack([p[0] for p in mf.simulate.forward(x, tfs, [[diag] for _ in tfs])])
+    diag.kde = False
+    hard = torch.stack([p[0] for p in mf.simulate.forward(x, tfs, [[diag] for _ in tfs])])
+    xm = torch.randn(50000, d).float() * 0.9
+    meas = torch.stack([p[0] for p in mf.simulate.forward(xm, tfs, [[diag] for _ in tfs])])
+    diag.kde = True
+    meas = meas / meas.sum(dim=1, keepdim=True) / (edges[1] - edges[0])
+    logq = (-0.5 * (x ** 2).sum(dim=1) - 3.0).float()
+    prior = mf.prior.Gaussian(ndim=d, scale=3.0)
+
+    class Fixed(torch.nn.Module):
+        def sample_and_log_prob(self, n_):
+            return x[:n_], logq[:n_]
+
+    model = mf.MENTFlow(transforms=tfs, diagnostics=[[diag] for _ in tfs], measurements=[[m] for m in meas],
+                        generator=Fixed(), prior=prior, entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                        discrepancy_function=mf.loss.kl_divergence, penalty_parameter=25.0)
+    L, H, D = model.loss(n)
+    np.savez_compressed(os.path.join(OUT, "c3_k100.npz"), x=npy(x).astype(np.float32), logq=npy(logq), edges=npy(edges),
+                        matrix_seed=0, kde=npy(kde), hard=npy(hard), meas=npy(meas), loss_L=npy(L), loss_H=npy(H),
+                        loss_D=npy(torch.stack(D)), prior_scale=3.0, penalty=25.0)
+    print("wrote c3_k100.npz")
+    # ---- C4
+    torch.manual_seed(52)
+    n4 = 5000
+    x4 = (torch.randn(n4, d) * torch.tensor([1.0, 0.7, 1.3, 0.9, 0.8, 1.1])).float()
+    x4[:, 2] += 0.5 * x4[:, 0] ** 2 - 0.5
+    mats4 = corner_matrices(d)
+    e4 = torch.linspace(-3.5, 3.5, 86)
+    diag4 = mf.diagnostics.Histogram2D(axis=(0, 2), edges=[e4, e4.clone()], bandwidth=(0.5, 0.5))
+    tfs4 = [mf.simulate.LinearTransform(m) for m in mats4]
+    kde4 = torch.stack([p[0] for p in mf.simulate.forward(x4, tfs4, [[diag4] for _ in tfs4])])
+    np.savez_compressed(os.path.join(OUT, "c4_6d_85.npz"), x=npy(x4), edges=npy(e4), kde=npy(kde4).astype(np.float32))
+    print("wrote c4_6d_85.npz")
+    # ---- C5
+    torch.manual_seed(53)
+    k5, nb5, res = 25, 64, 8
+    mats5 = isotropic_matrices(k5, d, seed=7)
+    e5 = torch.linspace(-3.5, 3.5, nb5 + 1)
+    diag5 = mf.diagnostics.Histogram1D(axis=0, edges=e5, bandwidth=0.5)
+    tfs5 = [mf.simulate.LinearTransform(m) for m in mats5]
+    xt = torch.randn(100000, d).float() * torch.tensor([1.0, 0.8, 1.2, 0.9, 1.1, 0.7])
+    diag5.kde = False
+    meas5 = [p[0] for p in mf.simulate.forward(xt, tfs5, [[diag5] for _ in tfs5])]
+    diag5.kde = True
+    meas5 = [m / m.sum() / (e5[1] - e5[0]) for m in meas5]
+    sampler = mf.sample.GridSampler(limits=d * [(-3.5, 3.5)], shape=tuple(d * [res]))
+    ment = mf.ment.MENT(ndim=d, transforms=tfs5, diagnostics=[[diag5] for _ in tfs5], measurements=[[m] for m in meas5],
+                        prior=mf.prior.Gaussian(ndim=d, scale=2.0), mode="sample", sampler=sampler, n_samples=200000)
+    for i in range(k5):
+        lf = ment.lagrange_functions[i][0]
+        lf.set_values(lf.values * (0.6 + 0.8 * torch.rand(nb5)))
+    tables0 = torch.stack([ment.lagrange_functions[i][0].values.clone() for i in range(k5)])
+    prob_grid = ment.prob(sampler.get_grid_points())
+    torch.manual_seed(54)
+    ment.gauss_seidel_update(lr=0.9, thresh=1.0e-10)
+    tables1 = torch.stack([ment.lagrange_functions[i][0].values.clone() for i in range(k5)])
+    np.savez_compressed(os.path.join(OUT, "c5_ment_6d.npz"), matrix_seed=7, edges=npy(e5), meas=npy(torch.stack(meas5)),
+                        prior_scale=2.0, grid_res=res, grid_xmax=3.5, tables0=npy(tables0), prob_grid_stride=5,
+                        prob_grid_every5=npy(prob_grid[::5]), prob_grid_sum=npy(prob_grid.double().sum()),
+                        n_samples=200000, lr=0.9, tables1=npy(tables1))
+    print("wrote c5_ment_6d.npz")
+
+
 def make_noise():
     """Measurement noise of Histogram.forward (diagnostics/diagnostics.py:50-68): a generator re-seeded on
     every call, multiplicative gaussian / uniform noise, clamped at zero; 1-D and 2-D screens."""
@@ -423,8 +503,11 @@ if __name__ == "__main__":
         make_noise()
     elif "--only-ment2d" in sys.argv:
         make_ment_2d_screens()
+    elif "--only-baseline-sized" in sys.argv:
+        make_baseline_sized()
     else:
         main()
         make_multipole()
         make_noise()
         make_ment_2d_screens()
+        make_baseline_sized()

@@ -136,6 +136,20 @@ def test_ment_prob_sampling_and_update(golden):
     assert torch.allclose(torch.stack(cur), t32(g["tables1"]), rtol=1e-5, atol=1e-8)
 
 
+def test_projection_order_reproduces_reference_bits(golden):
+    """The CUDA kernels project with an ascending fused-multiply-add chain starting from zero
+    (kde1d.cu project_row).  Restated here in numpy (float64 product + sum rounded once = fmaf): it reproduces the
+    reference's `x @ M.T` bit for bit on its own stored projections, which is what makes fused exact histograms
+    through general matrices bit-exact."""
+    g = golden("kde1d_6d")
+    x, mats, uproj = g["x"].astype(np.float32), g["matrices"].astype(np.float32), g["uproj"].astype(np.float32)
+    for k in range(mats.shape[0]):
+        acc = np.zeros(x.shape[0], np.float32)
+        for i in range(x.shape[1]):
+            acc = (x[:, i].astype(np.float64) * np.float64(mats[k, 0, i]) + acc.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(acc.view(np.uint32), uproj[k].view(np.uint32))
+
+
 def test_ment_prob_with_2d_screens(golden):
     """N-D Lagrange tables (ment.py:20-52) on the reference's rec_nd_2d_ment set-up, plus a mixed 1-D / 2-D model
     and the integration-mode prediction of a 2-D screen (ment.py:267-317)."""
