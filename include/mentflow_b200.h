@@ -25,11 +25,15 @@
 extern "C" {
 #endif
 
-#define MFB_ABI_VERSION 1
+#define MFB_ABI_VERSION 2
 
 #define MFB_E_BADARG (-1)      /* null pointer / non-positive size / unsupported shape   */
 #define MFB_E_UNSUPPORTED (-2) /* combination not compiled (e.g. D > 8, hidden != 64)    */
 #define MFB_E_WORKSPACE (-3)   /* workspace too small                                    */
+
+/* per-call `flags` of the entry points that have a tensor-core and a CUDA-core implementation of the same
+ * result (A/B tests, parity cross-checks).  There is no process-wide switch: the library keeps no mutable state. */
+#define MFB_FLAG_NO_TENSOR_CORES 1
 
 int mfb_abi_version(void);
 const char* mfb_error_string(int code);
@@ -123,12 +127,11 @@ int mfb_project_hist1d(const float* x, int64_t n, int d, const float* proj, cons
 int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by);
 /* Screens of up to 128 x 96 bins and batches of at least 4096 particles run as tcgen05 GEMMs over the
  * particle axis (the reference's own formulation, diagnostics/histogram.py:47-74: P = Kx^T Ky), dense
- * kernel rows in split bf16; otherwise windowed fixed-point deposits.  enable: 1 / 0 switches the
- * tensor-core path, < 0 only queries; returns the previous setting (process-wide; for A/B tests).   */
-int mfb_kde2d_use_tensor_cores(int enable);
+ * kernel rows in split bf16; otherwise (or with MFB_FLAG_NO_TENSOR_CORES in `flags`) windowed fixed-point
+ * deposits.                                                                                          */
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom,
                           int k, int bx, int by, float max_sigma_over_delta, float* sums,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          void* workspace, int64_t workspace_bytes, int flags, void* stream);
 /* P <- P / (sum(P) dx dy + 1e-10)  (histogram.py:70-73) and its backward                */
 int mfb_kde2d_normalize(const float* sums, const float* geom, int k, int bx, int by,
                         float* profiles, void* stream);
@@ -189,16 +192,14 @@ int mfb_nsf_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hi
  * W1 [64][d] | Wl [64 out][64 in] x (L-1) | Wout [d*64 (59->64 padded rows)][64 in], no biases
  * (mfb_nsf_layer_param_om_floats floats).  dL/dlogq_in = glogq (pass-through).           */
 int64_t mfb_nsf_layer_param_om_floats(int d, int hidden_units, int hidden_layers);
-/* The data-gradient chain of mfb_nsf_layer_bwd (three dgrad GEMMs + the input gradient) runs on the
- * tensor cores for hidden_layers = 3 (nsf_tc_bwd.cu).  enable: 1 / 0 switches it, < 0 only queries;
- * returns the previous setting (process-wide; meant for A/B tests).                              */
-int mfb_nsf_bwd_use_tensor_cores(int enable);
+/* The backward of a layer runs as three tcgen05 kernels for hidden_layers = 3, bins = 20 (nsf_tc.cu kBwd,
+ * nsf_tc_bwd.cu) and on CUDA-core kernels otherwise, or when `flags` has MFB_FLAG_NO_TENSOR_CORES.   */
 int64_t mfb_nsf_layer_bwd_workspace_bytes(int64_t n, int d, int hidden_layers);
 int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d,
                       int hidden_units, int hidden_layers, int bins, const float* params,
                       const float* params_om, const int32_t* order_host, int first_layer, float* gv,
                       float* gparams, int accumulate, void* workspace, int64_t workspace_bytes,
-                      void* stream);
+                      int flags, void* stream);
 
 /* The same with the layer's tcgen05 operand image that mfb_nsf_tc_prepare built for the forward pass of
  * this step (tc_image, mfb_nsf_tc_image_bytes bytes, 16-byte aligned; NULL = build it here): a
@@ -207,7 +208,7 @@ int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, i
                           int hidden_units, int hidden_layers, int bins, const float* params,
                           const float* params_om, const int32_t* order_host, int first_layer,
                           const void* tc_image, float* gv, float* gparams, int accumulate,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
 /* ---- Monte-Carlo entropy pieces (entropy.py:58-62, prior.py:25-26) ----------------------
  * out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j

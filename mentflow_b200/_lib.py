@@ -32,8 +32,7 @@ SIGNATURES = {
     "mfb_project_hist1d_mp": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, P, P]),
     "mfb_project_hist1d": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, P, P]),
     "mfb_kde2d_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
-    "mfb_kde2d_use_tensor_cores": (c_int, [c_int]),
-    "mfb_project_kde2d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int64, P]),
+    "mfb_project_kde2d_fwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int64, c_int, P]),
     "mfb_kde2d_normalize": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "mfb_kde2d_normalize_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "mfb_project_kde2d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
@@ -47,12 +46,11 @@ SIGNATURES = {
     "mfb_nsf_tc_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_inv": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_param_om_floats": (c_int64, [c_int, c_int, c_int]),
-    "mfb_nsf_bwd_use_tensor_cores": (c_int, [c_int]),
     "mfb_nsf_layer_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "mfb_nsf_layer_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P,
-                                  c_int64, P]),
+                                  c_int64, c_int, P]),
     "mfb_nsf_layer_bwd_img": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P, c_int, P,
-                                      c_int64, P]),
+                                      c_int64, c_int, P]),
     "mfb_ment_prob": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_prob_grid": (c_int, [c_int, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mfb_ment_integrate": (c_int, [c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_float,

@@ -343,15 +343,8 @@ int64_t kde2d_tc_partial_bytes(int k, int bx, int by);
 int kde2d_tc_forward(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx, int by,
                      float* sums, unsigned long long* acc, float* partial, cudaStream_t st);
 }  // namespace mfb
-static int g_use_tc_kde2d = 1;
 
 extern "C" {
-
-int mfb_kde2d_use_tensor_cores(int enable) {
-  const int prev = g_use_tc_kde2d;
-  if (enable >= 0) g_use_tc_kde2d = enable ? 1 : 0;
-  return prev;
-}
 
 int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by) {
   (void)n;
@@ -363,7 +356,7 @@ int64_t mfb_kde2d_workspace_bytes(int64_t n, int d, int k, int bx, int by) {
 
 int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int bx,
                           int by, float max_sigma_over_delta, float* sums, void* workspace,
-                          int64_t workspace_bytes, void* stream) {
+                          int64_t workspace_bytes, int flags, void* stream) {
   MFB_CHECK_ARG(x && proj && geom && sums && workspace);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 2 && by >= 2);
   const int64_t len = (int64_t)k * bx * by;
@@ -372,7 +365,7 @@ int mfb_project_kde2d_fwd(const float* x, int64_t n, int d, const float* proj, c
   if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* acc = (unsigned long long*)workspace;
-  if (g_use_tc_kde2d && kde2d_tc_supported(n, d, bx, by) &&
+  if (!(flags & MFB_FLAG_NO_TENSOR_CORES) && kde2d_tc_supported(n, d, bx, by) &&
       workspace_bytes >= len * 16 + kde2d_tc_partial_bytes(k, bx, by)) {
     float* partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + len * 16);
     return kde2d_tc_forward(x, n, d, proj, geom, k, bx, by, sums, acc, partial, st);

@@ -475,8 +475,6 @@ nsf_bwd_input_kernel(const float* __restrict__ gvd, const float* __restrict__ g1
   }
 }
 
-// switch for A/B tests: 0 = CUDA-core dgrad kernels only (mfb_nsf_bwd_use_tensor_cores)
-static int g_use_tc_dgrad = 1;
 
 // ---- host-side orchestration of one layer ----------------------------------------------------------------
 // tcgen05 data-gradient chain (nsf_tc_bwd.cu); MFB_E_UNSUPPORTED for shapes it is not compiled for
@@ -542,7 +540,7 @@ template <int D>
 static int run_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int hidden_layers, int nb,
                          const float* params, const float* params_om, const FeatureOrder& order, int first,
                          float* gv, float* gparams, int accumulate, float* ws, cudaStream_t st,
-                         const void* ready_image = nullptr) {
+                         const void* ready_image = nullptr, int flags = 0) {
   const BwdPlan P = plan_bwd(n, D, hidden_layers);
   const int64_t np = nsf_param_floats(D, hidden_layers);
   float* acts = ws + P.acts;
@@ -556,7 +554,7 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
   MFB_CUDA(cudaMemsetAsync(gmaxes, 0, 8 * sizeof(int), st));
   // 1. recompute + spline backward: on the tensor cores where compiled, else the CUDA-core kernel
   bool tc_spline = false;
-  if (hidden_layers == 3 && g_use_tc_dgrad) {
+  if (hidden_layers == 3 && !(flags & MFB_FLAG_NO_TENSOR_CORES)) {
     int32_t ord[kMaxDim];
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
@@ -653,12 +651,6 @@ using namespace mfb;
 
 extern "C" {
 
-int mfb_nsf_bwd_use_tensor_cores(int enable) {
-  const int old = g_use_tc_dgrad;
-  if (enable >= 0) g_use_tc_dgrad = enable ? 1 : 0;
-  return old;
-}
-
 int64_t mfb_nsf_layer_bwd_workspace_bytes(int64_t n, int d, int hidden_layers) {
   if (n < 1 || d < 2 || d > 6 || hidden_layers < 1) return 0;
   return plan_bwd(n, d, hidden_layers).total * 4;
@@ -672,7 +664,7 @@ int64_t mfb_nsf_layer_param_om_floats(int d, int hidden_units, int hidden_layers
 static int layer_bwd_impl(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
                           int hidden_layers, int bins, const float* params, const float* params_om,
                           const int32_t* order_host, int first_layer, const void* tc_image, float* gv, float* gparams,
-                          int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+                          int accumulate, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
   MFB_CHECK_ARG(v && gy && params && params_om && gv && gparams && workspace && n >= 1);
   if (hidden_units != kH || hidden_layers < 1 || bins < 2 || 3 * bins - 1 > kPP || d < 2 || d > 6)
     return MFB_E_UNSUPPORTED;
@@ -683,7 +675,7 @@ static int layer_bwd_impl(const float* v, const float* gy, const float* glogq, i
   float* ws = (float*)workspace;
 #define MFB_BWD(DD)                                                                                              \
   return run_layer_bwd<DD>(v, gy, glogq, n, hidden_layers, bins, params, params_om, ord, first_layer, gv, gparams, \
-                           accumulate, ws, st, tc_image)
+                           accumulate, ws, st, tc_image, flags)
   switch (d) {
     case 2: MFB_BWD(2);
     case 3: MFB_BWD(3);
@@ -698,17 +690,18 @@ static int layer_bwd_impl(const float* v, const float* gy, const float* glogq, i
 int mfb_nsf_layer_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
                       int hidden_layers, int bins, const float* params, const float* params_om,
                       const int32_t* order_host, int first_layer, float* gv, float* gparams, int accumulate,
-                      void* workspace, int64_t workspace_bytes, void* stream) {
+                      void* workspace, int64_t workspace_bytes, int flags, void* stream) {
   return layer_bwd_impl(v, gy, glogq, n, d, hidden_units, hidden_layers, bins, params, params_om, order_host,
-                        first_layer, nullptr, gv, gparams, accumulate, workspace, workspace_bytes, stream);
+                        first_layer, nullptr, gv, gparams, accumulate, workspace, workspace_bytes, flags, stream);
 }
 
 int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_units,
                           int hidden_layers, int bins, const float* params, const float* params_om,
                           const int32_t* order_host, int first_layer, const void* tc_image, float* gv,
-                          float* gparams, int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+                          float* gparams, int accumulate, void* workspace, int64_t workspace_bytes, int flags,
+                          void* stream) {
   return layer_bwd_impl(v, gy, glogq, n, d, hidden_units, hidden_layers, bins, params, params_om, order_host,
-                        first_layer, tc_image, gv, gparams, accumulate, workspace, workspace_bytes, stream);
+                        first_layer, tc_image, gv, gparams, accumulate, workspace, workspace_bytes, flags, stream);
 }
 
 }  // extern "C"

@@ -157,12 +157,20 @@ class NSFGenerator(GenerativeModel):
         out[prefix + "_flow.base.scale"] = torch.ones(self.features)
         return out
 
+    # mentflow wraps the inverted flow, zuko.flows.Flow(flow.transform.inv, flow.base) (generate/build.py:44-46), and
+    # zuko keeps the wrapped transform of a LazyInverse under `.transform`: checkpoints written by the reference
+    # most likely carry `_flow.transform.transform.transforms.{t}...`.  zuko is not installable here, so both
+    # spellings are accepted on load (unverified against a real zuko 1.3.1 key list).
+    _ZUKO_PREFIXES = ("_flow.transform.transforms.", "_flow.transform.transform.transforms.")
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         missing = []
         with torch.no_grad():
             for name, tensor, idx, _ in self._zuko_items():
-                if name in state_dict:
-                    tensor[idx].copy_(state_dict[name])
+                tail = name[len(self._ZUKO_PREFIXES[0]):]
+                hit = next((p + tail for p in self._ZUKO_PREFIXES if p + tail in state_dict), None)
+                if hit is not None:
+                    tensor[idx].copy_(state_dict[hit])
                 else:
                     missing.append(name)
         if strict and missing:

@@ -15,6 +15,10 @@ import torch
 from . import _lib
 
 GEOM_STRIDE = 8
+FLAG_NO_TENSOR_CORES = 1            # MFB_FLAG_NO_TENSOR_CORES of the C ABI (per call; the library keeps no switches)
+# Python-side choices between two implementations of the same result, read at call time (A/B tests)
+KDE2D_USE_TENSOR_CORES = True
+NSF_BWD_USE_TENSOR_CORES = True
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -263,7 +267,8 @@ def kde2d_sums(x, proj, geom, ratio, bx, by):
         wbytes = int(lib.mfb_kde2d_workspace_bytes(n, d, k, bx, by))
         work = torch.empty((wbytes + 7) // 8, dtype=torch.int64, device=x.device)
         _lib.check(lib.mfb_project_kde2d_fwd(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, bx, by, float(ratio),
-                                             _ptr(sums), _ptr(work), wbytes, _stream()),
+                                             _ptr(sums), _ptr(work), wbytes,
+                                             0 if KDE2D_USE_TENSOR_CORES else FLAG_NO_TENSOR_CORES, _stream()),
                    "project_kde2d_fwd")
     acc = work[: 2 * k * bx * by].view(2, k, bx, by)
     return sums, acc
@@ -506,7 +511,8 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
                                                      _ptr(packed_om[t]), ctypes.cast(order_arr, ctypes.c_void_p),
                                                      1 if t == 0 else 0, _ptr(images[t]) if images is not None else None,
                                                      _ptr(out), _ptr(gpacked[t]), 1 if start > 0 else 0, _ptr(work),
-                                                     wbytes, _stream()), "nsf_layer_bwd")
+                                                     wbytes, 0 if NSF_BWD_USE_TENSOR_CORES else FLAG_NO_TENSOR_CORES,
+                                                     _stream()), "nsf_layer_bwd")
                 g = out
     return gz, gpacked
 

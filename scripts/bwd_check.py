@@ -4,11 +4,11 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import torch
 import mentflow_b200 as mf
-from mentflow_b200 import _lib
+from mentflow_b200 import _lib, ops
 lib = _lib.load()
 
 def grads(gen, z, a, b, flag, scale=1.0):
-    lib.mfb_nsf_bwd_use_tensor_cores(1 if flag else 0)
+    ops.NSF_BWD_USE_TENSOR_CORES = bool(flag)
     for p in gen.parameters(): p.grad = None
     zc = z.clone().requires_grad_(True)
     x, lq = gen.forward_and_log_prob(zc)

@@ -21,9 +21,9 @@ ex, ey = torch.linspace(-3.5, 3.5, bx + 1), torch.linspace(-3.5, 3.5, by + 1)
 gx, sx = geom_rows(ex, 0.5, k)
 gy, sy = geom_rows(ey, 0.5, k)
 geom = torch.stack([gx, gy], dim=1).cuda()
-lib.mfb_kde2d_use_tensor_cores(1)
+ops.KDE2D_USE_TENSOR_CORES = True
 tc = ops.kde2d_sums(x, w, geom, 0.5, bx, by)[0].double()
-lib.mfb_kde2d_use_tensor_cores(0)
+ops.KDE2D_USE_TENSOR_CORES = False
 fx = ops.kde2d_sums(x, w, geom, 0.5, bx, by)[0].double()
 # float64 dense reference on the GPU
 cx = (0.5 * (ex[1:] + ex[:-1])).double().cuda()
@@ -50,7 +50,7 @@ w = torch.randn(k, 2, d, device="cuda")
 w = w / w.norm(dim=2, keepdim=True)
 geom = torch.stack([geom_rows(ex, 0.5, k)[0], geom_rows(ey, 0.5, k)[0]], dim=1).cuda()
 for flag in (1, 0):
-    lib.mfb_kde2d_use_tensor_cores(flag)
+    ops.KDE2D_USE_TENSOR_CORES = bool(flag)
     for _ in range(2):
         ops.kde2d_sums(x, w, geom, 0.5, bx, by)
     torch.cuda.synchronize()
@@ -61,4 +61,4 @@ for flag in (1, 0):
     b.record()
     b.synchronize()
     print("tensor cores" if flag else "fixed point ", f"{a.elapsed_time(b) / 5:.3f} ms per 1e6 particles x 15 screens 85x85")
-lib.mfb_kde2d_use_tensor_cores(1)
+ops.KDE2D_USE_TENSOR_CORES = True

@@ -93,14 +93,15 @@ def test_kde2d_tensor_core_and_fixed_point_paths_agree():
     ex, ey = torch.linspace(-3.5, 3.5, bx + 1), torch.linspace(-3.5, 3.5, by + 1)
     (gx, sx), (gy, sy) = geom_rows(ex, 0.5, k), geom_rows(ey, 0.5, k)
     geom = torch.stack([gx, gy], dim=1).cuda()
-    prev = lib.mfb_kde2d_use_tensor_cores(1)
+    prev = ops.KDE2D_USE_TENSOR_CORES
     try:
+        ops.KDE2D_USE_TENSOR_CORES = True
         tc, acc = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
         tc2, _ = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
-        lib.mfb_kde2d_use_tensor_cores(0)
+        ops.KDE2D_USE_TENSOR_CORES = False           # MFB_FLAG_NO_TENSOR_CORES on the call
         fx, _ = ops.kde2d_sums(x, w, geom, 0.5, bx, by)
     finally:
-        lib.mfb_kde2d_use_tensor_cores(prev)
+        ops.KDE2D_USE_TENSOR_CORES = prev
     assert torch.equal(tc, tc2)
     assert not torch.equal(tc, fx)                   # the two paths really are different kernels
     cx, cy = (0.5 * (ex[1:] + ex[:-1])).double().cuda(), (0.5 * (ey[1:] + ey[:-1])).double().cuda()

@@ -248,11 +248,10 @@ def test_backward_matches_oracle_autograd(d, n, scale, hl, tr, bins):
 @pytest.fixture
 def cuda_core_backward():
     """Run a test with the fp32 CUDA-core backward kernels (the tcgen05 backward is the default)."""
-    from mentflow_b200 import _lib
-    lib = _lib.load()
-    old = lib.mfb_nsf_bwd_use_tensor_cores(0)
+    from mentflow_b200 import ops
+    old, ops.NSF_BWD_USE_TENSOR_CORES = ops.NSF_BWD_USE_TENSOR_CORES, False
     yield
-    lib.mfb_nsf_bwd_use_tensor_cores(old)
+    ops.NSF_BWD_USE_TENSOR_CORES = old
 
 
 def test_backward_cuda_core_kernels_match_oracle(cuda_core_backward):
@@ -264,8 +263,7 @@ def test_backward_cuda_core_kernels_match_oracle(cuda_core_backward):
 def test_backward_tensor_core_and_cuda_core_agree():
     """Same weights, inputs and upstream gradients through both backward implementations, with a
     1/N-sized loss (gradients far below fp16's range: exercises the operand scaling)."""
-    from mentflow_b200 import _lib
-    lib = _lib.load()
+    from mentflow_b200 import ops
     torch.manual_seed(11)
     d, n = 6, 20_000
     gen = mf.generate.NSFGenerator(d).to("cuda")
@@ -273,7 +271,7 @@ def test_backward_tensor_core_and_cuda_core_agree():
     a, b = torch.randn(n, d, device="cuda"), torch.randn(n, device="cuda")
     out = {}
     for flag in (1, 0):
-        old = lib.mfb_nsf_bwd_use_tensor_cores(flag)
+        old, ops.NSF_BWD_USE_TENSOR_CORES = ops.NSF_BWD_USE_TENSOR_CORES, bool(flag)
         try:
             for p in gen.parameters():
                 p.grad = None
@@ -282,7 +280,7 @@ def test_backward_tensor_core_and_cuda_core_agree():
             (((x * a).sum() + (lq * b).sum()) * 1e-7).backward()
             out[flag] = [zc.grad.clone()] + [p.grad.clone() for p in gen.parameters()]
         finally:
-            lib.mfb_nsf_bwd_use_tensor_cores(old)
+            ops.NSF_BWD_USE_TENSOR_CORES = old
     for g1, g0 in zip(out[1], out[0]):
         e = (g1 - g0).abs() / g0.abs().max().clamp_min(1e-30)
         # the two paths evaluate the knot sums differently (fp32 centred differences vs double): 2e-3 of the largest

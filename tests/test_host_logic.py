@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert lib.mfb_abi_version() == 1
+    assert lib.mfb_abi_version() == 2
     assert b"workspace" in lib.mfb_error_string(-3)
 
 
