@@ -665,7 +665,7 @@ def main():
         # the operand images are cached while the weights do not change: no prepare kernel in a forward-only step
         nsf_launches = {"nsf_tc_layer_kernel": layers} if tc else {"nsf_layer_fwd_kernel": layers}
         rest = {"randn_philox + advance": 2, "moments": 2, "kde1d deposit + merge/normalise/KL": 2}
-        if world > 1:
+        if world > 1 and getattr(reducer, "peer", None) is None:
             rest["f64 split/join (packed all-reduce)"] = 2
         pieces = len(graphed._chunk_bounds()) if graphed is not None else 1
         prof = NCU_PROFILE if (tc and d == 6 and n == 1_000_000) else {}
@@ -678,6 +678,9 @@ def main():
                                    f"NSF 5 layers x MaskedMLP[{d},64,64,64,{59 * d}] 20-bin RQ spline, forward "
                                    f"(base-noise draw + sample + log_prob + entropy + project + KDE + KL loss)",
                        "particles_per_gpu_per_step": n, "parallelism": f"particles sharded x{world}",
+                       "cross_rank_sum": ("none (one GPU)" if world == 1 else
+                                          "inside kde1d_finish_p2p_kernel: NVLink peer loads, epoch barrier in the kernel"
+                                          if getattr(reducer, "peer", None) is not None else "NCCL all-reduce (packed)"),
                        "l2": "256 MB flush write between timed iterations",
                        "launch": ("CUDA graph replay of the forward step, base-noise draw (Philox) inside the graph "
                                   "(mentflow_b200.graphs.GraphedLoss)" if use_graph else "eager launches"),

@@ -87,6 +87,20 @@ int mfb_kde1d_finish(const float* sums, double n_total, const float* geom, int k
 int mfb_kde1d_finish_bwd(const float* sums, double n_total, const float* geom, int k, int b,
                          const float* meas, float pad, const float* gprof, const float* gkl,
                          float* gsums, void* stream);
+/* The same tail at N > 1 GPUs with the cross-rank sum INSIDE the kernel (replaces the NCCL all-reduce of
+ * S[K][B] + the entropy sums that sat between deposit and tail): every rank owns a peer-mapped block of
+ * mfb_kde1d_p2p_block_floats(k, b, tail_doubles) floats, zero-initialised, whose addresses AS MAPPED IN THIS PROCESS
+ * are passed in peer_blocks_host[world] (host array).  The kernel copies local_sums[K][B] (+ local_tail doubles)
+ * into its own block, exchanges an epoch over NVLink, adds all ranks' rows in rank order (bit-identical on every
+ * rank) and finishes like mfb_kde1d_finish; sums[K][B] receives the reduced sums, tail_out the reduced doubles.
+ * state: 3 zero-initialised uint32 in local device memory (epoch, two arrival counters), advanced by the kernel
+ * itself so that a captured graph replays correctly.  Every rank must launch it once per step; k*b even,
+ * k <= 1024.                                                                                                 */
+int64_t mfb_kde1d_p2p_block_floats(int k, int b, int tail_doubles);
+int mfb_kde1d_finish_p2p(const uint64_t* peer_blocks_host, int rank, int world, uint32_t* state,
+                         const float* local_sums, const double* local_tail, int tail_doubles, double n_total,
+                         const float* geom, int k, int b, const float* meas, float pad, float* sums,
+                         float* profiles, float* kl, double* tail_out, void* stream);
 /* dL/dx[n][d] (+)= sum_k proj_k * sum_b gsums[k][b] K_nb (-(u-c_b)/sigma^2); accumulate!=0
  * adds into gx instead of overwriting it.                                               */
 int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom,

@@ -468,6 +468,125 @@ kde1d_finish_kernel(const float* __restrict__ partial, int nparts, int64_t len, 
   }
 }
 
+// ---- the same tail with the cross-rank sum inside: all-reduce over NVLink peer memory + normalise + KL ------------
+// Multi-GPU forward step (particles sharded over ranks): the unnormalised sums S[K][B] of every
+// rank (25.6 KB at K = 100, B = 64) have to be added before the non-linear tail.  Through NCCL that is a
+// latency-bound collective of its own on the critical path (+40..70 us per step at 2..8 GPUs); here the ranks
+// exchange the rows through peer-mapped ("symmetric") buffers inside the finish kernel:
+//   1. CTA k copies row k of the local sums (CTA 0 also the double tail: the entropy's moment sums) into this
+//      rank's symmetric buffer of the current parity; the last CTA to finish publishes the step's epoch in every
+//      peer's signal row (st.release.sys after __threadfence_system);
+//   2. every CTA waits until all ranks have published this epoch (ld.acquire.sys on the local signal row);
+//   3. CTA k adds row k of ALL ranks' buffers in rank order (plain loads over NVLink, bypassing L1), so every
+//      rank forms bit-identical sums, and carries on with the normalisation and the KL of kde1d_finish_kernel.
+// Buffers are double-buffered by epoch parity: a rank publishes epoch e only after its finish kernel of epoch
+// e-1 (which read the peers' buffers of parity (e-1)&1) is complete in stream order, so passing the barrier of
+// epoch e means every peer is done with parity (e+1)&1 -- the one the next step overwrites.  The epoch lives in
+// device memory and is advanced by the last CTA to leave, so a captured CUDA graph can be replayed as is.
+constexpr int kMaxRanks = 8;
+struct PeerSet {
+  float* buf[kMaxRanks];        // base of every rank's symmetric block: [signals 32 x u32][parity 0][parity 1]
+};
+constexpr int kP2PSignalFloats = 32;
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kFinishThreads)
+kde1d_finish_p2p_kernel(const __grid_constant__ PeerSet peers, int rank, int world, uint32_t* __restrict__ state,
+                        int64_t parity_floats /* floats per parity block (sums + tail, 8-byte multiple) */,
+                        const float* __restrict__ local_sums, const double* __restrict__ local_tail, int tail_n,
+                        float inv_n, const float* __restrict__ geom, int K, int B, const float* __restrict__ meas,
+                        float pad, float* __restrict__ sums_out, float* __restrict__ prof, float* __restrict__ kl,
+                        double* __restrict__ tail_out) {
+  extern __shared__ float fsm[];
+  __shared__ float red[33];
+  float* s = fsm;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  // state[0] = epoch of the last completed step, state[1] / state[2] = arrival counters of this launch
+  const uint32_t epoch = state[0] + 1u;
+  const int64_t off = kP2PSignalFloats + (int64_t)(epoch & 1u) * parity_floats;
+  float* mine = peers.buf[rank] + off;
+  for (int b = tid; b < B; b += kFinishThreads) mine[(size_t)k * B + b] = local_sums[(size_t)k * B + b];
+  if (k == 0 && tid < tail_n) reinterpret_cast<double*>(mine + (size_t)K * B)[tid] = local_tail[tid];
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int arrived = atomicAdd(&state[1], 1u);
+    if (arrived == (unsigned int)K - 1u) {           // every row of this rank is in place: publish the epoch
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys_u32(reinterpret_cast<uint32_t*>(peers.buf[r]) + rank, epoch);
+    }
+  }
+  if (tid < world) {
+    const uint32_t* sig = reinterpret_cast<const uint32_t*>(peers.buf[rank]) + tid;
+    long long spins = 0;
+    while ((int32_t)(ld_acquire_sys_u32(sig) - epoch) < 0) {
+      if (++spins > (1ll << 28)) __trap();             // a peer never arrived: fail loudly instead of hanging
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  // rank-ordered sum: bit-identical on every rank
+  for (int b = tid; b < B; b += kFinishThreads) {
+    float v = 0.f;
+    for (int r = 0; r < world; ++r) v += ld_peer_f32(peers.buf[r] + off + (size_t)k * B + b);
+    s[b] = v;
+  }
+  if (k == 0 && tid < tail_n) {
+    double v = 0.0;
+    for (int r = 0; r < world; ++r)
+      v += ld_peer_f64(reinterpret_cast<const double*>(peers.buf[r] + off + (size_t)K * B) + tid);
+    tail_out[tid] = v;
+  }
+  __syncthreads();
+  const float delta = geom[(size_t)k * MFB_GEOM_STRIDE + 3];
+  float acc = 0.f;
+  for (int b = tid; b < B; b += kFinishThreads) {
+    const float v = s[b];
+    sums_out[(size_t)k * B + b] = v;
+    acc += v * inv_n * delta;
+  }
+  const float z = block_sum_256(acc, red) + 1.0e-10f;
+  float term = 0.f;
+  for (int b = tid; b < B; b += kFinishThreads) {
+    const float p = s[b] * inv_n / z;
+    prof[(size_t)k * B + b] = p;
+    if (meas) term += kl_term(meas[(size_t)k * B + b], p, pad);
+  }
+  if (kl) {
+    const float tot = block_sum_256(term, red);
+    if (tid == 0) kl[k] = tot / (float)B;
+  }
+  // the last CTA to leave closes the step
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int left = atomicAdd(&state[2], 1u);
+    if (left == (unsigned int)K - 1u) {
+      state[1] = 0u;
+      state[2] = 0u;
+      __threadfence();
+      state[0] = epoch;
+    }
+  }
+}
+
 // gradient of (profiles, KL) w.r.t. the unnormalised sums:  gp_b = gprof_b - gkl * t_b / (p_b + pad) / B,
 // then the normalisation backward of kde1d_normalize_bwd_kernel
 __global__ void __launch_bounds__(kFinishThreads)
@@ -818,6 +937,31 @@ int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* pr
   kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, (int64_t)k * b,
                                                                  (float)(1.0 / n_total), geom, b, meas, pad, sums,
                                                                  profiles, kl);
+  return launch_status();
+}
+
+int64_t mfb_kde1d_p2p_block_floats(int k, int b, int tail_doubles) {
+  if (k < 1 || b < 2 || tail_doubles < 0) return 0;
+  const int64_t parity = (((int64_t)k * b + 1) & ~(int64_t)1) + 2 * (int64_t)tail_doubles;
+  return kP2PSignalFloats + 2 * parity;
+}
+
+int mfb_kde1d_finish_p2p(const uint64_t* peer_blocks_host, int rank, int world, uint32_t* state,
+                         const float* local_sums, const double* local_tail, int tail_doubles, double n_total,
+                         const float* geom, int k, int b, const float* meas, float pad, float* sums, float* profiles,
+                         float* kl, double* tail_out, void* stream) {
+  MFB_CHECK_ARG(peer_blocks_host && state && local_sums && geom && sums && profiles && k >= 1 && b >= 2 && n_total > 0);
+  MFB_CHECK_ARG(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world);
+  MFB_CHECK_ARG((meas != nullptr) == (kl != nullptr));
+  MFB_CHECK_ARG(tail_doubles >= 0 && tail_doubles <= 32 && (tail_doubles == 0 || (local_tail && tail_out)));
+  MFB_CHECK_ARG(((int64_t)k * b) % 2 == 0);           // keeps the double tail 8-byte aligned
+  if (k > 1024 || (size_t)b * 4 > 48 * 1024) return MFB_E_UNSUPPORTED;   // every CTA of the grid must be resident
+  PeerSet ps;
+  for (int r = 0; r < kMaxRanks; ++r) ps.buf[r] = r < world ? reinterpret_cast<float*>(peer_blocks_host[r]) : nullptr;
+  const int64_t parity = (int64_t)k * b + 2 * (int64_t)tail_doubles;
+  kde1d_finish_p2p_kernel<<<k, kFinishThreads, (size_t)b * 4, (cudaStream_t)stream>>>(
+      ps, rank, world, state, parity, local_sums, local_tail, tail_doubles, (float)(1.0 / n_total), geom, k, b, meas, pad,
+      sums, profiles, kl, tail_out);
   return launch_status();
 }
 

@@ -41,10 +41,29 @@ class ShardReducer:
         self.bytes = 0
         self._stash = None          # float64 partial sums waiting for a float32 all-reduce to ride on
         self._stash_result = None
+        self.peer = None            # PeerExchange: cross-rank sum inside the KDE tail kernel (enable_peer_exchange)
 
     @property
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def enable_peer_exchange(self) -> bool:
+        """Route the forward step's cross-rank sum through the fused NVLink kernel.  Returns False (and keeps the
+        NCCL path) when the ranks do not share a node with peer access or have unequal shards."""
+        if self.world_size == 1 or self.world_size > 8 or not self.equal_shards or dist.get_backend(self.group) != "nccl":
+            return False
+        try:
+            self.peer = PeerExchange(self.group)
+        except Exception:
+            self.peer = None
+        return self.peer is not None
+
+    def take_stash(self) -> Optional[torch.Tensor]:
+        m, self._stash = self._stash, None
+        return m
+
+    def set_stash_result(self, values: torch.Tensor) -> None:
+        self._stash_result = values
 
     # ---- one packed all-reduce per forward step (SURVEY 8e) --------------------------------------
     def stash(self, values: torch.Tensor) -> None:
@@ -88,7 +107,38 @@ class ShardReducer:
         return float(count.item())
 
 
-def shard_model(model, group: Optional[dist.ProcessGroup] = None, equal_shards: bool = True) -> ShardReducer:
+class PeerExchange:
+    """Peer-mapped ("symmetric") block of every rank for the fused KDE tail (``mfb_kde1d_finish_p2p``): the ranks
+    add each other's unnormalised sums through NVLink loads inside the finish kernel instead of running an NCCL
+    all-reduce between deposit and tail.  torch's symmetric-memory allocator provides the mapping (one CUDA VMM
+    allocation per rank, imported by all peers); the kernel, its epoch protocol and the buffers' layout are the
+    library's.  ``block_for`` is collective on first use for a given screen shape (all ranks run the same program)."""
+
+    def __init__(self, group=None) -> None:
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self._blocks = {}
+
+    def block_for(self, k: int, b: int, tail: int, device):
+        from . import _lib
+        key = (int(k), int(b), int(tail), str(device))
+        hit = self._blocks.get(key)
+        if hit is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            floats = int(_lib.load().mfb_kde1d_p2p_block_floats(k, b, tail))
+            block = symm_mem.empty(floats, dtype=torch.float32, device=device)
+            block.zero_()
+            handle = symm_mem.rendezvous(block, self.group)
+            ptrs = [int(p) for p in handle.buffer_ptrs]
+            state = torch.zeros(4, dtype=torch.int32, device=device)
+            torch.cuda.synchronize(device)
+            dist.barrier(self.group)          # every block is zeroed before anybody's first epoch arrives
+            hit = self._blocks[key] = (block, handle, ptrs, state)
+        return hit
+
+
+def shard_model(model, group: Optional[dist.ProcessGroup] = None, equal_shards: bool = True,
+                peer_exchange: bool = True) -> ShardReducer:
     """Attach a reducer to a ``MENTFlow`` model (and its entropy estimator) so that
     ``model.loss(n_local)`` returns the loss of the *global* batch on every rank, or to a classical
     ``MENT`` model so that ``gauss_seidel_update`` draws ``n_samples`` particles over all ranks."""
@@ -102,6 +152,10 @@ def shard_model(model, group: Optional[dist.ProcessGroup] = None, equal_shards: 
         model.shard = (dist.get_rank(group) if world > 1 else 0, world)
         if world > 1:
             reducer.equal_shards = False if model.n_samples % world else reducer.equal_shards
+    if peer_exchange:
+        # forward step: cross-rank sum inside the KDE tail kernel over NVLink peer memory (NCCL stays the path for
+        # gradients, 2-D screens, histogram counts, and whenever peer mapping is not available)
+        reducer.enable_peer_exchange()
     return reducer
 
 

@@ -12,10 +12,11 @@ def build_flow(name: str, input_features: int, output_features: int, hidden_laye
             f"flow '{name}': only the neural spline flow ('nsf', the reference's configured generator, "
             "experiments/config/gen/flow.yaml:1) has CUDA kernels")
     bins = int(kws.pop("bins", 8))   # zuko.flows.NSF default; experiments/setup.py:120-121 passes 20
+    passes = kws.pop("passes", None)  # zuko MAF option forwarded by **kws (generate/build.py:36-40): 2 = coupling layers
     if kws:
         raise TypeError(f"unsupported NSF options: {sorted(kws)}")
     return NSFGenerator(output_features, hidden_units=hidden_units, hidden_layers=hidden_layers,
-                        transforms=transforms, bins=bins, device=device)
+                        transforms=transforms, bins=bins, device=device, passes=passes)
 
 
 def build_generator(name: str, device: torch.device = None, **kws) -> GenerativeModel:

@@ -22,27 +22,37 @@ from .. import ops
 from .base import GenerativeModel
 
 
-def layer_order(features: int, layer: int) -> List[int]:
-    """Autoregressive order of layer ``layer``: natural for even layers, reversed for odd ones
-    (zuko MAF without randperm)."""
+def layer_order(features: int, layer: int, passes: Optional[int] = None) -> List[int]:
+    """Dependency order of layer ``layer``: natural for even layers, reversed for odd ones (zuko MAF without
+    randperm), then grouped into ``passes`` classes, ``order // ceil(features / passes)`` (zuko
+    MaskedAutoregressiveTransform).  passes = None or >= features: fully autoregressive; passes = 2: the
+    coupling variant (the first half of the features gets unconditional splines, the second half is
+    conditioned on the first)."""
     order = list(range(features))
-    return order if layer % 2 == 0 else order[::-1]
+    order = order if layer % 2 == 0 else order[::-1]
+    if passes is not None:
+        passes = min(max(int(passes), 1), features)
+        group = -(-features // passes)
+        order = [o // group for o in order]
+    return order
 
 
 def conditioner_masks(order: Sequence[int], total: int, hidden_units: int, hidden_layers: int):
     """Closed form of zuko's MaskedMLP masks for a strict autoregressive ordering.
 
-    A unit/output of dependency class c may read the c features whose order is smallest.
-    Hidden unit h has class 1 + h mod (D-1); output rows of feature i have class order[i];
+    A unit/output of dependency class c may read the features whose order is smaller than c.
+    With C distinct order values (C = D for a fully autoregressive layer, C = 2 for a coupling layer) hidden
+    unit h has class 1 + h mod (C-1); output rows of feature i have class order[i];
     a connection a -> b exists iff class(a) <= class(b) (for inputs: order[j] < class(b)).
     Returns [mask_in (H, D), mask_hid (H, H) x (L-1), mask_out (D*total, H)] as bool tensors.
     """
     d = len(order)
     order_t = torch.as_tensor(list(order))
-    if d > 1:
-        hid_class = 1 + torch.arange(hidden_units) % (d - 1)
+    classes = int(order_t.max()) + 1
+    if d > 1 and classes > 1:
+        hid_class = 1 + torch.arange(hidden_units) % (classes - 1)
     else:
-        raise ValueError("an autoregressive flow needs at least 2 features")
+        raise ValueError("a conditioned flow layer needs at least 2 features in 2 dependency classes")
     out_class = torch.repeat_interleave(order_t, total)
     masks = [order_t[None, :] < hid_class[:, None]]
     for _ in range(hidden_layers - 1):
@@ -53,7 +63,7 @@ def conditioner_masks(order: Sequence[int], total: int, hidden_units: int, hidde
 
 class NSFGenerator(GenerativeModel):
     def __init__(self, features: int, hidden_units: int = 64, hidden_layers: int = 3, transforms: int = 5,
-                 bins: int = 20, device=None) -> None:
+                 bins: int = 20, device=None, passes: Optional[int] = None) -> None:
         super().__init__()
         if hidden_units != 64:
             raise NotImplementedError("the CUDA conditioner is compiled for hidden_units=64")
@@ -63,6 +73,9 @@ class NSFGenerator(GenerativeModel):
             raise NotImplementedError("bins must satisfy 3*bins-1 <= 64")
         self.features, self.hidden_units, self.hidden_layers = features, hidden_units, hidden_layers
         self.transforms, self.bins = transforms, bins
+        # zuko's `passes`: None / >= features = autoregressive (tcgen05 kernels); 2 = coupling layers (the fp32
+        # CUDA-core kernels: the tensor-core operand images are laid out for strict orderings)
+        self.passes = None if passes is None or int(passes) >= features else max(int(passes), 2)
         self.total = 3 * bins - 1
         T, H, L, D, P = transforms, hidden_units, hidden_layers, features, self.total
         # default nn.Linear initialisation, drawn layer by layer in construction order
@@ -86,14 +99,14 @@ class NSFGenerator(GenerativeModel):
         self.b_out = nn.Parameter(torch.stack(b_out))    # (T, D*P)
         m_in, m_hid, m_out = [], [], []
         for t in range(T):
-            masks = conditioner_masks(layer_order(D, t), P, H, L)
+            masks = conditioner_masks(layer_order(D, t, self.passes), P, H, L)
             m_in.append(masks[0])
             m_hid.append(torch.stack(masks[1:-1]) if L > 1 else torch.zeros(0, H, H, dtype=torch.bool))
             m_out.append(masks[-1])
         self.register_buffer("m_in", torch.stack(m_in).float(), persistent=False)
         self.register_buffer("m_hid", torch.stack(m_hid).float(), persistent=False)
         self.register_buffer("m_out", torch.stack(m_out).float(), persistent=False)
-        self._orders = [layer_order(D, t) for t in range(T)]
+        self._orders = [layer_order(D, t, self.passes) for t in range(T)]
         self._pack_key, self._pack_cache = None, None
         self._rng = None
         if device is not None:
@@ -205,7 +218,7 @@ class NSFGenerator(GenerativeModel):
             with torch.no_grad():
                 packed = self.packed_parameters()
                 images = None
-                if ops.nsf_tc_supported(self.features, self.hidden_units, self.hidden_layers, self.bins):
+                if ops.nsf_tc_supported(self.features, self.hidden_units, self.hidden_layers, self.bins, self._orders):
                     images = ops.nsf_tc_images(packed, self._orders, self.hidden_units, self.hidden_layers, self.bins)
             self._pack_key, self._pack_cache = key, (packed, images)
         return self._pack_cache

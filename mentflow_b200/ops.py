@@ -160,6 +160,26 @@ def kde1d_finish_bwd(sums, n_total, geom, meas, gprof, gkl):
     return gsums
 
 
+def kde1d_finish_p2p(peer, sums_local, tail, n_total, geom, meas):
+    """Cross-rank sum over NVLink peer memory + normalisation (+ KL) in one kernel: (sums, profiles, kl, tail_sum).
+    ``peer``: ``distributed.PeerExchange``; ``tail``: float64 vector reduced alongside (or None)."""
+    lib = _lib.load()
+    k, b = sums_local.shape
+    nt = 0 if tail is None else int(tail.numel())
+    block, handle, ptrs, state = peer.block_for(k, b, nt, sums_local.device)
+    sums = torch.empty_like(sums_local)
+    prof = torch.empty_like(sums_local)
+    kl = torch.empty(k, dtype=torch.float32, device=sums_local.device) if meas is not None else None
+    tail_out = torch.empty(nt, dtype=torch.float64, device=sums_local.device) if nt else None
+    arr = (ctypes.c_uint64 * len(ptrs))(*ptrs)
+    with torch.cuda.device(sums_local.device):
+        _lib.check(lib.mfb_kde1d_finish_p2p(ctypes.cast(arr, ctypes.c_void_p), peer.rank, peer.world, _ptr(state),
+                                            _ptr(sums_local), _ptr(tail), nt, float(n_total), _ptr(geom), k, b, _ptr(meas),
+                                            KL_PAD, _ptr(sums), _ptr(prof), _ptr(kl), _ptr(tail_out), _stream()),
+                   "kde1d_finish_p2p")
+    return sums, prof, kl, tail_out
+
+
 _FINISH_MAX_BINS = 6000   # shared-memory bound of the fused tail kernel
 
 
@@ -184,6 +204,20 @@ class ProjectKDE1D(torch.autograd.Function):
         else:
             # sharded: the unnormalised sums are all-reduced before the non-linear tail; float64 partial sums
             # another op stashed on the reducer (the entropy moments) ride at the end of the same buffer
+            peer = getattr(reducer, "peer", None)
+            if (peer is not None and mp is None and x.shape[0] > 0 and proj.shape[0] <= 1024 and nbins <= 4096
+                    and (proj.shape[0] * nbins) % 2 == 0):
+                # the cross-rank sum happens inside the tail kernel, over NVLink peer memory
+                sums_local = kde1d_sums(x, proj, geom, ratio, nbins, mp)
+                n_total = reducer.global_count(n_total)
+                stash = reducer.take_stash()
+                sums, prof, kl, tail_sum = kde1d_finish_p2p(peer, sums_local, stash, n_total, geom, meas)
+                if stash is not None:
+                    reducer.set_stash_result(tail_sum)
+                reducer.calls += 1
+                ctx.save_for_backward(x, proj, geom, sums, meas, None, mp)
+                ctx.ratio, ctx.n_total = ratio, n_total
+                return prof if meas is None else (prof, kl)
             tail = reducer.tail_floats() if hasattr(reducer, "tail_floats") else 0
             if tail:
                 flat = torch.empty(proj.shape[0] * nbins + tail, dtype=torch.float32, device=x.device)
@@ -346,7 +380,15 @@ def nsf_layer_param_floats(d: int, hidden_units: int, hidden_layers: int, bins: 
 NSF_USE_TENSOR_CORES = True   # tcgen05 conditioner where the configuration is compiled; False = fp32 CUDA-core kernel
 
 
-def nsf_tc_supported(d: int, hidden_units: int, hidden_layers: int, bins: int) -> bool:
+def orders_autoregressive(orders) -> bool:
+    """every layer's order is a permutation (strict autoregressive ordering; coupling layers repeat values)"""
+    return all(sorted(int(v) for v in o) == list(range(len(o))) for o in orders)
+
+
+def nsf_tc_supported(d: int, hidden_units: int, hidden_layers: int, bins: int, orders=None) -> bool:
+    """the tcgen05 layer kernels are compiled for this shape (and, when ``orders`` is given, these orderings)"""
+    if orders is not None and not orders_autoregressive(orders):
+        return False
     return bool(NSF_USE_TENSOR_CORES and _lib.load().mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins))
 
 
@@ -395,7 +437,7 @@ def _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_l
     """All layers in sampling order; returns ([z, y_1, ..., x], log q).  ``images``: operand images
     of the tensor-core kernel when the caller has them cached for these weights."""
     d = z.shape[1]
-    if not nsf_tc_supported(d, hidden_units, hidden_layers, bins):
+    if not nsf_tc_supported(d, hidden_units, hidden_layers, bins, orders):
         images = None
     elif images is None:
         images = nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins)
@@ -459,7 +501,7 @@ class NSFForward(torch.autograd.Function):
         orders, hidden_units, hidden_layers, bins, want_logq, images = meta
         z = _check_f32("z", z)
         packed = _check_f32("packed", packed)
-        if images is None and NSF_USE_TENSOR_CORES and nsf_tc_supported(z.shape[1], hidden_units, hidden_layers, bins):
+        if images is None and NSF_USE_TENSOR_CORES and nsf_tc_supported(z.shape[1], hidden_units, hidden_layers, bins, orders):
             images = nsf_tc_images(packed, orders, hidden_units, hidden_layers, bins)
         steps, logq = _nsf_run_layers(z, packed, orders, hidden_units, hidden_layers, bins, want_logq, images)
         ctx.meta = meta
@@ -495,6 +537,7 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
     gz = torch.empty_like(inputs[0])
     if n == 0:
         return gz, gpacked
+    bwd_flags = 0 if (NSF_BWD_USE_TENSOR_CORES and orders_autoregressive(orders)) else FLAG_NO_TENSOR_CORES
     chunk = min(n, NSF_BWD_CHUNK)
     with torch.cuda.device(dev):
         wbytes = lib.mfb_nsf_layer_bwd_workspace_bytes(chunk, d, hidden_layers)
@@ -511,7 +554,7 @@ def nsf_backward(inputs, packed, packed_om, orders, hidden_units, hidden_layers,
                                                      _ptr(packed_om[t]), ctypes.cast(order_arr, ctypes.c_void_p),
                                                      1 if t == 0 else 0, _ptr(images[t]) if images is not None else None,
                                                      _ptr(out), _ptr(gpacked[t]), 1 if start > 0 else 0, _ptr(work),
-                                                     wbytes, 0 if NSF_BWD_USE_TENSOR_CORES else FLAG_NO_TENSOR_CORES,
+                                                     wbytes, bwd_flags,
                                                      _stream()), "nsf_layer_bwd")
                 g = out
     return gz, gpacked

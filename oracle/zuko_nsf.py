@@ -32,10 +32,16 @@ import torch.nn.functional as F
 # --------------------------------------------------------------------------------------
 # masks (zuko/nn.py MaskedMLP.__init__, zuko/flows/autoregressive.py)
 # --------------------------------------------------------------------------------------
-def layer_order(features: int, layer: int) -> torch.Tensor:
-    """MAF without randperm: arange for even layers, flipped arange for odd layers."""
+def layer_order(features: int, layer: int, passes: int = None) -> torch.Tensor:
+    """MAF without randperm: arange for even layers, flipped arange for odd layers; then
+    MaskedAutoregressiveTransform groups the order into `passes` classes: order // ceil(features / passes)
+    (passes = features: fully autoregressive, passes = 2: coupling)."""
     order = torch.arange(features)
-    return order if layer % 2 == 0 else torch.flipud(order)
+    order = order if layer % 2 == 0 else torch.flipud(order)
+    if passes is not None:
+        passes = min(max(int(passes), 1), features)
+        order = torch.div(order, math.ceil(features / passes), rounding_mode="floor")
+    return order
 
 
 def masked_mlp_masks(order: torch.Tensor, total: int, hidden: Sequence[int]) -> List[torch.Tensor]:
@@ -169,12 +175,12 @@ class NSFOracle(nn.Module):
     sampling direction z -> x is a single conditioner pass per layer."""
 
     def __init__(self, features: int, hidden_units: int = 64, hidden_layers: int = 3,
-                 transforms: int = 5, bins: int = 20):
+                 transforms: int = 5, bins: int = 20, passes: int = None):
         super().__init__()
         self.features = features
         self.layers = nn.ModuleList([
             AutoregressiveSplineLayer(features, [hidden_units] * hidden_layers, bins,
-                                      layer_order(features, i))
+                                      layer_order(features, i, passes))
             for i in range(transforms)])
 
     # base = DiagNormal(0, 1)

@@ -14,7 +14,8 @@ def cuda(a):
 def oracle_from_generator(gen, dtype=torch.float64):
     """NSFOracle carrying the weights of a mentflow_b200 NSFGenerator (via zuko-style names)."""
     from oracle.zuko_nsf import NSFOracle
-    flow = NSFOracle(gen.features, gen.hidden_units, gen.hidden_layers, gen.transforms, gen.bins)
+    flow = NSFOracle(gen.features, gen.hidden_units, gen.hidden_layers, gen.transforms, gen.bins,
+                     passes=getattr(gen, "passes", None))
     sd = gen.state_dict()
     new = {}
     for k, v in flow.state_dict().items():

@@ -143,6 +143,57 @@ def test_tensor_core_and_cuda_core_kernels_agree():
         assert float(e.median()) < 2e-6 and float((e > TOL).float().mean()) < 0.02
 
 
+@pytest.mark.parametrize("d,passes,n", [(6, 2, 20_000), (4, 2, 5_000), (5, 2, 3_000), (6, 3, 3_000)])
+def test_coupling_layers_match_oracle(d, passes, n):
+    """north_star's "autoregressive/coupling" bijectors: zuko NSF(..., passes=2) builds coupling layers (the first
+    half of the features transformed unconditionally, the second half conditioned on the first).  Sampling
+    direction, density direction and gradients against the float64 oracle."""
+    torch.manual_seed(70 + d + passes)
+    gen = mf.generate.build_generator("nsf", input_features=d, output_features=d, hidden_layers=3, hidden_units=64,
+                                      transforms=5, bins=20, passes=passes)
+    with torch.no_grad():
+        for p in gen.parameters():
+            p.mul_(2.0)
+    ref, ref32 = oracle_from_generator(gen), oracle_from_generator(gen, torch.float32)
+    gen = gen.to("cuda")
+    z = torch.randn(n, d)
+    z[: max(1, n // 100)] *= 4.0
+    with torch.no_grad():
+        x, logq = gen.forward_and_log_prob(z.cuda())
+        xr, lr = ref.forward_and_log_prob(z.double())
+        x32, l32 = ref32.forward_and_log_prob(z)
+        lp = gen.log_prob(x)
+        zi = gen.inverse(x)
+    assert_parity(x, xr, x32)
+    assert_parity(logq, lr, l32)
+    assert float(((lp.cpu().double() - lr).abs() / lr.abs().clamp_min(1.0)).median()) < 1e-5
+    assert float((zi.cpu() - z).abs().median()) < 1e-5
+    # gradients of a scalar of (x, log q) w.r.t. z and all parameters
+    a, b = torch.randn(n, d), torch.randn(n)
+    zc = z.clone().cuda().requires_grad_(True)
+    xg, lg = gen.forward_and_log_prob(zc)
+    ((xg * a.cuda()).sum() + (lg * b.cuda()).sum()).backward()
+    zr = z.double().clone().requires_grad_(True)
+    xo, lo = ref.forward_and_log_prob(zr)
+    ((xo * a.double()).sum() + (lo * b.double()).sum()).backward()
+    ez = (zc.grad.cpu().double() - zr.grad).abs() / zr.grad.abs().clamp_min(1.0)
+    assert float(ez.median()) < 2e-5 and float((ez > 1e-2).float().mean()) < 0.02
+    got = {k: v for k, v in zip(("w_in", "b_in", "w_hid", "b_hid", "w_out", "b_out"),
+                                (gen.w_in.grad, gen.b_in.grad, gen.w_hid.grad, gen.b_hid.grad, gen.w_out.grad, gen.b_out.grad))}
+    want_w_out = torch.stack([ref.layers[t].hyper[6].weight.grad * ref.layers[t].hyper[6].mask for t in range(5)])
+    # parameter gradients are sums over all particles, a few of them ill-conditioned in fp32: norm-wise agreement
+    def rel_l2(a, b):
+        return float((a.cpu().double() - b).norm() / b.norm())
+
+    assert rel_l2(got["w_out"], want_w_out) < 2e-3
+    want_b_in = torch.stack([ref.layers[t].hyper[0].bias.grad for t in range(5)])
+    assert rel_l2(got["b_in"], want_b_in) < 2e-3
+    want_w_hid = torch.stack([torch.stack([ref.layers[t].hyper[2 * (l + 1)].weight.grad * ref.layers[t].hyper[2 * (l + 1)].mask
+                                           for l in range(2)]) for t in range(5)])
+    assert rel_l2(got["w_hid"], want_w_hid) < 2e-3
+    assert float(got["w_out"].cpu()[want_w_out == 0].abs().max()) == 0.0     # masked weights: exactly zero gradient
+
+
 def test_other_architectures():
     for hl, tr, bins in [(1, 2, 8), (2, 3, 12), (4, 1, 21)]:
         torch.manual_seed(hl)

@@ -38,6 +38,28 @@ def test_closed_form_masks_equal_zuko_construction(d):
             assert torch.equal(a.bool(), b.bool())
 
 
+@pytest.mark.parametrize("d,passes", [(6, 2), (4, 2), (5, 2), (6, 3), (3, 2)])
+def test_coupling_masks_equal_zuko_construction(d, passes):
+    """zuko's `passes` option (coupling layers for passes = 2): orders repeat, every hidden unit of a coupling
+    layer has the single reachable class, the first half of the features gets bias-only splines."""
+    for layer in (0, 1):
+        order = mf.generate.layer_order(d, layer, passes)
+        assert order == layer_order(d, layer, passes).tolist()
+        mine = mf.generate.conditioner_masks(order, 59, 64, 3)
+        ref = masked_mlp_masks(layer_order(d, layer, passes), 59, [64] * 3)
+        for a, b in zip(mine, ref):
+            assert torch.equal(a.bool(), b.bool())
+    gen = mf.generate.build_generator("nsf", input_features=d, output_features=d, hidden_layers=3, hidden_units=64,
+                                      transforms=4, bins=20, passes=passes)
+    assert gen.passes == passes and not ops.orders_autoregressive(gen._orders)
+    assert not ops.nsf_tc_supported(d, 64, 3, 20, gen._orders)        # coupling layers run on the CUDA-core kernels
+    sd = gen.state_dict()
+    sd2 = {k.replace("_flow.transform.transforms.", "_flow.transform.transform.transforms."): v for k, v in sd.items()}
+    other = mf.generate.NSFGenerator(d, transforms=4, passes=passes)
+    other.load_state_dict(sd2)                                          # both zuko key spellings load
+    assert torch.equal(other.w_out, gen.w_out)
+
+
 def test_generator_matches_oracle_initialisation_and_names():
     torch.manual_seed(7)
     gen = mf.generate.build_generator("nsf", input_features=6, output_features=6, hidden_layers=3,
