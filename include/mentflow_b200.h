@@ -101,6 +101,14 @@ int mfb_kde1d_finish_p2p(const uint64_t* peer_blocks_host, int rank, int world, 
                          const float* local_sums, const double* local_tail, int tail_doubles, double n_total,
                          const float* geom, int k, int b, const float* meas, float pad, float* sums,
                          float* profiles, float* kl, double* tail_out, void* stream);
+/* deposit + (merge of the deposit's partials, cross-rank sum, normalise, KL) in two launches: the sharded counterpart
+ * of mfb_project_kde1d_loss_fwd; workspace as for mfb_project_kde1d_fwd.                                       */
+int mfb_project_kde1d_loss_fwd_p2p(const float* x, int64_t n, int d, const float* proj, const float* geom, int k,
+                                   int b, float max_sigma_over_delta, double n_total, const float* meas, float pad,
+                                   const uint64_t* peer_blocks_host, int rank, int world, uint32_t* state,
+                                   const double* local_tail, int tail_doubles, float* sums, float* profiles,
+                                   float* kl, double* tail_out, void* workspace, int64_t workspace_bytes,
+                                   void* stream);
 /* dL/dx[n][d] (+)= sum_k proj_k * sum_b gsums[k][b] K_nb (-(u-c_b)/sigma^2); accumulate!=0
  * adds into gx instead of overwriting it.                                               */
 int mfb_project_kde1d_bwd(const float* x, int64_t n, int d, const float* proj, const float* geom,

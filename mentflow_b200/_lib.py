@@ -27,6 +27,8 @@ SIGNATURES = {
     "mfb_kde1d_finish": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P]),
     "mfb_kde1d_p2p_block_floats": (c_int64, [c_int, c_int, c_int]),
     "mfb_kde1d_finish_p2p": (c_int, [P, c_int, c_int, P, P, P, c_int, c_double, P, c_int, c_int, P, c_float, P, P, P, P, P]),
+    "mfb_project_kde1d_loss_fwd_p2p": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, c_double, P, c_float, P,
+                                               c_int, c_int, P, P, c_int, P, P, P, P, P, c_int64, P]),
     "mfb_kde1d_finish_bwd": (c_int, [P, c_double, P, c_int, c_int, P, c_float, P, P, P, P]),
     "mfb_project_kde1d_bwd": (c_int, [P, c_int64, c_int, P, P, c_int, c_int, c_float, P, P, c_int, P]),
     "mfb_project_kde1d_mp_fwd": (c_int, [P, c_int64, c_int, P, P, P, c_int, c_int, c_float, P, P, c_int64, P]),

@@ -511,19 +511,21 @@ __device__ __forceinline__ double ld_peer_f64(const double* p) {
 __global__ void __launch_bounds__(kFinishThreads)
 kde1d_finish_p2p_kernel(const __grid_constant__ PeerSet peers, int rank, int world, uint32_t* __restrict__ state,
                         int64_t parity_floats /* floats per parity block (sums + tail, 8-byte multiple) */,
-                        const float* __restrict__ local_sums, const double* __restrict__ local_tail, int tail_n,
-                        float inv_n, const float* __restrict__ geom, int K, int B, const float* __restrict__ meas,
-                        float pad, float* __restrict__ sums_out, float* __restrict__ prof, float* __restrict__ kl,
-                        double* __restrict__ tail_out) {
+                        const float* __restrict__ local_sums /* [K][B], or the deposit's per-CTA partials */,
+                        int nparts /* 0: local_sums is merged already */, const double* __restrict__ local_tail,
+                        int tail_n, float inv_n, const float* __restrict__ geom, int K, int B,
+                        const float* __restrict__ meas, float pad, float* __restrict__ sums_out,
+                        float* __restrict__ prof, float* __restrict__ kl, double* __restrict__ tail_out) {
   extern __shared__ float fsm[];
   __shared__ float red[33];
   float* s = fsm;
   const int k = blockIdx.x, tid = threadIdx.x;
+  if (nparts > 0) merge_partials_to_smem(local_sums, nparts, (int64_t)K * B, k, B, fsm + B, s);   // fixed order
   // state[0] = epoch of the last completed step, state[1] / state[2] = arrival counters of this launch
   const uint32_t epoch = state[0] + 1u;
   const int64_t off = kP2PSignalFloats + (int64_t)(epoch & 1u) * parity_floats;
   float* mine = peers.buf[rank] + off;
-  for (int b = tid; b < B; b += kFinishThreads) mine[(size_t)k * B + b] = local_sums[(size_t)k * B + b];
+  for (int b = tid; b < B; b += kFinishThreads) mine[(size_t)k * B + b] = nparts > 0 ? s[b] : local_sums[(size_t)k * B + b];
   if (k == 0 && tid < tail_n) reinterpret_cast<double*>(mine + (size_t)K * B)[tid] = local_tail[tid];
   __threadfence_system();
   __syncthreads();
@@ -960,8 +962,39 @@ int mfb_kde1d_finish_p2p(const uint64_t* peer_blocks_host, int rank, int world, 
   for (int r = 0; r < kMaxRanks; ++r) ps.buf[r] = r < world ? reinterpret_cast<float*>(peer_blocks_host[r]) : nullptr;
   const int64_t parity = (int64_t)k * b + 2 * (int64_t)tail_doubles;
   kde1d_finish_p2p_kernel<<<k, kFinishThreads, (size_t)b * 4, (cudaStream_t)stream>>>(
-      ps, rank, world, state, parity, local_sums, local_tail, tail_doubles, (float)(1.0 / n_total), geom, k, b, meas, pad,
-      sums, profiles, kl, tail_out);
+      ps, rank, world, state, parity, local_sums, 0, local_tail, tail_doubles, (float)(1.0 / n_total), geom, k, b, meas,
+      pad, sums, profiles, kl, tail_out);
+  return launch_status();
+}
+
+/* deposit + (merge, cross-rank sum, normalise, KL) in two launches: the sharded counterpart of
+ * mfb_project_kde1d_loss_fwd */
+int mfb_project_kde1d_loss_fwd_p2p(const float* x, int64_t n, int d, const float* proj, const float* geom, int k, int b,
+                                   float max_sigma_over_delta, double n_total, const float* meas, float pad,
+                                   const uint64_t* peer_blocks_host, int rank, int world, uint32_t* state,
+                                   const double* local_tail, int tail_doubles, float* sums, float* profiles, float* kl,
+                                   double* tail_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  MFB_CHECK_ARG(x && proj && geom && sums && profiles && workspace && peer_blocks_host && state);
+  MFB_CHECK_ARG((meas != nullptr) == (kl != nullptr));
+  MFB_CHECK_ARG(n >= 1 && d >= 1 && d <= kMaxDim && k >= 1 && b >= 2 && n_total > 0);
+  MFB_CHECK_ARG(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && ((int64_t)k * b) % 2 == 0);
+  MFB_CHECK_ARG(tail_doubles >= 0 && tail_doubles <= 32 && (tail_doubles == 0 || (local_tail && tail_out)));
+  if (finish_smem(b) > 48 * 1024 || k > 1024) return MFB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int r = radius_from_hint(max_sigma_over_delta);
+  const int rr = r <= 4 ? 4 : (r <= 9 ? 9 : 13);
+  KdePlan L = plan_kde(n, d, k, b, rr);
+  if (L.smem > 227 * 1024) return MFB_E_UNSUPPORTED;
+  if (workspace_bytes < (int64_t)L.grid_x * k * b * 4) return MFB_E_WORKSPACE;
+  float* partial = (float*)workspace;
+  int rc = deposit_dispatch(r, L, x, n, d, proj, geom, k, b, partial, st, nullptr);
+  if (rc) return rc;
+  PeerSet ps;
+  for (int i = 0; i < kMaxRanks; ++i) ps.buf[i] = i < world ? reinterpret_cast<float*>(peer_blocks_host[i]) : nullptr;
+  const int64_t parity = (int64_t)k * b + 2 * (int64_t)tail_doubles;
+  kde1d_finish_p2p_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(
+      ps, rank, world, state, parity, partial, L.grid_x, local_tail, tail_doubles, (float)(1.0 / n_total), geom, k, b,
+      meas, pad, sums, profiles, kl, tail_out);
   return launch_status();
 }
 

@@ -160,6 +160,31 @@ def kde1d_finish_bwd(sums, n_total, geom, meas, gprof, gkl):
     return gsums
 
 
+def kde1d_loss_forward_p2p(peer, x, proj, geom, ratio, nbins, tail, n_total, meas):
+    """Sharded forward tail in two launches: deposit, then merge + cross-rank sum over NVLink peer memory +
+    normalisation (+ KL).  Returns (sums, profiles, kl, tail_sum)."""
+    lib = _lib.load()
+    x, proj, geom = _check_f32("x", x), _check_f32("proj", proj), _check_f32("geom", geom)
+    n, d = x.shape
+    k = proj.shape[0]
+    nt = 0 if tail is None else int(tail.numel())
+    block, handle, ptrs, state = peer.block_for(k, nbins, nt, x.device)
+    sums = torch.empty((k, nbins), dtype=torch.float32, device=x.device)
+    prof = torch.empty_like(sums)
+    kl = torch.empty(k, dtype=torch.float32, device=x.device) if meas is not None else None
+    tail_out = torch.empty(nt, dtype=torch.float64, device=x.device) if nt else None
+    arr = (ctypes.c_uint64 * len(ptrs))(*ptrs)
+    with torch.cuda.device(x.device):
+        wbytes = lib.mfb_kde1d_workspace_bytes(n, d, k, nbins)
+        work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.mfb_project_kde1d_loss_fwd_p2p(_ptr(x), n, d, _ptr(proj), _ptr(geom), k, nbins, float(ratio),
+                                                      float(n_total), _ptr(meas), KL_PAD, ctypes.cast(arr, ctypes.c_void_p),
+                                                      peer.rank, peer.world, _ptr(state), _ptr(tail), nt, _ptr(sums),
+                                                      _ptr(prof), _ptr(kl), _ptr(tail_out), _ptr(work), wbytes, _stream()),
+                   "project_kde1d_loss_fwd_p2p")
+    return sums, prof, kl, tail_out
+
+
 def kde1d_finish_p2p(peer, sums_local, tail, n_total, geom, meas):
     """Cross-rank sum over NVLink peer memory + normalisation (+ KL) in one kernel: (sums, profiles, kl, tail_sum).
     ``peer``: ``distributed.PeerExchange``; ``tail``: float64 vector reduced alongside (or None)."""
@@ -208,10 +233,9 @@ class ProjectKDE1D(torch.autograd.Function):
             if (peer is not None and mp is None and x.shape[0] > 0 and proj.shape[0] <= 1024 and nbins <= 4096
                     and (proj.shape[0] * nbins) % 2 == 0):
                 # the cross-rank sum happens inside the tail kernel, over NVLink peer memory
-                sums_local = kde1d_sums(x, proj, geom, ratio, nbins, mp)
                 n_total = reducer.global_count(n_total)
                 stash = reducer.take_stash()
-                sums, prof, kl, tail_sum = kde1d_finish_p2p(peer, sums_local, stash, n_total, geom, meas)
+                sums, prof, kl, tail_sum = kde1d_loss_forward_p2p(peer, x, proj, geom, ratio, nbins, stash, n_total, meas)
                 if stash is not None:
                     reducer.set_stash_result(tail_sum)
                 reducer.calls += 1

@@ -286,3 +286,44 @@ def test_multipole_chain_general_matrices_vs_oracle(d, order, skew):
     got = torch.stack([o[0] for o in out]).detach().cpu().double()
     assert float((got - ref.detach()).abs().max()) <= TOL * float(ref.abs().max())
     assert float((xg.grad.cpu().double() - xr.grad).abs().max()) <= TOL * float(xr.grad.abs().max())
+
+
+def test_p2p_finish_kernel_with_one_rank_matches_fused_tail():
+    """The sharded tail (cross-rank sum over peer memory inside the finish kernel) with world = 1: the "peer" block
+    is this rank's own buffer, so the result must equal the single-GPU fused tail bit for bit, across several
+    steps (epoch counter, double buffering) and with a double tail riding along.  Two or more ranks are checked by
+    bench.py's shard_parity at N > 1."""
+    from mentflow_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    n, d, k, nb = 50_001, 6, 10, 64
+    w = torch.randn(k, d)
+    w = (w / w.norm(dim=1, keepdim=True)).cuda()
+    edges = torch.linspace(-3.5, 3.5, nb + 1)
+    geom = geom_rows(edges, 0.5, k)[0].cuda()
+    meas = torch.rand(k, nb).cuda()
+    meas = meas / meas.sum(dim=1, keepdim=True) / float(edges[1] - edges[0])
+
+    class OneRank:
+        rank, world = 0, 1
+
+        def __init__(self):
+            self.block = torch.zeros(int(lib.mfb_kde1d_p2p_block_floats(k, nb, 2)), dtype=torch.float32, device="cuda")
+            self.state = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+        def block_for(self, k_, b_, tail_, device):
+            return self.block, None, [self.block.data_ptr()], self.state
+
+    peer = OneRank()
+    for step in range(1, 5):
+        x = torch.randn(n, d, device="cuda") * (0.5 + 0.2 * step)
+        tail = torch.tensor([1.5 * step, -2.25], dtype=torch.float64, device="cuda")
+        sums, prof, kl, tail_sum = ops.kde1d_loss_forward_p2p(peer, x, w, geom, 0.5, nb, tail, float(n), meas)
+        s0, p0, k0 = ops.kde1d_loss_forward(x, w, geom, 0.5, nb, float(n), meas)
+        assert torch.equal(sums, s0) and torch.equal(prof, p0) and torch.equal(kl, k0)
+        assert torch.equal(tail_sum, tail)
+        assert peer.state[:3].tolist() == [2 * step - 1, 0, 0]
+        # the already merged variant of the same kernel (a second epoch on the same block)
+        s1, p1, k1, t1 = ops.kde1d_finish_p2p(peer, s0, tail, float(n), geom, meas)
+        assert torch.equal(p1, p0) and torch.equal(k1, k0) and torch.equal(t1, tail)
+        assert peer.state[:3].tolist() == [2 * step, 0, 0]

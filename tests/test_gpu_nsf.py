@@ -181,9 +181,10 @@ def test_coupling_layers_match_oracle(d, passes, n):
     got = {k: v for k, v in zip(("w_in", "b_in", "w_hid", "b_hid", "w_out", "b_out"),
                                 (gen.w_in.grad, gen.b_in.grad, gen.w_hid.grad, gen.b_hid.grad, gen.w_out.grad, gen.b_out.grad))}
     want_w_out = torch.stack([ref.layers[t].hyper[6].weight.grad * ref.layers[t].hyper[6].mask for t in range(5)])
-    # parameter gradients are sums over all particles, a few of them ill-conditioned in fp32: norm-wise agreement
+    # parameter gradients are sums over all particles, a few of them ill-conditioned in fp32 (as in
+    # test_backward_matches_oracle_autograd): worst entry relative to the largest entry of the tensor
     def rel_l2(a, b):
-        return float((a.cpu().double() - b).norm() / b.norm())
+        return float((a.cpu().double() - b).abs().max() / b.abs().max())
 
     assert rel_l2(got["w_out"], want_w_out) < 2e-3
     want_b_in = torch.stack([ref.layers[t].hyper[0].bias.grad for t in range(5)])
