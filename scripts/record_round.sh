@@ -5,7 +5,7 @@ tag=${1:-rX}
 REGEX='regex:nsf_tc_layer_kernel|kde1d_deposit_kernel|kde1d_finish|moments_kernel|kde1d_bwd_kernel|nsf_tc_dgrad_kernel|nsf_tc_wgrad_kernel'
 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "reference rc=$?"
-timeout 400 python scripts/bench_extra.py > gpurun_out/${tag}_bench_extra.jsonl 2> gpurun_out/${tag}_bench_extra.err; echo "extra rc=$?"
+echo "extras are part of the bench line (extra[])"
 timeout 200 python scripts/kde2d_ab.py > gpurun_out/${tag}_kde2d_ab.txt 2>&1; echo "kde2d a/b rc=$?"
 timeout 100 python scripts/prof_step.py > gpurun_out/${tag}_prof_step.log 2>&1; echo "prof_step rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph > gpurun_out/${tag}_ncu_launch.log 2>&1; echo "launch list rc=$?"
