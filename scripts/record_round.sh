@@ -8,7 +8,7 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 echo "extras are part of the bench line (extra[])"
 timeout 200 python scripts/kde2d_ab.py > gpurun_out/${tag}_kde2d_ab.txt 2>&1; echo "kde2d a/b rc=$?"
 timeout 100 python scripts/prof_step.py > gpurun_out/${tag}_prof_step.log 2>&1; echo "prof_step rc=$?"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph > gpurun_out/${tag}_ncu_launch.log 2>&1; echo "launch list rc=$?"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra --no-graph > gpurun_out/${tag}_ncu_launch.log 2>&1; echo "launch list rc=$?"
 # one launch of each kernel of the forward step (layer, moments, deposit, finish), then of the backward
 # (finish_bwd, kde1d_bwd, layer<..,1>, dgrad, wgrad); the reports are reduced to their raw pages on the
 # box (the .ncu-rep files with source exceed what travels back)
