@@ -153,3 +153,66 @@ def test_graphed_train_step_reduces_the_loss():
     last = float(L)
     assert bool(step.finite) and last < first, (first, last)
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_graphed_train_step_equals_the_eager_loop_and_honours_lr_changes():
+    """The reference's training loop body (train/train.py:164-169, :205-207) as graph replays: after N steps the
+    parameters equal those of the eager loop on the same seed (the capture's warm-up passes leave parameters,
+    optimiser state and the random stream untouched), and a scheduler changing a float learning rate is honoured
+    (the step is re-captured)."""
+    import copy
+    import torch
+    import mentflow_b200 as mf
+    from mentflow_b200 import workloads
+    from mentflow_b200.graphs import GraphedTrainStep
+    dev = torch.device("cuda")
+    wl = workloads.isotropic_1d(ndim=4, num=8, bins=48, xmax=3.5, seed=2)
+    tfs = [mf.simulate.LinearTransform(m.to(dev)) for m in wl["matrices"]]
+    diag = mf.diagnostics.Histogram1D(axis=0, edges=wl["edges"], bandwidth=0.5).to(dev)
+    diags = [[diag] for _ in tfs]
+    truth = workloads.gaussian_mixture(50_000, ndim=4, seed=1, device=dev)
+    with torch.no_grad():
+        meas = [[p[0]] for p in mf.simulate.forward(truth, tfs, diags)]
+    prior = mf.prior.Gaussian(ndim=4, scale=3.0)
+
+    def make():
+        torch.manual_seed(5)
+        gen = mf.generate.NSFGenerator(4).to(dev)
+        model = mf.MENTFlow(transforms=tfs, diagnostics=diags, measurements=meas, generator=gen, prior=prior,
+                            entropy_estimator=mf.entropy.MonteCarloEntropyEstimator(prior=prior),
+                            discrepancy_function=mf.loss.kl_divergence, penalty_parameter=20.0)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.0, capturable=True)
+        return model, opt
+
+    n, steps = 10_000, 6
+    lrs = [1e-3, 1e-3, 1e-3, 4e-4, 4e-4, 4e-4]            # ReduceLROnPlateau-style drop after three steps
+    # eager loop
+    model_e, opt_e = make()
+    torch.manual_seed(123)
+    losses_e = []
+    for i in range(steps):
+        for g_ in opt_e.param_groups:
+            g_["lr"] = lrs[i]
+        opt_e.zero_grad(set_to_none=True)
+        L, H, D = model_e.loss(n)
+        L.backward()
+        opt_e.step()
+        losses_e.append(float(L))
+    # graph replays
+    model_g, opt_g = make()
+    before = [p.detach().clone() for p in model_g.parameters()]
+    step = GraphedTrainStep(model_g, opt_g, n)
+    torch.manual_seed(123)
+    step._capture()                                          # explicit capture: must be side-effect free
+    assert all(torch.equal(a, b) for a, b in zip(before, model_g.parameters()))
+    assert torch.cuda.default_generators[dev.index or 0].get_offset() == 0
+    losses_g = []
+    for i in range(steps):
+        for g_ in opt_g.param_groups:
+            g_["lr"] = lrs[i]
+        losses_g.append(float(step()[0]))
+    assert losses_g == losses_e, (losses_g, losses_e)
+    for a, b in zip(model_g.parameters(), model_e.parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7), float((a - b).abs().max())
+    st_g = opt_g.state[next(iter(model_g.parameters()))]["step"]
+    assert int(st_g) == steps                                # every counted step is one replay
