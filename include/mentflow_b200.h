@@ -232,6 +232,22 @@ int mfb_nsf_layer_bwd_img(const float* v, const float* gy, const float* glogq, i
                           const void* tc_image, float* gv, float* gparams, int accumulate,
                           void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
+/* ---- parameter layouts --------------------------------------------------------------------
+ * zuko keeps every MaskedLinear as weight [out][in] + a 0/1 mask applied on each call (zuko/nn.py, reached from
+ * generate/build.py:36-46); the kernels take pre-masked, transposed blocks.  One launch converts the whole flow:
+ * w_in [T][64][d], b_in [T][64], w_hid [T][L-1][64][64], b_hid [T][L-1][64], w_out [T][d*P][64], b_out [T][d*P]
+ * (P = 3*bins-1) and masks of the weights' shapes -> packed [T][mfb_nsf_layer_param_floats] and, if not NULL,
+ * packed_om [T][mfb_nsf_layer_param_om_floats].  mfb_nsf_unpack_grads is its backward: dL/dpacked -> dL/d(each
+ * tensor), masked entries exactly 0.                                                              */
+int mfb_nsf_pack_params(const float* w_in, const float* b_in, const float* w_hid, const float* b_hid,
+                        const float* w_out, const float* b_out, const float* m_in, const float* m_hid,
+                        const float* m_out, int transforms, int d, int hidden_units, int hidden_layers, int bins,
+                        float* packed, float* packed_om, void* stream);
+int mfb_nsf_unpack_grads(const float* gpacked, const float* m_in, const float* m_hid, const float* m_out,
+                         int transforms, int d, int hidden_units, int hidden_layers, int bins, float* g_w_in,
+                         float* g_b_in, float* g_w_hid, float* g_b_hid, float* g_w_out, float* g_b_out,
+                         void* stream);
+
 /* ---- Monte-Carlo entropy pieces (entropy.py:58-62, prior.py:25-26) ----------------------
  * out[0] = sum logq, out[1] = sum |x|^2, out[2+i] = sum x_i, out[2+d+i*d+j] = sum x_i x_j
  * (double precision, deterministic two-stage reduction; the x_i / x_i x_j block only when

@@ -74,6 +74,8 @@ SIGNATURES = {
     "mfb_gs_update": (c_int, [P, P, P, c_int, c_float, c_float, P]),
     "mfb_selftest_umma": (c_int, [P, P, c_int, P, P, P]),
     "mfb_selftest_umma_sw32": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "mfb_nsf_pack_params": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "mfb_nsf_unpack_grads": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "mfb_moments_workspace_bytes": (c_int64, [c_int64, c_int]),
     "mfb_moments": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
     "mfb_f64_split": (c_int, [P, c_int, P, P]),

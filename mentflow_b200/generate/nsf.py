@@ -116,9 +116,19 @@ class NSFGenerator(GenerativeModel):
     def dim(self) -> int:
         return self.features
 
+    def packed_pair(self):
+        """(packed, packed_om) on a CUDA device: one kernel launch (``ops.PackParameters``), differentiable w.r.t.
+        the six parameter tensors through one launch the other way."""
+        dims = (self.transforms, self.features, self.hidden_units, self.hidden_layers, self.bins)
+        return ops.PackParameters.apply(self.w_in, self.b_in, self.w_hid, self.b_hid, self.w_out, self.b_out,
+                                        self.m_in, self.m_hid, self.m_out, dims)
+
     def packed_parameters(self) -> torch.Tensor:
         """(T, floats_per_layer) block in the kernels' layout: masked, transposed to [in][out],
-        per-feature output blocks padded from 3*bins-1 to 64 (differentiable torch ops)."""
+        per-feature output blocks padded from 3*bins-1 to 64.  CUDA parameters: one launch of the packing kernel;
+        CPU parameters (host-side tests of the layout): the same layout spelled in differentiable torch ops."""
+        if self.w_in.is_cuda:
+            return self.packed_pair()[0]
         T, H, D, P = self.transforms, self.hidden_units, self.features, self.total
         parts = [(self.w_in * self.m_in).transpose(1, 2).reshape(T, -1), self.b_in]
         if self.hidden_layers > 1:
@@ -136,6 +146,9 @@ class NSFGenerator(GenerativeModel):
         W1 [64][D] | Wl [64][64] x (L-1) | Wout [D*64 (59->64 padded rows)][64]; detached (the
         parameter gradient flows through ``packed_parameters``)."""
         T, H, D, P = self.transforms, self.hidden_units, self.features, self.total
+        if self.w_in.is_cuda:
+            with torch.no_grad():
+                return self.packed_pair()[1]
         with torch.no_grad():
             parts = [(self.w_in * self.m_in).reshape(T, -1)]
             if self.hidden_layers > 1:
@@ -229,8 +242,11 @@ class NSFGenerator(GenerativeModel):
             packed, images = self._packed_cached()
             return ops.nsf_forward(z, packed, None, self._orders, self.hidden_units, self.hidden_layers, self.bins,
                                    want_logq, want_steps, images=images)
-        packed_om = self.packed_parameters_om() if need_grad else None
-        return ops.nsf_forward(z, self.packed_parameters(), packed_om, self._orders, self.hidden_units,
+        if self.w_in.is_cuda:
+            packed, packed_om = self.packed_pair()          # one launch for both layouts
+        else:
+            packed, packed_om = self.packed_parameters(), (self.packed_parameters_om() if need_grad else None)
+        return ops.nsf_forward(z, packed, packed_om, self._orders, self.hidden_units,
                                self.hidden_layers, self.bins, want_logq, want_steps)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:

@@ -513,6 +513,50 @@ def f64_join(pairs: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# zuko-layout parameters <-> packed blocks
+# --------------------------------------------------------------------------------------
+class PackParameters(torch.autograd.Function):
+    """(packed (T, floats_per_layer), packed_om (T, om_floats)) from the zuko-layout tensors of the whole flow in one
+    launch; backward = one launch the other way (masked entries get exactly zero gradient).  ``packed_om`` is the
+    same numbers in the backward kernels' out-major layout and carries no gradient of its own."""
+
+    @staticmethod
+    def forward(ctx, w_in, b_in, w_hid, b_hid, w_out, b_out, m_in, m_hid, m_out, dims):
+        lib = _lib.load()
+        T, d, hidden_units, hidden_layers, bins = dims
+        ts = [_check_f32(n, t) for n, t in zip(("w_in", "b_in", "w_hid", "b_hid", "w_out", "b_out", "m_in", "m_hid", "m_out"),
+                                                (w_in, b_in, w_hid, b_hid, w_out, b_out, m_in, m_hid, m_out))]
+        dev = w_in.device
+        with torch.cuda.device(dev):
+            np_ = int(lib.mfb_nsf_layer_param_floats(d, hidden_units, hidden_layers, bins))
+            nom = int(lib.mfb_nsf_layer_param_om_floats(d, hidden_units, hidden_layers))
+            packed = torch.empty((T, np_), dtype=torch.float32, device=dev)
+            packed_om = torch.empty((T, nom), dtype=torch.float32, device=dev)
+            _lib.check(lib.mfb_nsf_pack_params(*[_ptr(t) if t.numel() else None for t in ts], T, d, hidden_units,
+                                               hidden_layers, bins, _ptr(packed), _ptr(packed_om), _stream()),
+                       "nsf_pack_params")
+        ctx.save_for_backward(ts[6], ts[7], ts[8])
+        ctx.dims = dims
+        ctx.shapes = [t.shape for t in ts[:6]]
+        ctx.mark_non_differentiable(packed_om)
+        return packed, packed_om
+
+    @staticmethod
+    def backward(ctx, gpacked, _gom):
+        lib = _lib.load()
+        m_in, m_hid, m_out = ctx.saved_tensors
+        T, d, hidden_units, hidden_layers, bins = ctx.dims
+        gpacked = _check_f32("gpacked", gpacked)
+        grads = [torch.empty(sh, dtype=torch.float32, device=gpacked.device) for sh in ctx.shapes]
+        with torch.cuda.device(gpacked.device):
+            _lib.check(lib.mfb_nsf_unpack_grads(_ptr(gpacked), _ptr(m_in), _ptr(m_hid) if m_hid.numel() else None,
+                                                _ptr(m_out), T, d, hidden_units, hidden_layers, bins,
+                                                *[_ptr(g) if g.numel() else None for g in grads], _stream()),
+                       "nsf_unpack_grads")
+        return (*grads, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------
 # whole flow (all layers), differentiable
 # --------------------------------------------------------------------------------------
 class NSFForward(torch.autograd.Function):

@@ -179,6 +179,9 @@ def test_coupling_layers_match_oracle(d, passes, n):
     ref, ref32 = oracle_from_generator(gen), oracle_from_generator(gen, torch.float32)
     a, b = torch.randn(n, d), torch.randn(n)
     zc = z.clone().cuda().requires_grad_(True)
+    xg, lg = gen.forward_and_log_prob(zc)
+    ((xg * a.cuda()).sum() + (lg * b.cuda()).sum()).backward()
+
     def oracle_grads(flow, dtype):
         for q in flow.parameters():
             q.grad = None
@@ -383,3 +386,26 @@ def test_inverse_and_log_prob(d, n, scale):
     assert float(e.median()) < 1e-5 and float((e > 1e-3).float().mean()) < 2e-3
     el = ((lp - lq).abs() / lq.abs().clamp_min(1.0)).flatten()
     assert float(el.median()) < 1e-5 and float((el > 1e-3).float().mean()) < 5e-3
+
+
+@pytest.mark.parametrize("d,hl,bins,passes", [(6, 3, 20, None), (2, 3, 20, None), (4, 2, 12, None), (5, 1, 8, None), (6, 3, 20, 2)])
+def test_pack_kernel_equals_the_torch_spelling_of_the_layout(d, hl, bins, passes):
+    """One launch packs the zuko-layout parameters into both kernel layouts, one launch un-packs the gradient:
+    bit-identical to the layout spelled in torch ops (which the CPU tests check against the oracle's conditioner)."""
+    torch.manual_seed(d * 7 + hl)
+    cpu = mf.generate.NSFGenerator(d, hidden_layers=hl, transforms=3, bins=bins, passes=passes)
+    gpu = mf.generate.NSFGenerator(d, hidden_layers=hl, transforms=3, bins=bins, passes=passes)
+    gpu.load_state_dict(cpu.state_dict())
+    gpu = gpu.to("cuda")
+    want, want_om = cpu.packed_parameters(), cpu.packed_parameters_om()
+    got, got_om = gpu.packed_pair()
+    assert torch.equal(got.cpu(), want) and torch.equal(got_om.cpu(), want_om)
+    assert torch.equal(gpu.packed_parameters_om().cpu(), want_om)
+    gup = torch.randn_like(want)
+    (want * gup).sum().backward()
+    (got * gup.cuda()).sum().backward()
+    for name in ("w_in", "b_in", "w_hid", "b_hid", "w_out", "b_out"):
+        a, b = getattr(gpu, name).grad, getattr(cpu, name).grad
+        if getattr(cpu, name).numel() == 0:          # hidden_layers = 1: no hidden-to-hidden weights
+            continue
+        assert torch.equal(a.cpu(), b), name
