@@ -53,9 +53,15 @@ class ShardReducer:
         if self.world_size == 1 or self.world_size > 8 or not self.equal_shards or dist.get_backend(self.group) != "nccl":
             return False
         try:
-            self.peer = PeerExchange(self.group)
+            peer = PeerExchange(self.group)
+            # probe: allocate and map a small block now, so that a node without peer mapping (no NVLink / P2P,
+            # symmetric memory unavailable) falls back to NCCL on every rank alike instead of failing mid-step
+            peer.block_for(2, 2, 0, torch.device("cuda", torch.cuda.current_device()))
+            ok = torch.ones(1, device="cuda")
         except Exception:
-            self.peer = None
+            peer, ok = None, torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)     # all ranks or none
+        self.peer = peer if bool(ok.item()) else None
         return self.peer is not None
 
     def take_stash(self) -> Optional[torch.Tensor]:
