@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:kde2d_tc_kernel --launch-skip 3 -c 1 -o gpurun_out/r2p_kde2d -f python scripts/kde2d_ab.py > gpurun_out/r2p_ncu.log 2>&1; echo "ncu rc=$?"
+ncu -i gpurun_out/r2p_kde2d.ncu-rep --page raw --csv > gpurun_out/r2p_raw.csv 2>/dev/null
+ncu -i gpurun_out/r2p_kde2d.ncu-rep --page source --csv --print-source sass > gpurun_out/r2p_source_sass.csv 2>/dev/null
+rm -f gpurun_out/r2p_kde2d.ncu-rep; gzip -f gpurun_out/r2p_source_sass.csv; ls -la gpurun_out | grep r2p
