@@ -50,7 +50,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 struct ScreenAxis {
-  float c0, inv_delta, alpha;
+  float c0, inv_delta, scale;   // scale = sqrt(0.5 log2 e) * delta / sigma: kernel value = 2^-((a - r) scale)^2
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -92,7 +92,6 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
   const int ngroups = (K + kGroup - 1) / kGroup;
   const int nmma = (BY + 15) & ~15;                 // MMA N
   const uint32_t idesc = make_idesc_bf16(128, nmma);
-  const int rows_ab = BX + BY;                      // operand rows written per stage
 
   uint32_t it = 0;   // running stage use counter (same sequence in loaders and issuer)
   for (int g = 0; g < ngroups; ++g) {
@@ -109,7 +108,7 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
       const float r = gp[1] / gp[2];
       s_ax[i].c0 = gp[0];
       s_ax[i].inv_delta = 1.0f / gp[1];
-      s_ax[i].alpha = -0.5f * r * r * kLog2e;
+      s_ax[i].scale = sqrtf(0.5f * kLog2e) * r;
     }
     __syncthreads();
 
@@ -158,41 +157,45 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
           const uint32_t slot = it % kStages, par = (it / kStages) & 1;
           mbar_wait_bounded(&empty[slot], par ^ 1);
           unsigned char* st = stages + slot * kStageBytes;
-          const float ax_alpha = s_ax[2 * s].alpha, ay_alpha = s_ax[2 * s + 1].alpha;
+          const float ax_scale = s_ax[2 * s].scale, ay_scale = s_ax[2 * s + 1].scale;
           const float* cx = cbuf + (2 * s) * kCRow;
           const float* cy = cx + kCRow;
           // A thread owns one 8-particle chunk of the tile and every (kLoaders / 8)-th operand row: the chunk's
           // coordinates on both axes are read once per stage and stay in registers (re-reading them per row
           // cost as much shared-memory bandwidth as writing the operands).  Per (row, chunk): dense kernel
-          // values, bf16 (hi, mid), 16 B each.
+          // values 2^-(cs - r s)^2, bf16 (hi, mid), 16 B each.  hi is the value truncated to its upper 16 bits (one
+          // AND gives it back as a float, one PRMT packs a pair), mid the rounded remainder: 16 significant bits
+          // like a rounded hi, for 9 instead of 15 instructions per value (profiles/r2_kde2d_tc_metrics.txt).
           const int chunk = tid & 7;
-          float ccx[8], ccy[8];
-          {
-            const float4 a0 = *reinterpret_cast<const float4*>(cx + crow_index(chunk * 8));
-            const float4 a1 = *reinterpret_cast<const float4*>(cx + crow_index(chunk * 8) + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(cy + crow_index(chunk * 8));
-            const float4 b1 = *reinterpret_cast<const float4*>(cy + crow_index(chunk * 8) + 4);
-            ccx[0] = a0.x; ccx[1] = a0.y; ccx[2] = a0.z; ccx[3] = a0.w; ccx[4] = a1.x; ccx[5] = a1.y; ccx[6] = a1.z; ccx[7] = a1.w;
-            ccy[0] = b0.x; ccy[1] = b0.y; ccy[2] = b0.z; ccy[3] = b0.w; ccy[4] = b1.x; ccy[5] = b1.y; ccy[6] = b1.z; ccy[7] = b1.w;
-          }
-          for (int row = tid >> 3; row < rows_ab; row += kLoaders / 8) {
-            const bool isa = row < BX;
-            const int r = isa ? row : row - BX;
-            const float alpha = isa ? ax_alpha : ay_alpha;
-            __align__(16) __nv_bfloat162 hi[4], mid[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float ta = (isa ? ccx[2 * e] : ccy[2 * e]) - (float)r, tb = (isa ? ccx[2 * e + 1] : ccy[2 * e + 1]) - (float)r;
-              const float va = fast_exp2(alpha * ta * ta), vb = fast_exp2(alpha * tb * tb);
-              hi[e] = __floats2bfloat162_rn(va, vb);
-              const float2 hf = __bfloat1622float2(hi[e]);
-              mid[e] = __floats2bfloat162_rn(va - hf.x, vb - hf.y);
+          auto operand_rows = [&](const float* crow, float sc, int nrows, unsigned char* hi_tile, unsigned char* mid_tile) {
+            float cs[8];
+            {
+              const float4 a0 = *reinterpret_cast<const float4*>(crow + crow_index(chunk * 8));
+              const float4 a1 = *reinterpret_cast<const float4*>(crow + crow_index(chunk * 8) + 4);
+              cs[0] = a0.x; cs[1] = a0.y; cs[2] = a0.z; cs[3] = a0.w; cs[4] = a1.x; cs[5] = a1.y; cs[6] = a1.z; cs[7] = a1.w;
             }
-            unsigned char* base = st + (isa ? 0 : 2 * kABytes);
-            const uint32_t off = umma::sw128_offset(r, chunk);
-            *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(base + (isa ? kABytes : kBBytes) + off) = *reinterpret_cast<const uint4*>(mid);
-          }
+            for (int r = tid >> 3; r < nrows; r += kLoaders / 8) {
+              const float rs = (float)r;
+              uint32_t hi[4], mid[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // (a - r) first: r is an integer and a is within a few bins of it wherever the value matters, so the
+                // difference is exact; scaling the coordinates beforehand costs 2x the rounding error in the exponent
+                const float ta = (cs[2 * e] - rs) * sc, tb = (cs[2 * e + 1] - rs) * sc;
+                const float va = fast_exp2(-(ta * ta)), vb = fast_exp2(-(tb * tb));
+                const uint32_t ua = __float_as_uint(va), ub = __float_as_uint(vb);
+                hi[e] = __byte_perm(ua, ub, 0x7632);                         // (bf16 of vb) << 16 | bf16 of va, truncated
+                const __nv_bfloat162 m = __floats2bfloat162_rn(va - __uint_as_float(ua & 0xFFFF0000u),
+                                                               vb - __uint_as_float(ub & 0xFFFF0000u));
+                mid[e] = *reinterpret_cast<const uint32_t*>(&m);
+              }
+              const uint32_t off = umma::sw128_offset(r, chunk);
+              *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(mid_tile + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            }
+          };
+          operand_rows(cx, ax_scale, BX, st, st + kABytes);
+          operand_rows(cy, ay_scale, BY, st + 2 * kABytes, st + 2 * kABytes + kBBytes);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0)
