@@ -298,6 +298,8 @@ def project_hist1d(x: torch.Tensor, proj: torch.Tensor, edges: torch.Tensor,
     k, b = proj.shape[0], edges.shape[1] - 1
     if counts is None:
         counts = torch.zeros((k, b), dtype=torch.int64, device=x.device)
+    if n == 0:              # nothing to count
+        return counts
     with torch.cuda.device(x.device):
         if mp is None:
             _lib.check(lib.mfb_project_hist1d(_ptr(x), n, d, _ptr(proj), _ptr(edges), k, b, _ptr(counts), _stream()),
@@ -388,6 +390,8 @@ def project_hist2d(x, proj, edges_x, edges_y, counts=None):
     k, bx, by = proj.shape[0], edges_x.shape[1] - 1, edges_y.shape[1] - 1
     if counts is None:
         counts = torch.zeros((k, bx, by), dtype=torch.int64, device=x.device)
+    if n == 0:              # nothing to count
+        return counts
     with torch.cuda.device(x.device):
         _lib.check(lib.mfb_project_hist2d(_ptr(x), n, d, _ptr(proj), _ptr(edges_x), _ptr(edges_y), k, bx, by,
                                           _ptr(counts), _stream()), "project_hist2d")
@@ -441,6 +445,8 @@ def nsf_layer_forward(v, params, order, hidden_units, hidden_layers, bins, logq_
     n, d = v.shape
     y = torch.empty_like(v)
     logq_out = torch.empty(n, dtype=torch.float32, device=v.device) if want_logq else None
+    if n == 0:          # an empty batch has no storage to point at: nothing to launch
+        return y, logq_out
     order_arr = (ctypes.c_int32 * d)(*[int(o) for o in order])
     with torch.cuda.device(v.device):
         if image is not None:
@@ -656,6 +662,10 @@ def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=
             v = torch.empty_like(x)
             out = torch.empty(n, dtype=torch.float32, device=x.device) if want_logq else None
             order_arr = (ctypes.c_int32 * d)(*[int(o) for o in orders[t]])
+            if n == 0:          # empty batch: nothing to launch
+                acc = out
+                steps.append(v)
+                continue
             _lib.check(lib.mfb_nsf_layer_inv(_ptr(steps[-1]), n, d, hidden_units, hidden_layers, bins, _ptr(packed[t]),
                                              ctypes.cast(order_arr, ctypes.c_void_p), _ptr(acc), 1 if t == 0 else 0,
                                              _ptr(v), _ptr(out), _stream()), "nsf_layer_inv")
