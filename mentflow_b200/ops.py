@@ -914,7 +914,12 @@ class PhiloxStream:
         """Allocate / prime the device state; call right before the graph capture starts."""
         if self.state is None:
             self.state = torch.zeros(2, dtype=torch.int64, device=self.device)
-            self._pinned = torch.zeros(2, dtype=torch.int64).pin_memory()
+            # ring of pinned staging slots, each guarded by an event: a slot is rewritten by the host only after
+            # the asynchronous copy that last read it has completed (re-seeding every step without synchronising
+            # in between must not let a later state overtake an earlier replay)
+            self._pinned = torch.zeros((8, 2), dtype=torch.int64).pin_memory()
+            self._slot_events = [None] * 8
+            self._slot = 0
         self.captured_increment = 0
         self._mirror = None
         self.sync()
@@ -924,9 +929,16 @@ class PhiloxStream:
         g = self._generator()
         cur = (int(g.initial_seed()), int(g.get_offset()))
         if self._mirror != cur:
-            self._pinned[0] = self._as_i64(cur[0])
-            self._pinned[1] = self._as_i64(cur[1])
-            self.state.copy_(self._pinned, non_blocking=True)
+            i = self._slot
+            self._slot = (i + 1) % self._pinned.shape[0]
+            if self._slot_events[i] is not None:
+                self._slot_events[i].synchronize()
+            self._pinned[i, 0] = self._as_i64(cur[0])
+            self._pinned[i, 1] = self._as_i64(cur[1])
+            self.state.copy_(self._pinned[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot_events[i] = ev
             self._mirror = cur
 
     def consumed(self) -> None:
