@@ -212,6 +212,41 @@ __device__ __forceinline__ void gauss_taps(float f, float alpha, const float (&r
   }
 }
 
+// The same taps for a window ALIGNED to row pairs: 2R+2 slots starting at an even row, slot i at offset
+// o_i = i - (R + 1/2) from the window's centre, t in [-1, 1] = particle position relative to that centre:
+//   tap[i] = 2^(alpha (t - o_i)^2) = E_c * G^o_i * C_o_i,   E_c = 2^(alpha t^2), G = 2^(-2 alpha t), C_o = 2^(alpha o^2)
+// chalf = C_1/2 and rr[j] = C_(j+3/2) / C_(j+1/2) = 2^(alpha (2j + 2)) per projection.  The nine taps of the
+// unaligned window [fb-R, fb+R] are all inside (plus one more, 1e-18 of the centre) and land in their pair slots
+// without the shift-by-parity selects the unaligned form needed (11 FSEL per particle-projection).
+template <int R>
+__device__ __forceinline__ void gauss_taps_pairs(float t, float alpha, float chalf, const float (&rr)[R],
+                                                 float (&tap)[2 * R + 2]) {
+  const float at = alpha * t;
+  const float base = fast_exp2(at * t) * chalf;
+  const float h = fast_exp2(-at), hi = fast_exp2(at);     // G^(1/2), G^(-1/2)
+  const float g = h * h, gi = hi * hi;
+  float up = base * h, dn = base * hi;
+  tap[R + 1] = up;
+  tap[R] = dn;
+#pragma unroll
+  for (int j = 1; j <= R; ++j) {
+    up *= g * rr[j - 1];
+    dn *= gi * rr[j - 1];
+    tap[R + 1 + j] = up;
+    tap[R - j] = dn;
+  }
+}
+
+// particle row of an even-dimensional tile from shared memory with 8-byte loads (a generic pointer into the
+// staging buffers compiles to six generic 4-byte loads per row)
+template <int D>
+__device__ __forceinline__ void load_row_shared(uint32_t saddr, float (&xr)[kMaxDim]) {
+  static_assert(D % 2 == 0 && D >= 2, "even dimension");
+#pragma unroll
+  for (int i = 0; i < D; i += 2)
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xr[i]), "=f"(xr[i + 1]) : "r"(saddr + 4u * i));
+}
+
 template <int D, int R, bool kMP = false>
 __global__ void __launch_bounds__(kDepThreads)
 kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* __restrict__ proj,
@@ -243,10 +278,10 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
   __syncthreads();
 
   float w[kMaxDim];
-  float c0s = 0.f, inv_delta = 0.f, alpha = 0.f;
-  float rj[R];
+  float c0s = 0.f, inv_delta = 0.f, alpha = 0.f, chalf = 0.f;
+  float rr[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) rj[j] = 0.f;
+  for (int j = 0; j < R; ++j) rr[j] = 0.f;
   if (active) {
 #pragma unroll
     for (int i = 0; i < kMaxDim; ++i) w[i] = i < d ? proj[(size_t)k * d + i] : 0.f;
@@ -255,8 +290,9 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     c0s = g[0] * inv_delta;
     float r = g[1] / g[2];
     alpha = -0.5f * r * r * kLog2e;
+    chalf = exp2f(0.25f * alpha);
 #pragma unroll
-    for (int j = 0; j < R; ++j) rj[j] = exp2f(alpha * (float)(2 * j + 1));
+    for (int j = 0; j < R; ++j) rr[j] = exp2f(alpha * (float)(2 * j + 2));
   }
   MpTerms mpt;
   if constexpr (kMP) {
@@ -283,40 +319,50 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     int64_t rows64 = n - t * tile;
     const int rows = rows64 > tile ? tile : (int)rows64;
     const float* xs = tp.buf[stage];
+    const uint32_t xs_shared = smem_u32(xs);
+    (void)xs_shared;
     if (active) {
       // kPer particles per trip: their taps are independent (ILP for the MUFU / FMA work), only the
       // deposits into this thread's private bins are ordered
       constexpr int kPer = 4;
       for (int p = slice; p < rows; p += kPer * slices) {
-        float taps[kPer][2 * R + 1];
+        float taps[kPer][2 * R + 2];
         float2* dstp[kPer];
-        bool odd[kPer];
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
           const int pq = p + q * slices;
           const bool have = pq < rows;
-          const float* xr = xs + (size_t)(have ? pq : p) * d;
           float u;
-          if constexpr (kMP) u = project_row_mp(xr, w, mpt, d);
-          else u = project_row<D>(xr, w, d);
+          if constexpr (kMP) {
+            u = project_row_mp(xs + (size_t)(have ? pq : p) * d, w, mpt, d);
+          } else if constexpr (D > 0 && D % 2 == 0) {
+            float xr[kMaxDim];
+            load_row_shared<D>(xs_shared + (uint32_t)((have ? pq : p) * (D * 4)), xr);
+            u = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) u = fmaf(w[i], xr[i], u);     // ascending FMA chain from zero (= the reference's sgemm bits)
+          } else {
+            u = project_row<D>(xs + (size_t)(have ? pq : p) * d, w, d);
+          }
           float a = fmaf(u, inv_delta, -c0s);
           a = have ? fminf(fmaxf(a, lo), hi) : lo;   // a missing particle goes to the guard rows
-          const float fb = rintf(a);
-          gauss_taps<R>(a - fb, alpha, rj, taps[q]);
-          const int r0 = (int)fb + guard - R;         // first row of the window (>= 1)
-          odd[q] = r0 & 1;
-          dstp[q] = mypairs + (size_t)(r0 >> 1) * ld;
+          // window of 2R+2 rows starting at the even row 2 fp that holds the taps fb-R .. fb+R; t = position of the
+          // particle relative to the window's centre, |t| <= 1
+          const float ar = a + ((float)guard - ((float)R + 0.5f));
+          // round-to-nearest of ar / 2 through the 1.5 * 2^23 constant (0 <= ar / 2 < 2^22): the integer is in the low
+          // mantissa bits, no FRND / F2I
+          const float shifted = fmaf(0.5f, ar, 12582912.0f);
+          const float fp = shifted - 12582912.0f;
+          gauss_taps_pairs<R>(fmaf(-2.0f, fp, ar), alpha, chalf, rr, taps[q]);
+          dstp[q] = mypairs + (size_t)(__float_as_int(shifted) - 0x4B400000) * ld;
         }
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
 #pragma unroll
           for (int j = 0; j < kPairs; ++j) {
-            // slots 2j, 2j+1 of the pair window hold taps 2j - odd, 2j + 1 - odd (0 outside 0..2R)
-            const float e_lo = taps[q][2 * j], e_hi = 2 * j + 1 <= 2 * R ? taps[q][2 * j + 1] : 0.f;
-            const float o_lo = j > 0 ? taps[q][2 * j - 1] : 0.f, o_hi = taps[q][2 * j];
             float2 v = dstp[q][(size_t)j * ld];
-            v.x += odd[q] ? o_lo : e_lo;
-            v.y += odd[q] ? o_hi : e_hi;
+            v.x += taps[q][2 * j];
+            v.y += taps[q][2 * j + 1];
             dstp[q][(size_t)j * ld] = v;
           }
         }
