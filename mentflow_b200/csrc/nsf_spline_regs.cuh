@@ -66,19 +66,54 @@ MFB_HD void clip_exp2_pair(float t0, float t1, float c, float& e0, float& e1) {
 #endif
 }
 
+// Packed fp32 pairs (Blackwell FMUL2 / FADD2 / FFMA2: two IEEE round-to-nearest lanes for ONE issue slot -- the flow
+// kernel is bound by issue slots, not by the FMA pipe; scripts/micro/ffma2_bench.cu).  Lane results are bit-identical
+// to the scalar operations, so the host build (and the parity statistics) see the same arithmetic.
+#ifndef MFB_F32X2
+#define MFB_F32X2 1
+#endif
+MFB_HD void mul2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+#if defined(__CUDA_ARCH__) && MFB_F32X2
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+#else
+  c0 = a0 * b0;
+  c1 = a1 * b1;
+#endif
+}
+MFB_HD void add2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+#if defined(__CUDA_ARCH__) && MFB_F32X2
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+#else
+  c0 = sp_add(a0, b0);
+  c1 = sp_add(a1, b1);
+#endif
+}
+
 // the same for four parameters with ONE reciprocal (the spline phases are bound by the MUFU pipe:
 // 8 issue slots per MUFU instruction, so three extra multiplies per quad are the cheaper side)
 MFB_HD void clip_exp2_quad(float t0, float t1, float t2, float t3, float c, float& e0, float& e1,
                                                float& e2, float& e3) {
   const float d0 = fmaf(fabsf(t0), c, 1.0f), d1 = fmaf(fabsf(t1), c, 1.0f);
   const float d2 = fmaf(fabsf(t2), c, 1.0f), d3 = fmaf(fabsf(t3), c, 1.0f);
-  const float p01 = d0 * d1, p23 = d2 * d3;
+  // packed where the operands are pairs already: (t0, t1) and (t2, t3) are neighbours in the tcgen05.ld result
+  float p01, p23, x0, x1, x2, x3;
+  mul2(d0, d2, d1, d3, p01, p23);
   const float r = sp_rcp(p01 * p23);
   const float r01 = r * p23, r23 = r * p01;   // 1 / (d0 d1), 1 / (d2 d3)
-  e0 = sp_exp2(t0 * (r01 * d1));
-  e1 = sp_exp2(t1 * (r01 * d0));
-  e2 = sp_exp2(t2 * (r23 * d3));
-  e3 = sp_exp2(t3 * (r23 * d2));
+  mul2(t0, t1, r01 * d1, r01 * d0, x0, x1);
+  mul2(t2, t3, r23 * d3, r23 * d2, x2, x3);
+  e0 = sp_exp2(x0);
+  e1 = sp_exp2(x1);
+  e2 = sp_exp2(x2);
+  e3 = sp_exp2(x3);
 }
 
 // error-free addition (Knuth): s = fl(a + b), err = (a + b) - s exactly
@@ -125,7 +160,9 @@ MFB_HD float rq_spline_regs(const float (&a)[64], float v, float& jac) {
   plo[0] = 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const float gs = (e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]);
+    float s01, s23;
+    add2(e[4 * g], e[4 * g + 2], e[4 * g + 1], e[4 * g + 3], s01, s23);
+    const float gs = s01 + s23;
     if (MFB_SPLINE_COMP >= 1 && g > 0) {
       float err;
       two_sum(pre[g], gs, pre[g + 1], err);
@@ -172,7 +209,9 @@ MFB_HD float rq_spline_regs(const float (&a)[64], float v, float& jac) {
     h2s = take ? h2 : h2s;
     h3s = take ? h3 : h3s;
     yg = take ? run : yg;
-    const float gs = (h0 + h1) + (h2 + h3);
+    float s01, s23;
+    add2(h0, h2, h1, h3, s01, s23);
+    const float gs = s01 + s23;
     if (MFB_SPLINE_COMP >= 2 && g > 0) {
       ygl = take ? runl : ygl;
       float err;

@@ -274,7 +274,9 @@ __device__ __forceinline__ void split_relu_pair(float x0, float x1, uint32_t& hi
   asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const __half2 h = *reinterpret_cast<const __half2*>(&hi);
   const float2 hf = __half22float2(h);
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+  float r0, r1;
+  add2(x0, x1, -hf.x, -hf.y, r0, r1);     // exact residuals, one packed subtraction
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 // relu(acc) -> (hi, lo) fp16 rows of the A operand tile (row = particle); the bias is already in acc
