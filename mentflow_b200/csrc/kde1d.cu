@@ -14,6 +14,8 @@
 // touches only the 2R+1 bins within ~8.9 sigma of its projection (everything else is below
 // 1e-17 of a central tap), instead of all B.  Per-CTA partials are merged in a fixed
 // order by a second tiny kernel.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mfb {
@@ -218,20 +220,31 @@ __device__ __forceinline__ void gauss_taps(float f, float alpha, const float (&r
 // chalf = C_1/2 and rr[j] = C_(j+3/2) / C_(j+1/2) = 2^(alpha (2j + 2)) per projection.  The nine taps of the
 // unaligned window [fb-R, fb+R] are all inside (plus one more, 1e-18 of the centre) and land in their pair slots
 // without the shift-by-parity selects the unaligned form needed (11 FSEL per particle-projection).
+// two fp32 products for one issue slot (Blackwell FMUL2; lanes are IEEE round-to-nearest like the scalar multiply)
+__device__ __forceinline__ void mul_pair(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+
 template <int R>
 __device__ __forceinline__ void gauss_taps_pairs(float t, float alpha, float chalf, const float (&rr)[R],
                                                  float (&tap)[2 * R + 2]) {
   const float at = alpha * t;
   const float base = fast_exp2(at * t) * chalf;
   const float h = fast_exp2(-at), hi = fast_exp2(at);     // G^(1/2), G^(-1/2)
-  const float g = h * h, gi = hi * hi;
-  float up = base * h, dn = base * hi;
+  float g, gi, up, dn;
+  mul_pair(h, hi, h, hi, g, gi);
+  mul_pair(base, base, h, hi, up, dn);
   tap[R + 1] = up;
   tap[R] = dn;
 #pragma unroll
   for (int j = 1; j <= R; ++j) {
-    up *= g * rr[j - 1];
-    dn *= gi * rr[j - 1];
+    float gr, gir;
+    mul_pair(g, gi, rr[j - 1], rr[j - 1], gr, gir);
+    mul_pair(up, dn, gr, gir, up, dn);
     tap[R + 1 + j] = up;
     tap[R - j] = dn;
   }
@@ -301,14 +314,62 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
 
   const int64_t ntiles = (n + tile - 1) / tile;
   if ((int64_t)blockIdx.x < ntiles && tid == 0) issue_tile(tp, 0, x, n, d, tile, blockIdx.x);
-  // The column of a thread is stored as pairs of rows: float2 (row 2i, row 2i+1) at pair index i, pairs
-  // of the CTA's threads side by side (a warp touches 256 contiguous bytes: conflict free).  A window of
-  // 2R+1 taps starting at row r0 = b0 + guard - R covers the R+1 pairs from r0 >> 1; when r0 is odd the
-  // taps shift by one slot.  8-byte accesses halve the shared-memory INSTRUCTION count, which is what
-  // bounds this kernel (the LSU pipe issues one instruction per two cycles).
-  float2* mypairs = reinterpret_cast<float2*>(bins) + tid;
+  // The column of a thread is stored as pairs of rows, float2 (row 2i, row 2i+1) at pair index i, in blocks of one
+  // WARP: [warp][pair][lane].  A warp touches 256 contiguous bytes whatever pairs its lanes hit (conflict free), and
+  // consecutive pairs of a thread are a compile-time 256 bytes apart, so the R+1 pairs of a window are immediate
+  // offsets from ONE address, itself one multiply-add of the rounding constant's mantissa bits (see below).
+  // 8-byte accesses halve the shared-memory INSTRUCTION count (the LSU pipe issues one per two cycles).
+  const int npairs = rows_total >> 1;
+  const uint32_t mybase = smem_u32(bins) + (uint32_t)(((tid >> 5) * npairs * 32 + (tid & 31)) * 8);
+  const uint32_t cthread = mybase - 0x4B400000u * 256u;   // address = mantissa bits * 256 + cthread (mod 2^32)
   const float lo = -(float)(R + 1), hi = (float)(B + R);
   constexpr int kPairs = R + 1;
+  const float centre = (float)guard - ((float)R + 0.5f);
+
+  // kPer particles of this thread's slice from row p on: their taps are independent (ILP for the MUFU / FMA work),
+  // only the deposits into the private bins are ordered.  No bounds checks: the callers pass rows that exist.
+  auto deposit = [&](auto per, const float* xs, uint32_t xs_shared, int p, int stride) {
+    constexpr int kPer = decltype(per)::value;
+    float taps[kPer][2 * R + 2];
+    uint32_t dst[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int pq = p + q * stride;
+      float u;
+      if constexpr (kMP) {
+        u = project_row_mp(xs + (size_t)pq * d, w, mpt, d);
+      } else if constexpr (D > 0 && D % 2 == 0) {
+        float xr[kMaxDim];
+        load_row_shared<D>(xs_shared + (uint32_t)(pq * (D * 4)), xr);
+        u = 0.f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) u = fmaf(w[i], xr[i], u);     // ascending FMA chain from zero (= the reference's sgemm bits)
+      } else {
+        u = project_row<D>(xs + (size_t)pq * d, w, d);
+      }
+      const float a = fminf(fmaxf(fmaf(u, inv_delta, -c0s), lo), hi);   // beyond the screen (or NaN): guard rows
+      // window of 2R+2 rows starting at the even row 2 fp that holds the taps fb-R .. fb+R; t = position of the
+      // particle relative to the window's centre, |t| <= 1
+      const float ar = a + centre;
+      // round-to-nearest of ar / 2 through the 1.5 * 2^23 constant (0 <= ar / 2 < 2^22): the integer is in the low
+      // mantissa bits, no FRND / F2I
+      const float shifted = fmaf(0.5f, ar, 12582912.0f);
+      const float fp = shifted - 12582912.0f;
+      gauss_taps_pairs<R>(fmaf(-2.0f, fp, ar), alpha, chalf, rr, taps[q]);
+      dst[q] = __float_as_uint(shifted) * 256u + cthread;
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) {
+        float vx, vy;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(vx), "=f"(vy) : "r"(dst[q] + 256u * j));
+        vx += taps[q][2 * j];
+        vy += taps[q][2 * j + 1];
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst[q] + 256u * j), "f"(vx), "f"(vy) : "memory");
+      }
+    }
+  };
 
   int it = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -320,53 +381,10 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     const int rows = rows64 > tile ? tile : (int)rows64;
     const float* xs = tp.buf[stage];
     const uint32_t xs_shared = smem_u32(xs);
-    (void)xs_shared;
     if (active) {
-      // kPer particles per trip: their taps are independent (ILP for the MUFU / FMA work), only the
-      // deposits into this thread's private bins are ordered
-      constexpr int kPer = 4;
-      for (int p = slice; p < rows; p += kPer * slices) {
-        float taps[kPer][2 * R + 2];
-        float2* dstp[kPer];
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-          const int pq = p + q * slices;
-          const bool have = pq < rows;
-          float u;
-          if constexpr (kMP) {
-            u = project_row_mp(xs + (size_t)(have ? pq : p) * d, w, mpt, d);
-          } else if constexpr (D > 0 && D % 2 == 0) {
-            float xr[kMaxDim];
-            load_row_shared<D>(xs_shared + (uint32_t)((have ? pq : p) * (D * 4)), xr);
-            u = 0.f;
-#pragma unroll
-            for (int i = 0; i < D; ++i) u = fmaf(w[i], xr[i], u);     // ascending FMA chain from zero (= the reference's sgemm bits)
-          } else {
-            u = project_row<D>(xs + (size_t)(have ? pq : p) * d, w, d);
-          }
-          float a = fmaf(u, inv_delta, -c0s);
-          a = have ? fminf(fmaxf(a, lo), hi) : lo;   // a missing particle goes to the guard rows
-          // window of 2R+2 rows starting at the even row 2 fp that holds the taps fb-R .. fb+R; t = position of the
-          // particle relative to the window's centre, |t| <= 1
-          const float ar = a + ((float)guard - ((float)R + 0.5f));
-          // round-to-nearest of ar / 2 through the 1.5 * 2^23 constant (0 <= ar / 2 < 2^22): the integer is in the low
-          // mantissa bits, no FRND / F2I
-          const float shifted = fmaf(0.5f, ar, 12582912.0f);
-          const float fp = shifted - 12582912.0f;
-          gauss_taps_pairs<R>(fmaf(-2.0f, fp, ar), alpha, chalf, rr, taps[q]);
-          dstp[q] = mypairs + (size_t)(__float_as_int(shifted) - 0x4B400000) * ld;
-        }
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-#pragma unroll
-          for (int j = 0; j < kPairs; ++j) {
-            float2 v = dstp[q][(size_t)j * ld];
-            v.x += taps[q][2 * j];
-            v.y += taps[q][2 * j + 1];
-            dstp[q][(size_t)j * ld] = v;
-          }
-        }
-      }
+      int p = slice;
+      for (; p + 3 * slices < rows; p += 4 * slices) deposit(std::integral_constant<int, 4>{}, xs, xs_shared, p, slices);
+      for (; p < rows; p += slices) deposit(std::integral_constant<int, 1>{}, xs, xs_shared, p, slices);
     }
     __syncthreads();  // everyone is done with buf[stage] before it is refilled
   }
@@ -378,7 +396,10 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     if (kbase + kk < K) {
       float s = 0.f;
       const int row = b + guard;
-      for (int sl = 0; sl < slices; ++sl) s += bins[((size_t)(row >> 1) * ld + sl * kc + kk) * 2 + (row & 1)];
+      for (int sl = 0; sl < slices; ++sl) {
+        const int tt = sl * kc + kk;   // the thread that owns this column
+        s += bins[((size_t)((tt >> 5) * npairs + (row >> 1)) * 32 + (tt & 31)) * 2 + (row & 1)];
+      }
       out[(size_t)(kbase + kk) * B + b] = s;
     }
   }
