@@ -670,7 +670,8 @@ def main():
                       f"nsf_layer_fwd_kernel<{d}> x{layers} (fp32 CUDA-core kernel)")
         # the operand images are cached while the weights do not change: no prepare kernel in a forward-only step
         nsf_launches = {"nsf_tc_layer_kernel": layers} if tc else {"nsf_layer_fwd_kernel": layers}
-        rest = {"randn_philox + advance": 2, "moments": 2, "kde1d deposit + merge/normalise/KL": 2}
+        rest = {"randn_philox + advance": 2, "moments": 2, "mc_entropy": 1, "kde1d deposit + merge/normalise/KL": 2,
+                "loss_tail": 1}
         if world > 1 and getattr(reducer, "peer", None) is None:
             rest["f64 split/join (packed all-reduce)"] = 2
         pieces = len(graphed._chunk_bounds()) if graphed is not None else 1

@@ -255,6 +255,12 @@ int mfb_nsf_unpack_grads(const float* gpacked, const float* m_in, const float* m
 int64_t mfb_moments_workspace_bytes(int64_t n, int d);
 int mfb_moments(const float* x, const float* logq, int64_t n, int d, int with_cov, double* out,
                 void* workspace, int64_t workspace_bytes, void* stream);
+/* The scalar ends of MENTFlow.loss as one launch each (they sit on the critical path of every step):
+ * h[0] = (float)(a * sums[0] + b * sums[1] - c) in double -- entropy.py:58-62 with a = 1/N,
+ * b = 1/(2 s^2 N), c = log prior normalisation (prior.py:25-26);
+ * out[0] = h[0] + mu * mean(d[0..k)), out[1] = mean(d[0..k)) -- core.py:111-113 (h may be NULL: 0).   */
+int mfb_mc_entropy(const double* sums, double a, double b, double c, float* h, void* stream);
+int mfb_loss_tail(const float* d, int k, const float* h, float mu, float* out, void* stream);
 /* Multi-GPU plumbing of the entropy sums (ONE packed all-reduce per forward step): n doubles
  * <-> 2n floats (hi[0..n), lo[0..n)), hi + lo = value to 2^-48, so that they can ride at the tail of the
  * float32 all-reduce of the profile sums; the two halves are summed over ranks separately.            */

@@ -80,6 +80,8 @@ SIGNATURES = {
     "mfb_moments": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
     "mfb_f64_split": (c_int, [P, c_int, P, P]),
     "mfb_f64_join": (c_int, [P, c_int, P, P]),
+    "mfb_mc_entropy": (c_int, [P, c_double, c_double, c_double, P, P]),
+    "mfb_loss_tail": (c_int, [P, c_int, P, c_float, P, P]),
 }
 
 _lib = None

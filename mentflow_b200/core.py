@@ -4,6 +4,7 @@ from typing import Callable, Iterator, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import ops
 from .loss import kl_divergence
 from .simulate import forward as simulate_forward
 from .utils import unravel
@@ -112,6 +113,10 @@ class MENTFlow(nn.Module):
         dvec = self._batched_discrepancy(stacked, n_slots)
         if dvec is not None:
             D = list(dvec.unbind(0))
+            if dvec.is_cuda and dvec.dtype == torch.float32 and (not torch.is_tensor(H) or H.dtype == torch.float32):
+                # the scalar tail as one launch: it is on the critical path of every step
+                h = H if torch.is_tensor(H) else (None if H == 0.0 else torch.full((), float(H), device=dvec.device))
+                return ops.LossTail.apply(h, dvec, float(self.penalty_parameter)), H, D
             mean_d = dvec.mean()
         else:
             D = self.discrepancy_vector(predictions)

@@ -96,11 +96,41 @@ __global__ void f64_join_kernel(const float* __restrict__ in, int n, double* __r
   if (i < n) out[i] = (double)in[i] + (double)in[n + i];
 }
 
+// H = a * sums[0] + b * sums[1] - c in double, rounded once to float (replaces four elementwise launches)
+__global__ void mc_entropy_kernel(const double* __restrict__ sums, double a, double b, double c, float* __restrict__ h) {
+  if (threadIdx.x == 0) h[0] = (float)(fma(a, sums[0], b * sums[1]) - c);
+}
+
+// L = H + mu * mean_k D_k: one warp, lanes stride over k, fixed shuffle tree (deterministic)
+__global__ void loss_tail_kernel(const float* __restrict__ d, int k, const float* __restrict__ h, float mu,
+                                 float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < k; i += 32) s += d[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) {
+    const float mean = s / (float)k;
+    out[1] = mean;
+    out[0] = fmaf(mu, mean, h ? h[0] : 0.f);
+  }
+}
+
 }  // namespace mfb
 
 using namespace mfb;
 
 extern "C" {
+
+int mfb_mc_entropy(const double* sums, double a, double b, double c, float* h, void* stream) {
+  MFB_CHECK_ARG(sums && h);
+  mc_entropy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, a, b, c, h);
+  return launch_status();
+}
+
+int mfb_loss_tail(const float* d, int k, const float* h, float mu, float* out, void* stream) {
+  MFB_CHECK_ARG(d && out && k >= 1);
+  loss_tail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, k, h, mu, out);
+  return launch_status();
+}
 
 int mfb_f64_split(const double* in, int n, float* out_hi_lo, void* stream) {
   MFB_CHECK_ARG(in && out_hi_lo && n >= 1);

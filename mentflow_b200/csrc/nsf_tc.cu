@@ -305,6 +305,9 @@ __device__ __forceinline__ void mma_slot(uint32_t tmem_d, uint64_t a_hi, uint64_
 // kBwd = false: forward layer (y, log q).  kBwd = true: the first stage of the backward of the same
 // layer -- conditioner recomputed, then spline forward + backward per feature: writes the post-ReLU
 // activations, dL/dphi, the direct dL/dv and the gradient maxima of BwdIO; y / log q are not written.
+#ifndef MFB_TC_PDL
+#define MFB_TC_PDL 1
+#endif
 template <int D, int L, int NB, bool kBwd>
 __global__ void __launch_bounds__(kThreads, 1)
 nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char* __restrict__ image,
@@ -345,6 +348,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     tma_load_1d(img, image, (uint32_t)kImg, &bars[0]);
   }
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+#if MFB_TC_PDL
+  // Programmatic dependent launch: the layers of a flow are launched back to back, and the next layer's CTA may take
+  // this SM as soon as the current layer's CTA has left it -- set-up and the 111 KB operand image (written by the
+  // prepare kernel, which never triggers early, so it is complete before any layer kernel starts) are loaded while
+  // the slower SMs of the previous layer finish their last tiles.  Everything the previous layer wrote (v, log q) is
+  // read only after griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   mbar_wait_bounded(&bars[0], 0);
 
   // TMEM buffers of a warpgroup: slot s lands in buffer s & 1; the hidden chain of the NEXT tile
@@ -366,7 +378,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
     const int w = __shfl_sync(0xffffffffu, (tid - kWG * 128) >> 5, 0);
     if (w < kWG) {   // the whole warp walks the schedule; one elected lane issues
-      const int64_t first = (int64_t)blockIdx.x * kWG + w;
+      const int64_t first = first_tile_of(w);
       const int cnt = first < ntiles ? (int)((ntiles - first + tstride - 1) / tstride) : 0;
       uint64_t* req_chain = &reqs[3 * w];
       uint64_t* wbar = &bars[1 + 2 * w];
@@ -558,7 +570,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     if (bulk) tma_load_1d(dst, src, bulk, &sbar[buf]);
   };
 
-  int64_t tile = (int64_t)blockIdx.x * kWG + wg;
+  int64_t tile = first_tile_of(wg);
   // Software-pipelined over the tiles of this warpgroup: iteration i computes the splines of tile i
   // ("cur") and, interleaved with its last splines, the conditioner chain of tile i+1 ("next"), so
   // every MMA has a spline's worth of CUDA-core work to hide behind.  The first iteration has no
@@ -766,7 +778,21 @@ static int launch_layer(const float* v, int64_t n, const unsigned char* image, c
   const int64_t ntiles = (n + 127) / 128;
   int64_t grid = sm_count();
   if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
+#if MFB_TC_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MFB_CUDA(cudaLaunchKernelEx(&cfg, kern, v, n, image, meta, logq_in, first, y, logq_out, BwdIO{}));
+#else
   kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, logq_in, first, y, logq_out, BwdIO{});
+#endif
   return launch_status();
 }
 

@@ -157,7 +157,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
     const int w = __shfl_sync(0xffffffffu, (tid - kWG * 128) >> 5, 0);
     if (w < kWG) {
-      const int64_t first = (int64_t)blockIdx.x * kWG + w;
+      const int64_t first = first_tile_of(w);
       const int cnt = first < ntiles ? (int)((ntiles - first + tstride - 1) / tstride) : 0;
       uint32_t rp = 0;
       unsigned char* wa_hi = a_all + w * kABytes;
@@ -222,7 +222,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
       ph ^= 1;
       umma::fence_after_sync();
     };
-    for (int64_t tile = (int64_t)blockIdx.x * kWG + wg; tile < ntiles; tile += tstride) {
+    for (int64_t tile = first_tile_of(wg); tile < ntiles; tile += tstride) {
       const int64_t p = tile * 128 + t;
       const bool valid = p < n;
       // ---- output layer: slots in descending order (the last slot reads every hidden unit: it

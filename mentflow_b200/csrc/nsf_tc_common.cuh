@@ -13,6 +13,20 @@ constexpr int kRegsCompute = 160, kRegsIssuer = 32;   // setmaxnreg: 3*128*160 +
 constexpr int kTileBytes = 8192;     // 64 rows x 128 B (one fp16 operand tile, K = 64)
 constexpr int kABytes = 32768;       // 128 rows x 128 B, hi then lo
 
+// Tiles are dealt to the (CTA, warpgroup) slots warpgroup-major: slot = wg * gridDim.x + cta, so the slots that get one
+// tile more than the others (n / 128 is not a multiple of 3 x grid) are spread over all SMs -- the warpgroups of an SM
+// share its issue slots, so what matters is the tile count per SM (1e6 particles on 148 SMs: 53 / 52 instead of 54 / 51).
+#ifndef MFB_TC_DEAL_BY_WG
+#define MFB_TC_DEAL_BY_WG 1
+#endif
+__device__ __forceinline__ int64_t first_tile_of(int wg) {
+#if MFB_TC_DEAL_BY_WG
+  return (int64_t)wg * gridDim.x + blockIdx.x;
+#else
+  return (int64_t)blockIdx.x * kWG + wg;
+#endif
+}
+
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity);
 
 // mbarrier wait that traps instead of hanging the device if an MMA / TMA never arrives

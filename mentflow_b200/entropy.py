@@ -13,20 +13,6 @@ from . import ops
 from .prior import Gaussian
 
 
-_coef_cache = {}
-
-
-def _coef(a: float, b: float, device) -> torch.Tensor:
-    """Device-resident float64 pair (a, b): cached so that a step issues no host-to-device copy."""
-    key = (a, b, str(device))
-    t = _coef_cache.get(key)
-    if t is None:
-        if len(_coef_cache) > 64:
-            _coef_cache.clear()
-        t = _coef_cache[key] = torch.tensor([a, b], dtype=torch.float64, device=device)
-    return t
-
-
 class _MCEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, log_prob, inv_s2, log_norm, reducer):
@@ -37,8 +23,7 @@ class _MCEntropy(torch.autograd.Function):
         ctx.save_for_backward(x)
         ctx.inv_s2, ctx.n = inv_s2, n
         # H = mean(log q) - mean(log prior),  log prior = -0.5 |x|^2 / s^2 + log_norm
-        coef = _coef(1.0 / n, 0.5 * inv_s2 / n, x.device)
-        return ((m * coef).sum() - log_norm).to(torch.float32)
+        return ops.mc_entropy(m, 1.0 / n, 0.5 * inv_s2 / n, log_norm)
 
     @staticmethod
     def backward(ctx, g):
@@ -55,8 +40,7 @@ class _MCEntropyFromSums(torch.autograd.Function):
     def forward(ctx, x, log_prob, m, inv_s2, log_norm, n):
         ctx.save_for_backward(x)
         ctx.inv_s2, ctx.n = inv_s2, n
-        coef = _coef(1.0 / n, 0.5 * inv_s2 / n, x.device)
-        return ((m * coef).sum() - log_norm).to(torch.float32)
+        return ops.mc_entropy(m, 1.0 / n, 0.5 * inv_s2 / n, log_norm)
 
     @staticmethod
     def backward(ctx, g):

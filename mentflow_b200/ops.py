@@ -500,6 +500,36 @@ def moments(x: torch.Tensor, logq: Optional[torch.Tensor], with_cov: bool = Fals
     return out
 
 
+def mc_entropy(sums: torch.Tensor, a: float, b: float, c: float) -> torch.Tensor:
+    """float32 scalar a * sums[0] + b * sums[1] - c, evaluated in double by one launch."""
+    lib = _lib.load()
+    assert sums.dtype == torch.float64 and sums.numel() >= 2 and sums.is_contiguous()
+    h = torch.empty((), dtype=torch.float32, device=sums.device)
+    with torch.cuda.device(sums.device):
+        _lib.check(lib.mfb_mc_entropy(_ptr(sums), float(a), float(b), float(c), _ptr(h), _stream()), "mc_entropy")
+    return h
+
+
+class LossTail(torch.autograd.Function):
+    """L = H + mu * mean(D) as one launch (core.py:111-113); dL/dH = 1, dL/dD_k = mu / K."""
+
+    @staticmethod
+    def forward(ctx, h, d, mu):
+        lib = _lib.load()
+        dd = _check_f32("d", d.detach())
+        hh = None if h is None else _check_f32("h", h.detach())
+        out = torch.empty(2, dtype=torch.float32, device=dd.device)
+        with torch.cuda.device(dd.device):
+            _lib.check(lib.mfb_loss_tail(_ptr(dd), dd.numel(), _ptr(hh), float(mu), _ptr(out), _stream()), "loss_tail")
+        ctx.k, ctx.mu, ctx.shape, ctx.has_h = dd.numel(), float(mu), d.shape, h is not None
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gd = (g * (ctx.mu / ctx.k)).expand(ctx.shape)
+        return (g if ctx.has_h else None), gd, None
+
+
 def f64_split(values: torch.Tensor, out: torch.Tensor) -> None:
     """float64 (n,) -> float32 (2n,) [hi | lo] written into ``out`` (a slice of an all-reduce buffer)."""
     lib = _lib.load()
