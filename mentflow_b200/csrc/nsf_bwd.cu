@@ -479,14 +479,14 @@ nsf_bwd_input_kernel(const float* __restrict__ gvd, const float* __restrict__ g1
 // ---- host-side orchestration of one layer ----------------------------------------------------------------
 // tcgen05 data-gradient chain (nsf_tc_bwd.cu); MFB_E_UNSUPPORTED for shapes it is not compiled for
 int64_t nsf_tc_dgrad_image_bytes(int d);
-int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
+int nsf_tc_dgrad(const float* gphi, const float* gmax, const uint32_t* masks, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
                  int* gmaxes, cudaStream_t st);
 // tcgen05 recompute + spline forward/backward (nsf_tc.cu); image: mfb_nsf_tc_image_bytes scratch the operand
 // image is built in, unless ready_image (the image mfb_nsf_tc_prepare built for the forward pass) is given
 int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
                       int bins, const float* params, const int32_t* order, int first_layer, float* acts,
-                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
+                      float* gphi, uint32_t* masks, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
                       cudaStream_t st);
 // tcgen05 weight + bias gradients of the whole layer (nsf_tc_bwd.cu)
 int64_t nsf_tc_wgrad_partial_floats(int d);
@@ -495,7 +495,7 @@ int nsf_tc_wgrad(const float* gphi, const float* gz, const float* acts, const fl
                  int accumulate, cudaStream_t st);
 
 struct BwdPlan {
-  int64_t acts, gphi, ga, gb, gvd, gmax, gmaxes, image, partial, total;  // float offsets (ga: [L][64][n] when the tcgen05 chain runs)
+  int64_t acts, gphi, masks, ga, gb, gvd, gmax, gmaxes, image, partial, total;  // float offsets (ga: [L][64][n] when the tcgen05 chain runs)
   int nsplit;
   int64_t per_split;
 };
@@ -511,6 +511,7 @@ static BwdPlan plan_bwd(int64_t n, int d, int hidden_layers) {
   const int64_t npad = (n + 127) / 128 * 128;   // the tensor-core kernels store these matrices tile-major
   P.acts = take((int64_t)hidden_layers * kH * npad);
   P.gphi = take((int64_t)d * kPP * npad);
+  P.masks = take((int64_t)hidden_layers * 2 * npad);   // ReLU masks of the tensor-core path (uint32)
   P.ga = take((int64_t)hidden_layers * kH * npad);
   P.gb = take((int64_t)kH * n);
   P.gvd = take(n * d);
@@ -558,8 +559,8 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     int32_t ord[kMaxDim];
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
-    int rc = nsf_tc_spline_bwd(v, gy, glogq, n, D, hidden_layers, nb, params, ord, first, acts, gphi, gvd, ws + P.gmax,
-                               gmaxes, image, ready_image, st);
+    int rc = nsf_tc_spline_bwd(v, gy, glogq, n, D, hidden_layers, nb, params, ord, first, acts, gphi,
+                               reinterpret_cast<uint32_t*>(ws + P.masks), gvd, ws + P.gmax, gmaxes, image, ready_image, st);
     if (rc == 0) tc_spline = true;
     else if (rc != MFB_E_UNSUPPORTED) return rc;
   }
@@ -582,7 +583,8 @@ static int run_layer_bwd(const float* v, const float* gy, const float* glogq, in
     int32_t ord[kMaxDim];
     for (int i = 0; i < D; ++i) ord[i] = order.v[i];
     unsigned char* image = reinterpret_cast<unsigned char*>(((uintptr_t)(ws + P.image) + 1023) & ~(uintptr_t)1023);
-    int rc = nsf_tc_dgrad(gphi, ws + P.gmax, acts, gvd, n, D, hidden_layers, params, ord, ga, gv, image, gmaxes, st);
+    int rc = nsf_tc_dgrad(gphi, ws + P.gmax, reinterpret_cast<const uint32_t*>(ws + P.masks), gvd, n, D, hidden_layers, params,
+                          ord, ga, gv, image, gmaxes, st);
     if (rc) return rc;
     tc_chain = true;
     // 1c. every weight and bias gradient of the layer in one tensor-core kernel

@@ -283,8 +283,12 @@ MFB_HD void clip_exp2_quad_bwd(float& t0, float& t1, float& t2, float& t3, float
 // formulas are those of rq_spline_backward in nsf_bwd.cu, prototype scripts/proto_spline_bwd.py).
 // a[]: raw parameters (x log2 e) in, dL/d(raw natural parameter) out (j < 3NB-1).  gy = dL/dy,
 // gl = dL/d(log dy/dv).  Returns the direct dL/dv.
+struct KnotGrad {   // the derivative block of dL/dphi has two non-zero entries: knots k-1 and k of the particle's bin k
+  float left, right;
+  int bin;
+};
 template <int NB>
-MFB_HD float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl) {
+MFB_HD float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl, KnotGrad* kg = nullptr) {
   static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
   constexpr int G = NB / 4;
   constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
@@ -402,6 +406,11 @@ MFB_HD float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl) {
   const float gd0 = g_d0 * d0 * ri0 * ri0 * live, gd1 = g_d1 * d1 * ri1 * ri1 * live;
 #pragma unroll
   for (int j = 0; j < NB - 1; ++j) a[2 * NB + j] = (j == k - 1) ? gd0 : ((j == k) ? gd1 : 0.f);
+  if (kg) {   // the outer knots (k - 1 = -1, k = NB - 1) have fixed slope 1: no parameter
+    kg->left = k > 0 ? gd0 : 0.f;
+    kg->right = k < NB - 1 ? gd1 : 0.f;
+    kg->bin = k;
+  }
   return inside ? gv : gy;
 }
 

@@ -47,7 +47,8 @@ struct BwdIO {
   const float* gy;      // [n][D] dL/dy
   const float* glogq;   // [n] dL/dlogq_out or null
   float* acts;          // 192 rows (3 x 64): post-ReLU activations (sorted unit order: row c = unit perm[c])
-  float* gphi;          // D*64 rows: dL/d(raw conditioner output)
+  float* gphi;          // D*kGRows rows: dL/d(raw conditioner output), compact (nsf_tc_common.cuh)
+  uint32_t* masks;      // 3 x 2 rows: ReLU masks of the hidden layers (bit c of word w = unit perm[32 w + c] is active)
   float* gvd;           // [n][D] direct dL/dv through the spline (+ base density term)
   float* gmax;          // [n] max |gphi| of the particle
   int* gmaxes;          // [0]: batch maximum of |gphi| (float bits, atomicMax)
@@ -544,8 +545,16 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       // overlap the GEMM
       if (next_valid) {
         float* al = bio.acts + ((size_t)(next_p >> 7) * (L * kH) + l * kH) * 128 + t;
+        uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) al[c * 128] = fmaxf(acc[c], 0.f);
+        for (int c = 0; c < 64; ++c) {
+          al[c * 128] = fmaxf(acc[c], 0.f);
+          if (c < 32) m0 |= (acc[c] > 0.f ? 1u : 0u) << c;
+          else m1 |= (acc[c] > 0.f ? 1u : 0u) << (c - 32);
+        }
+        uint32_t* mk = bio.masks + ((size_t)(next_p >> 7) * (L * 2) + l * 2) * 128 + t;
+        mk[0] = m0;
+        mk[128] = m1;
       }
     }
     TRACE(4 + l);
@@ -609,18 +618,21 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
 #pragma unroll
       for (int i = 1; i < D; ++i) gyf = (f == i) ? gyr[i] : gyf;
       // logq_out = logq_in - ladj  =>  dL/d(ladj) = -dL/dlogq
-      float gvf = rq_spline_regs_bwd<NB>(acc, vf, gyf, -glq);
+      KnotGrad kg;
+      float gvf = rq_spline_regs_bwd<NB>(acc, vf, gyf, -glq, &kg);
       if (first_layer) gvf -= glq * vf;   // d/dv of log N(v; 0, I)
       sc[f] = gvf;
       if (valid) {
-        float* gp = bio.gphi + ((size_t)tile * (D * kPP) + f * kPP) * 128 + t;
+        float* gp = bio.gphi + ((size_t)tile * (D * kGRows) + f * kGRows) * 128 + t;
 #pragma unroll
-        for (int j = 0; j < 3 * NB - 1; ++j) {
+        for (int j = 0; j < 2 * NB; ++j) {
           gp[j * 128] = acc[j];
           amax = fmaxf(amax, fabsf(acc[j]));
         }
-#pragma unroll
-        for (int j = 3 * NB - 1; j < kPP; ++j) gp[j * 128] = 0.f;
+        gp[(2 * NB) * 128] = kg.left;
+        gp[(2 * NB + 1) * 128] = kg.right;
+        gp[(2 * NB + 2) * 128] = (float)kg.bin;
+        amax = fmaxf(amax, fmaxf(fabsf(kg.left), fabsf(kg.right)));
       }
     };
     // backward variant: the bias-only feature is iteration s = -1 of the same loop (its raw parameters
@@ -817,7 +829,7 @@ static int launch_layer_bwd(const float* v, int64_t n, const unsigned char* imag
 // forward/backward.  MFB_E_UNSUPPORTED for shapes the tcgen05 kernels are not compiled for.
 int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64_t n, int d, int hidden_layers,
                       int bins, const float* params, const int32_t* order, int first_layer, float* acts,
-                      float* gphi, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
+                      float* gphi, uint32_t* masks, float* gvd, float* gmax, int* gmaxes, void* image, const void* ready_image,
                       cudaStream_t st) {
   if (!(d >= 2 && d <= 6 && hidden_layers == 3 && bins == 20)) return MFB_E_UNSUPPORTED;
   if (!tc::valid_order(d, order)) return MFB_E_BADARG;
@@ -838,7 +850,7 @@ int nsf_tc_spline_bwd(const float* v, const float* gy, const float* glogq, int64
   } else if ((reinterpret_cast<uintptr_t>(img) & 15u) != 0) {
     return MFB_E_BADARG;    // the image is loaded with a bulk copy: 16-byte aligned
   }
-  const tc::BwdIO bio = {gy, glogq, acts, gphi, gvd, gmax, gmaxes};
+  const tc::BwdIO bio = {gy, glogq, acts, gphi, masks, gvd, gmax, gmaxes};
   switch (d) {
     case 2: return tc::launch_layer_bwd<2>(v, n, img, meta, first_layer, bio, st);
     case 3: return tc::launch_layer_bwd<3>(v, n, img, meta, first_layer, bio, st);

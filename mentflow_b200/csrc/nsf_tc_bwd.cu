@@ -106,9 +106,9 @@ __device__ __forceinline__ void store_row_split(const float (&x)[64], float scal
 
 template <int D, int L>
 __global__ void __launch_bounds__(kThreads, 1)
-nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (BwdIO in nsf_tc.cu) */,
+nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, tile-major, compact (nsf_tc_common.cuh) */,
                     const float* __restrict__ gmax /* [n] */,
-                    const float* __restrict__ acts /* L*64 rows, tile-major */, const float* __restrict__ gvd /* [n][D] */,
+                    const uint32_t* __restrict__ masks /* L*2 rows, tile-major: ReLU masks */, const float* __restrict__ gvd /* [n][D] */,
                     int64_t n, const unsigned char* __restrict__ image, const __grid_constant__ DgradMeta meta,
                     float* __restrict__ gz /* L*64 rows, tile-major: dL/d(pre-activation) of hidden layer l */,
                     float* __restrict__ gv /* [n][D] */,
@@ -230,29 +230,32 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
       float inv0;
       const float sc0 = pow2_scale(valid ? gmax[p] : 0.f, inv0);
       float g[64];
-      {
-        const float* gp = gphi + ((size_t)tile * (D * kPP) + meta.slot_feature[S - 1] * kPP) * 128 + t;
+      // dL/dphi of one feature from its compact rows: 2 NB dense, then (left, right, bin) of the derivative block
+      auto load_gphi = [&](int f) {
+        constexpr int NB2 = kGRows - 4;
+        const float* gp = gphi + ((size_t)tile * (D * kGRows) + f * kGRows) * 128 + t;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[j * 128] : 0.f;
-      }
+        for (int j = 0; j < NB2; ++j) g[j] = valid ? gp[j * 128] : 0.f;
+        const float left = valid ? gp[NB2 * 128] : 0.f, right = valid ? gp[(NB2 + 1) * 128] : 0.f;
+        const int k = valid ? (int)gp[(NB2 + 2) * 128] : 0;
+#pragma unroll
+        for (int j = 0; j < 64 - NB2; ++j) g[NB2 + j] = (j == k - 1) ? left : ((j == k) ? right : 0.f);   // j >= NB - 1 never matches a stored value: left / right are zero there
+      };
+      load_gphi(meta.slot_feature[S - 1]);
       // global loads are always issued BEFORE waiting for the tensor core and global stores AFTER the
       // hand-off to the issuer, so HBM latency and the release-fence of the arrive overlap the MMAs
-      auto load_mask = [&](int l, float (&hv)[64]) {
-        const float* hl = acts + ((size_t)tile * (L * kH) + l * kH) * 128 + t;
-#pragma unroll
-        for (int c = 0; c < 64; ++c) hv[c] = valid ? hl[c * 128] : 0.f;   // rows are in sorted unit order
+      uint32_t m0 = 0, m1 = 0;
+      auto load_mask = [&](int l) {
+        const uint32_t* mk = masks + ((size_t)tile * (L * 2) + l * 2) * 128 + t;
+        m0 = valid ? mk[0] : 0u;
+        m1 = valid ? mk[128] : 0u;
       };
 #pragma unroll 1
       for (int s = S - 1; s >= 0; --s) {
         store_row_split(g, sc0, a_hi, a_lo, t);
         publish();
-        if (s > 0) {   // next slot's gradient rows travel while the tensor core works
-          const float* gp = gphi + ((size_t)tile * (D * kPP) + meta.slot_feature[s - 1] * kPP) * 128 + t;
-#pragma unroll
-          for (int j = 0; j < 64; ++j) g[j] = (valid && j < 59) ? gp[j * 128] : 0.f;
-        } else {
-          load_mask(L - 1, g);   // g now holds h3 (sorted unit order): the ReLU mask of the first chain step
-        }
+        if (s > 0) load_gphi(meta.slot_feature[s - 1]);   // next slot's gradient rows travel while the tensor core works
+        else load_mask(L - 1);                            // ReLU mask of the first chain step
         wait_done();
       }
       // ---- hidden layers, last to first; then the first layer
@@ -264,7 +267,8 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
         float amax = 0.f;
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          acc[c] = g[c] > 0.f ? acc[c] * unscale : 0.f;
+          const bool on = ((c < 32 ? m0 >> c : m1 >> (c - 32)) & 1u) != 0u;
+          acc[c] = on ? acc[c] * unscale : 0.f;
           amax = fmaxf(amax, fabsf(acc[c]));
         }
         float inv;
@@ -283,7 +287,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
 #pragma unroll
           for (int c = 0; c < 64; ++c) gl[c * 128] = acc[c];   // sorted unit order, like acts
         }
-        if (l > 0) load_mask(l - 1, g);
+        if (l > 0) load_mask(l - 1);
         wait_done();
       }
       // ---- dL/dv = direct (through the spline) + g1 W1
@@ -304,7 +308,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*64 rows, tile-major (Bwd
 }
 
 template <int D>
-static int launch_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n,
+static int launch_dgrad(const float* gphi, const float* gmax, const uint32_t* masks, const float* gvd, int64_t n,
                         const float* params, const int32_t* order, float* gz, float* gv, unsigned char* image,
                         int* gmaxes, cudaStream_t st) {
   constexpr int L = 3;
@@ -331,7 +335,7 @@ static int launch_dgrad(const float* gphi, const float* gmax, const float* acts,
   const int64_t ntiles = (n + 127) / 128;
   int64_t grid = sm_count();
   if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
-  kern<<<(int)grid, kThreads, smem, st>>>(gphi, gmax, acts, gvd, n, image, meta, gz, gv, gmaxes);
+  kern<<<(int)grid, kThreads, smem, st>>>(gphi, gmax, masks, gvd, n, image, meta, gz, gv, gmaxes);
   return launch_status();
 }
 
@@ -365,7 +369,7 @@ __host__ __device__ constexpr int wgrad_rows(int D) { return kWgCols + D + 3; } 
 
 template <int D>
 __global__ void __launch_bounds__(512, 1)
-nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float* __restrict__ gz /* 192 rows */,
+nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */, const float* __restrict__ gz /* 192 rows */,
                     const float* __restrict__ acts /* 192 rows, all tile-major */, const float* __restrict__ v /* [n][D] */,
                     int64_t n, const int* __restrict__ gmaxes, const __grid_constant__ WgradMeta meta,
                     float* __restrict__ partial /* [grid][wgrad_rows][64] */) {
@@ -422,7 +426,7 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
     constexpr int kRows = (64 + kWgLoaders - 1) / kWgLoaders;
     // rows w, w + 12, ... of the next staged block -> registers (masked beyond particle n), then the
     // staging slot is handed back to the producer
-    auto take = [&](float (&x)[kRows][4], int nrows, int64_t p0, bool strided_v) {
+    auto take = [&](float (&x)[kRows][4], int nrows, int64_t p0, bool strided_v, bool compact = false) {
       const uint32_t slot = sc_ % kWgS, par = (sc_ / kWgS) & 1;
       mbar_wait_bounded(&s_full[slot], par);
       const float* st = stage_ring + (size_t)slot * (kWgStage / 4);
@@ -431,7 +435,17 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
         const int r = warp + i * kWgLoaders;
         x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
         if (r < nrows) {
-          if (!strided_v) {
+          constexpr int NB2 = kGRows - 4;
+          if (compact && r >= NB2) {   // derivative block of a compact dL/dphi block: rows (left, right, bin) -> row r
+            const float4 lf = *reinterpret_cast<const float4*>(st + (size_t)NB2 * 128 + 4 * lane);
+            const float4 rt = *reinterpret_cast<const float4*>(st + (size_t)(NB2 + 1) * 128 + 4 * lane);
+            const float4 kb = *reinterpret_cast<const float4*>(st + (size_t)(NB2 + 2) * 128 + 4 * lane);
+            const float j = (float)(r - NB2);
+            x[i][0] = (j == kb.x - 1.f) ? lf.x : ((j == kb.x) ? rt.x : 0.f);
+            x[i][1] = (j == kb.y - 1.f) ? lf.y : ((j == kb.y) ? rt.y : 0.f);
+            x[i][2] = (j == kb.z - 1.f) ? lf.z : ((j == kb.z) ? rt.z : 0.f);
+            x[i][3] = (j == kb.w - 1.f) ? lf.w : ((j == kb.w) ? rt.w : 0.f);
+          } else if (!strided_v) {
             const float4 q = *reinterpret_cast<const float4*>(st + (size_t)r * 128 + 4 * lane);
             x[i][0] = q.x; x[i][1] = q.y; x[i][2] = q.z; x[i][3] = q.w;
           } else {   // the block is v[p0 .. p0+127][D], particle-major: row r of v^T is feature r
@@ -469,9 +483,9 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
         }
       }
     };
-    auto fill_g = [&](int64_t p0, float scale, float* bsum) {
+    auto fill_g = [&](int64_t p0, float scale, float* bsum, bool compact = false) {
       float x[kRows][4];
-      take(x, 64, p0, false);
+      take(x, 64, p0, false, compact);
       const uint32_t slot = gi % kWgG, par = (gi / kWgG) & 1;
       mbar_wait_bounded(&g_empty[slot], par ^ 1);
       convert(g_ring + slot * kWgTile, x, 64, scale, bsum);
@@ -495,10 +509,10 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t p0 = tile * 128;
       fill_h(64, p0, false);                                                              // h3
-      for (int s = 0; s < S; ++s) fill_g(p0, gsc[0], bias + meta.slot_feature[s] * 64);   // dL/dphi of the slots
+      for (int s = 0; s < S; ++s) fill_g(p0, gsc[0], bias + meta.slot_feature[s] * 64, true);   // dL/dphi of the slots
       {                                                                                   // bias-only feature: row sums
         float x[kRows][4];
-        take(x, 64, p0, false);
+        take(x, 64, p0, false, true);
         convert(nullptr, x, 64, 1.0f, bias + meta.const_feature * 64);
       }
       fill_h(64, p0, false);                                                              // h2
@@ -526,10 +540,11 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*64 rows */, const float*
         const int64_t p0 = tile * 128;
         const float* at = acts + (size_t)tile * (3 * kH) * 128;       // rows of this tile
         const float* zt = gz + (size_t)tile * (3 * kH) * 128;
-        const float* pt = gphi + (size_t)tile * (D * kPP) * 128;
+        const float* pt = gphi + (size_t)tile * (D * kGRows) * 128;
+        constexpr uint32_t kGBlock = kGRows * 128 * 4;                                      // compact dL/dphi block
         push(at + 2 * kH * 128, kWgStage);                                                  // h3
-        for (int s = 0; s < S; ++s) push(pt + meta.slot_feature[s] * kPP * 128, kWgStage);
-        push(pt + meta.const_feature * kPP * 128, kWgStage);
+        for (int s = 0; s < S; ++s) push(pt + meta.slot_feature[s] * kGRows * 128, kGBlock);
+        push(pt + meta.const_feature * kGRows * 128, kGBlock);
         push(at + 1 * kH * 128, kWgStage);                                                  // h2
         push(zt + 2 * kH * 128, kWgStage);                                                  // g3
         push(at, kWgStage);                                                                 // h1
@@ -709,17 +724,17 @@ static int launch_wgrad(const float* gphi, const float* gz, const float* acts, c
 // not compiled (the caller then uses the CUDA-core kernels).
 int64_t nsf_tc_dgrad_image_bytes(int d) { return (d >= 2 && d <= 6) ? tc::dgrad_image_bytes(d, 3) : 0; }
 
-int nsf_tc_dgrad(const float* gphi, const float* gmax, const float* acts, const float* gvd, int64_t n, int d,
+int nsf_tc_dgrad(const float* gphi, const float* gmax, const uint32_t* masks, const float* gvd, int64_t n, int d,
                  int hidden_layers, const float* params, const int32_t* order, float* gz, float* gv, void* image,
                  int* gmaxes, cudaStream_t st) {
   if (hidden_layers != 3 || d < 2 || d > 6) return MFB_E_UNSUPPORTED;
   unsigned char* img = reinterpret_cast<unsigned char*>(image);
   switch (d) {
-    case 2: return tc::launch_dgrad<2>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
-    case 3: return tc::launch_dgrad<3>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
-    case 4: return tc::launch_dgrad<4>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
-    case 5: return tc::launch_dgrad<5>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
-    case 6: return tc::launch_dgrad<6>(gphi, gmax, acts, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 2: return tc::launch_dgrad<2>(gphi, gmax, masks, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 3: return tc::launch_dgrad<3>(gphi, gmax, masks, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 4: return tc::launch_dgrad<4>(gphi, gmax, masks, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 5: return tc::launch_dgrad<5>(gphi, gmax, masks, gvd, n, params, order, gz, gv, img, gmaxes, st);
+    case 6: return tc::launch_dgrad<6>(gphi, gmax, masks, gvd, n, params, order, gz, gv, img, gmaxes, st);
     default: return MFB_E_UNSUPPORTED;
   }
 }

@@ -12,6 +12,12 @@ constexpr int kThreads = (kWG + 1) * 128;   // 3 compute warpgroups + the warpgr
 constexpr int kRegsCompute = 160, kRegsIssuer = 32;   // setmaxnreg: 3*128*160 + 128*32 = 64 K registers
 constexpr int kTileBytes = 8192;     // 64 rows x 128 B (one fp16 operand tile, K = 64)
 constexpr int kABytes = 32768;       // 128 rows x 128 B, hi then lo
+// Backward workspace of the tensor-core kernels (tile-major: a row = the 128 particles of a tile).  dL/dphi of a
+// feature is stored COMPACT: rows [0, 2 NB) widths and heights (dense), then the only two non-zero entries of the
+// derivative block (knots k-1 and k of the particle's bin k) and k itself -- 2 NB + 3 rows instead of 64; the
+// consumers rebuild the 64-row operand.  ReLU masks of the hidden layers travel as two 32-bit words per layer.
+constexpr int kGRowsOf(int nb) { return 2 * nb + 4; }   // + one row of padding: blocks stay 16-byte multiples
+constexpr int kGRows = kGRowsOf(20);
 
 // Tiles are dealt to the (CTA, warpgroup) slots warpgroup-major: slot = wg * gridDim.x + cta, so the slots that get one
 // tile more than the others (n / 128 is not a multiple of 3 x grid) are spread over all SMs -- the warpgroups of an SM
