@@ -222,26 +222,35 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, tile-major,
       ph ^= 1;
       umma::fence_after_sync();
     };
+    float g[64];
+    float gmax_next = 0.f;
+    // dL/dphi of one feature of a tile from its compact rows: 2 NB dense, then (left, right, bin) of the derivative block
+    auto load_gphi = [&](int64_t tl, int f) {
+      constexpr int NB2 = kGRows - 4;
+      const bool ok = tl * 128 + t < n;
+      const float* gp = gphi + ((size_t)tl * (D * kGRows) + f * kGRows) * 128 + t;
+#pragma unroll
+      for (int j = 0; j < NB2; ++j) g[j] = ok ? gp[j * 128] : 0.f;
+      const float left = ok ? gp[NB2 * 128] : 0.f, right = ok ? gp[(NB2 + 1) * 128] : 0.f;
+      const int k = ok ? (int)gp[(NB2 + 2) * 128] : 0;
+#pragma unroll
+      for (int j = 0; j < 64 - NB2; ++j) g[NB2 + j] = (j == k - 1) ? left : ((j == k) ? right : 0.f);   // j >= NB - 1 never matches a stored value: left / right are zero there
+    };
+    // first rows of a tile (slot S-1) and its row scale: requested during the hidden chain of the tile before, so
+    // that no tile starts with an exposed trip to HBM
+    auto prefetch_tile = [&](int64_t tl) {
+      if (tl >= ntiles) return;
+      gmax_next = (tl * 128 + t < n) ? gmax[tl * 128 + t] : 0.f;
+      load_gphi(tl, meta.slot_feature[S - 1]);
+    };
+    prefetch_tile(first_tile_of(wg));
     for (int64_t tile = first_tile_of(wg); tile < ntiles; tile += tstride) {
       const int64_t p = tile * 128 + t;
       const bool valid = p < n;
       // ---- output layer: slots in descending order (the last slot reads every hidden unit: it
       //      initialises all 64 accumulator columns)
       float inv0;
-      const float sc0 = pow2_scale(valid ? gmax[p] : 0.f, inv0);
-      float g[64];
-      // dL/dphi of one feature from its compact rows: 2 NB dense, then (left, right, bin) of the derivative block
-      auto load_gphi = [&](int f) {
-        constexpr int NB2 = kGRows - 4;
-        const float* gp = gphi + ((size_t)tile * (D * kGRows) + f * kGRows) * 128 + t;
-#pragma unroll
-        for (int j = 0; j < NB2; ++j) g[j] = valid ? gp[j * 128] : 0.f;
-        const float left = valid ? gp[NB2 * 128] : 0.f, right = valid ? gp[(NB2 + 1) * 128] : 0.f;
-        const int k = valid ? (int)gp[(NB2 + 2) * 128] : 0;
-#pragma unroll
-        for (int j = 0; j < 64 - NB2; ++j) g[NB2 + j] = (j == k - 1) ? left : ((j == k) ? right : 0.f);   // j >= NB - 1 never matches a stored value: left / right are zero there
-      };
-      load_gphi(meta.slot_feature[S - 1]);
+      const float sc0 = pow2_scale(gmax_next, inv0);
       // global loads are always issued BEFORE waiting for the tensor core and global stores AFTER the
       // hand-off to the issuer, so HBM latency and the release-fence of the arrive overlap the MMAs
       uint32_t m0 = 0, m1 = 0;
@@ -254,7 +263,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, tile-major,
       for (int s = S - 1; s >= 0; --s) {
         store_row_split(g, sc0, a_hi, a_lo, t);
         publish();
-        if (s > 0) load_gphi(meta.slot_feature[s - 1]);   // next slot's gradient rows travel while the tensor core works
+        if (s > 0) load_gphi(tile, meta.slot_feature[s - 1]);   // next slot's gradient rows travel while the tensor core works
         else load_mask(L - 1);                            // ReLU mask of the first chain step
         wait_done();
       }
@@ -288,6 +297,7 @@ nsf_tc_dgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, tile-major,
           for (int c = 0; c < 64; ++c) gl[c * 128] = acc[c];   // sorted unit order, like acts
         }
         if (l > 0) load_mask(l - 1);
+        if (l == L - 1) prefetch_tile(tile + tstride);   // g[] is free from here on
         wait_done();
       }
       // ---- dL/dv = direct (through the spline) + g1 W1
@@ -352,10 +362,23 @@ static int launch_dgrad(const float* gphi, const float* gmax, const uint32_t* ma
 // scaled by a power of two from the batch maximum (fp16 has no range for 1/N-sized gradients).
 // =============================================================================================
 constexpr int kWgTile = 32768;                 // one operand tile: hi (2 halves x 8 KB) | lo (2 x 8 KB)
-constexpr int kWgG = 2, kWgH = 2;              // ring depths of the fp16 operand tiles
-constexpr int kWgS = 2;                        // ring depth of the fp32 staging blocks (64 rows x 512 B, filled by TMA)
+#ifndef MFB_WG_NOSLACK
+#define MFB_WG_NOSLACK 1   // three staging blocks fit only without the 1 KB alignment slack
+#endif
+#ifndef MFB_WG_H
+#define MFB_WG_H 2
+#endif
+#ifndef MFB_WG_S
+#define MFB_WG_S 3   // bytes in flight bound this kernel: 0.677 -> 0.604 ms per layer and 1e6 particles with a third block
+#endif
+#ifndef MFB_WG_LOADERS
+#define MFB_WG_LOADERS 12
+#endif
+constexpr int kWgG = 2, kWgH = MFB_WG_H;       // ring depths of the fp16 operand tiles
+constexpr int kWgS = MFB_WG_S;                        // ring depth of the fp32 staging blocks (64 rows x 512 B, filled by TMA)
 constexpr int kWgStage = 32768;
-constexpr int kWgLoaders = 12;                 // loader warps
+constexpr int kWgLoaders = MFB_WG_LOADERS;     // loader warps
+constexpr int kWgThreads = (kWgLoaders + 4) * 32;   // + issuer, producer, two spare warps (epilogue uses warps 0..3)
 constexpr int kWgCols = 464;                   // accumulator columns
 
 struct WgradMeta {
@@ -368,14 +391,19 @@ struct WgradMeta {
 __host__ __device__ constexpr int wgrad_rows(int D) { return kWgCols + D + 3; }   // + bias rows: D features, 3 hidden
 
 template <int D>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */, const float* __restrict__ gz /* 192 rows */,
                     const float* __restrict__ acts /* 192 rows, all tile-major */, const float* __restrict__ v /* [n][D] */,
                     int64_t n, const int* __restrict__ gmaxes, const __grid_constant__ WgradMeta meta,
                     float* __restrict__ partial /* [grid][wgrad_rows][64] */) {
   constexpr int S = D - 1;
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+#if MFB_WG_NOSLACK
+  unsigned char* smem = smem_raw;   // no static shared memory in this kernel: the dynamic window starts 1 KB aligned
+  if (smem_u32(smem_raw) & 1023u) __trap();
+#else
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#endif
   unsigned char* g_ring = smem;
   unsigned char* h_ring = smem + kWgG * kWgTile;
   // an M = 128 MMA reads 64 rows past a 64-row tile half: the staging ring that follows is the slack
@@ -391,7 +419,7 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < (D + 3) * 64; i += 512) bias[i] = 0.f;
+  for (int i = tid; i < (D + 3) * 64; i += kWgThreads) bias[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < kWgG; ++i) {
       mbar_init(&g_full[i], kWgLoaders);
@@ -697,13 +725,13 @@ static int launch_wgrad(const float* gphi, const float* gz, const float* acts, c
   meta.nslots = D - 1;
   meta.const_feature = feat_of_order[0];
   for (int s = 0; s < D - 1; ++s) meta.slot_feature[s] = feat_of_order[s + 1];
-  const size_t smem = (size_t)(kWgG + kWgH) * kWgTile + (size_t)kWgS * kWgStage + (size_t)(D + 3) * 64 * 4 + 256 + 1024;
+  const size_t smem = (size_t)(kWgG + kWgH) * kWgTile + (size_t)kWgS * kWgStage + (size_t)(D + 3) * 64 * 4 + 256 + (MFB_WG_NOSLACK ? 0 : 1024);
   auto kern = nsf_tc_wgrad_kernel<D>;
   MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (n + 127) / 128;
   int grid = sm_count();
   if (grid > ntiles) grid = (int)ntiles;
-  kern<<<grid, 512, smem, st>>>(gphi, gz, acts, v, n, gmaxes, meta, partial);
+  kern<<<grid, kWgThreads, smem, st>>>(gphi, gz, acts, v, n, gmaxes, meta, partial);
   int rc = launch_status();
   if (rc) return rc;
   const int entries = wgrad_rows(D) * 64;
