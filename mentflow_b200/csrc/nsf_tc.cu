@@ -46,7 +46,8 @@ struct Meta {
 struct BwdIO {
   const float* gy;      // [n][D] dL/dy
   const float* glogq;   // [n] dL/dlogq_out or null
-  float* acts;          // 192 rows (3 x 64): post-ReLU activations (sorted unit order: row c = unit perm[c])
+  float* acts;          // per tile and hidden layer: the 32 KB (hi, lo) fp16 operand tile of the post-ReLU activations
+                        // ([128 particles][64 units in sorted order], SWIZZLE_128B) -- see store_hidden
   float* gphi;          // D*kGRows rows: dL/d(raw conditioner output), compact (nsf_tc_common.cuh)
   uint32_t* masks;      // 3 x 2 rows: ReLU masks of the hidden layers (bit c of word w = unit perm[32 w + c] is active)
   float* gvd;           // [n][D] direct dL/dv through the spline (+ base density term)
@@ -293,6 +294,27 @@ __device__ __forceinline__ void store_hidden(const float (&acc)[64], unsigned ch
   }
 }
 
+// Backward variant: the rows a warp has just written to the A tile (32 rows x 128 B = 4 KB of the hi plane and 4 KB
+// of the lo plane, contiguous: the swizzle only permutes 16-byte chunks inside a row) go to HBM as they are, with two
+// bulk copies issued by one lane.  The weight-gradient kernel reads the 32 KB tile back with one bulk copy and uses it
+// as an MN-major operand (units contiguous, K = particles): no conversion pass on either side, no store instructions.
+__device__ __forceinline__ void mirror_rows(const unsigned char* a_hi, unsigned char* g_img, int warp_in_wg) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t off = (uint32_t)warp_in_wg * 4096u;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(g_img + off), "r"(smem_u32(a_hi + off)) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(g_img + kABytes / 2 + off),
+                 "r"(smem_u32(a_hi + kABytes / 2 + off))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+// ... and before the rows are written again, the copies must have read them
+__device__ __forceinline__ void mirror_wait() {
+  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
 // output-layer tile of one feature: nk K steps, N = 64
 __device__ __forceinline__ void mma_slot(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                          int nk, uint32_t idesc) {
@@ -513,6 +535,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   // first masked layer of a tile: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...] (K = 16)
   auto start_tile = [&](const float* vv, uint64_t* landed, uint32_t parity) {
     mbar_wait_bounded(landed, parity);   // the TMA copy of this tile's particle rows has landed
+    if constexpr (kBwd) mirror_wait();   // the copy of the previous chain's last activations has read the A rows
     __align__(16) __half row[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
@@ -534,21 +557,21 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     wait_buf(kHB);
     float acc[64];
     tmem_ld64(col0 + (uint32_t)(kHB * 64) + lane_sel, acc);
+    if constexpr (kBwd) mirror_wait();
     store_hidden(acc, a_hi, a_lo, t);   // biases are already in the accumulator (bias MMA)
     fence_proxy_async();
     umma::fence_before_sync();
     request_arrive(req_chain);
     if constexpr (kBwd) {
-      // post-ReLU activations of the tile being started (= next tile), feature-major, in the SORTED unit
-      // order of the operand images (row c = unit meta.perm[c]; the weight-gradient reduce maps back):
-      // constant row offsets, no address arithmetic per element.  After the hand-off so that the stores
-      // overlap the GEMM
+      // post-ReLU activations of the tile being started (= next tile) for the weight gradients: the operand tile
+      // itself, columns in the SORTED unit order of the operand images (column c = unit meta.perm[c]; the
+      // weight-gradient reduce maps back).  Rows beyond n hold the activations of zero input (prefetch below).
+      mirror_rows(a_hi, reinterpret_cast<unsigned char*>(bio.acts) + ((size_t)(next_p >> 7) * L + l) * kABytes, t >> 5);
+      // ReLU masks for the data-gradient chain: bit c of word w = unit at sorted position 32 w + c is active
       if (next_valid) {
-        float* al = bio.acts + ((size_t)(next_p >> 7) * (L * kH) + l * kH) * 128 + t;
         uint32_t m0 = 0, m1 = 0;
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          al[c * 128] = fmaxf(acc[c], 0.f);
           if (c < 32) m0 |= (acc[c] > 0.f ? 1u : 0u) << c;
           else m1 |= (acc[c] > 0.f ? 1u : 0u) << (c - 32);
         }
@@ -575,6 +598,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     const float* src = v + tl * 128 * D;
     const uint32_t bytes = (uint32_t)(rows * D * 4), bulk = bytes & ~15u;
     for (uint32_t i = bulk / 4; i < bytes / 4; ++i) dst[i] = src[i];   // ragged tail (< 16 B)
+    for (uint32_t i = bytes / 4; i < 128u * D; ++i) dst[i] = 0.f;      // rows beyond n: defined (finite) input
     mbar_expect_tx(&sbar[buf], bulk);
     if (bulk) tma_load_1d(dst, src, bulk, &sbar[buf]);
   };
@@ -729,6 +753,10 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     has_next = false;   // recomputed at the top of the next iteration
     tile += tstride;
   }
+    if constexpr (kBwd) {   // the last activation tiles are in HBM before the CTA gives up its shared memory
+      if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
   }  // compute warpgroups
   umma::fence_before_sync();
   __syncthreads();

@@ -393,7 +393,7 @@ __host__ __device__ constexpr int wgrad_rows(int D) { return kWgCols + D + 3; } 
 template <int D>
 __global__ void __launch_bounds__(kWgThreads, 1)
 nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */, const float* __restrict__ gz /* 192 rows */,
-                    const float* __restrict__ acts /* 192 rows, all tile-major */, const float* __restrict__ v /* [n][D] */,
+                    const float* __restrict__ acts /* per tile: 3 x 32 KB fp16 (hi, lo) operand tiles (nsf_tc.cu store_hidden) */, const float* __restrict__ v /* [n][D] */,
                     int64_t n, const int* __restrict__ gmaxes, const __grid_constant__ WgradMeta meta,
                     float* __restrict__ partial /* [grid][wgrad_rows][64] */) {
   constexpr int S = D - 1;
@@ -536,17 +536,16 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */,
     // the block order below is the producer's (next branch) and the issuer's
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t p0 = tile * 128;
-      fill_h(64, p0, false);                                                              // h3
+      // h3, h2, h1 come straight from HBM into the H ring (activation producer below): uses 0..2 of this tile
       for (int s = 0; s < S; ++s) fill_g(p0, gsc[0], bias + meta.slot_feature[s] * 64, true);   // dL/dphi of the slots
       {                                                                                   // bias-only feature: row sums
         float x[kRows][4];
         take(x, 64, p0, false, true);
         convert(nullptr, x, 64, 1.0f, bias + meta.const_feature * 64);
       }
-      fill_h(64, p0, false);                                                              // h2
       fill_g(p0, gsc[3], bias + (D + 0) * 64);                                            // g3
-      fill_h(64, p0, false);                                                              // h1
       fill_g(p0, gsc[2], bias + (D + 1) * 64);                                            // g2
+      hi_ += 3;                                                                           // H ring uses of h3, h2, h1
       fill_h(D, p0, true);                                                                // v^T
       fill_g(p0, gsc[1], bias + (D + 2) * 64);                                            // g1
     }
@@ -566,20 +565,33 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */,
       };
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t p0 = tile * 128;
-        const float* at = acts + (size_t)tile * (3 * kH) * 128;       // rows of this tile
         const float* zt = gz + (size_t)tile * (3 * kH) * 128;
         const float* pt = gphi + (size_t)tile * (D * kGRows) * 128;
         constexpr uint32_t kGBlock = kGRows * 128 * 4;                                      // compact dL/dphi block
-        push(at + 2 * kH * 128, kWgStage);                                                  // h3
         for (int s = 0; s < S; ++s) push(pt + meta.slot_feature[s] * kGRows * 128, kGBlock);
         push(pt + meta.const_feature * kGRows * 128, kGBlock);
-        push(at + 1 * kH * 128, kWgStage);                                                  // h2
         push(zt + 2 * kH * 128, kWgStage);                                                  // g3
-        push(at, kWgStage);                                                                 // h1
         push(zt + 1 * kH * 128, kWgStage);                                                  // g2
         const int64_t rows = (n - p0 < 128) ? (n - p0) : 128;
         push(v + p0 * D, (uint32_t)(rows * D * 4));                                         // v rows of the tile
         push(zt, kWgStage);                                                                 // g1
+      }
+    }
+  } else if (warp == kWgLoaders + 2) {
+    // ===== activation producer: the (hi, lo) fp16 operand tiles the first backward kernel mirrored to HBM go
+    //       straight into the H ring (uses 0, 1, 2 of every tile = h3, h2, h1; use 3 = v^T is built by the loaders).
+    //       The barrier expects kWgLoaders arrivals per phase: this thread supplies all of them.
+    if (lane == 0) {
+      uint32_t use = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, use += 4) {
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(acts) + (size_t)tile * 3 * kWgTile;
+        for (int u = 0; u < 3; ++u) {
+          const uint32_t idx = use + u, slot = idx % kWgH, par = (idx / kWgH) & 1;
+          mbar_wait_bounded(&h_empty[slot], par ^ 1);
+          mbar_expect_tx(&h_full[slot], (uint32_t)kWgTile);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&h_full[slot])), "r"(kWgLoaders - 1) : "memory");
+          tma_load_1d(h_ring + slot * kWgTile, img + (size_t)(2 - u) * kWgTile, (uint32_t)kWgTile, &h_full[slot]);
+        }
       }
     }
   } else if (warp == kWgLoaders) {
@@ -587,24 +599,44 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */,
     uint32_t gi = 0, hi_ = 0;
     const uint32_t idesc64 = umma::make_idesc_f16(128, 64), idesc16 = umma::make_idesc_f16(128, 16);
     bool first = true;
-    auto job = [&](uint32_t dcol, uint32_t hslot, uint32_t idesc) {   // one (G, H) pair: K = 128 particles
+    // one (G, H) pair: K = 128 particles.  h_mn: H is an activation tile as the forward kernel wrote it -- [128
+    // particles][64 units], SWIZZLE_128B -- read as an MN-major operand (units contiguous, 8 particles per swizzle
+    // atom, 16 particles = one K step = 2 KB); otherwise a K-major tile built by the loaders (two 64-particle halves)
+    auto job = [&](uint32_t dcol, uint32_t hslot, uint32_t idesc, bool h_mn) {
       const uint32_t slot = gi % kWgG, par = (gi / kWgG) & 1;
       mbar_wait_polite(&g_full[slot], par);
       umma::fence_after_sync();
       const uint32_t ga = smem_u32(g_ring + slot * kWgTile), ha = smem_u32(h_ring + hslot * kWgTile);
       if (elect_one()) {
+        if (h_mn) {
+          const uint32_t id = idesc | (1u << 16);   // B operand MN-major
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), aL = umma::make_desc_sw128(ga + 16384 + half * 8192);
-          const uint64_t bH = umma::make_desc_sw128(ha + half * 8192), bL = umma::make_desc_sw128(ha + 16384 + half * 8192);
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t aH = umma::desc_advance_k(umma::make_desc_sw128(ga + (kk >> 2) * 8192), kk & 3);
+            const uint64_t aL = umma::desc_advance_k(umma::make_desc_sw128(ga + 16384 + (kk >> 2) * 8192), kk & 3);
+            const uint64_t bH = umma::make_desc_sw128(ha + kk * 2048), bL = umma::make_desc_sw128(ha + 16384 + kk * 2048);
+            umma::mma_f16_ss(dcol, aH, bL, id, (first && kk == 0) ? 0u : 1u);
+            umma::mma_f16_ss(dcol, aL, bH, id, 1);
+          }
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_cross(dcol, aH, aL, bH, bL, ks, idesc, (first && half == 0 && ks == 0) ? 0u : 1u);
-        }
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t aH = umma::desc_advance_k(umma::make_desc_sw128(ga + (kk >> 2) * 8192), kk & 3);
+            umma::mma_f16_ss(dcol, aH, umma::make_desc_sw128(ha + kk * 2048), id, 1);
+          }
+        } else {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), bH = umma::make_desc_sw128(ha + half * 8192);
+          for (int half = 0; half < 2; ++half) {
+            const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), aL = umma::make_desc_sw128(ga + 16384 + half * 8192);
+            const uint64_t bH = umma::make_desc_sw128(ha + half * 8192), bL = umma::make_desc_sw128(ha + 16384 + half * 8192);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_main(dcol, aH, bH, ks, idesc);
+            for (int ks = 0; ks < 4; ++ks) mma_cross(dcol, aH, aL, bH, bL, ks, idesc, (first && half == 0 && ks == 0) ? 0u : 1u);
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint64_t aH = umma::make_desc_sw128(ga + half * 8192), bH = umma::make_desc_sw128(ha + half * 8192);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_main(dcol, aH, bH, ks, idesc);
+          }
         }
         umma::commit(&g_empty[slot]);
       }
@@ -623,16 +655,16 @@ nsf_tc_wgrad_kernel(const float* __restrict__ gphi /* D*kGRows rows, compact */,
     };
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       uint32_t hs = take_h();                                   // h3
-      for (int s = 0; s < S; ++s) job(tmem_base + 64 * s, hs, idesc64);
+      for (int s = 0; s < S; ++s) job(tmem_base + 64 * s, hs, idesc64, true);
       release_h(hs);
       hs = take_h();                                            // h2
-      job(tmem_base + 320, hs, idesc64);
+      job(tmem_base + 320, hs, idesc64, true);
       release_h(hs);
       hs = take_h();                                            // h1
-      job(tmem_base + 384, hs, idesc64);
+      job(tmem_base + 384, hs, idesc64, true);
       release_h(hs);
       hs = take_h();                                            // v^T
-      job(tmem_base + 448, hs, idesc16);
+      job(tmem_base + 448, hs, idesc16, false);
       release_h(hs);
       first = false;
     }

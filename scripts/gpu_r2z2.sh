@@ -13,4 +13,4 @@ for r in rows[h+1:]:
     d=dict(zip(hdr,r)); agg[d["Kernel Name"].split("(")[0][-34:]].append(float(d["Metric Value"].replace(",","")))
 for k,v in agg.items(): print(k, round(sum(v)/len(v)/1e6,4), "ms", len(v))
 PY
-bash scripts/ab_bench.sh default default 2>&1 | tee gpurun_out/r2z2_ab.txt
+bash scripts/ab_bench.sh variants/lib_prev.so default variants/lib_prev.so default 2>&1 | tee gpurun_out/r2z2_ab.txt
