@@ -29,6 +29,37 @@ inline int sm_count() {
 
 inline int launch_status() { return (int)cudaGetLastError(); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The kernels of a step run back to back on one stream.  Launched with launch_pdl, a kernel may become resident while
+// its predecessor is still running -- its launch latency and whatever it does BEFORE pdl_enter() (shared-memory
+// set-up that touches no global memory) overlap the predecessor's tail -- and pdl_enter() then blocks until the
+// predecessor has completed and its writes are visible.  Rules that keep this as safe as plain stream order:
+// every PDL kernel calls pdl_enter() before its first global access and before it exits (so completion stays
+// transitive along the chain); a successor launched the plain way still waits for full completion.
+#ifndef MFB_PDL
+#define MFB_PDL 1
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if MFB_PDL
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = MFB_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- mbarrier + TMA (1-D bulk copy) wrappers: SASS shows SYNCS.* / UBLKCP ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

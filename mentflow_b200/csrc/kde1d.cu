@@ -288,6 +288,7 @@ kde1d_deposit_kernel(const float* __restrict__ x, int64_t n, int d_rt, const flo
     mbar_init(&tp.bar[1], 1);
     fence_mbar_init();
   }
+  pdl_enter();   // the 170 KB of private bins were cleared under the previous kernel's tail; global memory from here on
   __syncthreads();
 
   float w[kMaxDim];
@@ -510,6 +511,7 @@ kde1d_finish_kernel(const float* __restrict__ partial, int nparts, int64_t len, 
                     float* __restrict__ sums_out, float* __restrict__ prof, float* __restrict__ kl) {
   extern __shared__ float fsm[];
   __shared__ float red[33];
+  pdl_enter();
   const int k = blockIdx.x;
   float* s = fsm;
   float* part = fsm + B;
@@ -885,7 +887,7 @@ static int launch_kde1d_deposit(int r, const KdePlan& L, const float* x, int64_t
   {                                                                                                        \
     MFB_CUDA(cudaFuncSetAttribute(kde1d_deposit_kernel<D, RR, kMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)L.smem));                                                           \
-    kde1d_deposit_kernel<D, RR, kMP><<<grid, block, L.smem, st>>>(x, n, d, proj, geom, k, b, L.kc, L.tile, L.guard, L.ld, partial, mp); \
+    MFB_CUDA(launch_pdl(kde1d_deposit_kernel<D, RR, kMP>, grid, block, L.smem, st, x, n, d, proj, geom, k, b, L.kc, L.tile, L.guard, L.ld, partial, mp)); \
   }
   if (r <= 4) MFB_LAUNCH_R(4)
   else if (r <= 9) MFB_LAUNCH_R(9)
@@ -966,8 +968,8 @@ static int kde1d_fwd_impl(const float* x, int64_t n, int d, const float* proj, c
     reduce_partials_kernel<<<rgrid, 256, 0, st>>>(partial, L.grid_x, len, sums);
     return launch_status();
   }
-  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, len, 1.f, geom, b, nullptr, 0.f,
-                                                                 sums, nullptr, nullptr);
+  MFB_CUDA(launch_pdl(kde1d_finish_kernel, dim3(k), dim3(kFinishThreads), finish_smem(b), st, partial, L.grid_x, len, 1.f, geom, b, nullptr, 0.f,
+                                                                 sums, nullptr, nullptr));
   return launch_status();
 }
 
@@ -1003,9 +1005,9 @@ int mfb_project_kde1d_loss_fwd(const float* x, int64_t n, int d, const float* pr
   float* partial = (float*)workspace;
   int rc = deposit_dispatch(r, L, x, n, d, proj, geom, k, b, partial, st, nullptr);
   if (rc) return rc;
-  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), st>>>(partial, L.grid_x, (int64_t)k * b,
+  MFB_CUDA(launch_pdl(kde1d_finish_kernel, dim3(k), dim3(kFinishThreads), finish_smem(b), st, partial, L.grid_x, (int64_t)k * b,
                                                                  (float)(1.0 / n_total), geom, b, meas, pad, sums,
-                                                                 profiles, kl);
+                                                                 profiles, kl));
   return launch_status();
 }
 
@@ -1070,8 +1072,7 @@ int mfb_kde1d_finish(const float* sums, double n_total, const float* geom, int k
   MFB_CHECK_ARG(sums && geom && profiles && k >= 1 && b >= 2 && n_total > 0);
   MFB_CHECK_ARG((meas != nullptr) == (kl != nullptr));
   if (finish_smem(b) > 48 * 1024) return MFB_E_UNSUPPORTED;
-  kde1d_finish_kernel<<<k, kFinishThreads, finish_smem(b), (cudaStream_t)stream>>>(
-      sums, 1, (int64_t)k * b, (float)(1.0 / n_total), geom, b, meas, pad, nullptr, profiles, kl);
+  MFB_CUDA(launch_pdl(kde1d_finish_kernel, dim3(k), dim3(kFinishThreads), finish_smem(b), (cudaStream_t)stream, sums, 1, (int64_t)k * b, (float)(1.0 / n_total), geom, b, meas, pad, nullptr, profiles, kl));
   return launch_status();
 }
 

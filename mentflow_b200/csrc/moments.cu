@@ -14,6 +14,7 @@ constexpr int kMomThreads = 256;
 template <int D, bool COV>
 __global__ void __launch_bounds__(kMomThreads)
 moments_kernel(const float* __restrict__ x, const float* __restrict__ logq, int64_t n, double* __restrict__ partial) {
+  pdl_enter();
   constexpr int M = COV ? 2 + D + D * D : 2;
   double acc[M];
 #pragma unroll
@@ -51,6 +52,7 @@ moments_kernel(const float* __restrict__ x, const float* __restrict__ logq, int6
 }
 
 __global__ void moments_finish_kernel(const double* __restrict__ partial, int nparts, int m, double* __restrict__ out) {
+  pdl_enter();
   // one warp per output: lanes stride over the partials, fixed shuffle tree => deterministic
   const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x >> 5; i < m; i += nwarps) {
@@ -73,11 +75,11 @@ static int launch_moments(const float* x, const float* logq, int64_t n, int cov,
                           cudaStream_t st) {
   const int grid = moments_grid(n);
   const int m = cov ? 2 + D + D * D : 2;
-  if (cov) moments_kernel<D, true><<<grid, kMomThreads, 0, st>>>(x, logq, n, partial);
-  else moments_kernel<D, false><<<grid, kMomThreads, 0, st>>>(x, logq, n, partial);
+  if (cov) MFB_CUDA(launch_pdl(moments_kernel<D, true>, dim3(grid), dim3(kMomThreads), 0, st, x, logq, n, partial));
+  else MFB_CUDA(launch_pdl(moments_kernel<D, false>, dim3(grid), dim3(kMomThreads), 0, st, x, logq, n, partial));
   int rc = launch_status();
   if (rc) return rc;
-  moments_finish_kernel<<<1, 256, 0, st>>>(partial, grid, m, out);
+  MFB_CUDA(launch_pdl(moments_finish_kernel, dim3(1), dim3(256), 0, st, (const double*)partial, grid, m, out));
   return launch_status();
 }
 
@@ -98,12 +100,14 @@ __global__ void f64_join_kernel(const float* __restrict__ in, int n, double* __r
 
 // H = a * sums[0] + b * sums[1] - c in double, rounded once to float (replaces four elementwise launches)
 __global__ void mc_entropy_kernel(const double* __restrict__ sums, double a, double b, double c, float* __restrict__ h) {
+  pdl_enter();
   if (threadIdx.x == 0) h[0] = (float)(fma(a, sums[0], b * sums[1]) - c);
 }
 
 // L = H + mu * mean_k D_k: one warp, lanes stride over k, fixed shuffle tree (deterministic)
 __global__ void loss_tail_kernel(const float* __restrict__ d, int k, const float* __restrict__ h, float mu,
                                  float* __restrict__ out) {
+  pdl_enter();
   float s = 0.f;
   for (int i = threadIdx.x; i < k; i += 32) s += d[i];
   s = warp_sum(s);
@@ -122,13 +126,13 @@ extern "C" {
 
 int mfb_mc_entropy(const double* sums, double a, double b, double c, float* h, void* stream) {
   MFB_CHECK_ARG(sums && h);
-  mc_entropy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, a, b, c, h);
+  MFB_CUDA(launch_pdl(mc_entropy_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, a, b, c, h));
   return launch_status();
 }
 
 int mfb_loss_tail(const float* d, int k, const float* h, float mu, float* out, void* stream) {
   MFB_CHECK_ARG(d && out && k >= 1);
-  loss_tail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, k, h, mu, out);
+  MFB_CUDA(launch_pdl(loss_tail_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, d, k, h, mu, out));
   return launch_status();
 }
 

@@ -25,6 +25,7 @@ constexpr int kRandThreads = 256;
 __global__ void __launch_bounds__(kRandThreads)
 randn_philox_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint64_t offset,
                     const uint64_t* __restrict__ state) {
+  pdl_enter();
   if (state) {
     seed = state[0];
     offset = state[1];
@@ -45,7 +46,10 @@ randn_philox_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint6
   }
 }
 
-__global__ void philox_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
+__global__ void philox_advance_kernel(uint64_t* state, uint64_t inc) {
+  pdl_enter();
+  state[1] += inc;
+}
 
 // launch shape of ATen's calc_execution_policy for `numel` elements on the current device
 static int randn_grid(int64_t numel, uint64_t* counter_offset) {
@@ -77,7 +81,8 @@ int mfb_randn_philox(float* out, int64_t numel, uint64_t seed, uint64_t offset, 
   MFB_CHECK_ARG(numel >= 0 && (out || numel == 0));
   if (numel == 0) return 0;
   const int grid = randn_grid(numel, nullptr);
-  randn_philox_kernel<<<grid, kRandThreads, 0, (cudaStream_t)stream>>>(out, numel, seed, offset, nullptr);
+  MFB_CUDA(launch_pdl(randn_philox_kernel, dim3(grid), dim3(kRandThreads), 0, (cudaStream_t)stream, out, numel, seed, offset,
+                      (const uint64_t*)nullptr));
   return launch_status();
 }
 
@@ -86,11 +91,12 @@ int mfb_randn_philox_state(float* out, int64_t numel, uint64_t* state, int advan
   if (numel == 0) return 0;
   uint64_t inc = 0;
   const int grid = randn_grid(numel, &inc);
-  randn_philox_kernel<<<grid, kRandThreads, 0, (cudaStream_t)stream>>>(out, numel, 0, 0, state);
+  MFB_CUDA(launch_pdl(randn_philox_kernel, dim3(grid), dim3(kRandThreads), 0, (cudaStream_t)stream, out, numel, (uint64_t)0,
+                      (uint64_t)0, (const uint64_t*)state));
   int rc = launch_status();
   if (rc) return rc;
   if (advance) {
-    philox_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, inc);
+    MFB_CUDA(launch_pdl(philox_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state, inc));
     rc = launch_status();
   }
   return rc;

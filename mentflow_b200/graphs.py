@@ -58,8 +58,12 @@ class GraphedLoss:
         return self.model.loss_from_particles(x, logq)
 
     def _weights_key(self):
+        # checked on every call: the parameter list is walked once per generator object, not per step
         gen = self.model.generator
-        return tuple((p.data_ptr(), p._version) for p in gen.parameters()) + (float(self.model.penalty_parameter),)
+        cached = getattr(self, "_param_list", None)
+        if cached is None or cached[0] is not gen:
+            cached = self._param_list = (gen, list(gen.parameters()))
+        return tuple((p.data_ptr(), p._version) for p in cached[1]) + (float(self.model.penalty_parameter),)
 
     def _capture(self) -> None:
         gen = self.model.generator

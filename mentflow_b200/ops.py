@@ -948,6 +948,7 @@ class PhiloxStream:
             # the asynchronous copy that last read it has completed (re-seeding every step without synchronising
             # in between must not let a later state overtake an earlier replay)
             self._pinned = torch.zeros((8, 2), dtype=torch.int64).pin_memory()
+            self._pinned_np = self._pinned.numpy()       # the same memory: element writes without a dispatcher trip
             self._slot_events = [None] * 8
             self._slot = 0
         self.captured_increment = 0
@@ -961,14 +962,15 @@ class PhiloxStream:
         if self._mirror != cur:
             i = self._slot
             self._slot = (i + 1) % self._pinned.shape[0]
-            if self._slot_events[i] is not None:
-                self._slot_events[i].synchronize()
-            self._pinned[i, 0] = self._as_i64(cur[0])
-            self._pinned[i, 1] = self._as_i64(cur[1])
+            ev = self._slot_events[i]
+            if ev is not None:
+                ev.synchronize()
+            else:
+                ev = self._slot_events[i] = torch.cuda.Event()
+            self._pinned_np[i, 0] = self._as_i64(cur[0])
+            self._pinned_np[i, 1] = self._as_i64(cur[1])
             self.state.copy_(self._pinned[i], non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record()
-            self._slot_events[i] = ev
             self._mirror = cur
 
     def consumed(self) -> None:
