@@ -342,6 +342,8 @@ int mfb_randn_philox_state(float* out, int64_t numel, uint64_t* state, int advan
  * fp16 (hi,lo)-split kind::f16 MMAs with TMEM accumulators (n = 64, 128 or 256).  *err != 0
  * if the MMA never completed.                                                              */
 int mfb_selftest_umma(const float* a, const float* b, int n, float* d, int* err, void* stream);
+/* the same GEMM with the A operand in tensor memory (tcgen05.st + tcgen05.mma with a TMEM A address), n <= 128 */
+int mfb_selftest_umma_ts(const float* a, const float* b, int n, float* d, int* err, void* stream);
 /* One K step (16) with 32-byte-row SWIZZLE_32B operand tiles: d[128][n] = a[128][16] * b[n][16]^T
  * (values rounded to fp16).  mode 0: both operands SWIZZLE_32B; mode 1: a sits in K step `kstep`
  * of a 64-wide SWIZZLE_128B tile (the layouts the flow kernel mixes).  n = 64 or 128.        */

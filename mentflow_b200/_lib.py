@@ -73,6 +73,7 @@ SIGNATURES = {
     "mfb_cdf_sample": (c_int, [P, c_int64, P, c_int, P, P, P, c_int, c_uint64, c_uint64, c_int64, P, P]),
     "mfb_gs_update": (c_int, [P, P, P, c_int, c_float, c_float, P]),
     "mfb_selftest_umma": (c_int, [P, P, c_int, P, P, P]),
+    "mfb_selftest_umma_ts": (c_int, [P, P, c_int, P, P, P]),
     "mfb_selftest_umma_sw32": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "mfb_nsf_pack_params": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "mfb_nsf_unpack_grads": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),

@@ -46,3 +46,23 @@ def test_umma_sw32_tiles(n, mode, kstep):
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     assert torch.equal(d, a @ b.T)
+
+
+@pytest.mark.parametrize("n", [64, 96, 128])
+def test_umma_a_operand_in_tensor_memory(n):
+    """the split GEMM with A written to TMEM by tcgen05.st and read from there by tcgen05.mma"""
+    lib = _lib.load()
+    torch.manual_seed(100 + n)
+    a = (torch.randn(128, 64) * 3).cuda()
+    b = (torch.randn(n, 64) * 0.2).cuda()
+    d = torch.zeros(128, n, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.mfb_selftest_umma_ts(a.data_ptr(), b.data_ptr(), n, d.data_ptr(), err.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    want = a.double() @ b.double().T
+    scale = (a.double().abs() @ b.double().abs().T)
+    e = ((d.double() - want).abs() / scale).max()
+    assert float(e) < 2e-6, f"split-fp16 error {float(e):.2e}"
