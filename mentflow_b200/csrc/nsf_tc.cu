@@ -294,6 +294,30 @@ __device__ __forceinline__ void store_hidden(const float (&acc)[64], unsigned ch
   }
 }
 
+// Forward variant: the hi half of the A operand lives in TENSOR MEMORY (32 packed columns per warpgroup, written by
+// the thread that owns the row with one tcgen05.st), only the lo half goes through shared memory.  Two of the three
+// MMAs of a K step then read A from TMEM: per K step the tensor core fetches 10 KB from shared memory instead of 18 KB
+// (an N = 64 MMA with both operands in shared memory is bound by that fetch, 48 cycles against the 32 of the math).
+#ifndef MFB_TC_TS
+#define MFB_TC_TS 1
+#endif
+__device__ __forceinline__ void store_hidden_ts(const float (&acc)[64], uint32_t tmem_a_hi, unsigned char* a_lo, int row) {
+#pragma unroll
+  for (int c2 = 0; c2 < 4; ++c2) {   // two 16-byte chunks = eight packed columns at a time: few registers in flight
+    uint32_t hi[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * c2 + h;
+      uint32_t lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_relu_pair(acc[8 * c + 2 * e], acc[8 * c + 2 * e + 1], hi[4 * h + e], lo[e]);
+      *reinterpret_cast<uint4*>(a_lo + umma::sw128_offset(row, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    umma::tmem_st8(tmem_a_hi + 8 * c2, hi);
+  }
+  umma::tmem_wait_st();
+}
+
 // Backward variant: the rows a warp has just written to the A tile (32 rows x 128 B = 4 KB of the hi plane and 4 KB
 // of the lo plane, contiguous: the swizzle only permutes 16-byte chunks inside a row) go to HBM as they are, with two
 // bulk copies issued by one lane.  The weight-gradient kernel reads the 32 KB tile back with one bulk copy and uses it
@@ -389,6 +413,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   const int64_t ntiles = (n + 127) / 128;
   const int64_t tstride = (int64_t)gridDim.x * kWG;
   const uint32_t idesc64 = umma::make_idesc_f16(128, 64);
+  constexpr bool kTS = MFB_TC_TS && !kBwd;   // the backward variant mirrors the whole A tile from shared memory
 
   if (wg == kWG) {
     // =========================================================================================
@@ -412,6 +437,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
       const uint64_t dOnes = umma::make_desc_sw32(smem_u32(img + off_ones()));
       const uint64_t dB1 = umma::make_desc_sw32(smem_u32(img + off_b1()));
       const uint32_t col0 = tmem_base + (uint32_t)(w * 128);
+      const uint32_t tA = tmem_base + (uint32_t)(kWG * 128 + w * 32);   // A hi in tensor memory: K step ks = columns 8 ks ..
       // output-layer tile of slot `slot`: bias (ones x bias tile), then the cross terms of all its
       // non-zero K steps, then the hi*hi terms (see mma_cross)
       auto issue_slot = [&](int slot) {
@@ -426,12 +452,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
           for (int ks = 0; ks < nk; ++ks) {
             const uint64_t dBh = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile));
             const uint64_t dBl = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile + kKTile));
-            umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), dBl, idesc64, 1);
+            if constexpr (kTS) umma::mma_f16_ts(dcol, tA + 8 * ks, dBl, idesc64, 1);
+            else umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), dBl, idesc64, 1);
             umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_lo, ks), dBh, idesc64, 1);
           }
-          for (int ks = 0; ks < nk; ++ks)
-            umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks),
-                             umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile)), idesc64, 1);
+          for (int ks = 0; ks < nk; ++ks) {
+            const uint64_t dBh = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile));
+            if constexpr (kTS) umma::mma_f16_ts(dcol, tA + 8 * ks, dBh, idesc64, 1);
+            else umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), dBh, idesc64, 1);
+          }
           umma::commit(wbar + bsel);
         }
         __syncwarp();
@@ -466,7 +495,15 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
               const int n0 = meta.hid_n0[ks];
               const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
               const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
-              if (pass == 0)
+              if constexpr (kTS) {
+                const uint32_t dd = col0 + kHB * 64 + n0;
+                if (pass == 0) {
+                  umma::mma_f16_ts(dd, tA + 8 * ks, umma::desc_advance_k(dBl + boff, ks), idesc, 1);
+                  umma::mma_f16_ss(dd, umma::desc_advance_k(dA_lo, ks), umma::desc_advance_k(dBh + boff, ks), idesc, 1);
+                } else {
+                  umma::mma_f16_ts(dd, tA + 8 * ks, umma::desc_advance_k(dBh + boff, ks), idesc, 1);
+                }
+              } else if (pass == 0)
                 mma_cross(col0 + kHB * 64 + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, 1);
               else
                 mma_main(col0 + kHB * 64 + n0, dA_hi, dBh + boff, ks, idesc);
@@ -515,6 +552,7 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   uint32_t ph0 = 0, ph1 = 0;
   const uint32_t lane_sel = (uint32_t)((t >> 5) * 32) << 16;
   const uint32_t col0 = tmem_base + (uint32_t)(wg * 128);
+  const uint32_t ta_hi = tmem_base + (uint32_t)(kWG * 128 + wg * 32);   // this warpgroup's A hi columns (forward variant)
   const float* ctab = reinterpret_cast<const float*>(img + off_f32(D, L));
 
 #ifdef MFB_TC_TRACE
@@ -558,7 +596,9 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
     float acc[64];
     tmem_ld64(col0 + (uint32_t)(kHB * 64) + lane_sel, acc);
     if constexpr (kBwd) mirror_wait();
-    store_hidden(acc, a_hi, a_lo, t);   // biases are already in the accumulator (bias MMA)
+    // biases are already in the accumulator (bias MMA)
+    if constexpr (kTS) store_hidden_ts(acc, ta_hi + lane_sel, a_lo, t);
+    else store_hidden(acc, a_hi, a_lo, t);
     fence_proxy_async();
     umma::fence_before_sync();
     request_arrive(req_chain);
