@@ -216,3 +216,26 @@ def test_graphed_train_step_equals_the_eager_loop_and_honours_lr_changes():
         assert torch.allclose(a, b, rtol=0, atol=1e-7), float((a - b).abs().max())
     st_g = opt_g.state[next(iter(model_g.parameters()))]["step"]
     assert int(st_g) == steps                                # every counted step is one replay
+
+
+def test_scalar_tail_kernels_match_torch():
+    """mfb_mc_entropy and mfb_loss_tail (one launch each) against the expressions they replace, values and gradients
+    (entropy.py:58-62, core.py:111-113)."""
+    from mentflow_b200 import ops
+    torch.manual_seed(3)
+    m = torch.tensor([-1234.5678, 9876.54321], dtype=torch.float64, device="cuda")
+    a, b, c = 1.0 / 1000.0, 0.5 / 9.0 / 1000.0, -3.25
+    h = ops.mc_entropy(m, a, b, c)
+    want = (m[0] * a + m[1] * b - c).float()
+    assert h.dtype == torch.float32 and abs(float(h) - float(want)) <= 1e-6 * abs(float(want))
+    for k in (1, 7, 100, 333):
+        d = torch.rand(k, device="cuda", requires_grad=True)
+        hh = torch.tensor(0.7, device="cuda", requires_grad=True)
+        L = ops.LossTail.apply(hh, d, 12.5)
+        ref = hh.detach() + 12.5 * d.detach().mean()
+        assert abs(float(L.detach()) - float(ref)) <= 2e-6 * abs(float(ref))
+        (L * 3.0).backward()
+        assert abs(float(hh.grad) - 3.0) < 1e-6
+        assert torch.allclose(d.grad, torch.full_like(d, 3.0 * 12.5 / k), rtol=1e-6)
+        L0 = ops.LossTail.apply(None, d.detach(), 2.0)
+        assert abs(float(L0) - 2.0 * float(d.detach().mean())) <= 2e-6

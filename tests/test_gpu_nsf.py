@@ -249,7 +249,7 @@ def test_sampling_statistics_full_size():
     assert rel_err(x1[idx], xr) < TOL and rel_err(l1[idx], lr) < TOL
 
 
-def _grads_case(d, n, scale, hidden_layers=3, transforms=5, bins=20, seed=0, keep=None):
+def _grads_case(d, n, scale, hidden_layers=3, transforms=5, bins=20, seed=0, keep=None, wide=False):
     torch.manual_seed(seed)
     gen = mf.generate.NSFGenerator(d, hidden_layers=hidden_layers, transforms=transforms, bins=bins)
     with torch.no_grad():
@@ -258,6 +258,8 @@ def _grads_case(d, n, scale, hidden_layers=3, transforms=5, bins=20, seed=0, kee
     ref = oracle_from_generator(gen)
     gen = gen.to("cuda")
     z = torch.randn(n, d)
+    if wide:      # the whole spline box and beyond: first / last bins, identity outside [-5, 5]
+        z = (torch.rand(n, d) - 0.5) * 13.0
     a, b = torch.randn(n, d), torch.randn(n)
     if keep is not None:
         z, a, b = z[keep], a[keep], b[keep]
@@ -309,6 +311,22 @@ def test_backward_matches_oracle_autograd(d, n, scale, hl, tr, bins):
         assert float(e.median()) < 2e-5, f"{name}: median {float(e.median()):.2e}"
     got, want = grads["w_out0"]
     assert float(got.cpu()[want == 0].abs().max()) == 0.0      # masked weights: exactly zero gradient
+
+
+@pytest.mark.parametrize("d,n", [(6, 2049), (2, 4000)])
+def test_backward_edge_bins_and_outside_the_box(d, n):
+    """Inputs spread over [-6.5, 6.5]^D: particles in the first and last bins (whose outer knot has no derivative
+    parameter: the compact dL/dphi rows carry a zero there), outside the box (identity: no parameter gradient) and a
+    last tile with a single row (n = 16 x 128 + 1)."""
+    first = _grads_case(d, n, 1.0, seed=5 + d, wide=True)
+    per_particle = _rel(*first["z"]).max(dim=1).values
+    suspects = per_particle > 1e-4
+    assert int(suspects.sum()) <= 2 + n // 100, f"{int(suspects.sum())} of {n} particles disagree in dL/dz"
+    grads = _grads_case(d, n, 1.0, seed=5 + d, wide=True, keep=~suspects)
+    for name, (got, want) in grads.items():
+        e = _rel(got, want).flatten()
+        assert float(e.max()) < 1e-3, f"{name}: max {float(e.max()):.2e}"
+        assert float(e.median()) < 2e-5, f"{name}: median {float(e.median()):.2e}"
 
 
 @pytest.fixture
