@@ -22,6 +22,10 @@
 
 #include "nsf_tc_common.cuh"
 
+#ifndef MFB_KDE2D_PACKED
+#define MFB_KDE2D_PACKED 1
+#endif
+
 namespace mfb {
 namespace k2tc {
 
@@ -47,6 +51,22 @@ constexpr float kHalfScale = 4194304.0f;         // 2^22 (fixed-point planes of 
 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return umma::make_idesc_f16(M, N) | (1u << 7) | (1u << 10);   // a_format = b_format = BF16
+}
+
+// two fp32 lanes for one issue slot (FADD2 / FMUL2; IEEE round-to-nearest like the scalar forms)
+__device__ __forceinline__ void sub2(float a0, float a1, float b, float& c0, float& c1) {
+  unsigned long long a, bb, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(-b));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
+}
+__device__ __forceinline__ void mul2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(c));
 }
 
 struct ScreenAxis {
@@ -181,12 +201,32 @@ kde2d_tc_kernel(const float* __restrict__ x, int64_t n, int d, const float* __re
               for (int e = 0; e < 4; ++e) {
                 // (a - r) first: r is an integer and a is within a few bins of it wherever the value matters, so the
                 // difference is exact; scaling the coordinates beforehand costs 2x the rounding error in the exponent
+#if MFB_KDE2D_PACKED
+                float da, db, ta, tb, qa, qb;
+                sub2(cs[2 * e], cs[2 * e + 1], rs, da, db);
+                mul2(da, db, sc, sc, ta, tb);
+                mul2(ta, tb, ta, tb, qa, qb);
+                const float va = fast_exp2(-qa), vb = fast_exp2(-qb);
+#else
                 const float ta = (cs[2 * e] - rs) * sc, tb = (cs[2 * e + 1] - rs) * sc;
                 const float va = fast_exp2(-(ta * ta)), vb = fast_exp2(-(tb * tb));
+#endif
                 const uint32_t ua = __float_as_uint(va), ub = __float_as_uint(vb);
                 hi[e] = __byte_perm(ua, ub, 0x7632);                         // (bf16 of vb) << 16 | bf16 of va, truncated
+#if MFB_KDE2D_PACKED
+                float ra, rb;
+                {
+                  unsigned long long pv, ph, pr;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(pv) : "f"(va), "f"(vb));
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(ph) : "f"(-__uint_as_float(ua & 0xFFFF0000u)), "f"(-__uint_as_float(ub & 0xFFFF0000u)));
+                  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pv), "l"(ph));
+                  asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(pr));
+                }
+                const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+#else
                 const __nv_bfloat162 m = __floats2bfloat162_rn(va - __uint_as_float(ua & 0xFFFF0000u),
                                                                vb - __uint_as_float(ub & 0xFFFF0000u));
+#endif
                 mid[e] = *reinterpret_cast<const uint32_t*>(&m);
               }
               const uint32_t off = umma::sw128_offset(r, chunk);
