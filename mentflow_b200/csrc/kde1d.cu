@@ -702,11 +702,19 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
                  float* __restrict__ gx, int accumulate, const float* __restrict__ mp = nullptr) {
   const int d = D > 0 ? D : d_rt;
   extern __shared__ __align__(16) float sm[];
-  float* s_g = sm;                          // [K][B]
-  float* s_w = s_g + (((size_t)K * B + 3) & ~(size_t)3);   // [K][d]; 16-byte aligned so that s_q is
+  // gradient table with kPad zero bins on either side of every row: the 2R+1 taps of a (clamped) particle never need a
+  // bounds check
+  constexpr int kPad = 2 * R + 2;
+  const int BP = B + 2 * kPad;
+  float* s_g = sm;                          // [K][BP]
+  float* s_w = s_g + (((size_t)K * BP + 3) & ~(size_t)3);   // [K][d]; 16-byte aligned so that s_q is
   float4* s_q = reinterpret_cast<float4*>(s_w + (((size_t)K * d + 3) & ~(size_t)3));  // [K] c0, inv_delta, alpha, beta
-  float* s_mp = reinterpret_cast<float*>(s_q + K);   // [K][2d + 4] (multipole variant only)
-  for (int i = threadIdx.x; i < K * B; i += blockDim.x) s_g[i] = gsums[i];
+  float* s_rr = reinterpret_cast<float*>(s_q + K);   // [K][R]: 2^(alpha (2 j + 1)), ratios of the tap recurrence
+  float* s_mp = s_rr + (size_t)K * R;                // [K][2d + 4] (multipole variant only)
+  for (int i = threadIdx.x; i < K * BP; i += blockDim.x) {
+    const int kk = i / BP, b = i % BP - kPad;
+    s_g[i] = (b >= 0 && b < B) ? gsums[(size_t)kk * B + b] : 0.f;
+  }
   for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_w[i] = proj[i];
   if constexpr (kMP) {
     for (int i = threadIdx.x; i < K * MFB_MP_STRIDE(d); i += blockDim.x) s_mp[i] = mp[i];
@@ -714,7 +722,9 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float* g = geom + (size_t)k * MFB_GEOM_STRIDE;
     const float r = g[1] / g[2];
-    s_q[k] = make_float4(g[0], 1.0f / g[1], -0.5f * r * r * kLog2e, -g[1] / (g[2] * g[2]));
+    const float alpha = -0.5f * r * r * kLog2e;
+    s_q[k] = make_float4(g[0], 1.0f / g[1], alpha, -g[1] / (g[2] * g[2]));
+    for (int j = 0; j < R; ++j) s_rr[(size_t)k * R + j] = exp2f(alpha * (float)(2 * j + 1));
   }
   __syncthreads();
   const float lo = -(float)(R + 2), hi = (float)(B + R + 1);
@@ -753,17 +763,29 @@ kde1d_bwd_kernel(const float* __restrict__ x, int64_t n, int d_rt, const float* 
       const float4 q = s_q[k];
       float a = (u - q.x) * q.y;
       a = fminf(fmaxf(a, lo), hi);
-      const float fb = rintf(a);
-      const int b0 = (int)fb;
+      // nearest bin through the 1.5 * 2^23 rounding constant (no FRND / F2I), taps by the factorised Gaussian of the
+      // forward kernel: value at offset j = E G^j C_j, E = 2^(alpha f^2), G = 2^(-2 alpha f), C_(j+1) / C_j = rr[j] --
+      // three MUFU per particle-projection instead of 2R+1, the up / down recurrences as packed multiplies
+      const float shifted = a + 12582912.0f;
+      const float fb = shifted - 12582912.0f;
       const float f = a - fb;
-      const float* grow = s_g + (size_t)k * B;
-      float acc = 0.f;
+      const float* grow = s_g + (size_t)k * BP + ((__float_as_int(shifted) - 0x4B400000) + kPad);
+      const float af = q.z * f;
+      const float e0 = fast_exp2(af * f);
+      const float gup = fast_exp2(-2.0f * af), gdn = fast_exp2(2.0f * af);
+      const float* rr = s_rr + (size_t)k * R;
+      float acc = grow[0] * (e0 * f);
+      float up = e0, dn = e0;
 #pragma unroll
-      for (int j = -R; j <= R; ++j) {
-        const int b = b0 + j;
-        const float tt = f - (float)j;
-        const float val = fast_exp2(q.z * tt * tt);
-        if ((unsigned)b < (unsigned)B) acc = fmaf(grow[b], val * tt, acc);
+      for (int j = 0; j < R; ++j) {
+        const float rj = rr[j];
+        float ru, rd;
+        mul_pair(gup, gdn, rj, rj, ru, rd);
+        mul_pair(up, dn, ru, rd, up, dn);
+        float wu, wd;
+        mul_pair(up, dn, f - (float)(j + 1), f + (float)(j + 1), wu, wd);
+        acc = fmaf(grow[j + 1], wu, acc);
+        acc = fmaf(grow[-(j + 1)], wd, acc);
       }
       const float gu = q.w * acc;
 #pragma unroll
@@ -1110,7 +1132,9 @@ static int kde1d_bwd_impl(const float* x, int64_t n, int d, const float* proj, c
   cudaStream_t st = (cudaStream_t)stream;
   const int r = radius_from_hint(max_sigma_over_delta);
   // projections are processed in chunks whose gradient table fits in shared memory
-  const size_t per_k = (size_t)b * 4 + (size_t)d * 4 + 16 + (mp ? (size_t)MFB_MP_STRIDE(d) * 4 : 0);
+  const int rt = r <= 4 ? 4 : (r <= 9 ? 9 : 13);                      // the template radius the launch picks
+  const size_t bp = (size_t)b + 2 * (2 * rt + 2);                       // padded gradient row
+  const size_t per_k = bp * 4 + (size_t)d * 4 + 16 + (size_t)rt * 4 + (mp ? (size_t)MFB_MP_STRIDE(d) * 4 : 0);
   int kchunk = (int)((160 * 1024) / per_k);
   if (kchunk < 1) return MFB_E_UNSUPPORTED;
   if (kchunk > k) kchunk = k;
@@ -1118,8 +1142,8 @@ static int kde1d_bwd_impl(const float* x, int64_t n, int d, const float* proj, c
   int64_t blocks = (n + 255) / 256;
   for (int k0 = 0; k0 < k; k0 += kchunk) {
     const int kk = (k - k0 < kchunk) ? (k - k0) : kchunk;
-    const size_t smem = (size_t)kk * b * 4 + (((size_t)kk * d + 3) & ~(size_t)3) * 4 + (size_t)kk * 16 + 16 +
-                        (mp ? (size_t)kk * MFB_MP_STRIDE(d) * 4 : 0);
+    const size_t smem = (((size_t)kk * bp + 3) & ~(size_t)3) * 4 + (((size_t)kk * d + 3) & ~(size_t)3) * 4 + (size_t)kk * 16 + 16 +
+                        (size_t)kk * rt * 4 + (mp ? (size_t)kk * MFB_MP_STRIDE(d) * 4 : 0);
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
