@@ -193,14 +193,22 @@ kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
   __shared__ float s_w[2 * kMaxDim];
   __shared__ float s_geo[2 * MFB_GEOM_STRIDE];
   const int nbins = BX * BY;
-  for (int64_t p0 = (int64_t)blockIdx.x * k2dThreads; p0 < n; p0 += (int64_t)gridDim.x * k2dThreads) {
-    const int64_t p = p0 + threadIdx.x;
-    const bool valid = p < n;
-    float xr[kMaxDim], g[kMaxDim];
+  // kPT particles per thread: a screen's gradient table (BX x BY floats, 29 KB at 85 x 85) is loaded into shared memory
+  // once per kPT x 256 particles -- with one particle per thread the kernel was bound by re-reading the tables from
+  // L2 (15 x 29 KB per 256 particles), not by its arithmetic
+  constexpr int kPT = 4;
+  for (int64_t p0 = (int64_t)blockIdx.x * (k2dThreads * kPT); p0 < n; p0 += (int64_t)gridDim.x * (k2dThreads * kPT)) {
+    float xr[kPT][kMaxDim], g[kPT][kMaxDim];
+    bool valid[kPT];
 #pragma unroll
-    for (int i = 0; i < kMaxDim; ++i) {
-      xr[i] = (valid && i < d) ? x[p * d + i] : 0.f;
-      g[i] = 0.f;
+    for (int q = 0; q < kPT; ++q) {
+      const int64_t p = p0 + q * k2dThreads + threadIdx.x;
+      valid[q] = p < n;
+#pragma unroll
+      for (int i = 0; i < kMaxDim; ++i) {
+        xr[q][i] = (valid[q] && i < d) ? x[p * d + i] : 0.f;
+        g[q][i] = 0.f;
+      }
     }
     for (int k = 0; k < K; ++k) {
       __syncthreads();
@@ -215,49 +223,55 @@ kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
       if (threadIdx.x < 2 * MFB_GEOM_STRIDE) s_geo[threadIdx.x] = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + threadIdx.x];
       __syncthreads();
       const Axis ax = load_axis(s_geo), ay = load_axis(s_geo + MFB_GEOM_STRIDE);
-      float ux = 0.f, uy = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < kPT; ++q) {
+        float ux = 0.f, uy = 0.f;
 #pragma unroll
-      for (int i = 0; i < kMaxDim; ++i)
-        if (i < d) {
-          ux = fmaf(s_w[i], xr[i], ux);
-          uy = fmaf(s_w[d + i], xr[i], uy);
-        }
-      int bx0, by0;
-      float vx[2 * R + 1], vy[2 * R + 1], tx[2 * R + 1], ty[2 * R + 1];
-      window<R>(ax, ux, BX, bx0, vx, tx);
-      window<R>(ay, uy, BY, by0, vy, ty);
-      float gux = 0.f, guy = 0.f;
-#pragma unroll
-      for (int ja = 0; ja <= 2 * R; ++ja) {
-        const int a = bx0 + ja - R;
-        if ((unsigned)a < (unsigned)BX) {
-          const float* row = s_g + a * BY;
-          float r0 = 0.f, r1 = 0.f;  // sum_b g_ab Ky_b  and  sum_b g_ab Ky_b ty_b
-#pragma unroll
-          for (int jb = 0; jb <= 2 * R; ++jb) {
-            const int b = by0 + jb - R;
-            if ((unsigned)b < (unsigned)BY) {
-              const float gv = row[b] * vy[jb];
-              r0 += gv;
-              r1 = fmaf(gv, ty[jb], r1);
-            }
+        for (int i = 0; i < kMaxDim; ++i)
+          if (i < d) {
+            ux = fmaf(s_w[i], xr[q][i], ux);
+            uy = fmaf(s_w[d + i], xr[q][i], uy);
           }
-          gux = fmaf(vx[ja] * tx[ja], r0, gux);
-          guy = fmaf(vx[ja], r1, guy);
-        }
-      }
-      gux *= ax.beta;
-      guy *= ay.beta;
+        int bx0, by0;
+        float vx[2 * R + 1], vy[2 * R + 1], tx[2 * R + 1], ty[2 * R + 1];
+        window<R>(ax, ux, BX, bx0, vx, tx);
+        window<R>(ay, uy, BY, by0, vy, ty);
+        float gux = 0.f, guy = 0.f;
 #pragma unroll
-      for (int i = 0; i < kMaxDim; ++i)
-        if (i < d) g[i] = fmaf(s_w[i], gux, fmaf(s_w[d + i], guy, g[i]));
+        for (int ja = 0; ja <= 2 * R; ++ja) {
+          const int a = bx0 + ja - R;
+          if ((unsigned)a < (unsigned)BX) {
+            const float* row = s_g + a * BY;
+            float r0 = 0.f, r1 = 0.f;  // sum_b g_ab Ky_b  and  sum_b g_ab Ky_b ty_b
+#pragma unroll
+            for (int jb = 0; jb <= 2 * R; ++jb) {
+              const int b = by0 + jb - R;
+              if ((unsigned)b < (unsigned)BY) {
+                const float gv = row[b] * vy[jb];
+                r0 += gv;
+                r1 = fmaf(gv, ty[jb], r1);
+              }
+            }
+            gux = fmaf(vx[ja] * tx[ja], r0, gux);
+            guy = fmaf(vx[ja], r1, guy);
+          }
+        }
+        gux *= ax.beta;
+        guy *= ay.beta;
+#pragma unroll
+        for (int i = 0; i < kMaxDim; ++i)
+          if (i < d) g[q][i] = fmaf(s_w[i], gux, fmaf(s_w[d + i], guy, g[q][i]));
+      }
     }
-    if (valid) {
+#pragma unroll
+    for (int q = 0; q < kPT; ++q) {
+      if (!valid[q]) continue;
+      const int64_t p = p0 + q * k2dThreads + threadIdx.x;
 #pragma unroll
       for (int i = 0; i < kMaxDim; ++i)
         if (i < d) {
-          if (accumulate) gx[p * d + i] += g[i];
-          else gx[p * d + i] = g[i];
+          if (accumulate) gx[p * d + i] += g[q][i];
+          else gx[p * d + i] = g[q][i];
         }
     }
   }
@@ -420,7 +434,7 @@ int mfb_project_kde2d_bwd(const float* x, int64_t n, int d, const float* proj, c
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;
   int64_t grid = (int64_t)sm_count() * per_sm;
-  const int64_t blocks = (n + k2dThreads - 1) / k2dThreads;
+  const int64_t blocks = (n + 4 * k2dThreads - 1) / (4 * k2dThreads);   // four particles per thread (kPT)
   if (grid > blocks) grid = blocks;
   const int r = radius2d(max_sigma_over_delta);
   if (r <= 4) {
