@@ -54,6 +54,35 @@ __device__ __forceinline__ void window(const Axis& ax, float u, int nb, int& b0,
   }
 }
 
+// The same window by the factorised Gaussian of the 1-D kernels (kde1d.cu): value at offset j = E G^j C_j with
+// E = 2^(alpha f^2), G = 2^(-2 alpha f), C_(j+1) / C_j = 2^(alpha (2 j + 1)) -- three MUFU per axis instead of 2R+1 --
+// and the nearest bin through the 1.5 * 2^23 rounding constant.
+template <int R>
+__device__ __forceinline__ void window_fact(const Axis& ax, float u, int nb, int& b0, float (&val)[2 * R + 1],
+                                            float (&tt)[2 * R + 1]) {
+  float a = (u - ax.c0) * ax.inv_delta;
+  a = fminf(fmaxf(a, -(float)(R + 2)), (float)(nb + R + 1));
+  const float shifted = a + 12582912.0f;
+  const float fb = shifted - 12582912.0f;
+  b0 = __float_as_int(shifted) - 0x4B400000;
+  const float f = a - fb, af = ax.alpha * f;
+  const float e0 = fast_exp2(af * f), gup = fast_exp2(-2.0f * af), gdn = fast_exp2(2.0f * af);
+  val[R] = e0;
+  tt[R] = f;
+  float up = e0, dn = e0, c = exp2f(ax.alpha);          // c = C_1 / C_0; the ratio of ratios is 2^(2 alpha)
+  const float c2 = c * c;
+#pragma unroll
+  for (int j = 1; j <= R; ++j) {
+    up *= gup * c;
+    dn *= gdn * c;
+    c *= c2;
+    val[R + j] = up;
+    val[R - j] = dn;
+    tt[R + j] = f - (float)j;
+    tt[R - j] = f + (float)j;
+  }
+}
+
 template <int R>
 __global__ void __launch_bounds__(k2dThreads)
 kde2d_deposit_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
@@ -189,10 +218,14 @@ __global__ void __launch_bounds__(k2dThreads)
 kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ proj,
                  const float* __restrict__ geom, int K, int BX, int BY, const float* __restrict__ gsums,
                  float* __restrict__ gx, int accumulate) {
-  extern __shared__ __align__(16) float s_g[];  // [BX][BY] of the current screen
+  // gradient table of the current screen with kPad zero bins around it: the (2R+1)^2 taps of a (clamped) particle never
+  // need a bounds check
+  constexpr int kPad = 2 * R + 2;
+  extern __shared__ __align__(16) float s_g[];  // [BX + 2 kPad][BY + 2 kPad]
   __shared__ float s_w[2 * kMaxDim];
   __shared__ float s_geo[2 * MFB_GEOM_STRIDE];
-  const int nbins = BX * BY;
+  const int nbins = BX * BY, BYP = BY + 2 * kPad;
+  for (int i = threadIdx.x; i < (BX + 2 * kPad) * BYP; i += k2dThreads) s_g[i] = 0.f;   // the pads stay zero
   // kPT particles per thread: a screen's gradient table (BX x BY floats, 29 KB at 85 x 85) is loaded into shared memory
   // once per kPT x 256 particles -- with one particle per thread the kernel was bound by re-reading the tables from
   // L2 (15 x 29 KB per 256 particles), not by its arithmetic
@@ -212,12 +245,9 @@ kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
     }
     for (int k = 0; k < K; ++k) {
       __syncthreads();
-      const float4* src = reinterpret_cast<const float4*>(gsums + (size_t)k * nbins);
-      if ((((size_t)k * nbins) & 3) == 0) {
-        for (int i = threadIdx.x; i < (nbins >> 2); i += k2dThreads) reinterpret_cast<float4*>(s_g)[i] = src[i];
-        for (int i = (nbins & ~3) + threadIdx.x; i < nbins; i += k2dThreads) s_g[i] = gsums[(size_t)k * nbins + i];
-      } else {
-        for (int i = threadIdx.x; i < nbins; i += k2dThreads) s_g[i] = gsums[(size_t)k * nbins + i];
+      for (int i = threadIdx.x; i < nbins; i += k2dThreads) {
+        const int a = i / BY, b = i - a * BY;
+        s_g[(a + kPad) * BYP + (b + kPad)] = gsums[(size_t)k * nbins + i];
       }
       if (threadIdx.x < 2 * d) s_w[threadIdx.x] = proj[(size_t)k * 2 * d + threadIdx.x];
       if (threadIdx.x < 2 * MFB_GEOM_STRIDE) s_geo[threadIdx.x] = geom[(size_t)(2 * k) * MFB_GEOM_STRIDE + threadIdx.x];
@@ -234,27 +264,22 @@ kde2d_bwd_kernel(const float* __restrict__ x, int64_t n, int d, const float* __r
           }
         int bx0, by0;
         float vx[2 * R + 1], vy[2 * R + 1], tx[2 * R + 1], ty[2 * R + 1];
-        window<R>(ax, ux, BX, bx0, vx, tx);
-        window<R>(ay, uy, BY, by0, vy, ty);
+        window_fact<R>(ax, ux, BX, bx0, vx, tx);
+        window_fact<R>(ay, uy, BY, by0, vy, ty);
         float gux = 0.f, guy = 0.f;
+        const float* base = s_g + (bx0 - R + kPad) * BYP + (by0 - R + kPad);
 #pragma unroll
         for (int ja = 0; ja <= 2 * R; ++ja) {
-          const int a = bx0 + ja - R;
-          if ((unsigned)a < (unsigned)BX) {
-            const float* row = s_g + a * BY;
-            float r0 = 0.f, r1 = 0.f;  // sum_b g_ab Ky_b  and  sum_b g_ab Ky_b ty_b
+          const float* row = base + ja * BYP;
+          float r0 = 0.f, r1 = 0.f;  // sum_b g_ab Ky_b  and  sum_b g_ab Ky_b ty_b
 #pragma unroll
-            for (int jb = 0; jb <= 2 * R; ++jb) {
-              const int b = by0 + jb - R;
-              if ((unsigned)b < (unsigned)BY) {
-                const float gv = row[b] * vy[jb];
-                r0 += gv;
-                r1 = fmaf(gv, ty[jb], r1);
-              }
-            }
-            gux = fmaf(vx[ja] * tx[ja], r0, gux);
-            guy = fmaf(vx[ja], r1, guy);
+          for (int jb = 0; jb <= 2 * R; ++jb) {
+            const float gv = row[jb] * vy[jb];
+            r0 += gv;
+            r1 = fmaf(gv, ty[jb], r1);
           }
+          gux = fmaf(vx[ja] * tx[ja], r0, gux);
+          guy = fmaf(vx[ja], r1, guy);
         }
         gux *= ax.beta;
         guy *= ay.beta;
@@ -427,7 +452,9 @@ int mfb_project_kde2d_bwd(const float* x, int64_t n, int d, const float* proj, c
   MFB_CHECK_ARG(x && proj && geom && gsums && gx);
   MFB_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxDim && k >= 1 && bx >= 2 && by >= 2);
   if (n == 0) return 0;
-  const size_t smem = (size_t)bx * by * 4;
+  const int rr_ = radius2d(max_sigma_over_delta);
+  const int pad = 2 * (rr_ <= 4 ? 4 : 9) + 2;                     // kPad of the template radius the launch picks
+  const size_t smem = (size_t)(bx + 2 * pad) * (by + 2 * pad) * 4;
   if (smem > 200 * 1024) return MFB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   int per_sm = (int)((200 * 1024) / (smem + 2048));
