@@ -206,6 +206,13 @@ int mfb_nsf_tc_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int
 int mfb_nsf_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hidden_layers,
                       int bins, const float* params, const int32_t* order_host, const float* ladj_in,
                       int last_layer, float* v, float* ladj_out, void* stream);
+/* The same on the tensor cores, from one layer's operand image of mfb_nsf_tc_prepare (shapes of
+ * mfb_nsf_tc_supported): the feature first in the order inverts its bias-only spline, every further
+ * feature takes one pass of the conditioner (first layer, two hidden GEMMs, its own output tile) and
+ * the inverse spline in registers -- S x 4 GEMM round trips per 128-particle tile instead of D sweeps. */
+int mfb_nsf_tc_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hidden_layers, int bins,
+                         const void* image, const int32_t* order_host, const float* ladj_in, int last_layer,
+                         float* v, float* ladj_out, void* stream);
 
 /* Backward of one layer (replaces torch autograd through the zuko graph).  Activations are
  * recomputed from the layer input v.  gy = dL/dy [n][d], glogq = dL/dlogq_out [n] (may be NULL);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mfb_nsf_tc_prepare": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int64, P]),
     "mfb_nsf_tc_layer_fwd": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_inv": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
+    "mfb_nsf_tc_layer_inv": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P]),
     "mfb_nsf_layer_param_om_floats": (c_int64, [c_int, c_int, c_int]),
     "mfb_nsf_layer_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "mfb_nsf_layer_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P,

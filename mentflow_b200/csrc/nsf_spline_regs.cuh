@@ -414,6 +414,111 @@ MFB_HD float rq_spline_regs_bwd(float (&a)[64], float v, float gy, float gl, Kno
   return inside ? gv : gy;
 }
 
+// Inverse of the same spline (density direction, generate/flows/zuko.py:21-22,31-32,43-50): returns v with RQS(v) = y
+// and multiplies jac by dy/dv at v (the forward Jacobian log_prob needs).  The bin is searched over the HEIGHT
+// prefixes with the same centred differences as the forward search over the widths; inside the bin, with
+// eta = (y - y0) / dy in [0, 1]:  a = (s - d0) + eta A,  b = d0 - eta A,  c = -s eta,  A = d0 + d1 - 2 s,
+// z = 2 c / (-b - sqrt(b^2 - 4 a c))  (zuko's numerically stable root), v = x0 + z dx.
+template <int NB>
+MFB_HD float rq_spline_regs_inv(const float (&a)[64], float y, float& jac) {
+  static_assert(NB % 4 == 0 && NB >= 8, "bins are searched in groups of four");
+  constexpr int G = NB / 4;
+  constexpr float cW = kClipW / kLog2e, cD = kClipD / kLog2e;
+  float e[NB], h[NB], pre[G + 1], preh[G + 1];
+#pragma unroll
+  for (int j = 0; j < NB; j += 4) {
+    clip_exp2_quad(a[j], a[j + 1], a[j + 2], a[j + 3], cW, e[j], e[j + 1], e[j + 2], e[j + 3]);
+    clip_exp2_quad(a[NB + j], a[NB + j + 1], a[NB + j + 2], a[NB + j + 3], cW, h[j], h[j + 1], h[j + 2], h[j + 3]);
+  }
+  pre[0] = 0.f;
+  preh[0] = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    pre[g + 1] = pre[g] + ((e[4 * g] + e[4 * g + 1]) + (e[4 * g + 2] + e[4 * g + 3]));
+    preh[g + 1] = preh[g] + ((h[4 * g] + h[4 * g + 1]) + (h[4 * g + 2] + h[4 * g + 3]));
+  }
+  const float sum = pre[G], sumh = preh[G];
+  const float halfh = 0.5f * sumh, uy = y * (0.5f / kBound);
+  const float targeth = fmaf(uy, sumh, halfh);
+  float q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], xg = 0.f;
+  float h0s = h[0], h1s = h[1], h2s = h[2], h3s = h[3], yg = 0.f;
+  float um = 0.f, u0 = a[2 * NB], u1 = a[2 * NB + 1], u2 = a[2 * NB + 2], u3 = a[2 * NB + 3];
+#pragma unroll
+  for (int g = 1; g < G; ++g) {
+    const bool pgm = preh[g] < targeth;
+    um = pgm ? a[2 * NB + 4 * g - 1] : um;
+    u0 = pgm ? a[2 * NB + 4 * g] : u0;
+    u1 = pgm ? a[2 * NB + 4 * g + 1] : u1;
+    u2 = pgm ? a[2 * NB + 4 * g + 2] : u2;
+    u3 = pgm ? ((4 * g + 3 < NB - 1) ? a[2 * NB + 4 * g + 3] : 0.f) : u3;
+    q0 = pgm ? e[4 * g] : q0;
+    q1 = pgm ? e[4 * g + 1] : q1;
+    q2 = pgm ? e[4 * g + 2] : q2;
+    q3 = pgm ? e[4 * g + 3] : q3;
+    xg = pgm ? pre[g] : xg;
+    h0s = pgm ? h[4 * g] : h0s;
+    h1s = pgm ? h[4 * g + 1] : h1s;
+    h2s = pgm ? h[4 * g + 2] : h2s;
+    h3s = pgm ? h[4 * g + 3] : h3s;
+    yg = pgm ? preh[g] : yg;
+  }
+  const float remh = fmaf(uy, sumh, halfh - yg);
+  const float j1 = h0s + h1s, j2 = j1 + h2s;
+  const bool r0 = h0s < remh, r1 = j1 < remh, r2 = j2 < remh;
+  const float numer = remh - (r2 ? j2 : (r1 ? j1 : (r0 ? h0s : 0.f)));       // (y - y0) in un-normalised height units
+  const float hk = r2 ? h3s : (r1 ? h2s : (r0 ? h1s : h0s));
+  const float i1 = q0 + q1, i2 = i1 + q2;
+  const float xcen = (xg - 0.5f * sum) + (r2 ? i2 : (r1 ? i1 : (r0 ? q0 : 0.f)));   // left knot of the bin from the centre
+  const float ek = r2 ? q3 : (r1 ? q2 : (r0 ? q1 : q0));
+  const float tl = r2 ? u2 : (r1 ? u1 : (r0 ? u0 : um));
+  const float tr = r2 ? u3 : (r1 ? u2 : (r0 ? u1 : u0));
+  float d0, d1;
+  clip_exp2_pair(tl, tr, cD, d0, d1);
+  const float r_s = rcp_nr(sum), r_hk = rcp_nr(hk);
+  float eta = numer * r_hk;
+  eta = fminf(fmaxf(eta, 0.0f), 1.0f);
+  const float s = (hk * rcp_nr(sumh)) * sum * rcp_nr(ek);   // dy / dx
+  const float A = d0 + d1 - 2.0f * s;
+  const float qa = fmaf(eta, A, s - d0), qb = fmaf(-eta, A, d0), qc = -s * eta;
+  const float disc = fmaxf(fmaf(qb, qb, -4.0f * qa * qc), 0.0f);
+  float z = (2.0f * qc) * rcp_nr(-qb - sqrtf(disc));
+  z = fminf(fmaxf(z, 0.0f), 1.0f);
+  const float omz = 1.0f - z, zomz = z * omz;
+  const float den = fmaf(A, zomz, s);
+  const float r_den = rcp_nr(den);
+  const float jj = s * s * (2.0f * s * zomz + d0 * omz * omz + d1 * z * z) * r_den * r_den;
+  const float v = 2.0f * kBound * (fmaf(z, ek, xcen) * r_s);
+  const bool inside = (y > -kBound) && (y <= kBound);
+  jac *= inside ? jj : 1.0f;
+  return inside ? v : y;
+}
+
+// ... and of the bias-only spline from the knot tables
+template <int NB>
+MFB_HD float rq_spline_const_inv(const float* __restrict__ ct, float y, float& jac) {
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j < NB; ++j) k += (ct[2 * kCT + j] < y) ? 1 : 0;
+  const float x0 = ct[k], dx = ct[kCT + k], y0 = ct[2 * kCT + k], dy = ct[3 * kCT + k];
+  const float d0 = ct[4 * kCT + k], d1 = ct[5 * kCT + k];
+  const float s = dy * rcp_nr(dx);
+  float eta = (y - y0) * rcp_nr(dy);
+  eta = fminf(fmaxf(eta, 0.0f), 1.0f);
+  const float A = d0 + d1 - 2.0f * s;
+  const float qa = fmaf(eta, A, s - d0), qb = fmaf(-eta, A, d0), qc = -s * eta;
+  const float disc = fmaxf(fmaf(qb, qb, -4.0f * qa * qc), 0.0f);
+  float z = (2.0f * qc) * rcp_nr(-qb - sqrtf(disc));
+  z = fminf(fmaxf(z, 0.0f), 1.0f);
+  const float omz = 1.0f - z, zomz = z * omz;
+  const float den = fmaf(A, zomz, s);
+  const float r_den = rcp_nr(den);
+  const float jj = s * s * (2.0f * s * zomz + d0 * omz * omz + d1 * z * z) * r_den * r_den;
+  const float v = fmaf(z, dx, x0) + ct[6 * kCT + k];
+  const bool inside = (y > -kBound) && (y <= kBound);
+  jac *= inside ? jj : 1.0f;
+  return inside ? v : y;
+}
+
 // bias-only spline from the precomputed knot tables (shared memory, broadcast reads)
 template <int NB>
 MFB_HD float rq_spline_const(const float* __restrict__ ct, float v, float& jac) {

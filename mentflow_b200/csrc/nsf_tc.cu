@@ -803,6 +803,227 @@ nsf_tc_layer_kernel(const float* __restrict__ v, int64_t n, const unsigned char*
   if (tid < 32) umma::tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================
+// Density direction on the same machinery: v = A^-1(y), one layer per launch (generate/flows/zuko.py:21-22,31-32,
+// 43-50: log_prob / inverse / inverse_steps).  The autoregressive inverse is sequential in the features: the feature
+// that is first in the layer's order inverts its bias-only spline, then every further feature needs the conditioner
+// of the values found so far -- first layer, two hidden GEMMs, ONE output-feature tile -- followed by the inverse
+// spline in registers (rq_spline_regs_inv).  Per 128-particle tile a warpgroup therefore makes S x 4 round trips to
+// the tensor core; the three warpgroups of a CTA run their tiles independently, so the issuer warps interleave them.
+// Same operand image, TMEM layout and hand-off as the forward kernel; one accumulator buffer, nothing pipelined inside
+// a tile (each step depends on the one before).  Replaces D full sweeps of the CUDA-core kernel (nsf_inv.cu).
+// =============================================================================================
+template <int D, int L, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+nsf_tc_inverse_kernel(const float* __restrict__ y, int64_t n, const unsigned char* __restrict__ image,
+                      const __grid_constant__ Meta meta, const float* __restrict__ ladj_in, int last_layer,
+                      float* __restrict__ v_out, float* __restrict__ ladj_out) {
+  static_assert(L == 3, "compiled for three hidden layers");
+  constexpr int S = D - 1;
+  constexpr int kImg = image_bytes(D, L);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* img = smem;
+  unsigned char* a_all = smem + kImg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_all + kWG * kABytes);   // [0] image, [1 + wg] MMA done, [1 + kWG + wg] request
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kWG);
+
+  const int tid = threadIdx.x;
+  const int wg = __shfl_sync(0xffffffffu, tid >> 7, 0);
+  const int t = tid & 127;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    for (int i = 0; i < kWG; ++i) {
+      mbar_init(&bars[1 + i], 1);
+      mbar_init(&bars[1 + kWG + i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (tid < 32) umma::tmem_alloc(tmem_slot, 256);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], (uint32_t)kImg);
+    tma_load_1d(img, image, (uint32_t)kImg, &bars[0]);
+  }
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  mbar_wait_bounded(&bars[0], 0);
+
+  const int64_t ntiles = (n + 127) / 128;
+  const int64_t tstride = (int64_t)gridDim.x * kWG;
+  const uint32_t idesc64 = umma::make_idesc_f16(128, 64);
+
+  if (wg == kWG) {
+    // ===== issuers: warp i serves warpgroup i; per tile and slot: first layer, two hidden GEMMs, the slot's tile =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
+    const int w = __shfl_sync(0xffffffffu, (tid - kWG * 128) >> 5, 0);
+    if (w < kWG) {
+      uint64_t* done = &bars[1 + w];
+      uint64_t* req = &bars[1 + kWG + w];
+      uint32_t rp = 0;
+      unsigned char* wa_hi = a_all + w * kABytes;
+      const uint64_t dA_hi = umma::make_desc_sw128(smem_u32(wa_hi));
+      const uint64_t dA_lo = umma::make_desc_sw128(smem_u32(wa_hi + kABytes / 2));
+      const uint64_t dOnes = umma::make_desc_sw32(smem_u32(img + off_ones()));
+      const uint64_t dB1 = umma::make_desc_sw32(smem_u32(img + off_b1()));
+      const uint32_t dcol = tmem_base + (uint32_t)(w * 64);
+      auto wait_req = [&]() {
+        mbar_wait_polite(req, rp);
+        rp ^= 1;
+        umma::fence_after_sync();
+      };
+      for (int64_t tile = first_tile_of(w); tile < ntiles; tile += tstride) {
+#pragma unroll 1
+        for (int slot = 0; slot < S; ++slot) {
+          // first masked layer (K = 16, bias folded into the weights' spare K columns)
+          wait_req();
+          if (elect_one()) {
+            umma::mma_f16_ss(dcol, dA_hi, dB1, idesc64, 0);
+            umma::mma_f16_ss(dcol, dA_hi, dB1 + (uint64_t)(kKTile >> 4), idesc64, 1);
+            umma::commit(done);
+          }
+          __syncwarp();
+          // hidden -> hidden
+#pragma unroll 1
+          for (int l = 0; l < L - 1; ++l) {
+            wait_req();
+            const uint64_t dBh = umma::make_desc_sw128(smem_u32(img + off_hid(0) + l * 2 * kTileBytes));
+            const uint64_t dBl = umma::make_desc_sw128(smem_u32(img + off_hid(0) + l * 2 * kTileBytes + kTileBytes));
+            if (elect_one()) {
+              umma::mma_f16_ss(dcol, dOnes, umma::make_desc_sw32(smem_u32(img + off_bias(L, 0) + l * kKTile)), idesc64, 0);
+#pragma unroll
+              for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const int n0 = meta.hid_n0[ks];
+                  const uint32_t idesc = umma::make_idesc_f16(128, 64 - n0);
+                  const uint64_t boff = (uint64_t)((n0 * 128) >> 4);
+                  if (pass == 0) mma_cross(dcol + n0, dA_hi, dA_lo, dBh + boff, dBl + boff, ks, idesc, 1);
+                  else mma_main(dcol + n0, dA_hi, dBh + boff, ks, idesc);
+                }
+              }
+              umma::commit(done);
+            }
+            __syncwarp();
+          }
+          // the output-feature tile of this slot
+          wait_req();
+          if (elect_one()) {
+            int koff = 0;
+            for (int i = 0; i < slot; ++i) koff += meta.slot_ksteps[i];
+            const uint32_t tiles = smem_u32(img + off_slot(D, L, 0, 0, 0)) + (uint32_t)(koff * 2 * kKTile);
+            const int nk = meta.slot_ksteps[slot];
+            umma::mma_f16_ss(dcol, dOnes, umma::make_desc_sw32(smem_u32(img + off_bias(L, (L - 1) + slot))), idesc64, 0);
+            for (int ks = 0; ks < nk; ++ks) {
+              const uint64_t dBh = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile));
+              const uint64_t dBl = umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile + kKTile));
+              umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), dBl, idesc64, 1);
+              umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_lo, ks), dBh, idesc64, 1);
+            }
+            for (int ks = 0; ks < nk; ++ks)
+              umma::mma_f16_ss(dcol, umma::desc_advance_k(dA_hi, ks), umma::make_desc_sw32(tiles + (uint32_t)(ks * 2 * kKTile)),
+                               idesc64, 1);
+            umma::commit(done);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== compute warpgroups: thread = particle row =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    unsigned char* a_hi = a_all + wg * kABytes;
+    unsigned char* a_lo = a_hi + kABytes / 2;
+    uint64_t* done = &bars[1 + wg];
+    uint64_t* req = &bars[1 + kWG + wg];
+    uint32_t ph = 0;
+    const uint32_t taddr = tmem_base + (uint32_t)(wg * 64) + ((uint32_t)((t >> 5) * 32) << 16);
+    const float* ctab = reinterpret_cast<const float*>(img + off_f32(D, L));
+    auto hand_off = [&]() {
+      fence_proxy_async();
+      umma::fence_before_sync();
+      request_arrive(req);
+    };
+    auto wait_done = [&]() {
+      mbar_wait_bounded(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+    };
+    for (int64_t tile = first_tile_of(wg); tile < ntiles; tile += tstride) {
+      const int64_t p = tile * 128 + t;
+      const bool valid = p < n;
+      float yy[D], vv[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        yy[i] = valid ? y[p * D + i] : 0.f;
+        vv[i] = yy[i];        // features not found yet: any finite value (their weights are masked)
+      }
+      const float la_in = (valid && ladj_in) ? ladj_in[p] : 0.f;
+      float jac = 1.0f;
+      {
+        float yc = yy[0];
+#pragma unroll
+        for (int i = 1; i < D; ++i) yc = (meta.const_feature == i) ? yy[i] : yc;
+        const float vc = rq_spline_const_inv<NB>(ctab, yc, jac);
+#pragma unroll
+        for (int i = 0; i < D; ++i) vv[i] = (meta.const_feature == i) ? vc : vv[i];
+      }
+#pragma unroll 1
+      for (int slot = 0; slot < S; ++slot) {
+        const int f = meta.slot_feature[slot];
+        {   // first layer: A row = [v_hi (D) | v_lo (D) | 1 | 1 | 0 ...]
+          __align__(16) __half row[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) row[e] = __float2half_rn(0.f);
+#pragma unroll
+          for (int i = 0; i < D; ++i) umma::split_f16(vv[i], row[i], row[D + i]);
+          row[2 * D] = __float2half_rn(1.0f);
+          row[2 * D + 1] = __float2half_rn(1.0f);
+          *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 0)) = reinterpret_cast<const uint4*>(row)[0];
+          *reinterpret_cast<uint4*>(a_hi + umma::sw128_offset(t, 1)) = reinterpret_cast<const uint4*>(row)[1];
+          hand_off();
+        }
+        float acc[64];
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) {
+          wait_done();
+          tmem_ld64(taddr, acc);
+          store_hidden(acc, a_hi, a_lo, t);
+          hand_off();
+        }
+        wait_done();
+        tmem_ld64(taddr, acc);
+        umma::fence_before_sync();
+        float yf = yy[0];
+#pragma unroll
+        for (int i = 1; i < D; ++i) yf = (f == i) ? yy[i] : yf;
+        const float vf = rq_spline_regs_inv<NB>(acc, yf, jac);
+#pragma unroll
+        for (int i = 0; i < D; ++i) vv[i] = (f == i) ? vf : vv[i];
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) v_out[p * D + i] = vv[i];
+        if (ladj_out) {
+          float tot = fmaf(0.69314718055994531f, fast_lg2(jac), la_in);
+          if (last_layer) {   // log q(x) = log N(z; 0, I) - sum of the forward log-Jacobians
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) ss = fmaf(vv[i], vv[i], ss);
+            tot = -0.5f * ss - (float)D * kHalfLog2Pi - tot;
+          }
+          ladj_out[p] = tot;
+        }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem_base, 256);
+}
+
 // ---- host side ----------------------------------------------------------------------------
 static void make_meta(int d, const int32_t* order, Meta* m, PrepMeta* pm) {
   int cls[kH], perm[kH];
@@ -887,6 +1108,20 @@ static int launch_layer_bwd(const float* v, int64_t n, const unsigned char* imag
   int64_t grid = sm_count();
   if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
   kern<<<(int)grid, kThreads, smem, st>>>(v, n, image, meta, nullptr, first, nullptr, nullptr, bio);
+  return launch_status();
+}
+
+template <int D>
+static int launch_inverse(const float* y, int64_t n, const unsigned char* image, const Meta& meta, const float* ladj_in,
+                          int last, float* v, float* ladj_out, cudaStream_t st) {
+  constexpr int L = 3, NB = 20;
+  const size_t smem = (size_t)image_bytes(D, L) + kWG * kABytes + 256 + 1024;
+  auto kern = nsf_tc_inverse_kernel<D, L, NB>;
+  MFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + 127) / 128;
+  int64_t grid = sm_count();
+  if (grid * kWG > ntiles) grid = (ntiles + kWG - 1) / kWG;
+  kern<<<(int)grid, kThreads, smem, st>>>(y, n, image, meta, ladj_in, last, v, ladj_out);
   return launch_status();
 }
 
@@ -999,6 +1234,27 @@ int mfb_nsf_tc_layer_fwd(const float* v, int64_t n, int d, int hidden_units, int
     case 4: return tc::launch_layer<4>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
     case 5: return tc::launch_layer<5>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
     case 6: return tc::launch_layer<6>(v, n, img, meta, logq_in, first_layer, y, logq_out, st);
+    default: return MFB_E_UNSUPPORTED;
+  }
+}
+
+int mfb_nsf_tc_layer_inv(const float* y, int64_t n, int d, int hidden_units, int hidden_layers, int bins,
+                         const void* image, const int32_t* order_host, const float* ladj_in, int last_layer, float* v,
+                         float* ladj_out, void* stream) {
+  MFB_CHECK_ARG(y && image && v && order_host && n >= 0);
+  if (!mfb_nsf_tc_supported(d, hidden_units, hidden_layers, bins)) return MFB_E_UNSUPPORTED;
+  if (!tc::valid_order(d, order_host)) return MFB_E_BADARG;
+  if (n == 0) return 0;
+  tc::Meta meta;
+  tc::make_meta(d, order_host, &meta, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(image);
+  switch (d) {
+    case 2: return tc::launch_inverse<2>(y, n, img, meta, ladj_in, last_layer, v, ladj_out, st);
+    case 3: return tc::launch_inverse<3>(y, n, img, meta, ladj_in, last_layer, v, ladj_out, st);
+    case 4: return tc::launch_inverse<4>(y, n, img, meta, ladj_in, last_layer, v, ladj_out, st);
+    case 5: return tc::launch_inverse<5>(y, n, img, meta, ladj_in, last_layer, v, ladj_out, st);
+    case 6: return tc::launch_inverse<6>(y, n, img, meta, ladj_in, last_layer, v, ladj_out, st);
     default: return MFB_E_UNSUPPORTED;
   }
 }

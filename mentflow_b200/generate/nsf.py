@@ -268,15 +268,20 @@ class NSFGenerator(GenerativeModel):
         return steps
 
     # ------------------------------------------------------------------ density direction
+    def _inverse(self, x: torch.Tensor, want_logq: bool, want_steps: bool):
+        if x.is_cuda:
+            packed, images = self._packed_cached()      # tensor-core operand images where the shape has them
+        else:
+            packed, images = self.packed_parameters(), None
+        return ops.nsf_inverse(x, packed, self._orders, self.hidden_units, self.hidden_layers, self.bins, want_logq,
+                               want_steps, images=images)
+
     def inverse(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
-                               self.bins, False, False)[0]
+        return self._inverse(x, False, False)[0]
 
     def inverse_steps(self, x: torch.Tensor) -> List[torch.Tensor]:
         with torch.no_grad():
-            return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units,
-                                   self.hidden_layers, self.bins, False, True)[2]
+            return self._inverse(x, False, True)[2]
 
     def log_prob(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.nsf_inverse(x, self.packed_parameters(), self._orders, self.hidden_units, self.hidden_layers,
-                               self.bins, True, False)[1]
+        return self._inverse(x, True, False)[1]

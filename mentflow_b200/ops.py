@@ -678,9 +678,14 @@ def nsf_forward(z, packed, packed_om, orders, hidden_units, hidden_layers, bins,
     return x, (logq if want_logq else None), None
 
 
-def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False):
+NSF_INV_USE_TENSOR_CORES = True   # tcgen05 inverse where the forward's operand images exist; False = fp32 CUDA-core kernel
+
+
+def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=True, want_steps=False, images=None):
     """Density direction: returns (z, log q(x) or None, steps or None).  Not differentiable (no
-    experiment of the reference trains through log_prob(x))."""
+    experiment of the reference trains through log_prob(x)).  ``images``: the forward kernel's operand
+    images (``nsf_tc_images``): with them each layer is one tensor-core launch (S x 4 GEMM round trips per tile)
+    instead of D full sweeps of the CUDA-core kernel."""
     lib = _lib.load()
     x = _check_f32("x", x.detach())
     packed = _check_f32("packed", packed.detach())
@@ -696,9 +701,14 @@ def nsf_inverse(x, packed, orders, hidden_units, hidden_layers, bins, want_logq=
                 acc = out
                 steps.append(v)
                 continue
-            _lib.check(lib.mfb_nsf_layer_inv(_ptr(steps[-1]), n, d, hidden_units, hidden_layers, bins, _ptr(packed[t]),
-                                             ctypes.cast(order_arr, ctypes.c_void_p), _ptr(acc), 1 if t == 0 else 0,
-                                             _ptr(v), _ptr(out), _stream()), "nsf_layer_inv")
+            if images is not None and NSF_INV_USE_TENSOR_CORES:
+                _lib.check(lib.mfb_nsf_tc_layer_inv(_ptr(steps[-1]), n, d, hidden_units, hidden_layers, bins,
+                                                    _ptr(images[t]), ctypes.cast(order_arr, ctypes.c_void_p), _ptr(acc),
+                                                    1 if t == 0 else 0, _ptr(v), _ptr(out), _stream()), "nsf_tc_layer_inv")
+            else:
+                _lib.check(lib.mfb_nsf_layer_inv(_ptr(steps[-1]), n, d, hidden_units, hidden_layers, bins, _ptr(packed[t]),
+                                                 ctypes.cast(order_arr, ctypes.c_void_p), _ptr(acc), 1 if t == 0 else 0,
+                                                 _ptr(v), _ptr(out), _stream()), "nsf_layer_inv")
             acc = out
             steps.append(v)
     return steps[-1], acc, (steps if want_steps else None)

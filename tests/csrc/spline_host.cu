@@ -34,6 +34,17 @@ void spline_host_bwd(const float* phi, const float* v, const float* gy, const fl
   }
 }
 
+// inverse: v with RQS(v) = y, jac = dy/dv at v
+void spline_host_inv(const float* phi, const float* y, int64_t n, float* v, float* jac) {
+  for (int64_t p = 0; p < n; ++p) {
+    float a[64];
+    for (int j = 0; j < 64; ++j) a[j] = phi[p * 64 + j] * kLog2e;
+    float jc = 1.0f;
+    v[p] = tc::rq_spline_regs_inv<20>(a, y[p], jc);
+    jac[p] = jc;
+  }
+}
+
 int spline_host_comp() { return MFB_SPLINE_COMP; }
 
 }  // extern "C"

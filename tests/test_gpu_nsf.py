@@ -373,8 +373,18 @@ def test_backward_tensor_core_and_cuda_core_agree():
         assert float(g0.abs().max()) < 1e-3        # the gradients really are tiny
 
 
-@pytest.mark.parametrize("d,n,scale", [(2, 2000, 1.5), (6, 20000, 1.0), (4, 999, 2.0)])
-def test_inverse_and_log_prob(d, n, scale):
+@pytest.fixture(params=["tensor-core", "cuda-core"])
+def inverse_path(request):
+    """Both implementations of the density direction (the tcgen05 kernel is the default where the forward's operand
+    images exist)."""
+    from mentflow_b200 import ops
+    old, ops.NSF_INV_USE_TENSOR_CORES = ops.NSF_INV_USE_TENSOR_CORES, request.param == "tensor-core"
+    yield request.param
+    ops.NSF_INV_USE_TENSOR_CORES = old
+
+
+@pytest.mark.parametrize("d,n,scale", [(2, 2000, 1.5), (6, 20000, 1.0), (4, 999, 2.0), (6, 130, 1.5), (3, 4097, 1.0), (5, 777, 2.0)])
+def test_inverse_and_log_prob(d, n, scale, inverse_path):
     """Density direction (generate/flows/zuko.py:21-22,31-32,43-50): round trip through the CUDA
     forward, and log_prob(x) / inverse(x) / inverse_steps(x) vs the float64 oracle."""
     torch.manual_seed(100 + d)

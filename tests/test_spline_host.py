@@ -39,6 +39,7 @@ def lib():
     fp = ctypes.POINTER(ctypes.c_float)
     L.spline_host_fwd.argtypes = [fp, fp, ctypes.c_int64, fp, fp]
     L.spline_host_bwd.argtypes = [fp, fp, fp, fp, ctypes.c_int64, fp, fp]
+    L.spline_host_inv.argtypes = [fp, fp, ctypes.c_int64, fp, fp]
     return L
 
 
@@ -147,3 +148,32 @@ def test_spline_backward_matches_autograd(lib):
     ev = (torch.from_numpy(gv).double() - v64.grad).abs() / v64.grad.abs().clamp_min(1.0)
     assert float(e.median()) < 1e-6 and float((e > 1e-3).float().mean()) < 2e-3
     assert float(ev.median()) < 1e-6 and float((ev > 1e-3).float().mean()) < 5e-3
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0])
+def test_register_spline_inverse_matches_float64(lib, scale):
+    """rq_spline_regs_inv (the density direction of the tensor-core kernels) against zuko's MonotonicRQSTransform in
+    float64: v = RQS^-1(y) and the forward Jacobian at v; also the round trip through the forward spline."""
+    torch.manual_seed(7)
+    n = 20000
+    phi = torch.randn(n, 59) * scale
+    y = (torch.rand(n) - 0.5) * 12.0                       # inside and outside the box
+    a = np.zeros((n, 64), dtype=np.float32)
+    a[:, :59] = phi.numpy()
+    yy = np.ascontiguousarray(y.numpy(), dtype=np.float32)
+    v = np.empty(n, dtype=np.float32)
+    jac = np.empty(n, dtype=np.float32)
+    lib.spline_host_inv(_ptr(a), _ptr(yy), n, _ptr(v), _ptr(jac))
+    v, jac = torch.from_numpy(v), torch.from_numpy(jac)
+    p64 = phi.double()
+    sp = RQSpline(p64[:, :20], p64[:, 20:40], p64[:, 40:])
+    v64 = sp.inverse(y.double())
+    _, ladj64 = sp.call_and_ladj(v64)
+    ev = rel(v, v64)
+    el = rel(jac.double().log(), ladj64)
+    assert float(ev.median()) < 1e-6 and float(el.median()) < 1e-6
+    # isolated ill-conditioned bins (tiny widths next to large heights) leave a tail, as in the forward direction
+    assert int((ev > TOL).sum()) <= n // 500 and int((el > TOL).sum()) <= n // 200, (int((ev > TOL).sum()), int((el > TOL).sum()))
+    back, _ = host_spline(lib, phi, v)
+    eb = rel(back, y)
+    assert float(eb.median()) < 1e-6 and int((eb > TOL).sum()) <= n // 500
