@@ -320,6 +320,22 @@ def extras(args, device, pk):
         entry("C3 optimisation step (zero_grad + loss + backward + fused AdamW) as one CUDA-graph replay", nb, ms,
               tensor_roof(3 * FLOP_MASK_AWARE[6], nb, ms, "nsf_tc_layer_kernel<6,3,20,bwd> + dgrad + wgrad x5"))
         del gts, opt
+    # density direction: log_prob(x) of the flow (generate/flows/zuko.py:21-22), tensor-core inverse kernel, default-init
+    # x 1.5 weights (the inverse of a x3 flow is ill-conditioned in any fp32 arithmetic)
+    torch.manual_seed(0)
+    ginv = mf.generate.NSFGenerator(6)
+    with torch.no_grad():
+        for p_ in ginv.parameters():
+            p_.mul_(1.5)
+        ginv = ginv.to(device)
+        xi, lqi = ginv.sample_and_log_prob(N)
+        ms = _timed(lambda: ginv.log_prob(xi), reps=5, flush=flush)
+        dev_lp = float((ginv.log_prob(xi) - lqi).abs().max())
+    entry("flow log_prob(x), density direction: 6-D NSF inverse x5 (tcgen05 inverse kernel, eager launches)", N, ms,
+          tensor_roof(5 * 5 * 2 * (16 * 64 + 2 * 64 * 64 + 64 * 64), N, ms,
+                      "nsf_tc_inverse_kernel<6,3,20> x5 (dense-equivalent FLOP of 5 conditioner passes per layer)"),
+          max_abs_round_trip_error=dev_lp)
+    del ginv, xi, lqi
     del m3
     # C4 rec_nd_2d: 15 two-dimensional screens 85 x 85
     m4 = model_for(workloads.corner_2d(6, 85, 3.5), 6, "2d", n_truth=100_000)
