@@ -28,8 +28,10 @@ struct MentPrior {
 };
 
 // shared-memory tables: coords[K][B] (bin centres) and values[K][B] (h_k)
-__device__ __forceinline__ float lagrange_eval(const float* __restrict__ c, const float* __restrict__ h, int B,
-                                               float inv_step, float u) {
+// dinv[i] = 1 / (c[i+1] - c[i]) in double, tabulated once per CTA: the normalised distance is then a double
+// multiply instead of a double division (one ulp of double apart: invisible after the cast to fp32)
+__device__ __forceinline__ float lagrange_eval(const float* __restrict__ c, const float* __restrict__ h,
+                                               const double* __restrict__ dinv, int B, float inv_step, float u) {
   // scipy RegularGridInterpolator(method="linear", bounds_error=False, fill_value=0) on the bin
   // centres, evaluated in double like the reference (ment.py:45-52), then cast to fp32 (:233)
   if (!(u >= c[0] && u <= c[B - 1])) return 0.f;
@@ -37,8 +39,7 @@ __device__ __forceinline__ float lagrange_eval(const float* __restrict__ c, cons
   i = min(max(i, 0), B - 2);
   while (i > 0 && u < c[i]) --i;
   while (i < B - 2 && u > c[i + 1]) ++i;
-  const double x0 = (double)c[i], x1 = (double)c[i + 1];
-  const double w = ((double)u - x0) / (x1 - x0);
+  const double w = ((double)u - (double)c[i]) * dinv[i];
   return (float)((double)h[i] * (1.0 - w) + (double)h[i + 1] * w);
 }
 
@@ -97,15 +98,18 @@ __device__ __forceinline__ float tables2d_product(const float (&x)[D], const Tab
 template <int D>
 __device__ __forceinline__ float ment_density(const float (&x)[D], const float* __restrict__ s_proj,
                                               const float* __restrict__ s_c, const float* __restrict__ s_h,
-                                              const float* __restrict__ s_inv, int K, int B, MentPrior prior) {
+                                              const float* __restrict__ s_inv, const double* __restrict__ s_dinv, int K,
+                                              int B, MentPrior prior) {
   float prob = 1.0f;
   for (int k = 0; k < K; ++k) {
     float u = 0.f;
 #pragma unroll
     for (int i = 0; i < D; ++i) u = fmaf(s_proj[k * D + i], x[i], u);
-    float h = lagrange_eval(s_c + (size_t)k * B, s_h + (size_t)k * B, B, s_inv[k], u);
+    float h = lagrange_eval(s_c + (size_t)k * B, s_h + (size_t)k * B, s_dinv + (size_t)k * B, B, s_inv[k], u);
     h = fminf(fmaxf(h, 0.0f), 1.0e10f);   // ment.py:246
     prob *= h;
+    if (prob == 0.f) break;               // every remaining factor is finite (clamped): the product stays 0 -- on a 6-D
+                                          // sampler grid 9 cells in 10 project outside some screen
   }
   float ss = 0.f;
 #pragma unroll
@@ -113,13 +117,14 @@ __device__ __forceinline__ float ment_density(const float (&x)[D], const float* 
   return prob * expf(fmaf(prior.neg_half_inv_s2, ss, prior.log_norm));
 }
 
-__device__ __forceinline__ void load_tables(float* s_proj, float* s_c, float* s_h, float* s_inv,
+__device__ __forceinline__ void load_tables(float* s_proj, float* s_c, float* s_h, float* s_inv, double* s_dinv,
                                             const float* __restrict__ proj, const float* __restrict__ coords,
                                             const float* __restrict__ tables, int K, int B, int D) {
   for (int i = threadIdx.x; i < K * D; i += blockDim.x) s_proj[i] = proj[i];
   for (int i = threadIdx.x; i < K * B; i += blockDim.x) {
     s_c[i] = coords[i];
     s_h[i] = tables[i];
+    s_dinv[i] = (i % B < B - 1) ? 1.0 / ((double)coords[i + 1] - (double)coords[i]) : 0.0;
   }
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     s_inv[k] = (float)(B - 1) / (coords[(size_t)k * B + B - 1] - coords[(size_t)k * B]);
@@ -136,7 +141,8 @@ ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const fl
   float* s_c = s_proj + (((size_t)K * D + 3) & ~(size_t)3);
   float* s_h = s_c + (size_t)K * B;
   float* s_inv = s_h + (size_t)K * B;
-  load_tables(s_proj, s_c, s_h, s_inv, proj, coords, tables, K, B, D);
+  double* s_dinv = reinterpret_cast<double*>(s_inv + ((K + 1) & ~1));
+  load_tables(s_proj, s_c, s_h, s_inv, s_dinv, proj, coords, tables, K, B, D);
   __syncthreads();
   for (int64_t g = (int64_t)blockIdx.x * kMentThreads + threadIdx.x; g < G; g += (int64_t)gridDim.x * kMentThreads) {
     float xr[D];
@@ -152,7 +158,7 @@ ment_prob_kernel(const float* __restrict__ x, int64_t G, MentGrid grid, const fl
         xr[i] = fmaf((float)idx, grid.step[i], grid.lo[i]);
       }
     }
-    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, s_dinv, K, B, prior);
     if (t2.k > 0) rho *= tables2d_product<D>(xr, t2);
     out[g] = rho;
   }
@@ -174,7 +180,8 @@ ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int me
   float* s_inv = s_h + (size_t)K * B;
   __shared__ float s_minv[D * D];
   __shared__ double red[kMentThreads / 32];
-  load_tables(s_proj, s_c, s_h, s_inv, proj, coords, tables, K, B, D);
+  double* s_dinv = reinterpret_cast<double*>(s_inv + ((K + 1) & ~1));
+  load_tables(s_proj, s_c, s_h, s_inv, s_dinv, proj, coords, tables, K, B, D);
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_minv[i] = minv[i];
   __syncthreads();
   int64_t Q = 1;
@@ -210,7 +217,7 @@ ment_integrate_kernel(const float* __restrict__ meas_coords, int nb_meas, int me
       for (int j = 0; j < D; ++j) s = fmaf(u[j], s_minv[i * D + j], s);
       xr[i] = s;
     }
-    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, K, B, prior);
+    float rho = ment_density<D>(xr, s_proj, s_c, s_h, s_inv, s_dinv, K, B, prior);
     if (t2.k > 0) rho *= tables2d_product<D>(xr, t2);
     dacc += (double)rho;
   }
@@ -359,7 +366,7 @@ __global__ void gs_update_kernel(float* __restrict__ table, const float* __restr
 }
 
 static size_t ment_smem(int K, int B, int d) {
-  return ((((size_t)K * d + 3) & ~(size_t)3) + 2 * (size_t)K * B + K) * 4 + 16;
+  return ((((size_t)K * d + 3) & ~(size_t)3) + 2 * (size_t)K * B + ((K + 1) & ~1)) * 4 + (size_t)K * B * 8 + 16;
 }
 
 static MentGrid make_grid(int ndim, const int32_t* shape, const float* lo, const float* step) {
