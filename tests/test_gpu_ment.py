@@ -83,6 +83,35 @@ def test_grid_sampler_statistics(golden):
     assert (torch.cov(x.double().T).cpu() - torch.from_numpy(g["xs_cov"])).abs().max() < 0.08
 
 
+@pytest.mark.parametrize("shape", [(3,), (5,), (37,), (1000,), (7, 13), (65, 63), (4, 4, 4, 5), (17, 16, 16)])
+def test_cdf_sample_on_ragged_grid_sizes(shape):
+    """The pivot-level search of cdf_sample (four keys per sector, partial groups at every level) picks cells with the
+    probabilities of the density for cell counts that are not powers of four, never a zero-probability cell, and the
+    last cell is reachable."""
+    torch.manual_seed(sum(shape))
+    g = 1
+    for s_ in shape:
+        g *= s_
+    rho = torch.rand(g) ** 3
+    rho[torch.rand(g) < 0.3] = 0.0
+    rho[-1] = rho.max() * 2            # the last cell carries weight: the descent must reach it
+    rho[0] = 0.0
+    n = 2_000_000
+    d = len(shape)
+    x = ops.cdf_sample(rho.cuda(), list(shape), [0.0] * d, [1.0] * d, n, seed=3)
+    idx = torch.floor(x.double()).long()
+    flat = torch.zeros(n, dtype=torch.long, device=x.device)
+    for i, s_ in enumerate(shape):
+        flat = flat * s_ + idx[:, i].clamp_(0, s_ - 1)
+    freq = torch.bincount(flat, minlength=g).double().cpu()
+    pmf = (rho.double() / rho.double().sum())
+    assert float(freq[pmf == 0].sum()) == 0
+    big = pmf * n > 50
+    z = (freq[big] - pmf[big] * n) / torch.sqrt(pmf[big] * n * (1 - pmf[big]))
+    assert float(z.abs().max()) < 6.0, float(z.abs().max())
+    assert freq[-1] > 0
+
+
 def test_sample_mode_update_is_statistically_consistent(golden):
     g = golden("ment_4d")
     torch.manual_seed(0)
