@@ -183,9 +183,9 @@ def time_cpu(step, n, reps, warmup=1, budget_s=12.0):
 # ncu --set full capture of ONE nsf_tc_layer_kernel<6,3,20> launch of this workload (profiles/, this round)
 NCU_PROFILE = {
     "file": "profiles/r2_full_metrics.txt",
-    "dram_bytes_per_launch": 28.18e6 + 0.24e6,          # dram__bytes_read.sum + dram__bytes_write.sum
-    "pipes": {"issue_active_pct": 62.6, "xu_mufu_pct": 40.4, "tensor_pct": 40.3, "fma_pct": 29.2, "lsu_pct": 8.1,
-              "dram_pct": 1.8, "warps_active_pct": 24.9,
+    "dram_bytes_per_launch": 28.18e6 + 0.20e6,          # dram__bytes_read.sum + dram__bytes_write.sum
+    "pipes": {"issue_active_pct": 62.8, "xu_mufu_pct": 40.6, "tensor_pct": 40.4, "fma_pct": 29.3, "lsu_pct": 8.1,
+              "dram_pct": 1.8, "warps_active_pct": 25.0,
               "note": "no pipe is saturated: three compute warps per scheduler at the latency-bound issue rate"},
 }
 
