@@ -9,11 +9,15 @@
 // Design (B200): the particle block streams HBM -> smem through the TMA engine
 // (cp.async.bulk + mbarrier, double buffered).  Thread t of a CTA owns projection
 // k = t % Kc and particle slice t / Kc, and a PRIVATE column of bins in shared memory
-// (bins[b][t]: bank = t % 32, conflict free), so deposits are plain LDS/FADD/STS -- no
-// atomics, and the accumulation order is fixed => run-to-run deterministic.  Each particle
-// touches only the 2R+1 bins within ~8.9 sigma of its projection (everything else is below
-// 1e-17 of a central tap), instead of all B.  Per-CTA partials are merged in a fixed
-// order by a second tiny kernel.
+// (pairs of rows as float2, blocked per warp: [warp][pair][lane] -- a warp touches 256
+// contiguous bytes whatever bins its lanes hit, conflict free), so deposits are plain 8-byte
+// LDS/FADD/STS -- no atomics, and the accumulation order is fixed => run-to-run deterministic.
+// Each particle touches only the pair-aligned window of 2R+2 bins around its projection
+// (everything beyond ~8.9 sigma is below 1e-17 of a central tap), instead of all B; the taps
+// come from a factorised Gaussian (3 MUFU) with packed-fp32 recurrences.  Per-CTA partials are
+// merged in a fixed order by a second tiny kernel (kde1d_finish_kernel), which also normalises
+// and evaluates the KL term.  The kernel sits at its shared-memory floor (80 B read + written
+// per particle-projection); the backward kernel uses the same taps on a zero-padded table.
 #include <type_traits>
 
 #include "common.cuh"

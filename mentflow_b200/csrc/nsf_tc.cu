@@ -23,6 +23,12 @@
 // triangular; K steps whose weights are all zero for a block of outputs are not issued (14 of 20
 // output-layer K steps at D = 6).  The feature that is first in the layer's order has a bias-only
 // spline: its knots are precomputed into a table in the image.
+//
+// Also in this file, on the same machinery: the backward variant of the layer kernel (kBwd: recompute + spline
+// backward, writes the compact dL/dphi rows, ReLU masks and a bulk-copied mirror of the activation operand tiles for
+// nsf_tc_bwd.cu), the forward variant's A hi operand in tensor memory (tcgen05.st + TMEM-A MMAs), programmatic
+// dependent launch of consecutive layers, and nsf_tc_inverse_kernel (density direction: one conditioner pass plus a
+// register-resident inverse spline per feature).
 #include "nsf_spline_regs.cuh"
 #include "nsf_tc_common.cuh"
 
